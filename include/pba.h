@@ -1,0 +1,280 @@
+/* pba.h — C ABI of the B200-native bundle-adjustment engine (libpba_b200.so).
+ *
+ * This is the drop-in boundary for the reference's single hot entry point
+ *
+ *   void visnav::bundle_adjustment(const Corners&, const BundleAdjustmentOptions&,
+ *                                  const std::set<FrameCamId>& fixed_cameras,
+ *                                  Calibration&, Cameras&, Landmarks&)
+ *   (reference: include/visnav/map_utils.h:322-399, caller src/sfm.cpp:1903-1913)
+ *
+ * A host shim (include/visnav_b200/bundle_adjustment.h)
+ * flattens the reference containers into the SoA `pba_problem` below, calls
+ * `pba_solve`, and writes poses / inverse distances back in place — the same
+ * in/out contract Ceres has through raw parameter pointers (map_utils.h:331,
+ * :373).  Only plain pointers and sizes cross this boundary; no C++/torch
+ * types.  Every function returns a pba_status; nothing throws.
+ *
+ * There is no CPU fallback: every compute entry point returns
+ * PBA_ERR_NO_DEVICE when no CUDA device is present.
+ */
+#ifndef PBA_H_
+#define PBA_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PBA_ABI_VERSION 1
+
+typedef enum pba_status {
+  PBA_OK = 0,
+  PBA_ERR_INVALID_ARGUMENT = 1,
+  PBA_ERR_NO_DEVICE = 2,
+  PBA_ERR_CUDA = 3,
+  PBA_ERR_UNSUPPORTED = 4, /* e.g. optimize_intrinsics=true (map_utils.h:339) */
+  PBA_ERR_NUMERICAL_FAILURE = 5,
+  PBA_ERR_NCCL = 6,
+  PBA_ERR_OUT_OF_MEMORY = 7
+} pba_status;
+
+/* Residual family.  GEOMETRIC is the reference's
+ * BundleAdjustmentReprojectionCostFunctor (reprojection.h:74-118): 2 residuals,
+ * local Jacobian 2 x (6 host pose | 6 target pose | 1 inverse distance).
+ * PHOTOMETRIC is SURVEY.md §8(a-P): 8 residuals (DSO pattern), local Jacobian
+ * 8 x (6 host pose | 6 target pose | 2 target affine (a,b) | 1 inverse distance). */
+enum { PBA_MODE_GEOMETRIC = 0, PBA_MODE_PHOTOMETRIC = 1 };
+
+/* Camera models, reference camera_models.h:47-420; names as in
+ * AbstractCamera::from_data (camera_models.h:452-474). */
+enum { PBA_CAM_PINHOLE = 0, PBA_CAM_DS = 1, PBA_CAM_KB4 = 2, PBA_CAM_EUCM = 3 };
+
+enum { PBA_SOLVER_AUTO = 0, PBA_SOLVER_CHOLESKY = 1, PBA_SOLVER_PCG = 2 };
+
+/* Ceres termination types (include/ceres/types.h) kept so reports line up. */
+enum { PBA_CONVERGENCE = 0, PBA_NO_CONVERGENCE = 1, PBA_FAILURE = 2 };
+
+#define PBA_PATTERN_SIZE 8
+#define PBA_GEOM_RES 2
+#define PBA_GEOM_COLS 13  /* 6 + 6 + 1 */
+#define PBA_PHOTO_RES 8
+#define PBA_PHOTO_COLS 15 /* 6 + 6 + 2 + 1 */
+
+/* Flat (SoA) bundle-adjustment problem.  All arrays are HOST memory owned by
+ * the caller.  "pose index" = position of the keyframe in `poses`
+ * (the reference's Cameras map iterates in FrameCamId order, common_types.h:87).
+ * in/out arrays are updated in place on success, exactly like Ceres does
+ * through T_w_c.data() / &landmark.inv_depth (map_utils.h:331,373). */
+typedef struct pba_problem {
+  int32_t mode;     /* PBA_MODE_* */
+  int32_t n_poses;  /* keyframes / cameras in the map */
+  int32_t n_calib;  /* intrinsics blocks (Calibration::intrinsics.size()) */
+  int32_t n_landmarks;
+  int64_t n_obs;    /* residual blocks = sum over landmarks of (|obs| - 1) */
+
+  double* poses;              /* [n_poses*7] Sophus order qx qy qz qw tx ty tz; in/out */
+  const uint8_t* pose_fixed;  /* [n_poses] 1 = constant (fixed_cameras) */
+  const int32_t* pose_calib;  /* [n_poses] index into intrinsics (FrameCamId::cam_id) */
+  const int32_t* calib_model; /* [n_calib] PBA_CAM_* */
+  const double* intrinsics;   /* [n_calib*8] fx fy cx cy p1..p4 (camera_models.h:119-123) */
+
+  double* inv_depth;          /* [n_landmarks] inverse distance along host ray; in/out */
+  const int32_t* lm_host;     /* [n_landmarks] pose index of host = obs.begin() (map_utils.h:351) */
+  const double* lm_host_uv;   /* [n_landmarks*2] host pixel z_h */
+  const int64_t* lm_obs_ptr;  /* [n_landmarks+1] CSR offsets into obs_* (non-host obs only) */
+  const int32_t* obs_target;  /* [n_obs] pose index of the target keyframe */
+  const double* obs_uv;       /* [n_obs*2] target pixel z_t (GEOMETRIC only, else NULL) */
+
+  /* PHOTOMETRIC only: one 8-bit grey image per pose, all the same size.
+   * Either image_ptrs[i] (if non-NULL) or images + i*image_stride. */
+  const uint8_t* images;
+  const uint8_t* const* image_ptrs;
+  int64_t image_stride;       /* bytes between consecutive images in `images` */
+  int32_t width, height, pitch;
+  double* affine;             /* [n_poses*2] (a,b) per keyframe; in/out */
+} pba_problem;
+
+/* First five fields = BundleAdjustmentOptions (map_utils.h:304-319), same
+ * defaults via pba_options_init.  The rest default to Ceres 2.0.0's
+ * Solver::Options values (include/ceres/solver.h:277-322). */
+typedef struct pba_options {
+  int32_t verbosity_level;     /* 0 silent, 1 brief report, 2 full report */
+  int32_t optimize_intrinsics; /* must be 0 (reference marks it broken, map_utils.h:339) */
+  int32_t use_huber;
+  double huber_parameter;
+  int32_t max_num_iterations;
+
+  int32_t solver;              /* PBA_SOLVER_*; AUTO = Cholesky when RCS dim <= cholesky_max_dim */
+  int32_t cholesky_max_dim;    /* default 4096 */
+  int32_t pcg_max_iterations;  /* default 500 */
+  double pcg_tolerance;        /* relative residual ||r||/||b||, default 1e-10 */
+  double initial_trust_region_radius; /* 1e4 */
+  double max_trust_region_radius;     /* 1e16 */
+  double min_trust_region_radius;     /* 1e-32 */
+  double min_relative_decrease;       /* 1e-3 */
+  double min_lm_diagonal;             /* 1e-6 */
+  double max_lm_diagonal;             /* 1e32 */
+  double function_tolerance;          /* 1e-6 */
+  double gradient_tolerance;          /* 1e-10 */
+  double parameter_tolerance;         /* 1e-8 */
+  int32_t max_num_consecutive_invalid_steps; /* 5 */
+  int32_t jacobi_scaling;             /* 1 */
+  int32_t device;                     /* CUDA device ordinal, default 0 */
+  int32_t profile;                    /* 1 = bracket every kernel with CUDA events */
+} pba_options;
+
+/* One row of Ceres' Solver::Summary::iterations (include/ceres/iteration_callback.h). */
+typedef struct pba_iteration {
+  int32_t iteration;
+  int32_t step_is_valid;
+  int32_t step_is_successful;
+  int32_t linear_solver_iterations;
+  double cost;
+  double cost_change;
+  double gradient_max_norm;
+  double gradient_norm;
+  double step_norm;
+  double relative_decrease;
+  double trust_region_radius;
+  double model_cost_change;
+} pba_iteration;
+
+/* Same wall-clock buckets as ceres::Solver::Summary (solver.h:822-851). */
+typedef struct pba_summary {
+  int32_t termination_type; /* PBA_CONVERGENCE / NO_CONVERGENCE / FAILURE */
+  int32_t num_iterations;   /* entries written to `iterations` (incl. iteration 0) */
+  int32_t num_successful_steps;
+  int32_t num_unsuccessful_steps;
+  int32_t num_residual_evaluations;
+  int32_t num_jacobian_evaluations;
+  int32_t num_linear_solves;
+  int32_t rcs_dim;           /* reduced camera system dimension */
+  int64_t rcs_blocks;        /* stored upper-triangular blocks */
+  int64_t num_residual_blocks;
+  int64_t num_residuals;
+  int64_t num_effective_parameters;
+  int64_t gpu_kernel_launches;
+  double initial_cost;
+  double final_cost;
+  double setup_time_in_seconds;      /* flatten + sort + H2D */
+  double residual_evaluation_time_in_seconds;
+  double jacobian_evaluation_time_in_seconds;
+  double linear_solver_time_in_seconds;
+  double minimizer_time_in_seconds;
+  double total_time_in_seconds;
+  pba_iteration* iterations;         /* caller-provided, may be NULL */
+  int32_t iterations_capacity;
+  char message[256];
+} pba_summary;
+
+typedef struct pba_kernel_stat {
+  char name[48];
+  int64_t launches;
+  double total_ms; /* CUDA-event time, only when options.profile = 1 */
+} pba_kernel_stat;
+
+typedef struct pba_handle pba_handle; /* device-resident problem */
+
+/* ---- library ---- */
+int32_t pba_abi_version(void);
+const char* pba_status_string(pba_status s);
+int32_t pba_device_count(void); /* 0 when no CUDA device is usable */
+void pba_options_init(pba_options* o); /* BundleAdjustmentOptions + Ceres defaults */
+
+/* ---- the drop-in call: replaces bundle_adjustment() (map_utils.h:322) ----
+ * HOST buffers in, HOST buffers updated in place.  On PBA_FAILURE termination
+ * the inputs are left untouched (Ceres restores them, solver.cc:438-447);
+ * otherwise the lowest-cost accepted iterate is written back
+ * (trust_region_minimizer.cc:316-318). */
+pba_status pba_solve(pba_problem* problem, const pba_options* options,
+                     pba_summary* summary);
+
+/* ---- split entry points (tests / bench): device-resident problem ---- */
+/* Replaces Problem construction + Ceres preprocessing (map_utils.h:327-375,
+ * trust_region_preprocessor.cc:373): validates, orders observations by
+ * (host,target) edge, builds the RCS block structure, uploads everything.
+ * (rank, world_size): landmark shard for multi-GPU; (0,1) = whole problem. */
+pba_status pba_create(const pba_problem* problem, const pba_options* options,
+                      int32_t rank, int32_t world_size, pba_handle** out);
+void pba_destroy(pba_handle* h);
+
+/* Use an existing stream (a cudaStream_t, e.g. torch's current stream) so the
+ * caller can bracket work with its own CUDA events.  NULL = library stream. */
+pba_status pba_set_stream(pba_handle* h, void* cuda_stream);
+pba_status pba_synchronize(pba_handle* h);
+
+/* Replaces ProgramEvaluator::Evaluate (program_evaluator.h:139-286) for this
+ * rank's observations: with_jacobian=1 runs the residual+Jacobian kernel (K1)
+ * and materialises the robustified local Jacobian; 0 runs the cost-only
+ * kernel (K2).  *cost (host, may be NULL) = sum over blocks of rho(s)/2.
+ * When cost is NULL the call is asynchronous on the handle's stream. */
+pba_status pba_evaluate(pba_handle* h, int32_t with_jacobian, double* cost);
+
+/* Download per-block outputs of the last pba_evaluate(h,1,..) in the
+ * CALLER'S observation order (local shard): residuals [n_obs*R], jacobians
+ * [n_obs*R*C] row-major per block with columns (host pose 6 | target pose 6 |
+ * [affine 2] | rho 1), robustified like residual_block.cc:166-196.
+ * Columns of constant (fixed) poses are zero. */
+pba_status pba_get_residuals(pba_handle* h, double* residuals);
+pba_status pba_get_jacobians(pba_handle* h, double* jacobians);
+
+/* Replaces SchurEliminator::Eliminate (schur_eliminator_impl.h:177-306) on the
+ * last evaluated Jacobian with Jacobi scaling and LM damping for `radius`
+ * (levenberg_marquardt_strategy.cc:76-88); multi-GPU: includes the NCCL
+ * all-reduce.  pba_get_rcs copies the dense symmetric RCS [dim*dim] and rhs
+ * [dim] to the host (test sizes only). */
+pba_status pba_build_rcs(pba_handle* h, double radius);
+pba_status pba_get_rcs_dim(pba_handle* h, int32_t* dim);
+pba_status pba_get_rcs(pba_handle* h, double* S_dense, double* rhs);
+
+/* Solve the RCS built by pba_build_rcs with the configured solver; copy the
+ * (Jacobi-scaled, un-negated) camera solution to `y_cam` [dim] if non-NULL. */
+pba_status pba_solve_rcs(pba_handle* h, int32_t solver, double* y_cam,
+                         int32_t* iterations);
+
+/* Replaces TrustRegionMinimizer::Minimize (trust_region_minimizer.cc:67-132)
+ * on the resident problem.  State stays on the device. */
+pba_status pba_minimize(pba_handle* h, pba_summary* summary);
+
+/* Move optimisation state (poses [n_poses*7], inv_depth [n_landmarks local
+ * shard order = caller order], affine [n_poses*2] or NULL). */
+pba_status pba_set_state(pba_handle* h, const double* poses,
+                         const double* inv_depth, const double* affine);
+pba_status pba_get_state(pba_handle* h, double* poses, double* inv_depth,
+                         double* affine);
+
+/* Local shard sizes (after landmark partitioning). */
+pba_status pba_get_sizes(pba_handle* h, int64_t* n_obs_local,
+                         int32_t* n_landmarks_local, int64_t* first_landmark);
+
+/* Kernel accounting: every kernel launch is counted; durations need profile=1. */
+pba_status pba_reset_kernel_stats(pba_handle* h);
+int32_t pba_get_kernel_stats(pba_handle* h, pba_kernel_stat* out, int32_t cap);
+
+/* ---- multi-GPU: one process per GPU, NCCL all-reduce of the partial RCS ----
+ * Rank 0 obtains an id (128 bytes), the caller broadcasts it by any means
+ * (torch.distributed in bench.py), every rank calls pba_comm_init before
+ * pba_build_rcs / pba_minimize. */
+#define PBA_NCCL_ID_BYTES 128
+pba_status pba_nccl_unique_id(uint8_t id[PBA_NCCL_ID_BYTES]);
+pba_status pba_comm_init(pba_handle* h, const uint8_t id[PBA_NCCL_ID_BYTES]);
+
+/* ---- stand-alone primitives exposed for parity tests ---- */
+/* Camera models on the device (camera_models.h project/unproject), n points. */
+pba_status pba_camera_project(int32_t model, const double intr[8], int64_t n,
+                              const double* xyz, double* uv, double* duv_dxyz);
+pba_status pba_camera_unproject(int32_t model, const double intr[8], int64_t n,
+                                const double* uv, double* xyz);
+/* LocalParameterizationSE3::Plus (local_parameterization_se3.hpp:44-51). */
+pba_status pba_se3_plus(int64_t n, const double* poses7, const double* delta6,
+                        double* out7);
+/* Dense fp64 Cholesky solve A x = b on the device (A symmetric [n*n]). */
+pba_status pba_cholesky_solve(int32_t n, const double* A, const double* b,
+                              double* x);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PBA_H_ */

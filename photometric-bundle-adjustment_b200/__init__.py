@@ -1,0 +1,21 @@
+"""photometric-bundle-adjustment_b200 — B200-native bundle adjustment behind the
+reference's `bundle_adjustment()` boundary (include/visnav/map_utils.h:322).
+
+Python here is only the host-side mirror of that interface over the C ABI
+(include/pba.h, libpba_b200.so).  All compute is hand-written CUDA for sm_100a;
+there is no CPU / PyTorch fallback — calls raise if the extension is missing or
+no GPU is present.
+"""
+from . import _ffi
+from ._ffi import (CAM_DS, CAM_EUCM, CAM_KB4, CAM_PINHOLE, CONVERGENCE, FAILURE, MODE_GEOMETRIC,
+                   MODE_PHOTOMETRIC, NO_CONVERGENCE, SOLVER_AUTO, SOLVER_CHOLESKY, SOLVER_PCG, ExtensionMissing)
+from .engine import BundleAdjustmentOptions, Engine, Summary, bundle_adjustment, device_count
+from .problem import Problem, partition_landmarks
+from .synth import make_scene
+
+__all__ = [
+    "BundleAdjustmentOptions", "Engine", "Summary", "bundle_adjustment", "device_count", "Problem",
+    "partition_landmarks", "make_scene", "MODE_GEOMETRIC", "MODE_PHOTOMETRIC", "CAM_PINHOLE", "CAM_DS",
+    "CAM_KB4", "CAM_EUCM", "SOLVER_AUTO", "SOLVER_CHOLESKY", "SOLVER_PCG", "CONVERGENCE", "NO_CONVERGENCE",
+    "FAILURE", "ExtensionMissing",
+]

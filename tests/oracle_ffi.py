@@ -1,0 +1,125 @@
+"""Test-only ctypes bindings for the checkers under oracle/.
+
+  * oracle/libpba_oracle.so  — the CPU restatement ("port"), always built.
+  * oracle/_ref/libpba_ref.so — the unmodified reference + vendored Ceres 2.0.0
+    (built here from /root/reference by oracle/ref/Makefile; travels to the GPU
+    box prebuilt, may be absent).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+reference legs may import this module.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+import pba_b200
+from pba_b200 import _ffi
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_SO = os.path.join(_ROOT, "oracle", "libpba_oracle.so")
+REF_SO = os.path.join(_ROOT, "oracle", "_ref", "libpba_ref.so")
+
+_d = _ffi.c_double_p
+
+
+def _bind_common(lib, prefix):
+    P = C.POINTER(_ffi.pba_problem)
+    getattr(lib, prefix + "_eval").argtypes = [P, C.c_int, C.c_double, C.c_int, _d, _d, _d]
+    getattr(lib, prefix + "_project").restype = C.c_int
+    getattr(lib, prefix + "_unproject").argtypes = [C.c_int, _d, C.c_int64, _d, _d]
+    getattr(lib, prefix + "_se3_plus").argtypes = [C.c_int64, _d, _d, _d]
+    getattr(lib, prefix + "_se3_plus_jacobian").argtypes = [_d, _d]
+
+
+_oracle = None
+_ref = None
+
+
+def oracle():
+    global _oracle
+    if _oracle is None:
+        lib = C.CDLL(ORACLE_SO)
+        _bind_common(lib, "pba_oracle")
+        lib.pba_oracle_project.argtypes = [C.c_int, _d, C.c_int64, _d, _d, _d]
+        lib.pba_oracle_solve.argtypes = [C.POINTER(_ffi.pba_problem), C.POINTER(_ffi.pba_options), C.c_int,
+                                         C.POINTER(_ffi.pba_summary)]
+        lib.pba_oracle_build_rcs.argtypes = [C.POINTER(_ffi.pba_problem), C.c_int, C.c_double, C.c_double, C.c_int,
+                                             _ffi.c_i32_p, _d, _d, _d]
+        _oracle = lib
+    return _oracle
+
+
+def have_ref():
+    return os.path.exists(REF_SO)
+
+
+def ref():
+    global _ref
+    if _ref is None:
+        lib = C.CDLL(REF_SO)
+        _bind_common(lib, "pba_ref")
+        lib.pba_ref_project.argtypes = [C.c_int, _d, C.c_int64, _d, _d]
+        lib.pba_ref_project_jacobian.argtypes = [C.c_int, _d, C.c_int64, _d, _d]
+        lib.pba_ref_solve.argtypes = [C.POINTER(_ffi.pba_problem), C.POINTER(_ffi.pba_options), C.c_int, C.c_int,
+                                      C.POINTER(_ffi.pba_summary)]
+        lib.pba_ref_hardware_threads.restype = C.c_int
+        _ref = lib
+    return _ref
+
+
+def default_options(**kw):
+    """pba_options with BundleAdjustmentOptions + Ceres defaults (no CUDA library needed)."""
+    o = _ffi.pba_options()
+    o.verbosity_level, o.optimize_intrinsics, o.use_huber, o.huber_parameter, o.max_num_iterations = 0, 0, 1, 1.0, 20
+    o.solver, o.cholesky_max_dim, o.pcg_max_iterations, o.pcg_tolerance = 0, 4096, 500, 1e-10
+    o.initial_trust_region_radius, o.max_trust_region_radius, o.min_trust_region_radius = 1e4, 1e16, 1e-32
+    o.min_relative_decrease, o.min_lm_diagonal, o.max_lm_diagonal = 1e-3, 1e-6, 1e32
+    o.function_tolerance, o.gradient_tolerance, o.parameter_tolerance = 1e-6, 1e-10, 1e-8
+    o.max_num_consecutive_invalid_steps, o.jacobi_scaling, o.device, o.profile = 5, 1, 0, 0
+    for k, v in kw.items():
+        setattr(o, k, v)
+    return o
+
+
+def evaluate(lib_kind, prob, use_huber=True, huber=1.0, threads=0, jac=True):
+    """(cost, residuals [n_obs,R], jacobians [n_obs,R,C]) from the oracle port or the reference."""
+    lib = oracle() if lib_kind == "oracle" else ref()
+    fn = lib.pba_oracle_eval if lib_kind == "oracle" else lib.pba_ref_eval
+    r = np.zeros((prob.n_obs, prob.res_per_obs))
+    J = np.zeros((prob.n_obs, prob.res_per_obs, prob.cols_per_obs)) if jac else None
+    cost = C.c_double()
+    pc = prob.c
+    rc = fn(C.byref(pc), int(use_huber), float(huber), threads if threads else (os.cpu_count() or 1),
+            _ffi.ptr(r, C.c_double), _ffi.ptr(J, C.c_double), C.byref(cost))
+    assert rc == 0, rc
+    return cost.value, r, J
+
+
+def solve(lib_kind, prob, opts=None, threads=0, use_reference_entry=False):
+    """Runs the checker's full solve IN PLACE on prob; returns a pba_b200.Summary."""
+    opts = opts or default_options()
+    s = pba_b200.Summary(max(64, opts.max_num_iterations))
+    pc = prob.c
+    threads = threads if threads else (os.cpu_count() or 1)
+    if lib_kind == "oracle":
+        rc = oracle().pba_oracle_solve(C.byref(pc), C.byref(opts), threads, C.byref(s.c))
+    else:
+        rc = ref().pba_ref_solve(C.byref(pc), C.byref(opts), threads, int(use_reference_entry), C.byref(s.c))
+    assert rc == 0, rc
+    return s
+
+
+def build_rcs(prob, use_huber=True, huber=1.0, radius=1e4, threads=0):
+    lib = oracle()
+    pc = prob.c
+    dim = C.c_int32()
+    threads = threads if threads else (os.cpu_count() or 1)
+    lib.pba_oracle_build_rcs(C.byref(pc), int(use_huber), float(huber), float(radius), threads, C.byref(dim),
+                             None, None, None)
+    S = np.zeros((dim.value, dim.value))
+    rhs = np.zeros(dim.value)
+    scale = np.zeros(dim.value)
+    lib.pba_oracle_build_rcs(C.byref(pc), int(use_huber), float(huber), float(radius), threads, C.byref(dim),
+                             _ffi.ptr(S, C.c_double), _ffi.ptr(rhs, C.c_double), _ffi.ptr(scale, C.c_double))
+    return S, rhs, scale
