@@ -1,0 +1,1104 @@
+// host.cu — the C ABI (include/pba.h): problem flattening/ordering, the
+// device-resident handle, and the Levenberg-Marquardt driver.
+//
+// pba_create  replaces ceres::Problem construction + preprocessing
+//             (include/visnav/map_utils.h:327-375,
+//             internal/ceres/trust_region_preprocessor.cc:373,
+//             schur_complement_solver.cc:250-297 for the RCS block pattern).
+// pba_minimize replaces TrustRegionMinimizer::Minimize with the
+//             LevenbergMarquardtStrategy and the monotonic
+//             TrustRegionStepEvaluator (trust_region_minimizer.cc:67-826,
+//             levenberg_marquardt_strategy.cc:66-162,
+//             trust_region_step_evaluator.cc:52-112), decision logic on the
+//             host, every vector operation on the device.
+// pba_solve   is the drop-in for visnav::bundle_adjustment (map_utils.h:322).
+#include <dlfcn.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <chrono>
+#include <limits>
+#include <array>
+#include <memory>
+#include <numeric>
+#include <string>
+#include <unordered_set>
+
+#include "launch.h"
+#include "pba_internal.h"
+
+#define PBA_API extern "C" __attribute__((visibility("default")))
+
+namespace pba {
+
+const char* const kKernelNames[K_NUM] = {
+    "init_landmarks", "edge_prep",  "residual_jacobian", "cost_only",  "reduce_sum", "edge_gram",
+    "landmark_gather", "landmark_scale", "schur_syrk", "rcs_reduce", "rcs_scale",  "cam_scale",
+    "dense_fill",     "chol_panel", "chol_trsm",         "chol_syrk_dmma", "chol_solve", "pcg",
+    "backsub",        "model_cost", "retract",           "copy",       "unpermute",  "primitive"};
+
+pba_status map_cuda(cudaError_t e) {
+  if (e == cudaSuccess) return PBA_OK;
+  if (e == cudaErrorMemoryAllocation) return PBA_ERR_OUT_OF_MEMORY;
+  if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) return PBA_ERR_NO_DEVICE;
+  fprintf(stderr, "[pba_b200] CUDA error: %s\n", cudaGetErrorString(e));
+  return PBA_ERR_CUDA;
+}
+
+cudaEvent_t KernelStats::get_event() {
+  if (!pool.empty()) {
+    cudaEvent_t e = pool.back();
+    pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+void KernelStats::begin(int id, cudaStream_t s) {
+  ++launches[id];
+  if (!profile) return;
+  Pending p;
+  p.id = id;
+  p.a = get_event();
+  p.b = get_event();
+  cudaEventRecord(p.a, s);
+  pending.push_back(p);
+}
+void KernelStats::end(cudaStream_t s) {
+  if (!profile) return;
+  cudaEventRecord(pending.back().b, s);
+}
+void KernelStats::resolve() {
+  for (auto& p : pending) {
+    float ms_ = 0;
+    if (cudaEventElapsedTime(&ms_, p.a, p.b) == cudaSuccess) ms[p.id] += ms_;
+    pool.push_back(p.a);
+    pool.push_back(p.b);
+  }
+  pending.clear();
+}
+void KernelStats::reset() {
+  resolve();
+  for (int i = 0; i < K_NUM; ++i) { launches[i] = 0; ms[i] = 0; }
+}
+KernelStats::~KernelStats() {
+  for (auto& p : pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+  for (auto e : pool) cudaEventDestroy(e);
+}
+
+// ------------------------------------------------------------------ NCCL ---
+// Loaded lazily with dlopen so the library has no link-time NCCL dependency
+// (single-GPU users never touch it).  The only collective on the path is the
+// fp64 sum all-reduce of the partial RCS (plus scalar reductions).
+namespace {
+struct NcclId { char b[128]; };
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(NcclId*) = nullptr;
+  int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  bool load() {
+    if (lib) return true;
+    const char* env = getenv("PBA_NCCL_LIB");
+    const char* names[] = {env, "libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+      if (!n) continue;
+      lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (lib) break;
+    }
+    if (!lib) return false;
+    GetUniqueId = (int (*)(NcclId*))dlsym(lib, "ncclGetUniqueId");
+    CommInitRank = (int (*)(void**, int, NcclId, int))dlsym(lib, "ncclCommInitRank");
+    AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(lib, "ncclAllReduce");
+    CommDestroy = (int (*)(void*))dlsym(lib, "ncclCommDestroy");
+    return GetUniqueId && CommInitRank && AllReduce && CommDestroy;
+  }
+};
+NcclApi g_nccl;
+constexpr int kNcclDouble = 8, kNcclSum = 0, kNcclMax = 2;
+}  // namespace
+
+Handle::~Handle() {
+  if (nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(nccl_comm);
+  if (h_scalars) cudaFreeHost(h_scalars);
+  if (own_stream && stream) cudaStreamDestroy(stream);
+}
+
+pba_status allreduce_rcs(Handle* h) {
+  if (h->world <= 1) return PBA_OK;
+  if (!h->nccl_comm) return PBA_ERR_NCCL;
+  const Sizes& z = h->sz;
+  const size_t count = size_t(z.n_blocks) * z.cd * z.cd + 3 * size_t(z.dim);
+  h->stats.begin(K_COPY, h->stream);
+  const int rc = g_nccl.AllReduce(h->rcs.p, h->rcs.p, count, kNcclDouble, kNcclSum, h->nccl_comm, h->stream);
+  h->stats.end(h->stream);
+  return rc == 0 ? PBA_OK : PBA_ERR_NCCL;
+}
+
+pba_status allreduce_scalars(Handle* h, double* dev, int n, bool max_op) {
+  if (h->world <= 1) return PBA_OK;
+  if (!h->nccl_comm) return PBA_ERR_NCCL;
+  const int rc = g_nccl.AllReduce(dev, dev, size_t(n), kNcclDouble, max_op ? kNcclMax : kNcclSum, h->nccl_comm, h->stream);
+  return rc == 0 ? PBA_OK : PBA_ERR_NCCL;
+}
+
+namespace {
+
+double wall() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// Contiguous landmark ranges balanced by observation count.
+// Same rule as Python's pba_b200.partition_landmarks.
+void partition_landmarks(const int64_t* lm_obs_ptr, int n_lm, int world, std::vector<int>& bounds) {
+  bounds.assign(world + 1, 0);
+  const int64_t total = lm_obs_ptr[n_lm];
+  for (int r = 1; r < world; ++r) {
+    const int64_t target = (total * r) / world;
+    int b = int(std::lower_bound(lm_obs_ptr, lm_obs_ptr + n_lm + 1, target) - lm_obs_ptr);
+    b = std::min(std::max(b, bounds[r - 1]), n_lm);
+    bounds[r] = b;
+  }
+  bounds[world] = n_lm;
+}
+
+pba_status validate(const pba_problem* p, const pba_options* o) {
+  if (!p || !o) return PBA_ERR_INVALID_ARGUMENT;
+  if (o->optimize_intrinsics) return PBA_ERR_UNSUPPORTED;  // map_utils.h:339
+  if (p->mode != PBA_MODE_GEOMETRIC && p->mode != PBA_MODE_PHOTOMETRIC) return PBA_ERR_INVALID_ARGUMENT;
+  if (p->n_poses < 0 || p->n_calib < 0 || p->n_landmarks < 0 || p->n_obs < 0) return PBA_ERR_INVALID_ARGUMENT;
+  if (p->n_poses > 0 && (!p->poses || !p->pose_calib)) return PBA_ERR_INVALID_ARGUMENT;
+  if (p->n_calib > 0 && (!p->calib_model || !p->intrinsics)) return PBA_ERR_INVALID_ARGUMENT;
+  if (p->n_landmarks > 0 && (!p->inv_depth || !p->lm_host || !p->lm_host_uv)) return PBA_ERR_INVALID_ARGUMENT;
+  if (!p->lm_obs_ptr) return PBA_ERR_INVALID_ARGUMENT;
+  if (p->n_obs > 0 && !p->obs_target) return PBA_ERR_INVALID_ARGUMENT;
+  if (p->lm_obs_ptr[0] != 0 || p->lm_obs_ptr[p->n_landmarks] != p->n_obs) return PBA_ERR_INVALID_ARGUMENT;
+  if (o->use_huber && !(o->huber_parameter > 0.0)) return PBA_ERR_INVALID_ARGUMENT;
+  for (int i = 0; i < p->n_poses; ++i)
+    if (p->pose_calib[i] < 0 || p->pose_calib[i] >= p->n_calib) return PBA_ERR_INVALID_ARGUMENT;
+  for (int i = 0; i < p->n_calib; ++i)
+    if (p->calib_model[i] < 0 || p->calib_model[i] > PBA_CAM_EUCM) return PBA_ERR_UNSUPPORTED;  // from_data aborts (camera_models.h:469)
+  for (int l = 0; l < p->n_landmarks; ++l) {
+    if (p->lm_obs_ptr[l + 1] < p->lm_obs_ptr[l]) return PBA_ERR_INVALID_ARGUMENT;
+    if (p->lm_host[l] < 0 || p->lm_host[l] >= p->n_poses) return PBA_ERR_INVALID_ARGUMENT;
+    for (int64_t k = p->lm_obs_ptr[l]; k < p->lm_obs_ptr[l + 1]; ++k)
+      if (p->obs_target[k] < 0 || p->obs_target[k] >= p->n_poses || p->obs_target[k] == p->lm_host[l])
+        return PBA_ERR_INVALID_ARGUMENT;
+  }
+  if (p->mode == PBA_MODE_GEOMETRIC) {
+    if (p->n_obs > 0 && !p->obs_uv) return PBA_ERR_INVALID_ARGUMENT;
+  } else {
+    if (p->n_poses > 0 && !p->images && !p->image_ptrs) return PBA_ERR_INVALID_ARGUMENT;
+    if (p->width < 2 || p->height < 2 || p->pitch < p->width) return PBA_ERR_INVALID_ARGUMENT;
+  }
+  return PBA_OK;
+}
+
+constexpr int kChunkObs = 512;
+
+pba_status create_impl(const pba_problem* p, const pba_options* o, int rank, int world, Handle** out) {
+  pba_status st = validate(p, o);
+  if (st != PBA_OK) return st;
+  if (world < 1 || rank < 0 || rank >= world) return PBA_ERR_INVALID_ARGUMENT;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return PBA_ERR_NO_DEVICE; }
+  if (o->device < 0 || o->device >= ndev) return PBA_ERR_INVALID_ARGUMENT;
+  PBA_CUDA_OK(cudaSetDevice(o->device));
+
+  std::unique_ptr<Handle> hh(new Handle);
+  Handle* h = hh.get();
+  h->opt = *o;
+  h->rank = rank; h->world = world; h->device = o->device;
+  h->stats.profile = o->profile != 0;
+  PBA_CUDA_OK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  h->own_stream = true;
+  Sizes& z = h->sz;
+  const bool photo = p->mode == PBA_MODE_PHOTOMETRIC;
+  z.mode = p->mode; z.R = photo ? 8 : 2; z.C = photo ? 15 : 13; z.cd = photo ? 8 : 6;
+  z.n_poses = p->n_poses; z.n_calib = p->n_calib;
+  z.width = p->width; z.height = p->height; z.pitch = p->pitch;
+  const int cd = z.cd;
+
+  // ---- global layout: which parameter blocks survive Ceres' reduced program ----
+  std::vector<uint8_t> used(p->n_poses, 0), is_target(p->n_poses, 0);
+  for (int l = 0; l < p->n_landmarks; ++l) {
+    if (p->lm_obs_ptr[l + 1] > p->lm_obs_ptr[l]) { used[p->lm_host[l]] = 1; ++h->n_active_lm; }
+    for (int64_t k = p->lm_obs_ptr[l]; k < p->lm_obs_ptr[l + 1]; ++k) { used[p->obs_target[k]] = 1; is_target[p->obs_target[k]] = 1; }
+  }
+  h->n_obs_global = p->n_obs;
+  h->slot.assign(p->n_poses, -1);
+  h->affine_active.assign(p->n_poses, 0);
+  for (int i = 0; i < p->n_poses; ++i) {
+    const bool fixed = p->pose_fixed && p->pose_fixed[i];
+    if (!fixed && used[i]) h->slot[i] = z.n_slots++;
+    h->affine_active[i] = photo && !fixed && is_target[i];
+  }
+  z.dim = z.n_slots * cd;
+  const std::vector<int>& slot = h->slot;
+
+  // ---- global RCS block pattern: all camera pairs co-observing a landmark
+  //      (schur_complement_solver.cc:261-297); identical on every rank ----
+  std::vector<std::vector<int>> adj(z.n_slots);
+  {
+    // many landmarks share a camera set: insert the pairs of each distinct set once
+    std::unordered_set<std::string> seen;
+    std::vector<int> cams;
+    for (int l = 0; l < p->n_landmarks; ++l) {
+      if (p->lm_obs_ptr[l + 1] == p->lm_obs_ptr[l]) continue;
+      cams.clear();
+      if (slot[p->lm_host[l]] >= 0) cams.push_back(slot[p->lm_host[l]]);
+      for (int64_t k = p->lm_obs_ptr[l]; k < p->lm_obs_ptr[l + 1]; ++k)
+        if (slot[p->obs_target[k]] >= 0) cams.push_back(slot[p->obs_target[k]]);
+      if (cams.empty()) continue;
+      std::sort(cams.begin(), cams.end());
+      if (!seen.emplace(reinterpret_cast<const char*>(cams.data()), cams.size() * sizeof(int)).second) continue;
+      for (size_t i = 0; i < cams.size(); ++i)
+        for (size_t j = i; j < cams.size(); ++j) adj[cams[i]].push_back(cams[j]);
+    }
+    for (auto& v : adj) { std::sort(v.begin(), v.end()); v.erase(std::unique(v.begin(), v.end()), v.end()); }
+  }
+  std::vector<int64_t> adj_ptr(z.n_slots + 1, 0);
+  for (int a = 0; a < z.n_slots; ++a) {
+    if (adj[a].empty() || adj[a][0] != a) adj[a].insert(adj[a].begin(), a);  // always keep the diagonal block
+    adj_ptr[a + 1] = adj_ptr[a] + int64_t(adj[a].size());
+  }
+  z.n_blocks = adj_ptr[z.n_slots];
+  h->blk_row.resize(z.n_blocks); h->blk_col.resize(z.n_blocks); h->diag_blk.assign(z.n_slots, 0);
+  for (int a = 0; a < z.n_slots; ++a)
+    for (size_t k = 0; k < adj[a].size(); ++k) {
+      h->blk_row[adj_ptr[a] + k] = a;
+      h->blk_col[adj_ptr[a] + k] = adj[a][k];
+      if (adj[a][k] == a) h->diag_blk[a] = int(adj_ptr[a] + k);
+    }
+  auto block_of = [&](int a, int b) -> int64_t {  // a <= b
+    const auto it = std::lower_bound(adj[a].begin(), adj[a].end(), b);
+    return adj_ptr[a] + (it - adj[a].begin());
+  };
+
+  // ---- local shard: landmarks ordered by host, observations by (host,target) edge ----
+  std::vector<int> bounds;
+  partition_landmarks(p->lm_obs_ptr, p->n_landmarks, world, bounds);
+  const int lm_lo = bounds[rank], lm_hi = bounds[rank + 1];
+  h->first_landmark = lm_lo;
+  z.n_lm = lm_hi - lm_lo;
+  const int64_t obs_lo = p->lm_obs_ptr[lm_lo];
+  z.n_obs = p->lm_obs_ptr[lm_hi] - obs_lo;
+  const int n_lm = z.n_lm;
+  const int64_t n = z.n_obs;
+
+  h->lm_order.resize(n_lm);
+  std::iota(h->lm_order.begin(), h->lm_order.end(), 0);
+  std::stable_sort(h->lm_order.begin(), h->lm_order.end(),
+                   [&](int a, int b) { return p->lm_host[lm_lo + a] < p->lm_host[lm_lo + b]; });
+
+  // lm-major arrays in internal landmark order
+  std::vector<int64_t> lm_ptr(n_lm + 1, 0);
+  std::vector<int> k_lm(n), k_h(n), k_t(n);
+  std::vector<int64_t> k_orig(n);
+  {
+    int64_t k = 0;
+    for (int li = 0; li < n_lm; ++li) {
+      const int l = lm_lo + h->lm_order[li];
+      for (int64_t q = p->lm_obs_ptr[l]; q < p->lm_obs_ptr[l + 1]; ++q, ++k) {
+        k_lm[k] = li; k_h[k] = p->lm_host[l]; k_t[k] = p->obs_target[q]; k_orig[k] = q - obs_lo;
+      }
+      lm_ptr[li + 1] = k;
+    }
+  }
+  // stable LSD counting sort by (host, target)
+  std::vector<int64_t> perm(n), tmp(n);
+  {
+    std::vector<int64_t> cnt(p->n_poses + 1, 0);
+    for (int64_t k = 0; k < n; ++k) ++cnt[k_t[k] + 1];
+    for (int i = 0; i < p->n_poses; ++i) cnt[i + 1] += cnt[i];
+    for (int64_t k = 0; k < n; ++k) tmp[cnt[k_t[k]]++] = k;
+    std::fill(cnt.begin(), cnt.end(), 0);
+    for (int64_t k = 0; k < n; ++k) ++cnt[k_h[k] + 1];
+    for (int i = 0; i < p->n_poses; ++i) cnt[i + 1] += cnt[i];
+    for (int64_t i = 0; i < n; ++i) { const int64_t k = tmp[i]; perm[cnt[k_h[k]]++] = k; }
+  }
+  std::vector<int> obs_lm(n), obs_edge(n);
+  std::vector<int64_t> lm_pos(n);
+  std::vector<int> edge_h, edge_t;
+  std::vector<int64_t> edge_ptr;
+  h->obs_order.resize(n);
+  for (int64_t i = 0; i < n; ++i) {
+    const int64_t k = perm[i];
+    if (i == 0 || k_h[k] != edge_h.back() || k_t[k] != edge_t.back()) {
+      edge_h.push_back(k_h[k]); edge_t.push_back(k_t[k]); edge_ptr.push_back(i);
+    }
+    obs_lm[i] = k_lm[k];
+    obs_edge[i] = int(edge_h.size()) - 1;
+    lm_pos[k] = i;
+    h->obs_order[i] = k_orig[k];
+  }
+  edge_ptr.push_back(n);
+  z.n_edges = int(edge_h.size());
+
+  // edge chunks (one CTA each in k_edge_gram)
+  std::vector<int> chunk_edge;
+  std::vector<int64_t> chunk_begin, chunk_end;
+  for (int e = 0; e < z.n_edges; ++e)
+    for (int64_t b = edge_ptr[e]; b < edge_ptr[e + 1]; b += kChunkObs) {
+      chunk_edge.push_back(e); chunk_begin.push_back(b); chunk_end.push_back(std::min<int64_t>(b + kChunkObs, edge_ptr[e + 1]));
+    }
+  z.n_chunks = int(chunk_edge.size());
+
+  // host groups and their camera lists
+  std::vector<int> grp_lm_ptr, grp_cam_ptr(1, 0), grp_cams, lm_group(n_lm), lm_hostcol(n_lm, -1), obs_col(n, -1);
+  std::vector<int64_t> grp_w_off, grp_part_off, lm_w_off(n_lm);
+  std::vector<int> lm_w_stride(n_lm);
+  int64_t w_total = 0, part_total = 0;
+  {
+    std::vector<int> col_of(z.n_slots, -1), cams;
+    int li = 0;
+    while (li < n_lm) {
+      const int host = p->lm_host[lm_lo + h->lm_order[li]];
+      int lj = li;
+      while (lj < n_lm && p->lm_host[lm_lo + h->lm_order[lj]] == host) ++lj;
+      const int g = int(grp_lm_ptr.size());
+      grp_lm_ptr.push_back(li);
+      cams.clear();
+      if (slot[host] >= 0) cams.push_back(slot[host]);
+      for (int64_t k = lm_ptr[li]; k < lm_ptr[lj]; ++k) if (slot[k_t[k]] >= 0) cams.push_back(slot[k_t[k]]);
+      std::sort(cams.begin(), cams.end());
+      cams.erase(std::unique(cams.begin(), cams.end()), cams.end());
+      const int c = int(cams.size());
+      for (int j = 0; j < c; ++j) col_of[cams[j]] = j;
+      const int stride = 8 * (c + 1);
+      h->max_w_stride = std::max(h->max_w_stride, stride);
+      grp_w_off.push_back(w_total);
+      grp_part_off.push_back(part_total);
+      for (int l = li; l < lj; ++l) {
+        lm_group[l] = g;
+        lm_hostcol[l] = slot[host] >= 0 ? col_of[slot[host]] : -1;
+        lm_w_off[l] = w_total + int64_t(l - li) * stride;
+        lm_w_stride[l] = stride;
+        for (int64_t k = lm_ptr[l]; k < lm_ptr[l + 1]; ++k)
+          obs_col[lm_pos[k]] = slot[k_t[k]] >= 0 ? col_of[slot[k_t[k]]] : -1;
+      }
+      w_total += int64_t(lj - li) * stride;
+      part_total += int64_t(c) * (c + 1) / 2 * cd * cd + int64_t(c) * cd;
+      grp_cams.insert(grp_cams.end(), cams.begin(), cams.end());
+      grp_cam_ptr.push_back(int(grp_cams.size()));
+      for (int j = 0; j < c; ++j) col_of[cams[j]] = -1;
+      li = lj;
+    }
+    grp_lm_ptr.push_back(n_lm);
+  }
+  z.n_groups = int(grp_w_off.size());
+  h->schur_tile_l = schur_tile_l(h->max_w_stride);
+
+  // per-block source lists for the RCS reduction (static)
+  const int dir_stride = 3 * cd * cd + 2 * cd;
+  std::vector<int64_t> dir_ptr(z.n_blocks + 1, 0), sch_ptr(z.n_blocks + 1, 0), vdir_ptr(z.n_slots + 1, 0), vsch_ptr(z.n_slots + 1, 0);
+  std::vector<int64_t> dir_src, sch_src, vdir_src, vsch_src;
+  {
+    struct Src { int64_t key, off; };
+    std::vector<Src> d, s, vd, vs;
+    for (int q = 0; q < z.n_chunks; ++q) {
+      const int e = chunk_edge[q];
+      const int hs = slot[edge_h[e]], ts = slot[edge_t[e]];
+      const int64_t base = int64_t(q) * dir_stride;
+      if (hs >= 0) { d.push_back({block_of(hs, hs), base}); vd.push_back({hs, base + 3 * cd * cd}); }
+      if (ts >= 0) { d.push_back({block_of(ts, ts), base + 2 * cd * cd}); vd.push_back({ts, base + 3 * cd * cd + cd}); }
+      if (hs >= 0 && ts >= 0) d.push_back({block_of(std::min(hs, ts), std::max(hs, ts)), base + cd * cd});
+    }
+    for (int g = 0; g < z.n_groups; ++g) {
+      const int c0 = grp_cam_ptr[g], c = grp_cam_ptr[g + 1] - c0;
+      int64_t off = grp_part_off[g];
+      for (int i = 0; i < c; ++i)
+        for (int j = i; j < c; ++j) { s.push_back({block_of(grp_cams[c0 + i], grp_cams[c0 + j]), off}); off += cd * cd; }
+      for (int i = 0; i < c; ++i) { vs.push_back({grp_cams[c0 + i], off}); off += cd; }
+    }
+    auto build = [](std::vector<Src>& v, int64_t nkeys, std::vector<int64_t>& ptr, std::vector<int64_t>& src) {
+      std::stable_sort(v.begin(), v.end(), [](const Src& a, const Src& b) { return a.key < b.key; });
+      ptr.assign(nkeys + 1, 0);
+      src.resize(v.size());
+      for (size_t i = 0; i < v.size(); ++i) { ++ptr[v[i].key + 1]; src[i] = v[i].off; }
+      for (int64_t i = 0; i < nkeys; ++i) ptr[i + 1] += ptr[i];
+    };
+    build(d, z.n_blocks, dir_ptr, dir_src);
+    build(s, z.n_blocks, sch_ptr, sch_src);
+    build(vd, z.n_slots, vdir_ptr, vdir_src);
+    build(vs, z.n_slots, vsch_ptr, vsch_src);
+  }
+  // symmetric block-row CSR for the PCG
+  std::vector<int> row_ptr(z.n_slots + 1, 0), row_blk, row_col;
+  std::vector<uint8_t> row_trans;
+  {
+    std::vector<std::vector<std::array<int, 3>>> rows(z.n_slots);
+    for (int64_t b = 0; b < z.n_blocks; ++b) {
+      const int a = h->blk_row[b], c = h->blk_col[b];
+      rows[a].push_back({int(b), c, 0});
+      if (a != c) rows[c].push_back({int(b), a, 1});
+    }
+    for (int a = 0; a < z.n_slots; ++a) {
+      std::sort(rows[a].begin(), rows[a].end(), [](const std::array<int, 3>& x, const std::array<int, 3>& y) { return x[1] < y[1]; });
+      for (auto& e : rows[a]) { row_blk.push_back(e[0]); row_col.push_back(e[1]); row_trans.push_back(uint8_t(e[2])); }
+      row_ptr[a + 1] = int(row_blk.size());
+    }
+  }
+
+  // ---- upload static data ----
+  cudaStream_t s = h->stream;
+  auto up = [&](auto& buf, const auto& vec) { return buf.upload(vec, s); };
+  std::vector<double> intr(p->intrinsics, p->intrinsics + size_t(8) * p->n_calib);
+  std::vector<int> pose_calib(p->pose_calib, p->pose_calib + p->n_poses), calib_model(p->calib_model, p->calib_model + p->n_calib);
+  PBA_CUDA_OK(up(h->intr, intr)); PBA_CUDA_OK(up(h->pose_calib, pose_calib)); PBA_CUDA_OK(up(h->calib_model, calib_model));
+  PBA_CUDA_OK(up(h->d_slot, h->slot)); PBA_CUDA_OK(up(h->d_affine_active, h->affine_active));
+  PBA_CUDA_OK(up(h->edge_h, edge_h)); PBA_CUDA_OK(up(h->edge_t, edge_t)); PBA_CUDA_OK(up(h->edge_ptr, edge_ptr));
+  PBA_CUDA_OK(up(h->obs_lm, obs_lm)); PBA_CUDA_OK(up(h->obs_edge, obs_edge));
+  PBA_CUDA_OK(up(h->lm_ptr, lm_ptr)); PBA_CUDA_OK(up(h->lm_pos, lm_pos));
+  PBA_CUDA_OK(up(h->lm_group, lm_group)); PBA_CUDA_OK(up(h->obs_col, obs_col)); PBA_CUDA_OK(up(h->lm_hostcol, lm_hostcol));
+  PBA_CUDA_OK(up(h->chunk_edge, chunk_edge)); PBA_CUDA_OK(up(h->chunk_begin, chunk_begin)); PBA_CUDA_OK(up(h->chunk_end, chunk_end));
+  PBA_CUDA_OK(up(h->grp_lm_ptr, grp_lm_ptr)); PBA_CUDA_OK(up(h->grp_cam_ptr, grp_cam_ptr)); PBA_CUDA_OK(up(h->grp_cams, grp_cams));
+  PBA_CUDA_OK(up(h->grp_w_off, grp_w_off)); PBA_CUDA_OK(up(h->grp_part_off, grp_part_off));
+  PBA_CUDA_OK(up(h->lm_w_off, lm_w_off)); PBA_CUDA_OK(up(h->lm_w_stride, lm_w_stride));
+  PBA_CUDA_OK(up(h->d_blk_row, h->blk_row)); PBA_CUDA_OK(up(h->d_blk_col, h->blk_col)); PBA_CUDA_OK(up(h->d_diag_blk, h->diag_blk));
+  PBA_CUDA_OK(up(h->blk_dir_ptr, dir_ptr)); PBA_CUDA_OK(up(h->blk_dir_src, dir_src));
+  PBA_CUDA_OK(up(h->blk_sch_ptr, sch_ptr)); PBA_CUDA_OK(up(h->blk_sch_src, sch_src));
+  PBA_CUDA_OK(up(h->vec_dir_ptr, vdir_ptr)); PBA_CUDA_OK(up(h->vec_dir_src, vdir_src));
+  PBA_CUDA_OK(up(h->vec_sch_ptr, vsch_ptr)); PBA_CUDA_OK(up(h->vec_sch_src, vsch_src));
+  PBA_CUDA_OK(up(h->row_ptr, row_ptr)); PBA_CUDA_OK(up(h->row_blk, row_blk)); PBA_CUDA_OK(up(h->row_col, row_col));
+  PBA_CUDA_OK(up(h->row_trans, row_trans));
+  {
+    std::vector<int> lm_host(n_lm);
+    std::vector<double> lm_uv(size_t(2) * n_lm), rho(n_lm);
+    for (int li = 0; li < n_lm; ++li) {
+      const int l = lm_lo + h->lm_order[li];
+      lm_host[li] = p->lm_host[l];
+      lm_uv[2 * li] = p->lm_host_uv[2 * l]; lm_uv[2 * li + 1] = p->lm_host_uv[2 * l + 1];
+      rho[li] = p->inv_depth[l];
+    }
+    PBA_CUDA_OK(up(h->lm_host, lm_host)); PBA_CUDA_OK(up(h->lm_uv, lm_uv)); PBA_CUDA_OK(up(h->rho, rho));
+    if (!photo) {
+      std::vector<double> uv(size_t(2) * n);
+      for (int64_t i = 0; i < n; ++i) {
+        const int64_t q = obs_lo + h->obs_order[i];
+        uv[i] = p->obs_uv[2 * q]; uv[n + i] = p->obs_uv[2 * q + 1];
+      }
+      PBA_CUDA_OK(up(h->obs_uv, uv));
+    }
+    PBA_CUDA_OK(cudaStreamSynchronize(s));  // the temporaries above go out of scope
+  }
+  {
+    std::vector<double> poses(p->poses, p->poses + size_t(7) * p->n_poses);
+    PBA_CUDA_OK(up(h->poses, poses));
+    std::vector<double> aff(size_t(2) * p->n_poses, 0.0);
+    if (photo && p->affine) aff.assign(p->affine, p->affine + size_t(2) * p->n_poses);
+    PBA_CUDA_OK(up(h->affine, aff));
+    PBA_CUDA_OK(cudaStreamSynchronize(s));
+  }
+  if (photo) {
+    z.image_stride = int64_t(p->pitch) * p->height;
+    PBA_CUDA_OK(h->images.alloc(size_t(z.image_stride) * p->n_poses));
+    if (p->image_ptrs) {
+      for (int i = 0; i < p->n_poses; ++i)
+        PBA_CUDA_OK(cudaMemcpyAsync(h->images.p + size_t(i) * z.image_stride, p->image_ptrs[i], z.image_stride, cudaMemcpyHostToDevice, s));
+    } else if (p->image_stride == z.image_stride) {
+      PBA_CUDA_OK(cudaMemcpyAsync(h->images.p, p->images, size_t(z.image_stride) * p->n_poses, cudaMemcpyHostToDevice, s));
+    } else {
+      for (int i = 0; i < p->n_poses; ++i)
+        PBA_CUDA_OK(cudaMemcpyAsync(h->images.p + size_t(i) * z.image_stride, p->images + size_t(i) * p->image_stride, z.image_stride, cudaMemcpyHostToDevice, s));
+    }
+  }
+
+  // ---- work buffers ----
+  const size_t nn = size_t(n);
+  PBA_CUDA_OK(h->poses_c.alloc(size_t(7) * p->n_poses)); PBA_CUDA_OK(h->poses_best.alloc(size_t(7) * p->n_poses));
+  PBA_CUDA_OK(h->affine_c.alloc(size_t(2) * p->n_poses)); PBA_CUDA_OK(h->affine_best.alloc(size_t(2) * p->n_poses));
+  PBA_CUDA_OK(h->rho_c.alloc(n_lm)); PBA_CUDA_OK(h->rho_best.alloc(n_lm));
+  PBA_CUDA_OK(h->lm_pat.alloc(size_t(n_lm) * (photo ? 32 : 4))); PBA_CUDA_OK(h->lm_ok.alloc(n_lm));
+  PBA_CUDA_OK(h->edge_T.alloc(size_t(16) * z.n_edges));
+  PBA_CUDA_OK(h->res.alloc(nn * z.R)); PBA_CUDA_OK(h->J.alloc(nn * z.R * z.C)); PBA_CUDA_OK(h->orec.alloc(nn * 16));
+  PBA_CUDA_OK(h->W.alloc(size_t(w_total)));
+  PBA_CUDA_OK(h->lm_c.alloc(n_lm)); PBA_CUDA_OK(h->lm_g.alloc(n_lm)); PBA_CUDA_OK(h->lm_scale.alloc(n_lm));
+  PBA_CUDA_OK(h->lm_diag.alloc(n_lm)); PBA_CUDA_OK(h->lm_s2.alloc(n_lm)); PBA_CUDA_OK(h->lm_iete.alloc(n_lm));
+  PBA_CUDA_OK(h->part_dir.alloc(size_t(z.n_chunks) * dir_stride)); PBA_CUDA_OK(h->part_sch.alloc(size_t(part_total)));
+  PBA_CUDA_OK(h->rcs.alloc(size_t(z.n_blocks) * cd * cd + 3 * size_t(z.dim)));
+  PBA_CUDA_OK(h->cam_scale.alloc(z.dim)); PBA_CUDA_OK(h->cam_diag.alloc(z.dim)); PBA_CUDA_OK(h->cam_D2.alloc(z.dim));
+  PBA_CUDA_OK(h->y_cam.alloc(z.dim)); PBA_CUDA_OK(h->d_cam.alloc(z.dim)); PBA_CUDA_OK(h->d_rho.alloc(n_lm));
+  PBA_CUDA_OK(h->blk_inv.alloc(size_t(z.n_slots) * cd * cd));
+  h->pcg_grid = pcg_max_grid(h->device);
+  PBA_CUDA_OK(h->pcg_ws.alloc(4 * size_t(z.dim) + 3 * size_t(h->pcg_grid) + 8));
+  const size_t red = std::max<size_t>(size_t(eval_grid(n)) + 8, 2 * ((size_t(p->n_poses) + n_lm + 255) / 256) + 8);
+  PBA_CUDA_OK(h->red_ws.alloc(std::max<size_t>(red, (nn + 255) / 256 + 8)));
+  PBA_CUDA_OK(h->scalars.alloc(S_NUM)); PBA_CUDA_OK(h->chol_fail.alloc(1));
+  PBA_CUDA_OK(cudaMemsetAsync(h->scalars.p, 0, sizeof(double) * S_NUM, s));
+  PBA_CUDA_OK(cudaMemsetAsync(h->chol_fail.p, 0, sizeof(int), s));
+  PBA_CUDA_OK(cudaMallocHost(&h->h_scalars, sizeof(double) * (S_NUM + 2)));
+  if (h->max_w_stride > 0) {
+    // k_schur_syrk needs > 48 KB of dynamic shared memory for wide groups
+    schur_set_smem((size_t(h->schur_tile_l) * h->max_w_stride + h->schur_tile_l) * sizeof(double));
+  }
+  st = launch_init_landmarks(h);
+  if (st != PBA_OK) return st;
+  PBA_CUDA_OK(cudaStreamSynchronize(s));
+  *out = hh.release();
+  return PBA_OK;
+}
+
+pba_status read_scalars(Handle* h) {
+  PBA_CUDA_OK(cudaMemcpyAsync(h->h_scalars, h->scalars.p, sizeof(double) * S_NUM, cudaMemcpyDeviceToHost, h->stream));
+  int* fail = reinterpret_cast<int*>(h->h_scalars + S_NUM);
+  PBA_CUDA_OK(cudaMemcpyAsync(fail, h->chol_fail.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  PBA_CUDA_OK(cudaStreamSynchronize(h->stream));
+  h->stats.resolve();
+  return PBA_OK;
+}
+
+int pick_solver(const Handle* h, int requested) {
+  int s = requested == PBA_SOLVER_AUTO ? h->opt.solver : requested;
+  if (s == PBA_SOLVER_AUTO) s = h->sz.dim <= h->opt.cholesky_max_dim ? PBA_SOLVER_CHOLESKY : PBA_SOLVER_PCG;
+  return s;
+}
+
+pba_status solve_rcs(Handle* h, int solver) {
+  h->last_solver = pick_solver(h, solver);
+  return h->last_solver == PBA_SOLVER_CHOLESKY ? launch_cholesky_rcs(h) : launch_pcg_rcs(h);
+}
+
+// EvaluateGradientAndJacobian (trust_region_minimizer.cc:228-300) + everything
+// that only depends on the new Jacobian: direct partials, landmark rows, the
+// RCS for `radius`, gradient norms.
+pba_status eval_jacobian_and_build(Handle* h, double radius) {
+  pba_status st = launch_evaluate(h, true, h->poses.p, h->affine.p, h->rho.p, S_COST);
+  if (st != PBA_OK) return st;
+  h->have_jac = true;
+  if ((st = launch_post_jacobian(h)) != PBA_OK) return st;
+  if ((st = launch_build_rcs(h, radius, true)) != PBA_OK) return st;
+  if ((st = launch_gradient_norms(h)) != PBA_OK) return st;
+  if (h->world > 1) {
+    if ((st = allreduce_scalars(h, h->scalars.p + S_COST, 1, false)) != PBA_OK) return st;
+    if ((st = allreduce_scalars(h, h->scalars.p + S_GNORM2, 1, false)) != PBA_OK) return st;
+    if ((st = allreduce_scalars(h, h->scalars.p + S_GMAX, 1, true)) != PBA_OK) return st;
+  }
+  return PBA_OK;
+}
+
+pba_status copy_state(Handle* h, DevBuf<double>& dp, DevBuf<double>& da, DevBuf<double>& dr, const DevBuf<double>& sp,
+                      const DevBuf<double>& sa, const DevBuf<double>& sr) {
+  PBA_CUDA_OK(cudaMemcpyAsync(dp.p, sp.p, sizeof(double) * sp.n, cudaMemcpyDeviceToDevice, h->stream));
+  PBA_CUDA_OK(cudaMemcpyAsync(da.p, sa.p, sizeof(double) * sa.n, cudaMemcpyDeviceToDevice, h->stream));
+  if (sr.n) PBA_CUDA_OK(cudaMemcpyAsync(dr.p, sr.p, sizeof(double) * sr.n, cudaMemcpyDeviceToDevice, h->stream));
+  return PBA_OK;
+}
+
+template <class T>
+void swap_buf(DevBuf<T>& a, DevBuf<T>& b) { std::swap(a.p, b.p); std::swap(a.n, b.n); }
+
+pba_status minimize_impl(Handle* h, pba_summary* sum) {
+  const double t_start = wall();
+  const pba_options& opt = h->opt;
+  const Sizes& z = h->sz;
+  pba_iteration* its = sum ? sum->iterations : nullptr;
+  const int cap = sum ? sum->iterations_capacity : 0;
+  if (sum) { memset(sum, 0, sizeof(*sum)); sum->iterations = its; sum->iterations_capacity = cap; }
+  int n_it = 0;
+  auto push = [&](const pba_iteration& it) { if (its && n_it < cap) its[n_it] = it; ++n_it; };
+  KernelStats& ks = h->stats;
+  const int64_t launches0 = std::accumulate(ks.launches, ks.launches + K_NUM, int64_t(0));
+
+  double radius = opt.initial_trust_region_radius, decrease_factor = 2.0;
+  double x_cost = 0, x_norm = -1.0, minimum_cost = std::numeric_limits<double>::max();
+  int termination = PBA_NO_CONVERGENCE;
+  char message[256] = "";
+  int num_successful = 0, num_unsuccessful = 0, consecutive_invalid = 0;
+  int n_jac = 0, n_res = 0, n_lin = 0;
+  pba_status st;
+  double* hs = h->h_scalars;
+  const int* chol_fail = reinterpret_cast<const int*>(hs + S_NUM);
+
+  h->scale_ready = false;  // Jacobi scaling is computed at iteration 0 of every solve
+  pba_iteration it;
+  memset(&it, 0, sizeof(it));
+  if ((st = eval_jacobian_and_build(h, radius)) != PBA_OK) return st;
+  if ((st = read_scalars(h)) != PBA_OK) return st;
+  ++n_jac; ++n_res;
+  x_cost = hs[S_COST];
+  bool ok = std::isfinite(x_cost);
+  if (!ok) {
+    termination = PBA_FAILURE;
+    snprintf(message, sizeof(message), "Residual and Jacobian evaluation failed.");
+  }
+  const double initial_cost = x_cost;
+  it.iteration = 0; it.cost = x_cost; it.step_is_valid = 1; it.step_is_successful = 1;
+  it.gradient_max_norm = hs[S_GMAX]; it.gradient_norm = sqrt(hs[S_GNORM2]);
+  double current_cost_se = x_cost, min_iteration_cost = x_cost;
+  bool have_best = false;
+
+  while (ok) {
+    // FinalizeIterationAndCheckIfMinimizerCanContinue (trust_region_minimizer.cc:311-359)
+    if (it.step_is_successful) {
+      ++num_successful;
+      if (x_cost < minimum_cost) {
+        minimum_cost = x_cost;
+        if ((st = copy_state(h, h->poses_best, h->affine_best, h->rho_best, h->poses, h->affine, h->rho)) != PBA_OK) return st;
+        have_best = true;
+      }
+    } else {
+      ++num_unsuccessful;
+    }
+    it.trust_region_radius = radius;
+    min_iteration_cost = std::min(min_iteration_cost, it.cost);
+    push(it);
+    if (it.iteration >= opt.max_num_iterations) {
+      snprintf(message, sizeof(message), "Maximum number of iterations reached. Number of iterations: %d.", it.iteration);
+      termination = PBA_NO_CONVERGENCE; break;
+    }
+    if (it.gradient_max_norm <= opt.gradient_tolerance) {
+      snprintf(message, sizeof(message), "Gradient tolerance reached. Gradient max norm: %e <= %e", it.gradient_max_norm, opt.gradient_tolerance);
+      termination = PBA_CONVERGENCE; break;
+    }
+    if (radius <= opt.min_trust_region_radius) {
+      snprintf(message, sizeof(message), "Minimum trust region radius reached.");
+      termination = PBA_CONVERGENCE; break;
+    }
+    const double prev_gmax = it.gradient_max_norm, prev_gnorm = it.gradient_norm;
+    const int next = it.iteration + 1;
+    memset(&it, 0, sizeof(it));
+    it.iteration = next;
+
+    // ---- ComputeTrustRegionStep; the RCS for `radius` is already on the device ----
+    if ((st = solve_rcs(h, PBA_SOLVER_AUTO)) != PBA_OK) return st;
+    if ((st = launch_backsub(h)) != PBA_OK) return st;
+    if ((st = launch_model_cost(h)) != PBA_OK) return st;
+    // speculative: candidate point and its cost (needed unless the step is invalid)
+    if ((st = launch_retract(h)) != PBA_OK) return st;
+    if ((st = launch_evaluate(h, false, h->poses_c.p, h->affine_c.p, h->rho_c.p, S_COST_C)) != PBA_OK) return st;
+    if (h->world > 1) {
+      // S_COST_C, S_MODEL, S_STEP2, S_XNORM2 are contiguous
+      if ((st = allreduce_scalars(h, h->scalars.p + S_COST_C, 4, false)) != PBA_OK) return st;
+    }
+    if ((st = read_scalars(h)) != PBA_OK) return st;
+    ++n_lin; ++n_res;
+    it.linear_solver_iterations = h->last_solver == PBA_SOLVER_PCG ? int(hs[S_PCG_ITERS]) : 1;
+    const double model_cost_change = hs[S_MODEL];
+    const bool solved = !(h->last_solver == PBA_SOLVER_CHOLESKY && *chol_fail) && std::isfinite(model_cost_change) && std::isfinite(hs[S_STEP2]);
+    it.model_cost_change = model_cost_change;
+    it.step_is_valid = solved && model_cost_change > 0.0;
+    if (!it.step_is_valid) {
+      // HandleInvalidStep (trust_region_minimizer.cc:450-485)
+      if (++consecutive_invalid >= opt.max_num_consecutive_invalid_steps) {
+        snprintf(message, sizeof(message), "Number of consecutive invalid steps more than Solver::Options::max_num_consecutive_invalid_steps: %d", opt.max_num_consecutive_invalid_steps);
+        termination = PBA_FAILURE; break;
+      }
+      radius = radius / decrease_factor; decrease_factor *= 2.0;
+      if ((st = launch_build_rcs(h, radius, false)) != PBA_OK) return st;
+      it.cost = x_cost; it.gradient_max_norm = prev_gmax; it.gradient_norm = prev_gnorm;
+      continue;
+    }
+    consecutive_invalid = 0;
+    double cand_cost = hs[S_COST_C];
+    if (!std::isfinite(cand_cost)) cand_cost = std::numeric_limits<double>::max();
+
+    // ParameterToleranceReached (:706-726) — runs before the accept test
+    it.step_norm = sqrt(hs[S_STEP2]);
+    if (it.step_norm <= opt.parameter_tolerance * (x_norm + opt.parameter_tolerance)) {
+      snprintf(message, sizeof(message), "Parameter tolerance reached. Relative step_norm: %e <= %e.",
+               it.step_norm / (x_norm + opt.parameter_tolerance), opt.parameter_tolerance);
+      termination = PBA_CONVERGENCE; break;
+    }
+    // FunctionToleranceReached (:729-748)
+    it.cost_change = x_cost - cand_cost;
+    if (fabs(it.cost_change) <= opt.function_tolerance * x_cost) {
+      snprintf(message, sizeof(message), "Function tolerance reached. |cost_change|/cost: %e <= %e",
+               fabs(it.cost_change) / x_cost, opt.function_tolerance);
+      termination = PBA_CONVERGENCE; break;
+    }
+    // IsStepSuccessful (:781-807), monotonic TrustRegionStepEvaluator
+    it.relative_decrease = cand_cost >= std::numeric_limits<double>::max()
+                               ? std::numeric_limits<double>::lowest()
+                               : (current_cost_se - cand_cost) / model_cost_change;
+    if (it.relative_decrease > opt.min_relative_decrease) {
+      // HandleSuccessfulStep (:812-826): x <- candidate, new Jacobian, StepAccepted
+      swap_buf(h->poses, h->poses_c); swap_buf(h->affine, h->affine_c); swap_buf(h->rho, h->rho_c);
+      x_norm = sqrt(hs[S_XNORM2]);
+      radius = radius / std::max(1.0 / 3.0, 1.0 - pow(2.0 * it.relative_decrease - 1.0, 3));
+      radius = std::min(opt.max_trust_region_radius, radius);
+      decrease_factor = 2.0;
+      if ((st = eval_jacobian_and_build(h, radius)) != PBA_OK) return st;
+      if ((st = read_scalars(h)) != PBA_OK) return st;
+      ++n_jac; ++n_res;
+      x_cost = hs[S_COST];
+      if (!std::isfinite(x_cost)) {
+        termination = PBA_FAILURE;
+        snprintf(message, sizeof(message), "Residual and Jacobian evaluation failed.");
+        break;
+      }
+      it.cost = x_cost; it.gradient_max_norm = hs[S_GMAX]; it.gradient_norm = sqrt(hs[S_GNORM2]);
+      it.step_is_successful = 1;
+      current_cost_se = cand_cost;
+    } else {
+      it.step_is_successful = 0;
+      it.cost = cand_cost;
+      it.gradient_max_norm = prev_gmax; it.gradient_norm = prev_gnorm;
+      radius = radius / decrease_factor; decrease_factor *= 2.0;
+      if ((st = launch_build_rcs(h, radius, false)) != PBA_OK) return st;
+    }
+  }
+  // Leave the best accepted iterate as the current state (solver.cc:438-447);
+  // on FAILURE the caller keeps its inputs (pba_solve does not write back).
+  if (have_best && termination != PBA_FAILURE) {
+    if ((st = copy_state(h, h->poses, h->affine, h->rho, h->poses_best, h->affine_best, h->rho_best)) != PBA_OK) return st;
+  }
+  PBA_CUDA_OK(cudaStreamSynchronize(h->stream));
+  ks.resolve();
+  h->have_jac = false;  // the stored Jacobian may belong to a later iterate than the state
+  h->have_rcs = false;
+  if (sum) {
+    sum->termination_type = termination;
+    sum->num_iterations = cap > 0 ? std::min(n_it, cap) : n_it;
+    sum->num_successful_steps = num_successful;
+    sum->num_unsuccessful_steps = num_unsuccessful;
+    sum->num_residual_evaluations = n_res;
+    sum->num_jacobian_evaluations = n_jac;
+    sum->num_linear_solves = n_lin;
+    sum->rcs_dim = z.dim;
+    sum->rcs_blocks = z.n_blocks;
+    sum->num_residual_blocks = h->n_obs_global;
+    sum->num_residuals = h->n_obs_global * z.R;
+    sum->num_effective_parameters = int64_t(z.n_slots) * 6 + h->n_active_lm;
+    for (int i = 0; i < z.n_poses; ++i) sum->num_effective_parameters += h->affine_active[i] ? 2 : 0;
+    sum->gpu_kernel_launches = std::accumulate(ks.launches, ks.launches + K_NUM, int64_t(0)) - launches0;
+    sum->initial_cost = initial_cost;
+    sum->final_cost = min_iteration_cost;
+    sum->jacobian_evaluation_time_in_seconds = 1e-3 * (ks.ms[K_RESJAC] + ks.ms[K_EDGE_PREP]);
+    sum->residual_evaluation_time_in_seconds = 1e-3 * ks.ms[K_COST];
+    double lin = 0;
+    for (int k : {K_EDGE_GRAM, K_LM_GATHER, K_LM_SCALE, K_SCHUR_SYRK, K_RCS_REDUCE, K_RCS_SCALE, K_CAM_SCALE, K_DENSE_FILL,
+                  K_CHOL_PANEL, K_CHOL_TRSM, K_CHOL_SYRK, K_CHOL_SOLVE, K_PCG, K_BACKSUB})
+      lin += ks.ms[k];
+    sum->linear_solver_time_in_seconds = 1e-3 * lin;
+    sum->minimizer_time_in_seconds = wall() - t_start;
+    sum->total_time_in_seconds = sum->minimizer_time_in_seconds;
+    snprintf(sum->message, sizeof(sum->message), "%s", message);
+  }
+  return PBA_OK;
+}
+
+void print_report(const pba_summary& s, int verbosity) {
+  if (verbosity <= 0) return;
+  const char* term = s.termination_type == PBA_CONVERGENCE ? "CONVERGENCE" : s.termination_type == PBA_NO_CONVERGENCE ? "NO_CONVERGENCE" : "FAILURE";
+  // same one-line shape as ceres::Solver::Summary::BriefReport (map_utils.h:384-388)
+  printf("B200 PBA Report: Iterations: %d, Initial cost: %e, Final cost: %e, Termination: %s\n", s.num_iterations,
+         s.initial_cost, s.final_cost, term);
+  if (verbosity >= 2) {
+    printf("  residual blocks %lld, residuals %lld, effective parameters %lld, RCS dim %d (%lld blocks)\n",
+           (long long)s.num_residual_blocks, (long long)s.num_residuals, (long long)s.num_effective_parameters, s.rcs_dim,
+           (long long)s.rcs_blocks);
+    printf("  steps: %d successful, %d unsuccessful; evaluations: %d residual, %d jacobian; linear solves %d\n",
+           s.num_successful_steps, s.num_unsuccessful_steps, s.num_residual_evaluations, s.num_jacobian_evaluations,
+           s.num_linear_solves);
+    printf("  time (s): setup %.4f, minimizer %.4f, total %.4f; kernel launches %lld\n  %s\n", s.setup_time_in_seconds,
+           s.minimizer_time_in_seconds, s.total_time_in_seconds, (long long)s.gpu_kernel_launches, s.message);
+    for (int i = 0; i < s.num_iterations && s.iterations && i < s.iterations_capacity; ++i) {
+      const pba_iteration& a = s.iterations[i];
+      printf("  %3d cost %.6e change %.2e |grad| %.2e |step| %.2e tr_ratio %.2e radius %.2e ls_iter %d\n", a.iteration,
+             a.cost, a.cost_change, a.gradient_max_norm, a.step_norm, a.relative_decrease, a.trust_region_radius,
+             a.linear_solver_iterations);
+    }
+  }
+}
+
+pba_status get_state_impl(Handle* h, double* poses, double* inv_depth, double* affine) {
+  const Sizes& z = h->sz;
+  if (poses) PBA_CUDA_OK(cudaMemcpyAsync(poses, h->poses.p, sizeof(double) * 7 * z.n_poses, cudaMemcpyDeviceToHost, h->stream));
+  if (affine && z.mode == PBA_MODE_PHOTOMETRIC)
+    PBA_CUDA_OK(cudaMemcpyAsync(affine, h->affine.p, sizeof(double) * 2 * z.n_poses, cudaMemcpyDeviceToHost, h->stream));
+  std::vector<double> rho(z.n_lm);
+  if (inv_depth && z.n_lm) PBA_CUDA_OK(cudaMemcpyAsync(rho.data(), h->rho.p, sizeof(double) * z.n_lm, cudaMemcpyDeviceToHost, h->stream));
+  PBA_CUDA_OK(cudaStreamSynchronize(h->stream));
+  if (inv_depth)
+    for (int li = 0; li < z.n_lm; ++li) inv_depth[h->lm_order[li]] = rho[li];
+  return PBA_OK;
+}
+
+}  // namespace
+}  // namespace pba
+
+using namespace pba;
+
+// ============================================================== C ABI =====
+PBA_API int32_t pba_abi_version(void) { return PBA_ABI_VERSION; }
+
+PBA_API const char* pba_status_string(pba_status s) {
+  switch (s) {
+    case PBA_OK: return "PBA_OK";
+    case PBA_ERR_INVALID_ARGUMENT: return "PBA_ERR_INVALID_ARGUMENT";
+    case PBA_ERR_NO_DEVICE: return "PBA_ERR_NO_DEVICE";
+    case PBA_ERR_CUDA: return "PBA_ERR_CUDA";
+    case PBA_ERR_UNSUPPORTED: return "PBA_ERR_UNSUPPORTED";
+    case PBA_ERR_NUMERICAL_FAILURE: return "PBA_ERR_NUMERICAL_FAILURE";
+    case PBA_ERR_NCCL: return "PBA_ERR_NCCL";
+    case PBA_ERR_OUT_OF_MEMORY: return "PBA_ERR_OUT_OF_MEMORY";
+  }
+  return "PBA_ERR_UNKNOWN";
+}
+
+PBA_API int32_t pba_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+PBA_API void pba_options_init(pba_options* o) {
+  if (!o) return;
+  memset(o, 0, sizeof(*o));
+  o->verbosity_level = 1; o->optimize_intrinsics = 0; o->use_huber = 1; o->huber_parameter = 1.0; o->max_num_iterations = 20;
+  o->solver = PBA_SOLVER_AUTO; o->cholesky_max_dim = 4096; o->pcg_max_iterations = 500; o->pcg_tolerance = 1e-10;
+  o->initial_trust_region_radius = 1e4; o->max_trust_region_radius = 1e16; o->min_trust_region_radius = 1e-32;
+  o->min_relative_decrease = 1e-3; o->min_lm_diagonal = 1e-6; o->max_lm_diagonal = 1e32;
+  o->function_tolerance = 1e-6; o->gradient_tolerance = 1e-10; o->parameter_tolerance = 1e-8;
+  o->max_num_consecutive_invalid_steps = 5; o->jacobi_scaling = 1; o->device = 0; o->profile = 0;
+}
+
+PBA_API pba_status pba_create(const pba_problem* problem, const pba_options* options, int32_t rank, int32_t world_size,
+                              pba_handle** out) {
+  if (!out) return PBA_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  Handle* h = nullptr;
+  pba_status st = create_impl(problem, options, rank, world_size, &h);
+  if (st == PBA_OK) *out = reinterpret_cast<pba_handle*>(h);
+  return st;
+}
+
+PBA_API void pba_destroy(pba_handle* hh) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  delete h;
+}
+
+PBA_API pba_status pba_set_stream(pba_handle* hh, void* cuda_stream) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h) return PBA_ERR_INVALID_ARGUMENT;
+  PBA_CUDA_OK(cudaStreamSynchronize(h->stream));
+  if (h->own_stream) { cudaStreamDestroy(h->stream); h->own_stream = false; }
+  if (cuda_stream) {
+    h->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+  } else {
+    PBA_CUDA_OK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    h->own_stream = true;
+  }
+  return PBA_OK;
+}
+
+PBA_API pba_status pba_synchronize(pba_handle* hh) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h) return PBA_ERR_INVALID_ARGUMENT;
+  PBA_CUDA_OK(cudaStreamSynchronize(h->stream));
+  h->stats.resolve();
+  return PBA_OK;
+}
+
+PBA_API pba_status pba_evaluate(pba_handle* hh, int32_t with_jacobian, double* cost) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h) return PBA_ERR_INVALID_ARGUMENT;
+  PBA_CUDA_OK(cudaSetDevice(h->device));
+  pba_status st = launch_evaluate(h, with_jacobian != 0, h->poses.p, h->affine.p, h->rho.p, S_COST);
+  if (st != PBA_OK) return st;
+  if (with_jacobian) { h->have_jac = true; h->have_rcs = false; }
+  if (cost) {
+    if (h->world > 1 && (st = allreduce_scalars(h, h->scalars.p + S_COST, 1, false)) != PBA_OK) return st;
+    if ((st = read_scalars(h)) != PBA_OK) return st;
+    *cost = h->h_scalars[S_COST];
+  }
+  return PBA_OK;
+}
+
+PBA_API pba_status pba_get_residuals(pba_handle* hh, double* residuals) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h || !residuals || !h->have_jac) return PBA_ERR_INVALID_ARGUMENT;
+  const Sizes& z = h->sz;
+  if (z.n_obs == 0) return PBA_OK;
+  DevBuf<double> tmp;
+  PBA_CUDA_OK(tmp.alloc(size_t(z.n_obs) * z.R));
+  pba_status st = launch_unpermute(h, h->res.p, z.R, tmp.p);
+  if (st != PBA_OK) return st;
+  PBA_CUDA_OK(cudaMemcpy(residuals, tmp.p, sizeof(double) * z.n_obs * z.R, cudaMemcpyDeviceToHost));
+  return PBA_OK;
+}
+
+PBA_API pba_status pba_get_jacobians(pba_handle* hh, double* jacobians) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h || !jacobians || !h->have_jac) return PBA_ERR_INVALID_ARGUMENT;
+  const Sizes& z = h->sz;
+  if (z.n_obs == 0) return PBA_OK;
+  DevBuf<double> tmp;
+  PBA_CUDA_OK(tmp.alloc(size_t(z.n_obs) * z.R * z.C));
+  pba_status st = launch_unpermute(h, h->J.p, z.R * z.C, tmp.p);
+  if (st != PBA_OK) return st;
+  PBA_CUDA_OK(cudaMemcpy(jacobians, tmp.p, sizeof(double) * z.n_obs * z.R * z.C, cudaMemcpyDeviceToHost));
+  return PBA_OK;
+}
+
+PBA_API pba_status pba_build_rcs(pba_handle* hh, double radius) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h || !(radius > 0.0)) return PBA_ERR_INVALID_ARGUMENT;
+  PBA_CUDA_OK(cudaSetDevice(h->device));
+  pba_status st;
+  if (!h->have_jac) {
+    if ((st = launch_evaluate(h, true, h->poses.p, h->affine.p, h->rho.p, S_COST)) != PBA_OK) return st;
+    h->have_jac = true;
+  }
+  // stand-alone use = iteration 0 semantics: scales and LM diagonal from this Jacobian
+  h->scale_ready = false;
+  if ((st = launch_post_jacobian(h)) != PBA_OK) return st;
+  if ((st = launch_build_rcs(h, radius, true)) != PBA_OK) return st;
+  return pba_synchronize(hh);
+}
+
+PBA_API pba_status pba_get_rcs_dim(pba_handle* hh, int32_t* dim) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h || !dim) return PBA_ERR_INVALID_ARGUMENT;
+  *dim = h->sz.dim;
+  return PBA_OK;
+}
+
+PBA_API pba_status pba_get_rcs(pba_handle* hh, double* S_dense, double* rhs) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h || !S_dense || !rhs || !h->have_rcs) return PBA_ERR_INVALID_ARGUMENT;
+  const Sizes& z = h->sz;
+  const int cd = z.cd;
+  std::vector<double> buf(size_t(z.n_blocks) * cd * cd + z.dim);
+  PBA_CUDA_OK(cudaMemcpyAsync(buf.data(), h->rcs.p, sizeof(double) * buf.size(), cudaMemcpyDeviceToHost, h->stream));
+  PBA_CUDA_OK(cudaStreamSynchronize(h->stream));
+  std::fill(S_dense, S_dense + size_t(z.dim) * z.dim, 0.0);
+  for (int64_t b = 0; b < z.n_blocks; ++b)
+    for (int r = 0; r < cd; ++r)
+      for (int c = 0; c < cd; ++c) {
+        const double v = buf[b * cd * cd + r * cd + c];
+        const int gr = h->blk_row[b] * cd + r, gc = h->blk_col[b] * cd + c;
+        S_dense[size_t(gr) * z.dim + gc] = v;
+        S_dense[size_t(gc) * z.dim + gr] = v;
+      }
+  memcpy(rhs, buf.data() + size_t(z.n_blocks) * cd * cd, sizeof(double) * z.dim);
+  return PBA_OK;
+}
+
+PBA_API pba_status pba_solve_rcs(pba_handle* hh, int32_t solver, double* y_cam, int32_t* iterations) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h || !h->have_rcs) return PBA_ERR_INVALID_ARGUMENT;
+  PBA_CUDA_OK(cudaSetDevice(h->device));
+  pba_status st = solve_rcs(h, solver);
+  if (st != PBA_OK) return st;
+  if ((st = read_scalars(h)) != PBA_OK) return st;
+  if (h->last_solver == PBA_SOLVER_CHOLESKY && *reinterpret_cast<int*>(h->h_scalars + S_NUM)) return PBA_ERR_NUMERICAL_FAILURE;
+  if (iterations) *iterations = h->last_solver == PBA_SOLVER_PCG ? int(h->h_scalars[S_PCG_ITERS]) : 1;
+  if (y_cam && h->sz.dim) PBA_CUDA_OK(cudaMemcpy(y_cam, h->y_cam.p, sizeof(double) * h->sz.dim, cudaMemcpyDeviceToHost));
+  return PBA_OK;
+}
+
+PBA_API pba_status pba_minimize(pba_handle* hh, pba_summary* summary) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h) return PBA_ERR_INVALID_ARGUMENT;
+  PBA_CUDA_OK(cudaSetDevice(h->device));
+  return minimize_impl(h, summary);
+}
+
+PBA_API pba_status pba_set_state(pba_handle* hh, const double* poses, const double* inv_depth, const double* affine) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h) return PBA_ERR_INVALID_ARGUMENT;
+  const Sizes& z = h->sz;
+  if (poses) PBA_CUDA_OK(cudaMemcpyAsync(h->poses.p, poses, sizeof(double) * 7 * z.n_poses, cudaMemcpyHostToDevice, h->stream));
+  if (affine && z.mode == PBA_MODE_PHOTOMETRIC)
+    PBA_CUDA_OK(cudaMemcpyAsync(h->affine.p, affine, sizeof(double) * 2 * z.n_poses, cudaMemcpyHostToDevice, h->stream));
+  std::vector<double> rho(z.n_lm);
+  if (inv_depth && z.n_lm) {
+    for (int li = 0; li < z.n_lm; ++li) rho[li] = inv_depth[h->lm_order[li]];
+    PBA_CUDA_OK(cudaMemcpyAsync(h->rho.p, rho.data(), sizeof(double) * z.n_lm, cudaMemcpyHostToDevice, h->stream));
+  }
+  PBA_CUDA_OK(cudaStreamSynchronize(h->stream));
+  h->have_jac = false; h->have_rcs = false;
+  return PBA_OK;
+}
+
+PBA_API pba_status pba_get_state(pba_handle* hh, double* poses, double* inv_depth, double* affine) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h) return PBA_ERR_INVALID_ARGUMENT;
+  return get_state_impl(h, poses, inv_depth, affine);
+}
+
+PBA_API pba_status pba_get_sizes(pba_handle* hh, int64_t* n_obs_local, int32_t* n_landmarks_local, int64_t* first_landmark) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h) return PBA_ERR_INVALID_ARGUMENT;
+  if (n_obs_local) *n_obs_local = h->sz.n_obs;
+  if (n_landmarks_local) *n_landmarks_local = h->sz.n_lm;
+  if (first_landmark) *first_landmark = h->first_landmark;
+  return PBA_OK;
+}
+
+PBA_API pba_status pba_reset_kernel_stats(pba_handle* hh) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h) return PBA_ERR_INVALID_ARGUMENT;
+  PBA_CUDA_OK(cudaStreamSynchronize(h->stream));
+  h->stats.reset();
+  return PBA_OK;
+}
+
+PBA_API int32_t pba_get_kernel_stats(pba_handle* hh, pba_kernel_stat* out, int32_t cap) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h || !out) return 0;
+  cudaStreamSynchronize(h->stream);
+  h->stats.resolve();
+  int n = 0;
+  for (int i = 0; i < K_NUM && n < cap; ++i) {
+    if (!h->stats.launches[i]) continue;
+    snprintf(out[n].name, sizeof(out[n].name), "%s", kKernelNames[i]);
+    out[n].launches = h->stats.launches[i];
+    out[n].total_ms = h->stats.ms[i];
+    ++n;
+  }
+  return n;
+}
+
+PBA_API pba_status pba_nccl_unique_id(uint8_t id[PBA_NCCL_ID_BYTES]) {
+  if (!id) return PBA_ERR_INVALID_ARGUMENT;
+  if (!g_nccl.load()) return PBA_ERR_NCCL;
+  NcclId nid;
+  if (g_nccl.GetUniqueId(&nid) != 0) return PBA_ERR_NCCL;
+  memcpy(id, nid.b, PBA_NCCL_ID_BYTES);
+  return PBA_OK;
+}
+
+PBA_API pba_status pba_comm_init(pba_handle* hh, const uint8_t id[PBA_NCCL_ID_BYTES]) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h || !id) return PBA_ERR_INVALID_ARGUMENT;
+  if (h->world <= 1) return PBA_OK;
+  if (!g_nccl.load()) return PBA_ERR_NCCL;
+  PBA_CUDA_OK(cudaSetDevice(h->device));
+  NcclId nid;
+  memcpy(nid.b, id, PBA_NCCL_ID_BYTES);
+  if (g_nccl.CommInitRank(&h->nccl_comm, h->world, nid, h->rank) != 0) return PBA_ERR_NCCL;
+  return PBA_OK;
+}
+
+// The drop-in call (map_utils.h:322): host buffers in, updated in place.
+PBA_API pba_status pba_solve(pba_problem* problem, const pba_options* options, pba_summary* summary) {
+  const double t0 = wall();
+  Handle* h = nullptr;
+  pba_status st = create_impl(problem, options, 0, 1, &h);
+  if (st != PBA_OK) return st;
+  std::unique_ptr<Handle> guard(h);
+  const double t1 = wall();
+  pba_summary local;
+  memset(&local, 0, sizeof(local));
+  pba_summary* s = summary ? summary : &local;
+  st = minimize_impl(h, s);
+  if (st != PBA_OK) return st;
+  if (s->termination_type != PBA_FAILURE) {
+    st = get_state_impl(h, problem->poses, problem->inv_depth, problem->mode == PBA_MODE_PHOTOMETRIC ? problem->affine : nullptr);
+    if (st != PBA_OK) return st;
+  }
+  s->setup_time_in_seconds = t1 - t0;
+  s->total_time_in_seconds = wall() - t0;
+  print_report(*s, options->verbosity_level);
+  return PBA_OK;
+}

@@ -1,0 +1,263 @@
+// pba_internal.h — device-resident problem layout and kernel launchers shared
+// by the .cu translation units of libpba_b200.so.  Not part of the ABI.
+//
+// HBM layout (all fp64 unless noted; n = local observations in EDGE ORDER,
+// i.e. sorted by (host pose, target pose, landmark)):
+//   res   [R][n]            residual planes (SoA: a warp of 32 consecutive
+//   J     [R*C][n]           observations writes 256 contiguous bytes per plane)
+//   orec  [n][16]           per-observation Schur record: E^T J_h (6) | E^T J_t
+//                           (cd) | E^T E | E^T r — AoS, one 128 B line each
+//   W     per host group g: [landmarks of g][8*(c_g+1)] dense rows
+//                           (F^T E per visible camera | g_l, c_l), zero padded
+//   direct partials: per edge chunk 3 cd x cd blocks + 2 cd-vectors
+//   schur partials: per host group (c_g+1)(c_g+2)/2 8x8 blocks
+//   RCS   [n_blocks][cd*cd] upper-triangular block list + rhs[dim]
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "pba.h"
+#include "pba_math.h"
+
+namespace pba {
+
+// ---------------------------------------------------------------- buffers --
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  DevBuf() {}
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  cudaError_t alloc(size_t count) {
+    release();
+    n = count;
+    if (count == 0) return cudaSuccess;
+    return cudaMalloc(&p, count * sizeof(T));
+  }
+  cudaError_t upload(const std::vector<T>& h, cudaStream_t s = 0) {
+    cudaError_t e = alloc(h.size());
+    if (e != cudaSuccess || h.empty()) return e;
+    return cudaMemcpyAsync(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, s);
+  }
+};
+
+// ---------------------------------------------------------- kernel stats ---
+enum KernelId {
+  K_INIT_LM = 0,
+  K_EDGE_PREP,
+  K_RESJAC,      // K1: residual + Jacobian (the roofline kernel)
+  K_COST,        // K2: cost-only evaluation
+  K_REDUCE_SUM,  // deterministic second-stage reductions
+  K_EDGE_GRAM,   // K4a: per-edge F^T F / F^T r
+  K_LM_GATHER,   // K3b: per-landmark E^T F rows, c_l, g_l
+  K_LM_SCALE,    // per-landmark Jacobi scale / damping / ete^-1
+  K_SCHUR_SYRK,  // K4c: per-host-group W^T diag(s) W
+  K_RCS_REDUCE,  // K4d: gather partial blocks into the RCS
+  K_RCS_SCALE,   // K4e: Jacobi scaling + LM damping of the RCS
+  K_CAM_SCALE,   // iteration-0 camera column scales / LM diagonal
+  K_DENSE_FILL,
+  K_CHOL_PANEL,
+  K_CHOL_TRSM,
+  K_CHOL_SYRK,   // DMMA trailing update
+  K_CHOL_SOLVE,
+  K_PCG,
+  K_BACKSUB,     // K6
+  K_MODEL_COST,  // K8
+  K_RETRACT,     // K7
+  K_COPY,
+  K_UNPERMUTE,
+  K_PRIMITIVE,
+  K_NUM
+};
+
+extern const char* const kKernelNames[K_NUM];
+
+struct KernelStats {
+  int64_t launches[K_NUM] = {0};
+  double ms[K_NUM] = {0};
+  bool profile = false;
+  // pending event pairs (resolved at synchronisation points)
+  struct Pending { int id; cudaEvent_t a, b; };
+  std::vector<Pending> pending;
+  std::vector<cudaEvent_t> pool;
+  cudaEvent_t get_event();
+  void begin(int id, cudaStream_t s);
+  void end(cudaStream_t s);
+  void resolve();  // call after a stream sync
+  void reset();
+  ~KernelStats();
+};
+
+// ------------------------------------------------------------- the handle --
+struct Sizes {
+  int mode = 0, R = 2, C = 13, cd = 6;  // residuals/obs, local columns/obs, RCS block dim
+  int n_poses = 0, n_calib = 0;
+  int n_lm = 0;         // local landmarks
+  int64_t n_obs = 0;    // local observations
+  int n_edges = 0;
+  int n_chunks = 0;     // edge chunks (direct partials)
+  int n_groups = 0;     // host groups
+  int n_slots = 0, dim = 0;
+  int64_t n_blocks = 0; // RCS upper blocks
+  int width = 0, height = 0, pitch = 0;
+  int64_t image_stride = 0;
+};
+
+struct Handle {
+  pba_options opt;
+  Sizes sz;
+  int rank = 0, world = 1;
+  int64_t first_landmark = 0;  // caller index of local landmark 0's shard start
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  KernelStats stats;
+
+  // ---- host-side structure kept for state I/O and the LM driver ----
+  std::vector<int> lm_order;      // internal landmark -> caller-local landmark (sorted by host)
+  std::vector<int64_t> obs_order; // sorted obs position -> caller-local obs index
+  std::vector<int> slot;          // pose -> RCS slot or -1
+  std::vector<uint8_t> affine_active;
+  std::vector<int> blk_row, blk_col;  // RCS block coordinates (slots), row <= col
+  std::vector<int> diag_blk;          // slot -> block index of (slot,slot)
+  int64_t n_active_lm = 0;            // landmarks with >= 1 observation (global, for counts)
+  int64_t n_obs_global = 0;
+
+  // ---- static device data ----
+  DevBuf<double> intr;             // [n_calib*8]
+  DevBuf<int> pose_calib, calib_model, d_slot;
+  DevBuf<uint8_t> d_affine_active;
+  DevBuf<uint8_t> images;          // photometric: all keyframes
+  DevBuf<int> edge_h, edge_t;      // [E]
+  DevBuf<int64_t> edge_ptr;        // [E+1]
+  DevBuf<int> obs_lm, obs_edge;    // [n]
+  DevBuf<double> obs_uv;           // geometric [2][n] SoA
+  DevBuf<double> lm_uv;            // [n_lm*2] host pixel
+  DevBuf<int> lm_host;             // [n_lm]
+  DevBuf<double> lm_pat;           // photometric [n_lm][8][4] (bx,by,bz,I_h); geometric [n_lm][4]
+  DevBuf<uint8_t> lm_ok;           // [n_lm]
+  DevBuf<int64_t> lm_ptr;          // [n_lm+1] landmark -> positions in sorted obs
+  DevBuf<int64_t> lm_pos;          // [n]
+  DevBuf<int> lm_group;            // [n_lm]
+  DevBuf<int> obs_col;             // [n] column (camera index within the host group) of the target
+  DevBuf<int> lm_hostcol;          // [n_lm] column of the host within its group or -1
+  // edge chunks
+  DevBuf<int> chunk_edge;          // [n_chunks]
+  DevBuf<int64_t> chunk_begin, chunk_end;
+  // host groups
+  DevBuf<int> grp_lm_ptr;          // [G+1] landmark ranges
+  DevBuf<int> grp_cam_ptr;         // [G+1] into grp_cams
+  DevBuf<int> grp_cams;            // slots, ascending
+  DevBuf<int64_t> grp_w_off;       // [G] offset of the group's W rows (doubles)
+  DevBuf<int64_t> grp_part_off;    // [G] offset of the group's Schur partial blocks (blocks of 64)
+  DevBuf<int64_t> lm_w_off;        // [n_lm] offset of the landmark's W row
+  DevBuf<int> lm_w_stride;         // [n_lm] row length = 8*(c_g+1)
+  // RCS structure
+  DevBuf<int> d_blk_row, d_blk_col;
+  DevBuf<int64_t> blk_dir_ptr, blk_sch_ptr;  // [n_blocks+1]
+  DevBuf<int64_t> blk_dir_src, blk_sch_src;  // offsets (doubles) into direct / schur partial buffers
+  DevBuf<int64_t> vec_dir_ptr, vec_sch_ptr;  // [n_slots+1]
+  DevBuf<int64_t> vec_dir_src, vec_sch_src;
+  // symmetric block-row CSR for the PCG SpMV
+  DevBuf<int> row_ptr, row_blk, row_col;
+  DevBuf<uint8_t> row_trans;
+
+  // ---- state ----
+  DevBuf<double> poses, affine, rho;            // current x
+  DevBuf<double> poses_c, affine_c, rho_c;      // candidate
+  DevBuf<double> poses_best, affine_best, rho_best;
+
+  // ---- per-evaluation data ----
+  DevBuf<double> edge_T;       // [E][16]
+  DevBuf<double> res;          // [R][n]
+  DevBuf<double> J;            // [R*C][n]
+  DevBuf<double> orec;         // [n][16]
+  DevBuf<double> W;            // grouped landmark rows
+  DevBuf<double> lm_c, lm_g;   // [n_lm] raw E^T E, E^T r
+  DevBuf<double> lm_scale;     // [n_lm] Jacobi scale sigma_l
+  DevBuf<double> lm_diag;      // [n_lm] frozen LM diagonal (scaled col norm, clamped)
+  DevBuf<double> lm_s2;        // [n_lm] sigma_l^2 / ete_l
+  DevBuf<double> lm_iete;      // [n_lm] 1 / ete_l
+  DevBuf<double> part_dir;     // direct partials
+  DevBuf<double> part_sch;     // schur partials
+  DevBuf<double> rcs;          // [n_blocks*cd*cd | rhs dim | diagB dim]  (one all-reduce buffer)
+  DevBuf<double> rcs_B;        // raw direct part (kept for model cost / diagnostics)
+  DevBuf<double> cam_scale;    // [dim]
+  DevBuf<double> cam_diag;     // [dim] frozen LM diagonal
+  DevBuf<double> cam_D2;       // [dim] D^2 of the current solve
+  DevBuf<double> y_cam;        // [dim] RCS solution (scaled space)
+  DevBuf<double> d_cam;        // [dim] tangent step (unscaled)
+  DevBuf<double> d_rho;        // [n_lm]
+  DevBuf<double> dense;        // [dim*dim] Cholesky workspace
+  DevBuf<double> pcg_ws;       // PCG vectors
+  DevBuf<double> blk_inv;      // block-Jacobi inverses [n_slots*cd*cd]
+  DevBuf<double> red_ws;       // reduction workspace
+  DevBuf<double> scalars;      // small device scalar bank
+  double* h_scalars = nullptr; // pinned mirror
+
+  bool have_jac = false;
+  bool have_rcs = false;
+  bool scale_ready = false;
+  double rcs_radius = 0;
+
+  DevBuf<int> chol_fail;       // set by the Cholesky when a pivot is not positive
+  DevBuf<int> d_diag_blk;      // slot -> diagonal block index
+  int schur_tile_l = 32;       // landmark rows staged per pass in k_schur_syrk
+  int max_w_stride = 8;        // longest W row (doubles)
+  int pcg_grid = 1;            // co-resident CTAs for the cooperative PCG kernel
+  int last_solver = 0;
+
+  // NCCL
+  void* nccl_comm = nullptr;
+
+  ~Handle();
+};
+
+// scalar bank indices
+enum { S_COST = 0, S_COST_C, S_MODEL, S_STEP2, S_XNORM2, S_GMAX, S_GNORM2, S_PCG_ITERS, S_PCG_RES, S_CHOL_FAIL, S_NUM = 16 };
+
+#define PBA_CUDA_OK(x)                          \
+  do {                                          \
+    cudaError_t _e = (x);                       \
+    if (_e != cudaSuccess) return map_cuda(_e); \
+  } while (0)
+
+pba_status map_cuda(cudaError_t e);
+
+// -------------------------------------------------------------- launchers --
+// eval.cu
+pba_status launch_init_landmarks(Handle* h);
+pba_status launch_evaluate(Handle* h, bool with_jacobian, const double* poses, const double* affine,
+                           const double* rho, int cost_slot);
+pba_status launch_model_cost(Handle* h);
+pba_status launch_unpermute(Handle* h, const double* src_planes, int planes, double* dst_host_order_dev);
+// schur.cu
+pba_status launch_post_jacobian(Handle* h);              // edge Gram + landmark gather (+ scales on first call)
+pba_status launch_build_rcs(Handle* h, double radius, bool refresh_diag);
+pba_status launch_backsub(Handle* h);
+pba_status launch_retract(Handle* h);
+pba_status launch_gradient_norms(Handle* h);
+// solve.cu
+pba_status launch_cholesky_rcs(Handle* h);
+pba_status launch_pcg_rcs(Handle* h);
+pba_status dense_cholesky_solve(Handle* h, double* A, double* b, int ld, int* fail_dev);
+int dense_ld(int n);
+int pcg_max_grid(int device);
+int schur_tile_l(int max_stride);
+void schur_set_smem(size_t bytes);
+int eval_grid(int64_t n);
+// host.cu
+pba_status allreduce_rcs(Handle* h);
+pba_status allreduce_scalars(Handle* h, double* dev, int n, bool max_op);
+
+}  // namespace pba

@@ -1,0 +1,648 @@
+// schur.cu — normal-equation assembly and Schur elimination of the inverse
+// distances into the reduced camera system (RCS), back-substitution,
+// retraction and gradient norms.
+//
+// Replaces Ceres' SchurEliminator::{Eliminate,BackSubstitute}
+// (internal/ceres/schur_eliminator_impl.h:177-375), the Jacobi column scaling
+// (trust_region_minimizer.cc:261-276), the LM diagonal
+// (levenberg_marquardt_strategy.cc:76-88) and Program::Plus
+// (local_parameterization_se3.hpp:44-51).
+//
+// No global atomics anywhere: every accumulation target has exactly one
+// producer.  The work is split so that each stage is a plain reduction:
+//   k_edge_gram    per (host,target) edge chunk:  [J_h J_t r]^T [J_h J_t r]
+//   k_lm_gather    per landmark:                  row of F^T E, c_l, g_l
+//   k_schur_syrk   per host group:                W^T diag(sigma^2/ete) W
+//   k_rcs_reduce   per RCS block:                 sum of its partial blocks
+// (the per-block source lists are static and built once in pba_create).
+#include "launch.h"
+#include "pba_internal.h"
+
+namespace pba {
+
+namespace {
+
+// ------------------------------------------------------------ edge Gram ----
+// One CTA per edge chunk.  M = [J(0..C-1) | r] as a (32*R) x 16 tile in shared
+// memory per 32 observations; 12 row-groups x 10 upper 4x4 tiles of the 16x16
+// Gram matrix are accumulated in registers.
+template <int R, int C>
+struct GramCfg {
+  static constexpr int CD = C - 7;
+  static constexpr int ROWS = 32 * R;
+  static constexpr int LD = 17;
+  static constexpr int TILE = ROWS * LD > 1920 ? ROWS * LD : 1920;
+  static constexpr int DIR_STRIDE = 3 * CD * CD + 2 * CD;
+};
+
+template <int R, int C>
+__global__ void __launch_bounds__(128) k_edge_gram(int64_t n, const int* __restrict__ chunk_edge,
+                                                    const int64_t* __restrict__ chunk_begin,
+                                                    const int64_t* __restrict__ chunk_end,
+                                                    const int* __restrict__ edge_h, const int* __restrict__ edge_t,
+                                                    const int* __restrict__ slot, const double* __restrict__ J,
+                                                    const double* __restrict__ res, double* __restrict__ part_dir) {
+  using Cfg = GramCfg<R, C>;
+  constexpr int CD = Cfg::CD, ROWS = Cfg::ROWS, LD = Cfg::LD;
+  __shared__ double M[Cfg::TILE];
+  __shared__ double G[256];
+  const int q = blockIdx.x;
+  const int e = chunk_edge[q];
+  const int64_t o0 = chunk_begin[q], o1 = chunk_end[q];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = warp * 3 + lane / 10;
+  const int tile = lane % 10;
+  const bool active = lane < 30;
+  // upper 4x4 tiles of a 4x4 tile grid: (0,0)(0,1)(0,2)(0,3)(1,1)(1,2)(1,3)(2,2)(2,3)(3,3)
+  const int ti = tile < 4 ? 0 : (tile < 7 ? 1 : (tile < 9 ? 2 : 3));
+  const int tj = tile < 4 ? tile : (tile < 7 ? tile - 3 : (tile < 9 ? tile - 5 : 3));
+  double acc[16];
+#pragma unroll
+  for (int x = 0; x < 16; ++x) acc[x] = 0.0;
+
+  for (int64_t base = o0; base < o1; base += 32) {
+    const int cnt = int(o1 - base < 32 ? o1 - base : 32);
+    __syncthreads();
+    for (int item = warp; item < 16 * R; item += 4) {
+      const int k = item >> 4, c = item & 15;
+      double v = 0.0;
+      if (lane < cnt) {
+        if (c < C) v = J[(int64_t(k) * C + c) * n + base + lane];
+        else if (c == 15) v = res[int64_t(k) * n + base + lane];
+      }
+      M[(k * 32 + lane) * LD + c] = v;
+    }
+    __syncthreads();
+    if (active) {
+      for (int kk = g; kk < ROWS; kk += 12) {
+        const double* row = M + kk * LD;
+        double a[4], b[4];
+#pragma unroll
+        for (int x = 0; x < 4; ++x) { a[x] = row[4 * ti + x]; b[x] = row[4 * tj + x]; }
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+          for (int y = 0; y < 4; ++y) acc[4 * x + y] += a[x] * b[y];
+      }
+    }
+  }
+  __syncthreads();
+  if (active) {
+#pragma unroll
+    for (int x = 0; x < 16; ++x) M[(g * 10 + tile) * 16 + x] = acc[x];
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 160; idx += 128) {
+    double s = 0.0;
+    for (int gg = 0; gg < 12; ++gg) s += M[(gg * 10 + idx / 16) * 16 + (idx & 15)];
+    const int tl = idx / 16;
+    const int a = tl < 4 ? 0 : (tl < 7 ? 1 : (tl < 9 ? 2 : 3));
+    const int b = tl < 4 ? tl : (tl < 7 ? tl - 3 : (tl < 9 ? tl - 5 : 3));
+    const int x = (idx & 15) >> 2, y = idx & 3;
+    G[(4 * a + x) * 16 + 4 * b + y] = s;
+    G[(4 * b + y) * 16 + 4 * a + x] = s;
+  }
+  __syncthreads();
+  // partial layout: [HH | HT (or its transpose when slot_h > slot_t) | TT | gh | gt]
+  const int hs = slot[edge_h[e]], ts = slot[edge_t[e]];
+  const bool trans = hs > ts;
+  double* out = part_dir + int64_t(q) * Cfg::DIR_STRIDE;
+  for (int idx = threadIdx.x; idx < Cfg::DIR_STRIDE; idx += 128) {
+    double v = 0.0;
+    if (idx < CD * CD) {
+      const int r = idx / CD, c = idx % CD;
+      if (r < 6 && c < 6) v = G[r * 16 + c];
+    } else if (idx < 2 * CD * CD) {
+      const int r = (idx - CD * CD) / CD, c = (idx - CD * CD) % CD;
+      if (!trans) { if (r < 6) v = G[r * 16 + 6 + c]; }
+      else        { if (c < 6) v = G[c * 16 + 6 + r]; }
+    } else if (idx < 3 * CD * CD) {
+      const int r = (idx - 2 * CD * CD) / CD, c = (idx - 2 * CD * CD) % CD;
+      v = G[(6 + r) * 16 + 6 + c];
+    } else if (idx < 3 * CD * CD + CD) {
+      const int r = idx - 3 * CD * CD;
+      if (r < 6) v = G[r * 16 + 15];
+    } else {
+      const int r = idx - 3 * CD * CD - CD;
+      v = G[(6 + r) * 16 + 15];
+    }
+    out[idx] = v;
+  }
+}
+
+// -------------------------------------------------------- landmark gather --
+// Per landmark: W row = [ F^T E per visible camera (8 wide each) | g_l c_l 0.. ],
+// c_l = sum E^T E, g_l = sum E^T r over the landmark's observations.
+__global__ void __launch_bounds__(128) k_lm_gather(int n_lm, int cd, const int64_t* __restrict__ lm_ptr,
+                                                    const int64_t* __restrict__ lm_pos,
+                                                    const int* __restrict__ obs_col,
+                                                    const int* __restrict__ lm_hostcol,
+                                                    const int64_t* __restrict__ lm_w_off,
+                                                    const int* __restrict__ lm_w_stride,
+                                                    const double* __restrict__ orec, double* __restrict__ W,
+                                                    double* __restrict__ lm_c, double* __restrict__ lm_g) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= n_lm) return;
+  double* row = W + lm_w_off[l];
+  const int stride = lm_w_stride[l];
+  for (int i = 0; i < stride; ++i) row[i] = 0.0;
+  double wh[6] = {0, 0, 0, 0, 0, 0};
+  double c = 0.0, g = 0.0;
+  for (int64_t k = lm_ptr[l]; k < lm_ptr[l + 1]; ++k) {
+    const int64_t pos = lm_pos[k];
+    const double2* rec = reinterpret_cast<const double2*>(orec + 16 * pos);
+    double v[16];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const double2 t = rec[i]; v[2 * i] = t.x; v[2 * i + 1] = t.y; }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) wh[i] += v[i];
+    c += v[14];
+    g += v[15];
+    const int col = obs_col[pos];
+    if (col >= 0) {
+      double* dst = row + 8 * col;
+      for (int i = 0; i < cd; ++i) dst[i] = v[6 + i];
+    }
+  }
+  const int hc = lm_hostcol[l];
+  if (hc >= 0) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) row[8 * hc + i] = wh[i];
+  }
+  row[stride - 8] = g;
+  row[stride - 7] = c;
+  lm_c[l] = c;
+  lm_g[l] = g;
+}
+
+// Per landmark, per linear solve: Jacobi scale sigma_l (iteration 0 only),
+// LM diagonal (refreshed after accepted steps only), ete^-1 and sigma^2/ete
+// (trust_region_minimizer.cc:261-272, levenberg_marquardt_strategy.cc:76-88,
+// schur_eliminator_impl.h:246-252).
+__global__ void k_lm_scale(int n_lm, int init_scale, int jacobi, int refresh_diag, double radius, double min_diag,
+                           double max_diag, const double* __restrict__ lm_c, double* __restrict__ lm_scale,
+                           double* __restrict__ lm_diag, double* __restrict__ lm_iete, double* __restrict__ lm_s2) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= n_lm) return;
+  const double c = lm_c[l];
+  if (init_scale) lm_scale[l] = jacobi ? 1.0 / (1.0 + sqrt(c)) : 1.0;
+  const double s = lm_scale[l];
+  const double cs = c * s * s;
+  if (refresh_diag) lm_diag[l] = fmin(fmax(cs, min_diag), max_diag);
+  const double ete = cs + lm_diag[l] / radius;
+  const double ie = 1.0 / ete;
+  lm_iete[l] = ie;
+  lm_s2[l] = s * s * ie;
+}
+
+// ------------------------------------------------------------ Schur SYRK ---
+// One CTA per host group: partial = W^T diag(s2) W over the group's landmarks,
+// as cd x cd blocks for camera pairs (i <= j) plus the vectors W^T (s2 g).
+// Landmark rows are staged in shared memory 'tile_l' at a time; each thread
+// owns up to two 4x4 register tiles per pass.
+__global__ void __launch_bounds__(256) k_schur_syrk(int cd, int tile_l, const int* __restrict__ grp_lm_ptr,
+                                                     const int* __restrict__ grp_cam_ptr,
+                                                     const int64_t* __restrict__ grp_w_off,
+                                                     const int64_t* __restrict__ grp_part_off,
+                                                     const double* __restrict__ W, const double* __restrict__ lm_s2,
+                                                     double* __restrict__ part_sch) {
+  extern __shared__ double sm[];
+  const int g = blockIdx.x;
+  const int l0 = grp_lm_ptr[g], l1 = grp_lm_ptr[g + 1];
+  const int c = grp_cam_ptr[g + 1] - grp_cam_ptr[g];
+  if (c == 0) return;
+  const int stride = 8 * (c + 1);
+  const double* Wg = W + grp_w_off[g];
+  double* out = part_sch + grp_part_off[g];
+  const int P = c * (c + 1) / 2;
+  const int T = 4 * P + 2 * c;
+  double* s_s2 = sm + size_t(tile_l) * stride;
+
+  for (int t0 = 0; t0 < T; t0 += 512) {
+    int ci[2], cj[2], ok[2];
+    double acc[2][16];
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const int t = t0 + b * 256 + threadIdx.x;
+      ok[b] = t < T;
+      ci[b] = 0; cj[b] = 0;
+      if (ok[b]) {
+        if (t < 4 * P) {
+          int p = t >> 2, i = 0;
+          while (p >= c - i) { p -= c - i; ++i; }
+          ci[b] = 8 * i + 4 * ((t & 3) >> 1);
+          cj[b] = 8 * (i + p) + 4 * (t & 1);
+        } else {
+          const int v = t - 4 * P;
+          ci[b] = 8 * (v >> 1) + 4 * (v & 1);
+          cj[b] = 8 * c;
+        }
+      }
+#pragma unroll
+      for (int x = 0; x < 16; ++x) acc[b][x] = 0.0;
+    }
+    for (int lb = l0; lb < l1; lb += tile_l) {
+      const int cnt = l1 - lb < tile_l ? l1 - lb : tile_l;
+      __syncthreads();
+      const double* src = Wg + size_t(lb - l0) * stride;
+      for (int i = threadIdx.x; i < cnt * stride; i += 256) sm[i] = src[i];
+      for (int i = threadIdx.x; i < cnt; i += 256) s_s2[i] = lm_s2[lb + i];
+      __syncthreads();
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        if (!ok[b]) continue;
+        for (int l = 0; l < cnt; ++l) {
+          const double* row = sm + size_t(l) * stride;
+          const double s2 = s_s2[l];
+          double a[4], bb[4];
+#pragma unroll
+          for (int x = 0; x < 4; ++x) { a[x] = s2 * row[ci[b] + x]; bb[x] = row[cj[b] + x]; }
+#pragma unroll
+          for (int x = 0; x < 4; ++x)
+#pragma unroll
+            for (int y = 0; y < 4; ++y) acc[b][4 * x + y] += a[x] * bb[y];
+        }
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      if (!ok[b]) continue;
+      const int t = t0 + b * 256 + threadIdx.x;
+      if (t < 4 * P) {
+        const int p = t >> 2;
+        const int r0 = 4 * ((t & 3) >> 1), c0 = 4 * (t & 1);
+        double* blk = out + size_t(p) * cd * cd;
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+          for (int y = 0; y < 4; ++y)
+            if (r0 + x < cd && c0 + y < cd) blk[(r0 + x) * cd + c0 + y] = acc[b][4 * x + y];
+      } else {
+        const int v = t - 4 * P;
+        double* vec = out + size_t(P) * cd * cd + size_t(v >> 1) * cd;
+        const int r0 = 4 * (v & 1);
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+          if (r0 + x < cd) vec[r0 + x] = acc[b][4 * x];
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------ RCS reduce ---
+// One CTA per RCS block (cd*cd threads): S = sum(direct) - sum(schur).  The
+// diagonal of the direct part (= squared camera column norms of J) is kept for
+// Jacobi scaling and the LM diagonal.  Extra CTAs handle the right-hand side.
+__global__ void k_rcs_reduce(int cd, int64_t n_blocks, int n_slots, const int64_t* __restrict__ dir_ptr,
+                             const int64_t* __restrict__ dir_src, const int64_t* __restrict__ sch_ptr,
+                             const int64_t* __restrict__ sch_src, const int64_t* __restrict__ vdir_ptr,
+                             const int64_t* __restrict__ vdir_src, const int64_t* __restrict__ vsch_ptr,
+                             const int64_t* __restrict__ vsch_src, const int* __restrict__ blk_row,
+                             const int* __restrict__ blk_col, const double* __restrict__ part_dir,
+                             const double* __restrict__ part_sch, double* __restrict__ S, double* __restrict__ rhs,
+                             double* __restrict__ diagB, double* __restrict__ gcam) {
+  const int64_t b = blockIdx.x;
+  const int e = threadIdx.x;
+  if (b < n_blocks) {
+    if (e >= cd * cd) return;
+    double d = 0.0, s = 0.0;
+    for (int64_t k = dir_ptr[b]; k < dir_ptr[b + 1]; ++k) d += part_dir[dir_src[k] + e];
+    for (int64_t k = sch_ptr[b]; k < sch_ptr[b + 1]; ++k) s += part_sch[sch_src[k] + e];
+    S[b * cd * cd + e] = d - s;
+    if (blk_row[b] == blk_col[b] && e / cd == e % cd) diagB[blk_row[b] * cd + e / cd] = d;
+  } else {
+    const int a = int(b - n_blocks);
+    if (a >= n_slots || e >= cd) return;
+    double d = 0.0, s = 0.0;
+    for (int64_t k = vdir_ptr[a]; k < vdir_ptr[a + 1]; ++k) d += part_dir[vdir_src[k] + e];
+    for (int64_t k = vsch_ptr[a]; k < vsch_ptr[a + 1]; ++k) s += part_sch[vsch_src[k] + e];
+    rhs[a * cd + e] = d - s;
+    gcam[a * cd + e] = d;
+  }
+}
+
+// Camera column scales / LM diagonal (same rules as k_lm_scale).
+__global__ void k_cam_scale(int dim, int init_scale, int jacobi, int refresh_diag, double radius, double min_diag,
+                            double max_diag, const double* __restrict__ diagB, double* __restrict__ cam_scale,
+                            double* __restrict__ cam_diag, double* __restrict__ cam_D2) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= dim) return;
+  const double c = diagB[i];
+  if (init_scale) cam_scale[i] = jacobi ? 1.0 / (1.0 + sqrt(c)) : 1.0;
+  const double s = cam_scale[i];
+  if (refresh_diag) cam_diag[i] = fmin(fmax(c * s * s, min_diag), max_diag);
+  cam_D2[i] = cam_diag[i] / radius;
+}
+
+// S_ab <- diag(sigma_a) S_ab diag(sigma_b) (+ D^2 on the diagonal); rhs <- sigma rhs.
+__global__ void k_rcs_scale(int cd, int64_t n_blocks, int n_slots, const int* __restrict__ blk_row,
+                            const int* __restrict__ blk_col, const double* __restrict__ cam_scale,
+                            const double* __restrict__ cam_D2, double* __restrict__ S, double* __restrict__ rhs) {
+  const int64_t b = blockIdx.x;
+  const int e = threadIdx.x;
+  if (b < n_blocks) {
+    if (e >= cd * cd) return;
+    const int r = e / cd, c = e % cd;
+    const int a = blk_row[b], bb = blk_col[b];
+    double v = S[b * cd * cd + e] * cam_scale[a * cd + r] * cam_scale[bb * cd + c];
+    if (a == bb && r == c) v += cam_D2[a * cd + r];
+    S[b * cd * cd + e] = v;
+  } else {
+    const int a = int(b - n_blocks);
+    if (a >= n_slots || e >= cd) return;
+    rhs[a * cd + e] *= cam_scale[a * cd + e];
+  }
+}
+
+// ------------------------------------------------------------- back-subst --
+// y_l = ete^-1 sigma_l (g_l - sum_a w_la . (sigma_a y_a))  (schur_eliminator_impl.h:309-375)
+// then the unscaled tangent step d_l = -sigma_l y_l.
+__global__ void __launch_bounds__(128) k_backsub(int n_lm, int cd, const int* __restrict__ lm_group,
+                                                  const int* __restrict__ grp_cam_ptr, const int* __restrict__ grp_cams,
+                                                  const int64_t* __restrict__ lm_w_off,
+                                                  const int* __restrict__ lm_w_stride, const int64_t* __restrict__ lm_ptr,
+                                                  const double* __restrict__ W, const double* __restrict__ lm_scale,
+                                                  const double* __restrict__ lm_iete, const double* __restrict__ d_cam,
+                                                  double* __restrict__ d_rho) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= n_lm) return;
+  if (lm_ptr[l + 1] == lm_ptr[l]) { d_rho[l] = 0.0; return; }
+  const int g = lm_group[l];
+  const int c0 = grp_cam_ptr[g], c = grp_cam_ptr[g + 1] - c0;
+  const double* row = W + lm_w_off[l];
+  const int stride = lm_w_stride[l];
+  // d_cam = -sigma y  =>  sum_a w_la . (sigma_a y_a) = -sum_a w_la . d_a
+  double acc = row[stride - 8];  // g_l
+  for (int j = 0; j < c; ++j) {
+    const double* d = d_cam + grp_cams[c0 + j] * cd;
+    const double* w = row + 8 * j;
+    for (int i = 0; i < cd; ++i) acc += w[i] * d[i];
+  }
+  const double s = lm_scale[l];
+  const double y = lm_iete[l] * s * acc;
+  d_rho[l] = -s * y;
+}
+
+__global__ void k_cam_step(int dim, const double* __restrict__ y, const double* __restrict__ scale,
+                           double* __restrict__ d) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < dim) d[i] = -y[i] * scale[i];
+}
+
+__device__ __forceinline__ double block_sum256(double v, double* smem) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) smem[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double s = 0.0;
+  if (threadIdx.x == 0)
+    for (int i = 0; i < int(blockDim.x >> 5); ++i) s += smem[i];
+  __syncthreads();
+  return s;
+}
+__device__ __forceinline__ double block_max256(double v, double* smem) {
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, o));
+  if ((threadIdx.x & 31) == 0) smem[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double s = 0.0;
+  if (threadIdx.x == 0)
+    for (int i = 0; i < int(blockDim.x >> 5); ++i) s = fmax(s, smem[i]);
+  __syncthreads();
+  return s;
+}
+
+// ------------------------------------------------------------ retraction ---
+// candidate = Plus(x, delta): T exp(d) for poses, + for affine / rho.  Items
+// [0, n_poses) are poses, [n_poses, n_poses + n_lm) landmarks.  Per-block
+// partials: [0] ||x - cand||^2, [1] ||cand||^2 over the reduced program's
+// ambient parameters (trust_region_minimizer.cc:706-726, :813-814).
+// `own_poses` = this rank accounts for the (replicated) pose terms.
+__global__ void __launch_bounds__(256) k_retract(int n_poses, int n_lm, int cd, int own_poses,
+                                                  const int* __restrict__ slot, const uint8_t* __restrict__ aff_active,
+                                                  const int64_t* __restrict__ lm_ptr, const double* __restrict__ poses,
+                                                  const double* __restrict__ affine, const double* __restrict__ rho,
+                                                  const double* __restrict__ d_cam, const double* __restrict__ d_rho,
+                                                  double* __restrict__ poses_c, double* __restrict__ affine_c,
+                                                  double* __restrict__ rho_c, double* __restrict__ part_step,
+                                                  double* __restrict__ part_norm) {
+  __shared__ double sm[8];
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  double st = 0.0, nm = 0.0;
+  if (i < n_poses) {
+    const int s = slot[i];
+    double T[7], O[7];
+    for (int k = 0; k < 7; ++k) T[k] = poses[7 * i + k];
+    if (s >= 0) {
+      se3_plus(T, d_cam + s * cd, O);
+      if (own_poses)
+        for (int k = 0; k < 7; ++k) { const double d = T[k] - O[k]; st += d * d; nm += O[k] * O[k]; }
+    } else {
+      for (int k = 0; k < 7; ++k) O[k] = T[k];
+    }
+    for (int k = 0; k < 7; ++k) poses_c[7 * i + k] = O[k];
+    if (affine) {
+      double a = affine[2 * i], b = affine[2 * i + 1];
+      if (s >= 0 && aff_active[i]) {
+        const double na = a + d_cam[s * cd + 6], nb = b + d_cam[s * cd + 7];
+        if (own_poses) { st += (na - a) * (na - a) + (nb - b) * (nb - b); nm += na * na + nb * nb; }
+        a = na; b = nb;
+      }
+      affine_c[2 * i] = a; affine_c[2 * i + 1] = b;
+    }
+  } else if (i < n_poses + n_lm) {
+    const int l = i - n_poses;
+    double r = rho[l];
+    if (lm_ptr[l + 1] > lm_ptr[l]) {
+      const double nr = r + d_rho[l];
+      st += (nr - r) * (nr - r);
+      nm += nr * nr;
+      r = nr;
+    }
+    rho_c[l] = r;
+  }
+  const double a = block_sum256(st, sm);
+  const double b = block_sum256(nm, sm);
+  if (threadIdx.x == 0) { part_step[blockIdx.x] = a; part_norm[blockIdx.x] = b; }
+}
+
+// Gradient norms the way Ceres reports them: ||x - Plus(x, -g)|| in max and
+// 2-norm (trust_region_minimizer.cc:279-298), g = J^T r of the unscaled J.
+__global__ void __launch_bounds__(256) k_grad_norms(int n_poses, int n_lm, int cd, int own_poses,
+                                                     const int* __restrict__ slot,
+                                                     const uint8_t* __restrict__ aff_active,
+                                                     const int64_t* __restrict__ lm_ptr,
+                                                     const double* __restrict__ poses, const double* __restrict__ gcam,
+                                                     const double* __restrict__ lm_g, double* __restrict__ part_max,
+                                                     double* __restrict__ part_sq) {
+  __shared__ double sm[8];
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  double mx = 0.0, sq = 0.0;
+  if (i < n_poses) {
+    const int s = slot[i];
+    if (s >= 0 && own_poses) {
+      double T[7], O[7], d[6];
+      for (int k = 0; k < 7; ++k) T[k] = poses[7 * i + k];
+      for (int k = 0; k < 6; ++k) d[k] = -gcam[s * cd + k];
+      se3_plus(T, d, O);
+      for (int k = 0; k < 7; ++k) { const double e = fabs(T[k] - O[k]); mx = fmax(mx, e); sq += e * e; }
+      if (cd == 8 && aff_active[i])
+        for (int k = 6; k < 8; ++k) { const double e = fabs(gcam[s * cd + k]); mx = fmax(mx, e); sq += e * e; }
+    }
+  } else if (i < n_poses + n_lm) {
+    const int l = i - n_poses;
+    if (lm_ptr[l + 1] > lm_ptr[l]) { const double e = fabs(lm_g[l]); mx = e; sq = e * e; }
+  }
+  const double a = block_max256(mx, sm);
+  const double b = block_sum256(sq, sm);
+  if (threadIdx.x == 0) { part_max[blockIdx.x] = a; part_sq[blockIdx.x] = b; }
+}
+
+__global__ void __launch_bounds__(1024) k_reduce2(const double* __restrict__ pa, const double* __restrict__ pb, int64_t n,
+                                                   int a_is_max, double* __restrict__ oa, double* __restrict__ ob) {
+  __shared__ double s[32], t[32];
+  double va = 0.0, vb = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += 1024) {
+    va = a_is_max ? fmax(va, pa[i]) : va + pa[i];
+    vb += pb[i];
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const double x = __shfl_down_sync(0xffffffffu, va, o);
+    va = a_is_max ? fmax(va, x) : va + x;
+    vb += __shfl_down_sync(0xffffffffu, vb, o);
+  }
+  if ((threadIdx.x & 31) == 0) { s[threadIdx.x >> 5] = va; t[threadIdx.x >> 5] = vb; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double x = 0.0, y = 0.0;
+    for (int i = 0; i < 32; ++i) { x = a_is_max ? fmax(x, s[i]) : x + s[i]; y += t[i]; }
+    *oa = x; *ob = y;
+  }
+}
+
+constexpr auto k_edge_gram_photo = k_edge_gram<8, 15>;
+constexpr auto k_edge_gram_geom = k_edge_gram<2, 13>;
+
+}  // namespace
+
+// After a Jacobian evaluation: direct normal-equation partials + landmark rows.
+pba_status launch_post_jacobian(Handle* h) {
+  const Sizes& z = h->sz;
+  if (z.n_chunks > 0) {
+    if (z.mode == PBA_MODE_PHOTOMETRIC) {
+      PBA_LAUNCH(h, K_EDGE_GRAM, k_edge_gram_photo, dim3(z.n_chunks), dim3(128), 0, z.n_obs, h->chunk_edge.p,
+                 h->chunk_begin.p, h->chunk_end.p, h->edge_h.p, h->edge_t.p, h->d_slot.p, h->J.p, h->res.p,
+                 h->part_dir.p);
+    } else {
+      PBA_LAUNCH(h, K_EDGE_GRAM, k_edge_gram_geom, dim3(z.n_chunks), dim3(128), 0, z.n_obs, h->chunk_edge.p,
+                 h->chunk_begin.p, h->chunk_end.p, h->edge_h.p, h->edge_t.p, h->d_slot.p, h->J.p, h->res.p,
+                 h->part_dir.p);
+    }
+  }
+  if (z.n_lm > 0) {
+    PBA_LAUNCH(h, K_LM_GATHER, k_lm_gather, dim3((z.n_lm + 127) / 128), dim3(128), 0, z.n_lm, z.cd, h->lm_ptr.p,
+               h->lm_pos.p, h->obs_col.p, h->lm_hostcol.p, h->lm_w_off.p, h->lm_w_stride.p, h->orec.p, h->W.p,
+               h->lm_c.p, h->lm_g.p);
+  }
+  return PBA_OK;
+}
+
+void schur_set_smem(size_t bytes) {
+  if (bytes > 48 * 1024) cudaFuncSetAttribute(k_schur_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
+}
+
+int schur_tile_l(int max_stride) {
+  int t = 32;
+  while (t > 1 && size_t(t) * (max_stride + 1) * sizeof(double) > 160 * 1024) t >>= 1;
+  return t;
+}
+
+// Build the damped, Jacobi-scaled RCS for `radius` from the partials of the
+// last Jacobian evaluation (SchurEliminator::Eliminate).
+pba_status launch_build_rcs(Handle* h, double radius, bool refresh_diag) {
+  const Sizes& z = h->sz;
+  const int init_scale = h->scale_ready ? 0 : 1;
+  const int jacobi = h->opt.jacobi_scaling;
+  if (z.n_lm > 0) {
+    PBA_LAUNCH(h, K_LM_SCALE, k_lm_scale, dim3((z.n_lm + 255) / 256), dim3(256), 0, z.n_lm, init_scale, jacobi,
+               refresh_diag ? 1 : 0, radius, h->opt.min_lm_diagonal, h->opt.max_lm_diagonal, h->lm_c.p,
+               h->lm_scale.p, h->lm_diag.p, h->lm_iete.p, h->lm_s2.p);
+  }
+  if (z.n_groups > 0) {
+    const int tile_l = h->schur_tile_l;
+    const size_t smem = (size_t(tile_l) * h->max_w_stride + tile_l) * sizeof(double);
+    PBA_LAUNCH(h, K_SCHUR_SYRK, k_schur_syrk, dim3(z.n_groups), dim3(256), smem, z.cd, tile_l, h->grp_lm_ptr.p,
+               h->grp_cam_ptr.p, h->grp_w_off.p, h->grp_part_off.p, h->W.p, h->lm_s2.p, h->part_sch.p);
+  }
+  double* S = h->rcs.p;
+  double* rhs = S + z.n_blocks * z.cd * z.cd;
+  double* diagB = rhs + z.dim;
+  double* gcam = diagB + z.dim;
+  const int64_t grid = z.n_blocks + z.n_slots;
+  if (grid > 0) {
+    PBA_LAUNCH(h, K_RCS_REDUCE, k_rcs_reduce, dim3((unsigned)grid), dim3(64), 0, z.cd, z.n_blocks, z.n_slots,
+               h->blk_dir_ptr.p, h->blk_dir_src.p, h->blk_sch_ptr.p, h->blk_sch_src.p, h->vec_dir_ptr.p,
+               h->vec_dir_src.p, h->vec_sch_ptr.p, h->vec_sch_src.p, h->d_blk_row.p, h->d_blk_col.p, h->part_dir.p,
+               h->part_sch.p, S, rhs, diagB, gcam);
+  }
+  if (h->world > 1) {
+    pba_status st = allreduce_rcs(h);
+    if (st != PBA_OK) return st;
+  }
+  if (z.dim > 0) {
+    PBA_LAUNCH(h, K_CAM_SCALE, k_cam_scale, dim3((z.dim + 255) / 256), dim3(256), 0, z.dim, init_scale, jacobi,
+               refresh_diag ? 1 : 0, radius, h->opt.min_lm_diagonal, h->opt.max_lm_diagonal, diagB, h->cam_scale.p,
+               h->cam_diag.p, h->cam_D2.p);
+    PBA_LAUNCH(h, K_RCS_SCALE, k_rcs_scale, dim3((unsigned)grid), dim3(64), 0, z.cd, z.n_blocks, z.n_slots,
+               h->d_blk_row.p, h->d_blk_col.p, h->cam_scale.p, h->cam_D2.p, S, rhs);
+  }
+  h->scale_ready = true;
+  h->have_rcs = true;
+  h->rcs_radius = radius;
+  return PBA_OK;
+}
+
+// y_cam (scaled space) -> unscaled tangent steps for cameras and landmarks.
+pba_status launch_backsub(Handle* h) {
+  const Sizes& z = h->sz;
+  if (z.dim > 0) {
+    PBA_LAUNCH(h, K_BACKSUB, k_cam_step, dim3((z.dim + 255) / 256), dim3(256), 0, z.dim, h->y_cam.p, h->cam_scale.p,
+               h->d_cam.p);
+  }
+  if (z.n_lm > 0) {
+    PBA_LAUNCH(h, K_BACKSUB, k_backsub, dim3((z.n_lm + 127) / 128), dim3(128), 0, z.n_lm, z.cd, h->lm_group.p,
+               h->grp_cam_ptr.p, h->grp_cams.p, h->lm_w_off.p, h->lm_w_stride.p, h->lm_ptr.p, h->W.p, h->lm_scale.p,
+               h->lm_iete.p, h->d_cam.p, h->d_rho.p);
+  }
+  return PBA_OK;
+}
+
+// candidate = Plus(x, d); scalars S_STEP2 = ||x - cand||^2, S_XNORM2 = ||cand||^2.
+pba_status launch_retract(Handle* h) {
+  const Sizes& z = h->sz;
+  const int items = z.n_poses + z.n_lm;
+  const int grid = (items + 255) / 256;
+  double* pa = h->red_ws.p;
+  double* pb = pa + grid;
+  const bool photo = z.mode == PBA_MODE_PHOTOMETRIC;
+  PBA_LAUNCH(h, K_RETRACT, k_retract, dim3(grid), dim3(256), 0, z.n_poses, z.n_lm, z.cd, h->rank == 0 ? 1 : 0,
+             h->d_slot.p, h->d_affine_active.p, h->lm_ptr.p, h->poses.p, photo ? h->affine.p : nullptr, h->rho.p,
+             h->d_cam.p, h->d_rho.p, h->poses_c.p, photo ? h->affine_c.p : nullptr, h->rho_c.p, pa, pb);
+  PBA_LAUNCH(h, K_REDUCE_SUM, k_reduce2, dim3(1), dim3(1024), 0, pa, pb, int64_t(grid), 0, h->scalars.p + S_STEP2,
+             h->scalars.p + S_XNORM2);
+  return PBA_OK;
+}
+
+pba_status launch_gradient_norms(Handle* h) {
+  const Sizes& z = h->sz;
+  const int items = z.n_poses + z.n_lm;
+  const int grid = (items + 255) / 256;
+  double* pa = h->red_ws.p;
+  double* pb = pa + grid;
+  const double* gcam = h->rcs.p + z.n_blocks * z.cd * z.cd + 2 * z.dim;
+  PBA_LAUNCH(h, K_REDUCE_SUM, k_grad_norms, dim3(grid), dim3(256), 0, z.n_poses, z.n_lm, z.cd, h->rank == 0 ? 1 : 0,
+             h->d_slot.p, h->d_affine_active.p, h->lm_ptr.p, h->poses.p, gcam, h->lm_g.p, pa, pb);
+  PBA_LAUNCH(h, K_REDUCE_SUM, k_reduce2, dim3(1), dim3(1024), 0, pa, pb, int64_t(grid), 1, h->scalars.p + S_GMAX,
+             h->scalars.p + S_GNORM2);
+  return PBA_OK;
+}
+
+}  // namespace pba

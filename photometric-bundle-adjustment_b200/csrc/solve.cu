@@ -1,0 +1,482 @@
+// solve.cu — solving the reduced camera system.
+//
+// Replaces Ceres' SparseSchurComplementSolver::SolveReducedLinearSystem
+// (internal/ceres/schur_complement_solver.cc:319-356; sparse LDL^T on the CPU,
+// internal/ceres/eigensparse.cc:56-106) with
+//   * a tiled dense fp64 Cholesky for small RCS — the one true dense
+//     contraction on the path, so its trailing update runs on the FP64 tensor
+//     cores (mma.sync.m8n8k4.f64 = DMMA; tcgen05 has no fp64 kind);
+//   * a block-Jacobi preconditioned conjugate-gradient solver on the
+//     block-sparse RCS for large problems (the analogue of Ceres' SCHUR_JACOBI
+//     PCG, conjugate_gradients_solver.cc:63-249), run as ONE cooperative
+//     kernel so a solve costs one launch, not five per iteration.
+#include <cooperative_groups.h>
+
+#include "launch.h"
+#include "pba_internal.h"
+
+namespace cg = cooperative_groups;
+
+namespace pba {
+
+namespace {
+
+constexpr int NB = 64;   // Cholesky tile
+constexpr int LDS = 68;  // padded shared-memory row stride (doubles)
+
+__device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// dense <- block list (both triangles), padded to a multiple of NB with identity.
+__global__ void k_dense_init(int n, int ld, double* __restrict__ A, double* __restrict__ b_pad) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= int64_t(ld) * ld) return;
+  const int r = int(i / ld), c = int(i % ld);
+  A[i] = (r == c && r >= n) ? 1.0 : 0.0;
+  if (c == 0 && r >= n) b_pad[r] = 0.0;
+}
+
+__global__ void k_dense_fill(int cd, int64_t n_blocks, int ld, const int* __restrict__ blk_row,
+                             const int* __restrict__ blk_col, const double* __restrict__ S, double* __restrict__ A) {
+  const int64_t b = blockIdx.x;
+  const int e = threadIdx.x;
+  if (b >= n_blocks || e >= cd * cd) return;
+  const int r = e / cd, c = e % cd;
+  const int gr = blk_row[b] * cd + r, gc = blk_col[b] * cd + c;
+  const double v = S[b * cd * cd + e];
+  A[int64_t(gr) * ld + gc] = v;
+  A[int64_t(gc) * ld + gr] = v;
+}
+
+// Factor the diagonal tile A_kk = L L^T in shared memory (one CTA).
+__global__ void __launch_bounds__(256) k_chol_diag(int ld, int k, double* __restrict__ A, int* __restrict__ fail) {
+  __shared__ double T[NB * (NB + 1)];
+  double* Akk = A + (int64_t(k) * NB) * ld + k * NB;
+  for (int i = threadIdx.x; i < NB * NB; i += 256) T[(i / NB) * (NB + 1) + i % NB] = Akk[int64_t(i / NB) * ld + i % NB];
+  __syncthreads();
+  for (int j = 0; j < NB; ++j) {
+    if (threadIdx.x == 0) {
+      const double d = T[j * (NB + 1) + j];
+      if (!(d > 0.0)) { *fail = 1; T[j * (NB + 1) + j] = 1.0; }
+      else T[j * (NB + 1) + j] = sqrt(d);
+    }
+    __syncthreads();
+    const double dj = T[j * (NB + 1) + j];
+    for (int i = j + 1 + threadIdx.x; i < NB; i += 256) T[i * (NB + 1) + j] /= dj;
+    __syncthreads();
+    // rank-1 update of the trailing lower triangle
+    const int m = NB - j - 1;
+    for (int idx = threadIdx.x; idx < m * m; idx += 256) {
+      const int r = j + 1 + idx / m, c = j + 1 + idx % m;
+      if (c <= r) T[r * (NB + 1) + c] -= T[r * (NB + 1) + j] * T[c * (NB + 1) + j];
+    }
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < NB * NB; i += 256) {
+    const int r = i / NB, c = i % NB;
+    Akk[int64_t(r) * ld + c] = c <= r ? T[r * (NB + 1) + c] : 0.0;
+  }
+}
+
+// A_ik <- A_ik L_kk^-T for all row tiles i > k (one CTA of 64 threads per tile;
+// each thread forward-substitutes one row).
+__global__ void __launch_bounds__(NB) k_chol_trsm(int ld, int k, double* __restrict__ A) {
+  __shared__ double L[NB * (NB + 1)];
+  const int i = k + 1 + blockIdx.x;
+  const double* Lkk = A + (int64_t(k) * NB) * ld + k * NB;
+  for (int x = threadIdx.x; x < NB * NB; x += NB) L[(x / NB) * (NB + 1) + x % NB] = Lkk[int64_t(x / NB) * ld + x % NB];
+  __syncthreads();
+  double* row = A + (int64_t(i) * NB + threadIdx.x) * ld + k * NB;
+  double x[NB];
+#pragma unroll
+  for (int c = 0; c < NB; ++c) x[c] = row[c];
+#pragma unroll
+  for (int c = 0; c < NB; ++c) {
+    double s = x[c];
+#pragma unroll
+    for (int j = 0; j < c; ++j) s -= x[j] * L[c * (NB + 1) + j];
+    x[c] = s / L[c * (NB + 1) + c];
+  }
+#pragma unroll
+  for (int c = 0; c < NB; ++c) row[c] = x[c];
+}
+
+// Trailing update A_ij -= L_ik L_jk^T for k < j <= i, one CTA (4 warps) per
+// 64x64 tile, fp64 tensor cores (DMMA m8n8k4).  Warp w owns rows 16w..16w+15.
+__global__ void __launch_bounds__(128) k_chol_syrk(int ld, int k, int nt, double* __restrict__ A) {
+  extern __shared__ double syrk_sm[];
+  double* Li = syrk_sm;
+  double* Lj = syrk_sm + NB * LDS;
+  // decode (i, j) with k < j <= i < nt from the linear tile index
+  const int m = nt - k - 1;
+  int t = blockIdx.x, ii = 0;
+  while (t >= ii + 1) { t -= ii + 1; ++ii; }
+  const int i = k + 1 + ii, j = k + 1 + t;
+  (void)m;
+  const double* Aik = A + (int64_t(i) * NB) * ld + k * NB;
+  const double* Ajk = A + (int64_t(j) * NB) * ld + k * NB;
+  for (int x = threadIdx.x; x < NB * NB; x += 128) {
+    const int r = x / NB, c = x % NB;
+    Li[r * LDS + c] = Aik[int64_t(r) * ld + c];
+    Lj[r * LDS + c] = Ajk[int64_t(r) * ld + c];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int fr = lane >> 2, fc = lane & 3;
+  double acc[2][8][2];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 8; ++b) { acc[a][b][0] = 0.0; acc[a][b][1] = 0.0; }
+#pragma unroll 4
+  for (int k0 = 0; k0 < NB; k0 += 4) {
+    double af[2], bf[8];
+#pragma unroll
+    for (int a = 0; a < 2; ++a) af[a] = Li[(16 * warp + 8 * a + fr) * LDS + k0 + fc];
+#pragma unroll
+    for (int b = 0; b < 8; ++b) bf[b] = Lj[(8 * b + fr) * LDS + k0 + fc];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 8; ++b) dmma8x8x4(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+  }
+  double* Aij = A + (int64_t(i) * NB) * ld + j * NB;
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      const int r = 16 * warp + 8 * a + fr, c = 8 * b + 2 * fc;
+      double2* p = reinterpret_cast<double2*>(Aij + int64_t(r) * ld + c);
+      double2 v = *p;
+      v.x -= acc[a][b][0];
+      v.y -= acc[a][b][1];
+      *p = v;
+    }
+}
+
+// Triangular solves with the tiled factor, one right-hand side.
+// forward:  solve L_kk y_k = b_k (one CTA), then b_i -= L_ik y_k for i > k.
+// backward: solve L_kk^T x_k = y_k, then y_i -= L_ki^T x_k for i < k.
+__global__ void __launch_bounds__(NB) k_tri_diag(int ld, int k, int transpose, const double* __restrict__ A,
+                                                  double* __restrict__ b) {
+  __shared__ double L[NB * (NB + 1)];
+  __shared__ double x[NB];
+  const double* Lkk = A + (int64_t(k) * NB) * ld + k * NB;
+  for (int i = threadIdx.x; i < NB * NB; i += NB) L[(i / NB) * (NB + 1) + i % NB] = Lkk[int64_t(i / NB) * ld + i % NB];
+  x[threadIdx.x] = b[k * NB + threadIdx.x];
+  __syncthreads();
+  if (!transpose) {
+    for (int j = 0; j < NB; ++j) {
+      if (threadIdx.x == j) x[j] /= L[j * (NB + 1) + j];
+      __syncthreads();
+      if (threadIdx.x > j) x[threadIdx.x] -= L[threadIdx.x * (NB + 1) + j] * x[j];
+      __syncthreads();
+    }
+  } else {
+    for (int j = NB - 1; j >= 0; --j) {
+      if (threadIdx.x == j) x[j] /= L[j * (NB + 1) + j];
+      __syncthreads();
+      if (threadIdx.x < j) x[threadIdx.x] -= L[j * (NB + 1) + threadIdx.x] * x[j];
+      __syncthreads();
+    }
+  }
+  b[k * NB + threadIdx.x] = x[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(NB) k_tri_update(int ld, int k, int transpose, const double* __restrict__ A,
+                                                    double* __restrict__ b) {
+  __shared__ double xk[NB];
+  xk[threadIdx.x] = b[k * NB + threadIdx.x];
+  __syncthreads();
+  double s = 0.0;
+  if (!transpose) {
+    const int i = k + 1 + blockIdx.x;
+    const double* row = A + (int64_t(i) * NB + threadIdx.x) * ld + k * NB;
+#pragma unroll 8
+    for (int c = 0; c < NB; ++c) s += row[c] * xk[c];
+    b[i * NB + threadIdx.x] -= s;
+  } else {
+    const int i = blockIdx.x;  // i < k
+    const double* col = A + (int64_t(k) * NB) * ld + i * NB + threadIdx.x;
+#pragma unroll 8
+    for (int c = 0; c < NB; ++c) s += col[int64_t(c) * ld] * xk[c];
+    b[i * NB + threadIdx.x] -= s;
+  }
+}
+
+// ------------------------------------------------------------------- PCG ---
+// Inverse of the (SPD) diagonal blocks: the block-Jacobi preconditioner.
+__global__ void k_block_inverse(int cd, int n_slots, const int* __restrict__ diag_blk, const double* __restrict__ S,
+                                double* __restrict__ inv) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= n_slots) return;
+  double M[64], X[64];
+  const double* src = S + int64_t(diag_blk[a]) * cd * cd;
+  for (int i = 0; i < cd * cd; ++i) M[i] = src[i];
+  // Cholesky M = L L^T (in place, lower)
+  for (int j = 0; j < cd; ++j) {
+    double d = M[j * cd + j];
+    for (int k = 0; k < j; ++k) d -= M[j * cd + k] * M[j * cd + k];
+    d = sqrt(fmax(d, 1e-300));
+    M[j * cd + j] = d;
+    for (int i = j + 1; i < cd; ++i) {
+      double s = M[i * cd + j];
+      for (int k = 0; k < j; ++k) s -= M[i * cd + k] * M[j * cd + k];
+      M[i * cd + j] = s / d;
+    }
+  }
+  // X = M^-1 column by column
+  for (int c = 0; c < cd; ++c) {
+    double y[8];
+    for (int i = 0; i < cd; ++i) {
+      double s = i == c ? 1.0 : 0.0;
+      for (int k = 0; k < i; ++k) s -= M[i * cd + k] * y[k];
+      y[i] = s / M[i * cd + i];
+    }
+    for (int i = cd - 1; i >= 0; --i) {
+      double s = y[i];
+      for (int k = i + 1; k < cd; ++k) s -= M[k * cd + i] * y[k];
+      y[i] = s / M[i * cd + i];
+    }
+    for (int i = 0; i < cd; ++i) X[i * cd + c] = y[i];
+  }
+  for (int i = 0; i < cd * cd; ++i) inv[int64_t(a) * cd * cd + i] = X[i];
+}
+
+struct PcgArgs {
+  int cd, n_slots, max_iter;
+  double tol;
+  const int* row_ptr;
+  const int* row_blk;
+  const int* row_col;
+  const uint8_t* row_trans;
+  const double* S;
+  const double* inv;
+  const double* b;
+  double* x;
+  double* r;
+  double* z;
+  double* p;
+  double* Ap;
+  double* part;     // [3][gridDim.x]
+  double* out;      // [0] iterations, [1] final sqrt(rz/rz0)
+};
+
+__device__ __forceinline__ double grid_total(const double* part, int n) {
+  double s = 0.0;
+  for (int i = 0; i < n; ++i) s += part[i];
+  return s;
+}
+
+// Deterministic: every per-CTA partial is produced by one CTA and summed in
+// index order by everyone.
+__device__ __forceinline__ void cta_partial(double v, double* dst, double* sm) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < int(blockDim.x >> 5); ++i) s += sm[i];
+    *dst = s;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) k_pcg(const PcgArgs a) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ double sm[8];
+  const int cd = a.cd, n = a.n_slots * a.cd;
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+  const int gwarp = gtid >> 5, nwarp = gsz >> 5, lane = threadIdx.x & 31;
+  const int fr = lane >> 2, fq = lane & 3;
+  const int G = gridDim.x;
+
+  // x = 0, r = b, z = M^-1 r, p = z, rz = r.z
+  double loc = 0.0;
+  for (int s = gwarp; s < a.n_slots; s += nwarp) {
+    // block-Jacobi apply: z_s = inv_s r_s ; lanes (fr, fq): row fr, columns 2fq,2fq+1
+    double v = 0.0;
+    if (fr < cd) {
+      const double* inv = a.inv + int64_t(s) * cd * cd + fr * cd;
+      for (int c = 2 * fq; c < 2 * fq + 2 && c < cd; ++c) v += inv[c] * a.b[s * cd + c];
+    }
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    if (fq == 0 && fr < cd) {
+      const int i = s * cd + fr;
+      const double ri = a.b[i];
+      a.x[i] = 0.0; a.r[i] = ri; a.z[i] = v; a.p[i] = v;
+      loc += ri * v;
+    }
+  }
+  cta_partial(loc, a.part + blockIdx.x, sm);
+  grid.sync();
+  double rz = grid_total(a.part, G);
+  const double rz0 = rz;
+  int it = 0;
+  if (rz0 > 0.0) {
+    for (it = 0; it < a.max_iter; ++it) {
+      // Ap = S p (symmetric block rows), pAp
+      loc = 0.0;
+      for (int s = gwarp; s < a.n_slots; s += nwarp) {
+        double v = 0.0;
+        if (fr < cd) {
+          for (int k = a.row_ptr[s]; k < a.row_ptr[s + 1]; ++k) {
+            const double* blk = a.S + int64_t(a.row_blk[k]) * cd * cd;
+            const double* pc = a.p + a.row_col[k] * cd;
+            if (!a.row_trans[k]) {
+              for (int c = 2 * fq; c < 2 * fq + 2 && c < cd; ++c) v += blk[fr * cd + c] * pc[c];
+            } else {
+              for (int c = 2 * fq; c < 2 * fq + 2 && c < cd; ++c) v += blk[c * cd + fr] * pc[c];
+            }
+          }
+        }
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        if (fq == 0 && fr < cd) {
+          a.Ap[s * cd + fr] = v;
+          loc += v * a.p[s * cd + fr];
+        }
+      }
+      cta_partial(loc, a.part + G + blockIdx.x, sm);
+      grid.sync();
+      const double pAp = grid_total(a.part + G, G);
+      const double alpha = rz / pAp;
+      // x += alpha p ; r -= alpha Ap ; z = M^-1 r ; rz_new
+      loc = 0.0;
+      for (int s = gwarp; s < a.n_slots; s += nwarp) {
+        double rn = 0.0;
+        if (fq == 0 && fr < cd) {
+          const int i = s * cd + fr;
+          a.x[i] += alpha * a.p[i];
+          rn = a.r[i] - alpha * a.Ap[i];
+          a.r[i] = rn;
+        }
+        // broadcast the slot's new residual: lane 4c holds row c (all lanes shuffle)
+        const int c0 = 2 * fq, c1 = 2 * fq + 1;
+        const double rc0 = __shfl_sync(0xffffffffu, rn, 4 * (c0 < cd ? c0 : 0));
+        const double rc1 = __shfl_sync(0xffffffffu, rn, 4 * (c1 < cd ? c1 : 0));
+        double v = 0.0;
+        if (fr < cd) {
+          const double* inv = a.inv + int64_t(s) * cd * cd + fr * cd;
+          if (c0 < cd) v += inv[c0] * rc0;
+          if (c1 < cd) v += inv[c1] * rc1;
+        }
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        if (fq == 0 && fr < cd) {
+          a.z[s * cd + fr] = v;
+          loc += rn * v;
+        }
+      }
+      cta_partial(loc, a.part + 2 * G + blockIdx.x, sm);
+      grid.sync();
+      const double rz_new = grid_total(a.part + 2 * G, G);
+      if (!(rz_new > a.tol * a.tol * rz0)) { rz = rz_new; ++it; break; }
+      const double beta = rz_new / rz;
+      rz = rz_new;
+      for (int i = gtid; i < n; i += gsz) a.p[i] = a.z[i] + beta * a.p[i];
+      grid.sync();
+    }
+  }
+  if (gtid == 0) {
+    a.out[0] = double(it);
+    a.out[1] = rz0 > 0.0 ? sqrt(fabs(rz) / rz0) : 0.0;
+  }
+}
+
+}  // namespace
+
+// In-place tiled Cholesky + solve of the padded dense system (ld = multiple of 64).
+pba_status dense_cholesky_solve(Handle* h, double* A, double* b, int ld, int* fail_dev) {
+  const int nt = ld / NB;
+  constexpr size_t kSyrkSmem = 2 * NB * LDS * sizeof(double);  // 69,632 B: needs the opt-in limit
+  static bool attr_set = false;
+  if (!attr_set) {
+    PBA_CUDA_OK(cudaFuncSetAttribute(k_chol_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSyrkSmem)));
+    attr_set = true;
+  }
+  for (int k = 0; k < nt; ++k) {
+    PBA_LAUNCH(h, K_CHOL_PANEL, k_chol_diag, dim3(1), dim3(256), 0, ld, k, A, fail_dev);
+    const int m = nt - k - 1;
+    if (m > 0) {
+      PBA_LAUNCH(h, K_CHOL_TRSM, k_chol_trsm, dim3(m), dim3(NB), 0, ld, k, A);
+      PBA_LAUNCH(h, K_CHOL_SYRK, k_chol_syrk, dim3(m * (m + 1) / 2), dim3(128), kSyrkSmem, ld, k, nt, A);
+    }
+  }
+  for (int k = 0; k < nt; ++k) {
+    PBA_LAUNCH(h, K_CHOL_SOLVE, k_tri_diag, dim3(1), dim3(NB), 0, ld, k, 0, A, b);
+    if (k + 1 < nt) { PBA_LAUNCH(h, K_CHOL_SOLVE, k_tri_update, dim3(nt - k - 1), dim3(NB), 0, ld, k, 0, A, b); }
+  }
+  for (int k = nt - 1; k >= 0; --k) {
+    PBA_LAUNCH(h, K_CHOL_SOLVE, k_tri_diag, dim3(1), dim3(NB), 0, ld, k, 1, A, b);
+    if (k > 0) { PBA_LAUNCH(h, K_CHOL_SOLVE, k_tri_update, dim3(k), dim3(NB), 0, ld, k, 1, A, b); }
+  }
+  return PBA_OK;
+}
+
+int dense_ld(int n) { return ((n + NB - 1) / NB) * NB; }
+
+pba_status launch_cholesky_rcs(Handle* h) {
+  const Sizes& z = h->sz;
+  if (z.dim == 0) return PBA_OK;
+  const int ld = dense_ld(z.dim);
+  if (h->dense.n < size_t(ld) * ld + ld) {
+    PBA_CUDA_OK(h->dense.alloc(size_t(ld) * ld + ld));
+  }
+  double* A = h->dense.p;
+  double* b = A + size_t(ld) * ld;
+  const double* S = h->rcs.p;
+  const double* rhs = S + z.n_blocks * z.cd * z.cd;
+  const int64_t tot = int64_t(ld) * ld;
+  PBA_LAUNCH(h, K_DENSE_FILL, k_dense_init, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, z.dim, ld, A, b);
+  PBA_LAUNCH(h, K_DENSE_FILL, k_dense_fill, dim3((unsigned)z.n_blocks), dim3(64), 0, z.cd, z.n_blocks, ld,
+             h->d_blk_row.p, h->d_blk_col.p, S, A);
+  PBA_CUDA_OK(cudaMemcpyAsync(b, rhs, sizeof(double) * z.dim, cudaMemcpyDeviceToDevice, h->stream));
+  PBA_CUDA_OK(cudaMemsetAsync(h->chol_fail.p, 0, sizeof(int), h->stream));
+  pba_status st = dense_cholesky_solve(h, A, b, ld, h->chol_fail.p);
+  if (st != PBA_OK) return st;
+  PBA_CUDA_OK(cudaMemcpyAsync(h->y_cam.p, b, sizeof(double) * z.dim, cudaMemcpyDeviceToDevice, h->stream));
+  return PBA_OK;
+}
+
+pba_status launch_pcg_rcs(Handle* h) {
+  const Sizes& z = h->sz;
+  if (z.dim == 0) return PBA_OK;
+  const double* S = h->rcs.p;
+  const double* rhs = S + z.n_blocks * z.cd * z.cd;
+  PBA_LAUNCH(h, K_PCG, k_block_inverse, dim3((z.n_slots + 63) / 64), dim3(64), 0, z.cd, z.n_slots, h->d_diag_blk.p, S,
+             h->blk_inv.p);
+  int grid = h->pcg_grid;
+  const int need = (z.n_slots * 32 + 255) / 256;
+  if (grid > need) grid = need;
+  if (grid < 1) grid = 1;
+  PcgArgs a;
+  a.cd = z.cd; a.n_slots = z.n_slots; a.max_iter = h->opt.pcg_max_iterations; a.tol = h->opt.pcg_tolerance;
+  a.row_ptr = h->row_ptr.p; a.row_blk = h->row_blk.p; a.row_col = h->row_col.p; a.row_trans = h->row_trans.p;
+  a.S = S; a.inv = h->blk_inv.p; a.b = rhs;
+  double* ws = h->pcg_ws.p;
+  a.x = h->y_cam.p; a.r = ws; a.z = ws + z.dim; a.p = ws + 2 * z.dim; a.Ap = ws + 3 * z.dim;
+  a.part = ws + 4 * z.dim;
+  a.out = h->scalars.p + S_PCG_ITERS;
+  void* args[] = {(void*)&a};
+  h->stats.begin(K_PCG, h->stream);
+  cudaError_t e = cudaLaunchCooperativeKernel((void*)k_pcg, dim3(grid), dim3(256), args, 0, h->stream);
+  h->stats.end(h->stream);
+  if (e != cudaSuccess) return map_cuda(e);
+  return PBA_OK;
+}
+
+int pcg_max_grid(int device) {
+  int sms = 0, per_sm = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg, 256, 0);
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 2) per_sm = 2;
+  return sms * per_sm;
+}
+
+}  // namespace pba
