@@ -21,7 +21,7 @@ $(PKG)/libpba_b200.so: $(CU_SRCS) $(CU_HDRS)
 	$(NVCC) $(NVFLAGS) -shared $(CU_SRCS) -o $@ -lcudart -ldl 2> $(PKG)/ptxas.log || (cat $(PKG)/ptxas.log; false)
 
 synth: $(PKG)/libpba_synth.so
-$(PKG)/libpba_synth.so: $(CSRC)/synth.cpp $(CSRC)/pba_math.h include/pba.h
+$(PKG)/libpba_synth.so: $(CSRC)/synth.cpp $(CSRC)/pba_math.h $(CSRC)/synth_scene.h include/pba.h include/pba_synth.h
 	$(HOSTCXX) -O2 -std=c++17 -fPIC -fopenmp -shared -Iinclude -I$(CSRC) $< -o $@
 
 oracle: oracle/libpba_oracle.so
@@ -29,7 +29,7 @@ oracle/libpba_oracle.so: oracle/pba_oracle.cpp include/pba.h
 	$(HOSTCXX) -O2 -std=c++17 -fPIC -fopenmp -fvisibility=hidden -shared -Iinclude $< -o $@
 
 ref:
-	@if [ -d /root/reference ]; then $(MAKE) -C oracle/ref; else echo "no /root/reference: using prebuilt oracle/_ref if present"; fi
+	@if [ -d /root/reference ]; then $(MAKE) -C oracle/ref both; else echo "no /root/reference: using prebuilt oracle/_ref if present"; fi
 
 clean:
 	rm -f $(PKG)/libpba_b200.so $(PKG)/libpba_synth.so oracle/libpba_oracle.so

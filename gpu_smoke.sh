@@ -1,7 +1,8 @@
 #!/bin/bash
-# quick GPU check used during development
+# development helper: GPU tests, smoke and a short bench on the B200 box
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=name,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
-nproc >> gpurun_out/gpu.txt; free -g >> gpurun_out/gpu.txt; lscpu | grep "Model name" >> gpurun_out/gpu.txt
-timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -150 > gpurun_out/pytest_gpu.log
-cat gpurun_out/pytest_gpu.log
+timeout 1200 python -m pytest tests -m gpu -q 2>&1 | tail -60 > gpurun_out/pytest_gpu.log
+cat gpurun_out/pytest_gpu.log | tail -30
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5
+timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -3 gpurun_out/bench.err; cat gpurun_out/bench.json
+timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; tail -3 gpurun_out/bench_ref.err; cat gpurun_out/bench_ref.json

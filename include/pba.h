@@ -238,6 +238,18 @@ pba_status pba_solve_rcs(pba_handle* h, int32_t solver, double* y_cam,
  * on the resident problem.  State stays on the device. */
 pba_status pba_minimize(pba_handle* h, pba_summary* summary);
 
+/* One complete LM iteration at the handle's CURRENT state with trust-region
+ * radius `radius` — exactly the work of one successful Ceres iteration:
+ * residual+Jacobian evaluation (K1), normal equations + Schur elimination
+ * (+ all-reduce), RCS solve, back-substitution, model cost, candidate = Plus(x,
+ * step) and its cost (K2).  Jacobi scaling / LM diagonal are taken from this
+ * Jacobian (iteration-0 semantics).  out->cost = cost at x, out->cost_change =
+ * cost(x) - cost(candidate), out->model_cost_change, out->relative_decrease,
+ * out->step_norm.  apply != 0 moves the state to the candidate when the step
+ * would be accepted (relative_decrease > min_relative_decrease); apply == 0
+ * leaves the state untouched, so repeated calls do identical work (bench.py). */
+pba_status pba_lm_iterate(pba_handle* h, double radius, int32_t apply, pba_iteration* out);
+
 /* Move optimisation state (poses [n_poses*7], inv_depth [n_landmarks local
  * shard order = caller order], affine [n_poses*2] or NULL). */
 pba_status pba_set_state(pba_handle* h, const double* poses,

@@ -111,6 +111,7 @@ PBA_SYMBOLS = [
     "pba_abi_version", "pba_status_string", "pba_device_count", "pba_options_init", "pba_solve",
     "pba_create", "pba_destroy", "pba_set_stream", "pba_synchronize", "pba_evaluate", "pba_get_residuals",
     "pba_get_jacobians", "pba_build_rcs", "pba_get_rcs_dim", "pba_get_rcs", "pba_solve_rcs", "pba_minimize",
+    "pba_lm_iterate",
     "pba_set_state", "pba_get_state", "pba_get_sizes", "pba_reset_kernel_stats", "pba_get_kernel_stats",
     "pba_nccl_unique_id", "pba_comm_init", "pba_camera_project", "pba_camera_unproject", "pba_se3_plus",
     "pba_cholesky_solve",
@@ -159,6 +160,7 @@ def load_lib():
         "pba_get_rcs": [H, c_double_p, c_double_p],
         "pba_solve_rcs": [H, C.c_int32, c_double_p, c_i32_p],
         "pba_minimize": [H, C.POINTER(pba_summary)],
+        "pba_lm_iterate": [H, C.c_double, C.c_int32, C.POINTER(pba_iteration)],
         "pba_set_state": [H, c_double_p, c_double_p, c_double_p],
         "pba_get_state": [H, c_double_p, c_double_p, c_double_p],
         "pba_get_sizes": [H, c_i64_p, c_i32_p, c_i64_p],
@@ -178,6 +180,8 @@ def load_lib():
     lib.pba_destroy.restype = None
     lib.pba_get_kernel_stats.argtypes = [H, C.POINTER(pba_kernel_stat), C.c_int32]
     lib.pba_get_kernel_stats.restype = C.c_int32
+    lib.pba_synth_render_gpu.argtypes = [C.POINTER(pba_synth_params), C.c_int, C.c_int, C.c_int, c_u8_p]
+    lib.pba_synth_render_gpu.restype = C.c_int
     _lib = lib
     return lib
 

@@ -1003,6 +1003,43 @@ PBA_API pba_status pba_minimize(pba_handle* hh, pba_summary* summary) {
   return minimize_impl(h, summary);
 }
 
+PBA_API pba_status pba_lm_iterate(pba_handle* hh, double radius, int32_t apply, pba_iteration* out) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h || !(radius > 0.0)) return PBA_ERR_INVALID_ARGUMENT;
+  PBA_CUDA_OK(cudaSetDevice(h->device));
+  pba_status st;
+  h->scale_ready = false;
+  if ((st = eval_jacobian_and_build(h, radius)) != PBA_OK) return st;
+  if ((st = solve_rcs(h, PBA_SOLVER_AUTO)) != PBA_OK) return st;
+  if ((st = launch_backsub(h)) != PBA_OK) return st;
+  if ((st = launch_model_cost(h)) != PBA_OK) return st;
+  if ((st = launch_retract(h)) != PBA_OK) return st;
+  if ((st = launch_evaluate(h, false, h->poses_c.p, h->affine_c.p, h->rho_c.p, S_COST_C)) != PBA_OK) return st;
+  if (h->world > 1 && (st = allreduce_scalars(h, h->scalars.p + S_COST_C, 4, false)) != PBA_OK) return st;
+  if ((st = read_scalars(h)) != PBA_OK) return st;
+  const double* hs = h->h_scalars;
+  const bool chol_failed = h->last_solver == PBA_SOLVER_CHOLESKY && *reinterpret_cast<const int*>(hs + S_NUM);
+  pba_iteration it;
+  memset(&it, 0, sizeof(it));
+  it.cost = hs[S_COST];
+  it.model_cost_change = hs[S_MODEL];
+  it.step_is_valid = !chol_failed && std::isfinite(hs[S_MODEL]) && hs[S_MODEL] > 0.0;
+  it.cost_change = hs[S_COST] - hs[S_COST_C];
+  it.step_norm = sqrt(hs[S_STEP2]);
+  it.gradient_max_norm = hs[S_GMAX];
+  it.gradient_norm = sqrt(hs[S_GNORM2]);
+  it.trust_region_radius = radius;
+  it.linear_solver_iterations = h->last_solver == PBA_SOLVER_PCG ? int(hs[S_PCG_ITERS]) : 1;
+  it.relative_decrease = it.step_is_valid ? it.cost_change / it.model_cost_change : 0.0;
+  it.step_is_successful = it.step_is_valid && it.relative_decrease > h->opt.min_relative_decrease;
+  if (apply && it.step_is_successful) {
+    swap_buf(h->poses, h->poses_c); swap_buf(h->affine, h->affine_c); swap_buf(h->rho, h->rho_c);
+    h->have_jac = false; h->have_rcs = false;
+  }
+  if (out) *out = it;
+  return PBA_OK;
+}
+
 PBA_API pba_status pba_set_state(pba_handle* hh, const double* poses, const double* inv_depth, const double* affine) {
   Handle* h = reinterpret_cast<Handle*>(hh);
   if (!h) return PBA_ERR_INVALID_ARGUMENT;

@@ -160,6 +160,11 @@ class Engine:
         _ffi.check(self.lib.pba_minimize(self._h, C.byref(s.c)), "pba_minimize")
         return s
 
+    def lm_iterate(self, radius=1e4, apply=False):
+        it = _ffi.pba_iteration()
+        _ffi.check(self.lib.pba_lm_iterate(self._h, float(radius), int(apply), C.byref(it)), "pba_lm_iterate")
+        return {f[0]: getattr(it, f[0]) for f in _ffi.pba_iteration._fields_}
+
     def set_state(self, poses, inv_depth, affine=None):
         poses = np.ascontiguousarray(poses, np.float64)
         inv_depth = np.ascontiguousarray(inv_depth, np.float64)

@@ -7,8 +7,12 @@ from . import _ffi
 from .problem import Problem
 
 
-def make_scene(mode, n_kf, n_pts, model="pinhole", width=752, height=480, render=True, **overrides):
-    """Returns (Problem with the perturbed initial state, ground-truth dict)."""
+def make_scene(mode, n_kf, n_pts, model="pinhole", width=752, height=480, render=True, gpu_render=False,
+               **overrides):
+    """Returns (Problem with the perturbed initial state, ground-truth dict).
+
+    gpu_render=True ray-casts the keyframe images on the current CUDA device
+    (libpba_b200.so: pba_synth_render_gpu) — for the 2,000-keyframe benchmark."""
     s = _ffi.load_synth()
     model_id = _ffi.CAM_NAMES[model] if isinstance(model, str) else int(model)
     prm = _ffi.pba_synth_params()
@@ -39,7 +43,10 @@ def make_scene(mode, n_kf, n_pts, model="pinhole", width=752, height=480, render
     images = None
     if photo:
         images = np.zeros((n_kf, height, width), np.uint8)
-        if render:
+        if render and gpu_render:
+            _ffi.check(_ffi.load_lib().pba_synth_render_gpu(C.byref(prm), 0, n_kf, width,
+                                                            _ffi.ptr(images, C.c_uint8)), "pba_synth_render_gpu")
+        elif render:
             s.pba_synth_render(C.byref(prm), 0, n_kf, width, _ffi.ptr(images, C.c_uint8))
     intr = np.array(list(prm.intrinsics)).reshape(1, 8)
     prob = Problem(mode, poses, fixed, np.zeros(n_kf, np.int32), np.array([model_id], np.int32), intr, rho,

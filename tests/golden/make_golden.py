@@ -1,0 +1,85 @@
+"""Generates tests/golden/*.npz from the REAL reference (oracle/_ref/libpba_ref.so:
+the unmodified visnav headers + vendored Ceres 2.0.0, built by oracle/ref/Makefile).
+
+Run in the build container (needs /root/reference to have been compiled):
+    python tests/golden/make_golden.py
+Each fixture holds the flat problem (inputs), the reference's robustified
+per-block residuals and local Jacobians (ceres::Problem::Evaluate), and the
+reference's full LM trace + final state (ceres::Solve with the options of
+include/visnav/map_utils.h:378-383).  The geometric fixtures' final state comes
+from the unmodified visnav::bundle_adjustment() entry point.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import oracle_ffi as of  # noqa: E402
+import pba_b200 as pb  # noqa: E402
+
+W, H = 192, 144
+SMALL_INTR = {
+    "pinhole": [95.0, 95.0, 95.5, 71.5, 0, 0, 0, 0],
+    "ds": [95.0, 95.0, 95.5, 71.5, -0.2, 0.55, 0, 0],
+    "kb4": [97.0, 97.0, 95.5, 71.5, 0.00693023, -0.0013828, -0.000272596, -0.000452646],
+    "eucm": [95.0, 95.0, 95.5, 71.5, 0.55, 1.05, 0, 0],
+}
+CASES = [(mode, model) for mode in (pb.MODE_GEOMETRIC, pb.MODE_PHOTOMETRIC) for model in ("pinhole", "ds", "kb4", "eucm")]
+
+
+def make_case(mode, model):
+    import ctypes as C
+    intr = (C.c_double * 8)(*SMALL_INTR[model])
+    over = dict(intrinsics=intr, min_len=4, max_len=6)
+    if mode == pb.MODE_PHOTOMETRIC:
+        over.update(pose_sigma=0.0015)
+    prob, gt = pb.make_scene(mode, 7, 70, model, width=W, height=H, **over)
+    return prob, gt
+
+
+def main():
+    assert of.have_ref(), "build oracle/_ref first (make ref)"
+    for mode, model in CASES:
+        prob, gt = make_case(mode, model)
+        hub = 9.0 if mode == pb.MODE_PHOTOMETRIC else 1.0
+        cost, r, J = of.evaluate("ref", prob, True, hub)
+        cost_nh, r_nh, J_nh = of.evaluate("ref", prob, False, hub)
+        sol = prob.copy()
+        s = of.solve("ref", sol, of.default_options(huber_parameter=hub))
+        out = dict(
+            mode=mode, model=pb._ffi.CAM_NAMES[model], huber=hub,
+            poses=prob.poses, pose_fixed=prob.pose_fixed, pose_calib=prob.pose_calib, calib_model=prob.calib_model,
+            intrinsics=prob.intrinsics, inv_depth=prob.inv_depth, lm_host=prob.lm_host, lm_host_uv=prob.lm_host_uv,
+            lm_obs_ptr=prob.lm_obs_ptr, obs_target=prob.obs_target,
+            ref_cost=cost, ref_residuals=r, ref_jacobians=J, ref_cost_nohuber=cost_nh, ref_residuals_nohuber=r_nh,
+            ref_jacobians_nohuber=J_nh,
+            sol_poses=sol.poses, sol_inv_depth=sol.inv_depth,
+            sol_initial_cost=s.initial_cost, sol_final_cost=s.final_cost, sol_termination=s.termination_type,
+            sol_iter_cost=np.array([i["cost"] for i in s.iterations]),
+            sol_iter_radius=np.array([i["trust_region_radius"] for i in s.iterations]),
+            sol_iter_success=np.array([i["step_is_successful"] for i in s.iterations]),
+            sol_iter_step_norm=np.array([i["step_norm"] for i in s.iterations]),
+            sol_iter_gradient_max_norm=np.array([i["gradient_max_norm"] for i in s.iterations]),
+        )
+        if mode == pb.MODE_GEOMETRIC:
+            out["obs_uv"] = prob.obs_uv
+            entry = prob.copy()
+            of.solve("ref", entry, of.default_options(huber_parameter=hub), use_reference_entry=True)
+            out["entry_poses"] = entry.poses          # unmodified visnav::bundle_adjustment()
+            out["entry_inv_depth"] = entry.inv_depth
+        else:
+            out["images"] = prob.images
+            out["affine"] = prob.affine
+            out["sol_affine"] = sol.affine
+        name = "%s_%s.npz" % ("photo" if mode else "geom", model)
+        np.savez_compressed(os.path.join(HERE, name), **out)
+        print(name, "obs", prob.n_obs, "cost %.6e -> %.6e in %d iterations" % (s.initial_cost, s.final_cost, s.num_iterations))
+
+
+if __name__ == "__main__":
+    main()

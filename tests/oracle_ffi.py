@@ -18,7 +18,22 @@ from pba_b200 import _ffi
 
 _ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_SO = os.path.join(_ROOT, "oracle", "libpba_oracle.so")
-REF_SO = os.path.join(_ROOT, "oracle", "_ref", "libpba_ref.so")
+
+
+def _pick_ref():
+    """AVX-512 build when the host supports it (so the CPU baseline is not handicapped), else AVX2."""
+    base = os.path.join(_ROOT, "oracle", "_ref")
+    v4 = os.path.join(base, "libpba_ref_v4.so")
+    try:
+        flags = open("/proc/cpuinfo").read()
+    except OSError:
+        flags = ""
+    if os.path.exists(v4) and all(f in flags for f in ("avx512f", "avx512dq", "avx512bw", "avx512vl", "avx512cd")):
+        return v4
+    return os.path.join(base, "libpba_ref.so")
+
+
+REF_SO = _pick_ref()
 
 _d = _ffi.c_double_p
 

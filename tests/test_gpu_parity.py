@@ -289,3 +289,52 @@ def test_properties_at_scale():
     poses, rho, aff = eng.get_state()
     assert np.abs(poses - gt["poses"]).max() < np.abs(prob.poses - gt["poses"]).max()
     eng.close()
+
+
+# ------------------------------------- golden vectors of the real reference --
+import golden_util as gu  # noqa: E402
+
+
+@pytest.mark.parametrize("path", gu.golden_files(), ids=lambda p: p.split("/")[-1][:-4])
+def test_cuda_matches_reference_golden_vectors(path):
+    """CUDA path vs the committed outputs of the unmodified reference
+    (visnav functor + vendored Ceres AutoDiff; tests/golden/make_golden.py)."""
+    prob, g = gu.load(path)
+    hub = float(g["huber"])
+    eng = pb.Engine(prob, pb.BundleAdjustmentOptions(verbosity_level=0, huber_parameter=hub))
+    cost = eng.evaluate(True)
+    assert abs(cost - float(g["ref_cost"])) <= 1e-12 * float(g["ref_cost"])
+    assert rel(eng.residuals(), g["ref_residuals"]) < RTOL_RJ
+    assert rel(eng.jacobians(), g["ref_jacobians"]) < RTOL_RJ
+    eng.close()
+    eng = pb.Engine(prob, pb.BundleAdjustmentOptions(verbosity_level=0, use_huber=False))
+    eng.evaluate(True)
+    assert rel(eng.residuals(), g["ref_residuals_nohuber"]) < RTOL_RJ
+    assert rel(eng.jacobians(), g["ref_jacobians_nohuber"]) < RTOL_RJ
+    eng.close()
+    s = pb.bundle_adjustment(prob, pb.BundleAdjustmentOptions(verbosity_level=0, huber_parameter=hub,
+                                                              solver=pb.SOLVER_CHOLESKY))
+    assert s.termination_type == int(g["sol_termination"])
+    assert s.num_iterations == len(g["sol_iter_cost"])
+    assert abs(s.final_cost - float(g["sol_final_cost"])) <= RTOL_COST * float(g["sol_final_cost"])
+    np.testing.assert_allclose([i["cost"] for i in s.iterations], g["sol_iter_cost"], rtol=1e-6)
+    assert [i["step_is_successful"] for i in s.iterations] == list(g["sol_iter_success"])
+    assert np.abs(prob.poses - g["sol_poses"]).max() < TOL_STATE
+    assert np.abs(prob.inv_depth - g["sol_inv_depth"]).max() < TOL_STATE
+    if "entry_poses" in g:  # output of the unmodified visnav::bundle_adjustment()
+        assert np.abs(prob.poses - g["entry_poses"]).max() < TOL_STATE
+        assert np.abs(prob.inv_depth - g["entry_inv_depth"]).max() < TOL_STATE
+
+
+def test_lm_iterate_is_repeatable_and_matches_minimize_first_step():
+    prob, _ = scene(pb.MODE_PHOTOMETRIC, "pinhole", n_kf=10, n_pts=400)
+    eng = pb.Engine(prob, pb.BundleAdjustmentOptions(verbosity_level=0, huber_parameter=9.0))
+    a = eng.lm_iterate(1e4)
+    b = eng.lm_iterate(1e4)
+    assert a == b                                   # state untouched, bit-identical work
+    s = eng.minimize()
+    it1 = s.iterations[1]
+    assert abs(a["cost"] - s.initial_cost) <= 1e-14 * s.initial_cost
+    assert abs(a["cost_change"] - it1["cost_change"]) <= 1e-9 * abs(it1["cost_change"])
+    assert abs(a["relative_decrease"] - it1["relative_decrease"]) <= 1e-9
+    eng.close()
