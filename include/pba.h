@@ -51,7 +51,10 @@ enum { PBA_MODE_GEOMETRIC = 0, PBA_MODE_PHOTOMETRIC = 1 };
  * AbstractCamera::from_data (camera_models.h:452-474). */
 enum { PBA_CAM_PINHOLE = 0, PBA_CAM_DS = 1, PBA_CAM_KB4 = 2, PBA_CAM_EUCM = 3 };
 
-enum { PBA_SOLVER_AUTO = 0, PBA_SOLVER_CHOLESKY = 1, PBA_SOLVER_PCG = 2 };
+/* RCS solvers: dense tiled Cholesky (FP64 tensor cores), block-Jacobi PCG, block-banded
+ * Cholesky (exact; needs windowed covisibility).  AUTO = BAND when the RCS half-bandwidth
+ * fits the shared-memory window, else CHOLESKY while dim <= cholesky_max_dim, else PCG. */
+enum { PBA_SOLVER_AUTO = 0, PBA_SOLVER_CHOLESKY = 1, PBA_SOLVER_PCG = 2, PBA_SOLVER_BAND = 3 };
 
 /* Ceres termination types (include/ceres/types.h) kept so reports line up. */
 enum { PBA_CONVERGENCE = 0, PBA_NO_CONVERGENCE = 1, PBA_FAILURE = 2 };
@@ -106,7 +109,7 @@ typedef struct pba_options {
   double huber_parameter;
   int32_t max_num_iterations;
 
-  int32_t solver;              /* PBA_SOLVER_*; AUTO = Cholesky when RCS dim <= cholesky_max_dim */
+  int32_t solver;              /* PBA_SOLVER_* (see above) */
   int32_t cholesky_max_dim;    /* default 4096 */
   int32_t pcg_max_iterations;  /* default 500 */
   double pcg_tolerance;        /* relative residual ||r||/||b||, default 1e-10 */
@@ -151,6 +154,8 @@ typedef struct pba_summary {
   int32_t num_jacobian_evaluations;
   int32_t num_linear_solves;
   int32_t rcs_dim;           /* reduced camera system dimension */
+  int32_t linear_solver;     /* PBA_SOLVER_* actually used */
+  int32_t reserved_;
   int64_t rcs_blocks;        /* stored upper-triangular blocks */
   int64_t num_residual_blocks;
   int64_t num_residuals;

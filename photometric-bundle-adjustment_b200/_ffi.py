@@ -17,7 +17,7 @@ STATUS_NAMES = {0: "PBA_OK", 1: "PBA_ERR_INVALID_ARGUMENT", 2: "PBA_ERR_NO_DEVIC
 MODE_GEOMETRIC, MODE_PHOTOMETRIC = 0, 1
 CAM_PINHOLE, CAM_DS, CAM_KB4, CAM_EUCM = 0, 1, 2, 3
 CAM_NAMES = {"pinhole": CAM_PINHOLE, "ds": CAM_DS, "kb4": CAM_KB4, "eucm": CAM_EUCM}
-SOLVER_AUTO, SOLVER_CHOLESKY, SOLVER_PCG = 0, 1, 2
+SOLVER_AUTO, SOLVER_CHOLESKY, SOLVER_PCG, SOLVER_BAND = 0, 1, 2, 3
 CONVERGENCE, NO_CONVERGENCE, FAILURE = 0, 1, 2
 NCCL_ID_BYTES = 128
 
@@ -72,6 +72,7 @@ class pba_summary(C.Structure):
         ("termination_type", C.c_int32), ("num_iterations", C.c_int32), ("num_successful_steps", C.c_int32),
         ("num_unsuccessful_steps", C.c_int32), ("num_residual_evaluations", C.c_int32),
         ("num_jacobian_evaluations", C.c_int32), ("num_linear_solves", C.c_int32), ("rcs_dim", C.c_int32),
+        ("linear_solver", C.c_int32), ("reserved_", C.c_int32),
         ("rcs_blocks", C.c_int64), ("num_residual_blocks", C.c_int64), ("num_residuals", C.c_int64),
         ("num_effective_parameters", C.c_int64), ("gpu_kernel_launches", C.c_int64),
         ("initial_cost", C.c_double), ("final_cost", C.c_double), ("setup_time_in_seconds", C.c_double),

@@ -34,9 +34,9 @@ struct EvalArgs {
   const double* lm_pat;
   const uint8_t* lm_ok;
   const double* obs_uv;  // geometric [2][n]
-  // images
-  const uint8_t* images;
-  int64_t image_stride;
+  // keyframes as quads: one uint32 (I00 | I10<<8 | I01<<16 | I11<<24) per pixel
+  const uint32_t* quads;
+  int64_t image_stride;  // pixels per keyframe
   int width, height, pitch;
   // state
   const double* rho;
@@ -78,13 +78,29 @@ __global__ void k_edge_prep(int n_edges, const int* __restrict__ edge_h, const i
   o[15] = 0.0;
 }
 
+// 2x2 bilinear footprints: quad(x,y) = I(x,y) | I(x+1,y)<<8 | I(x,y+1)<<16 | I(x+1,y+1)<<24
+// (clamped at the right/bottom border, which valid samples never touch).
+__global__ void k_build_quads(int width, int height, int pitch, int64_t n_img, const uint8_t* __restrict__ img,
+                              uint32_t* __restrict__ quads) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t per = int64_t(width) * height;
+  if (i >= per * n_img) return;
+  const int64_t f = i / per;
+  const int y = int((i % per) / width), x = int(i % width);
+  const int x1 = x + 1 < width ? x + 1 : x, y1 = y + 1 < height ? y + 1 : y;
+  const uint8_t* p = img + f * int64_t(pitch) * height;
+  quads[i] = uint32_t(p[int64_t(y) * pitch + x]) | (uint32_t(p[int64_t(y) * pitch + x1]) << 8) |
+             (uint32_t(p[int64_t(y1) * pitch + x]) << 16) | (uint32_t(p[int64_t(y1) * pitch + x1]) << 24);
+}
+
 // Landmark constants: unit host bearings (reprojection.h:106-107) and, for the
 // photometric residual, the bilinear host intensities of the 8-pixel pattern.
+// Photometric layout: SoA planes lm_pat[(k*4 + {bx,by,bz,I_h}) * n_lm + l].
 __global__ void k_init_landmarks(int n_lm, int photo, const int* __restrict__ lm_host,
                                  const double* __restrict__ lm_uv, const int* __restrict__ pose_calib,
                                  const int* __restrict__ calib_model, const double* __restrict__ intr,
-                                 const uint8_t* __restrict__ images, int64_t image_stride, int width, int height,
-                                 int pitch, double* __restrict__ lm_pat, uint8_t* __restrict__ lm_ok) {
+                                 const uint32_t* __restrict__ quads, int64_t image_stride, int width, int height,
+                                 double* __restrict__ lm_pat, uint8_t* __restrict__ lm_ok) {
   const int l = blockIdx.x * blockDim.x + threadIdx.x;
   if (l >= n_lm) return;
   const int h = lm_host[l];
@@ -100,7 +116,7 @@ __global__ void k_init_landmarks(int n_lm, int photo, const int* __restrict__ lm
     lm_ok[l] = 1;
     return;
   }
-  const uint8_t* img = images + int64_t(h) * image_stride;
+  const uint32_t* img = quads + int64_t(h) * image_stride;
   bool ok = true;
   for (int k = 0; k < 8; ++k) {
     const double pu = u + kPatternDev[k][0], pv = v + kPatternDev[k][1];
@@ -110,14 +126,15 @@ __global__ void k_init_landmarks(int n_lm, int photo, const int* __restrict__ lm
     if (pu >= 0.0 && pv >= 0.0 && pu < double(width - 1) && pv < double(height - 1)) {
       const int x0 = int(floor(pu)), y0 = int(floor(pv));
       const double fx = pu - x0, fy = pv - y0;
-      const uint8_t* p = img + int64_t(y0) * pitch + x0;
-      const double i00 = p[0], i10 = p[1], i01 = p[pitch], i11 = p[pitch + 1];
+      const uint32_t q = img[int64_t(y0) * width + x0];
+      const double i00 = double(q & 0xffu), i10 = double((q >> 8) & 0xffu), i01 = double((q >> 16) & 0xffu),
+                   i11 = double(q >> 24);
       I = (1.0 - fx) * (1.0 - fy) * i00 + fx * (1.0 - fy) * i10 + (1.0 - fx) * fy * i01 + fx * fy * i11;
     } else {
       ok = false;
     }
-    double* o = lm_pat + (int64_t(l) * 8 + k) * 4;
-    o[0] = b[0]; o[1] = b[1]; o[2] = b[2]; o[3] = I;
+    double* o = lm_pat + int64_t(4 * k) * n_lm + l;
+    o[0] = b[0]; o[int64_t(n_lm)] = b[1]; o[2 * int64_t(n_lm)] = b[2]; o[3 * int64_t(n_lm)] = I;
   }
   lm_ok[l] = ok;
 }
@@ -151,124 +168,196 @@ __device__ __forceinline__ double huber(double s, int use_huber, double a, doubl
 }
 
 // ------------------------------------------------------------ photometric --
-// K1 (WITH_J) / K2 (!WITH_J).  Per observation: 8 pattern pixels; pass 1
-// warps each pixel into the target, samples intensity + analytic bilinear
-// gradient and keeps r_k and p_k = grad^T dpi/dX; the block's Huber weight
-// needs all 8 residuals, so pass 2 forms the weighted Jacobian rows.
-template <bool WITH_J>
-__global__ void __launch_bounds__(kEvalThreads) k_eval_photo(const EvalArgs a) {
-  __shared__ double s_red[kEvalThreads / 32];
-  const int64_t i = int64_t(blockIdx.x) * kEvalThreads + threadIdx.x;
+// K1 (WITH_J) / K2 (!WITH_J).  One thread per observation, 8 pattern pixels per
+// thread; a warp's 32 consecutive observations make every store a full 256 B
+// run of one SoA plane.
+//
+// The first version of this kernel (profiles/r01a_*) was bound by L1 wavefronts,
+// not HBM: per observation it issued 32 single-byte image taps and 16 LDG.128
+// of an AoS landmark record, every one of them a 32-line gather.  Now
+//   * keyframes are stored as QUADS: one 32-bit word per pixel holding the 2x2
+//     bilinear footprint (I00 I10 I01 I11), so a pixel costs ONE gather;
+//   * landmark pattern constants are SoA planes [k][component][landmark]:
+//     consecutive observations of an edge read near-consecutive landmarks;
+//   * the block's Huber weight needs all 8 residuals before any Jacobian row
+//     can be scaled, so pass 1 computes residuals (this IS the K2 code) and
+//     keeps only the 8 quad words; pass 2 recomputes the warp + projection
+//     Jacobian from registers (no second gather) and streams the weighted rows;
+//   * the 128 B Schur record is transposed through shared memory per warp so
+//     it leaves as coalesced 256 B stores.
+// (A variant with 8 lanes per observation and shuffle reductions was measured
+// slower — 7.7 ms vs 6.7 ms at 18M observations: 4x the load instructions for
+// the per-edge constants.)
+constexpr int kPhotoThreads = 128;
+
+struct PhotoCtx {
+  double A[9], tr[3], ea, bb, in[8], irho;
+  int model;
+};
+
+__device__ __forceinline__ double quad_sample(uint32_t q, double fx, double fy) {
+  const double i00 = double(q & 0xffu), i10 = double((q >> 8) & 0xffu), i01 = double((q >> 16) & 0xffu),
+               i11 = double(q >> 24);
+  return (1.0 - fx) * (1.0 - fy) * i00 + fx * (1.0 - fy) * i10 + (1.0 - fx) * fy * i01 + fx * fy * i11;
+}
+
+// MODEL >= 0: every camera of the problem uses that model (the usual case): the
+// projection is branch-free, so the compiler can batch the gathers.  MODEL = -1:
+// mixed models, runtime switch per observation.
+template <bool WITH_J, int MODEL>
+__global__ void __launch_bounds__(kPhotoThreads, WITH_J ? 3 : 4) k_eval_photo(const EvalArgs a) {
+  __shared__ double s_red[kPhotoThreads / 32];
+  __shared__ double s_rec[WITH_J ? (kPhotoThreads / 32) * 32 * 17 : 1];
+  const int64_t i = int64_t(blockIdx.x) * kPhotoThreads + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double cost = 0.0;
+  double acc[16];
+#pragma unroll
+  for (int q = 0; q < 16; ++q) acc[q] = 0.0;
   if (i < a.n) {
     const int e = a.obs_edge[i];
     const int l = a.obs_lm[i];
     const int t = a.edge_t[e];
     const int tc = a.pose_calib[t];
-    const int model = a.calib_model[tc];
-    const double* T = a.edge_T + 16 * int64_t(e);
-    double A[9], tr[3], in[8];
+    PhotoCtx c;
+    c.model = MODEL >= 0 ? MODEL : a.calib_model[tc];
+    // ---- phase 0: all independent loads first (pattern constants, edge, intrinsics) ----
+    double bx[8], by[8], bz[8], Ih[8];
+    {
+      const double* pk = a.lm_pat + l;
+      const int64_t nl = a.n_lm;
 #pragma unroll
-    for (int k = 0; k < 9; ++k) A[k] = T[k];
-    tr[0] = T[9]; tr[1] = T[10]; tr[2] = T[11];
-    const double ea = T[12], bb = T[13];
+      for (int k = 0; k < 8; ++k) {
+        bx[k] = __ldg(pk + int64_t(4 * k) * nl);
+        by[k] = __ldg(pk + int64_t(4 * k + 1) * nl);
+        bz[k] = __ldg(pk + int64_t(4 * k + 2) * nl);
+        Ih[k] = __ldg(pk + int64_t(4 * k + 3) * nl);
+      }
+      const double2* T2 = reinterpret_cast<const double2*>(a.edge_T + 16 * int64_t(e));
+      const double2 t0 = T2[0], t1 = T2[1], t2 = T2[2], t3 = T2[3], t4 = T2[4], t5 = T2[5], t6 = T2[6];
+      c.A[0] = t0.x; c.A[1] = t0.y; c.A[2] = t1.x; c.A[3] = t1.y; c.A[4] = t2.x; c.A[5] = t2.y; c.A[6] = t3.x;
+      c.A[7] = t3.y; c.A[8] = t4.x; c.tr[0] = t4.y; c.tr[1] = t5.x; c.tr[2] = t5.y; c.ea = t6.x; c.bb = t6.y;
+      const double2* I2 = reinterpret_cast<const double2*>(a.intr + 8 * tc);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) in[k] = a.intr[8 * tc + k];
-    const double rho = a.rho[l];
-    const double irho = 1.0 / rho;
-    const uint8_t* img = a.images + int64_t(t) * a.image_stride;
-    const double4* pat = reinterpret_cast<const double4*>(a.lm_pat) + int64_t(l) * 8;
+      for (int q = 0; q < 4; ++q) { const double2 v = I2[q]; c.in[2 * q] = v.x; c.in[2 * q + 1] = v.y; }
+    }
+    c.irho = 1.0 / a.rho[l];
+    const uint32_t* img = a.quads + int64_t(t) * a.image_stride;
     bool ok = a.lm_ok[l] != 0;
 
+    // ---- phase 1: warp the 8 pixels, branch-free; then gather the 8 quads together ----
+    double fx[8], fy[8];
+    int off[8];
+    const double umax = double(a.width - 1), vmax = double(a.height - 1);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const double xh = bx[k] * c.irho, yh = by[k] * c.irho, zh = bz[k] * c.irho;
+      const double xt = c.A[0] * xh + c.A[1] * yh + c.A[2] * zh + c.tr[0];
+      const double yt = c.A[3] * xh + c.A[4] * yh + c.A[5] * zh + c.tr[1];
+      const double zt = c.A[6] * xh + c.A[7] * yh + c.A[8] * zh + c.tr[2];
+      double uv[2];
+      cam_project<false>(c.model, c.in, xt, yt, zt, uv, nullptr);
+      const bool inb = uv[0] >= 0.0 && uv[1] >= 0.0 && uv[0] < umax && uv[1] < vmax;  // false for NaN
+      ok &= inb;
+      const double u = inb ? uv[0] : 0.0, v = inb ? uv[1] : 0.0;
+      const double x0 = floor(u), y0 = floor(v);
+      fx[k] = u - x0; fy[k] = v - y0;
+      off[k] = int(y0) * a.pitch + int(x0);
+    }
+    uint32_t quad[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) quad[k] = __ldg(img + off[k]);
     double r[8];
-    double p[WITH_J ? 8 : 1][3];
     double s = 0.0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const double4 bk = pat[k];
-      const double xh = bk.x * irho, yh = bk.y * irho, zh = bk.z * irho;
-      const double xt = A[0] * xh + A[1] * yh + A[2] * zh + tr[0];
-      const double yt = A[3] * xh + A[4] * yh + A[5] * zh + tr[1];
-      const double zt = A[6] * xh + A[7] * yh + A[8] * zh + tr[2];
-      double uv[2], Jp[6];
-      cam_project<WITH_J>(model, in, xt, yt, zt, uv, Jp);
-      const double u = uv[0], v = uv[1];
-      double rk = 0.0;
-      if (u >= 0.0 && v >= 0.0 && u < double(a.width - 1) && v < double(a.height - 1)) {
-        const int x0 = int(floor(u)), y0 = int(floor(v));
-        const double fx = u - x0, fy = v - y0;
-        const uint8_t* q = img + int64_t(y0) * a.pitch + x0;
-        const double i00 = __ldg(q), i10 = __ldg(q + 1), i01 = __ldg(q + a.pitch), i11 = __ldg(q + a.pitch + 1);
-        const double I = (1.0 - fx) * (1.0 - fy) * i00 + fx * (1.0 - fy) * i10 + (1.0 - fx) * fy * i01 + fx * fy * i11;
-        rk = I - (ea * bk.w + bb);
-        if (WITH_J) {
-          const double gx = (1.0 - fy) * (i10 - i00) + fy * (i11 - i01);
-          const double gy = (1.0 - fx) * (i01 - i00) + fx * (i11 - i10);
-          p[k][0] = gx * Jp[0] + gy * Jp[3];
-          p[k][1] = gx * Jp[1] + gy * Jp[4];
-          p[k][2] = gx * Jp[2] + gy * Jp[5];
-        }
-      } else {
-        ok = false;
-        if (WITH_J) { p[k][0] = 0.0; p[k][1] = 0.0; p[k][2] = 0.0; }
-      }
-      r[k] = rk;
-      s += rk * rk;
+      r[k] = quad_sample(quad[k], fx[k], fy[k]) - (c.ea * Ih[k] + c.bb);
+      s += r[k] * r[k];
     }
     if (!ok) s = 0.0;  // invalid observation: r = 0, J = 0
     double w;
     cost = huber(s, a.use_huber, a.huber, &w);
     if (!ok) w = 0.0;
+
     if (WITH_J) {
-      double acc[16];
-#pragma unroll
-      for (int k = 0; k < 16; ++k) acc[k] = 0.0;
+      // ---- phase 2: recompute the warp with its projection Jacobian from registers
+      //      (no loads), weight, stream the rows out ----
       const int64_t n = a.n;
-#pragma unroll
+#pragma unroll 1
       for (int k = 0; k < 8; ++k) {
-        const double4 bk = pat[k];
-        const double xh = bk.x * irho, yh = bk.y * irho, zh = bk.z * irho;
-        const double xt = A[0] * xh + A[1] * yh + A[2] * zh + tr[0];
-        const double yt = A[3] * xh + A[4] * yh + A[5] * zh + tr[1];
-        const double zt = A[6] * xh + A[7] * yh + A[8] * zh + tr[2];
-        const double px = w * p[k][0], py = w * p[k][1], pz = w * p[k][2];
-        // a = p A   (d r / d upsilon_h);   d r / d omega_h = -(a x X_h)
-        const double ax = px * A[0] + py * A[3] + pz * A[6];
-        const double ay = px * A[1] + py * A[4] + pz * A[7];
-        const double az = px * A[2] + py * A[5] + pz * A[8];
+        const double xh = bx[k] * c.irho, yh = by[k] * c.irho, zh = bz[k] * c.irho;
+        const double xt = c.A[0] * xh + c.A[1] * yh + c.A[2] * zh + c.tr[0];
+        const double yt = c.A[3] * xh + c.A[4] * yh + c.A[5] * zh + c.tr[1];
+        const double zt = c.A[6] * xh + c.A[7] * yh + c.A[8] * zh + c.tr[2];
+        double uv[2], Jp[6];
+        cam_project<true>(c.model, c.in, xt, yt, zt, uv, Jp);
+        const uint32_t q = quad[k];
+        const double i00 = double(q & 0xffu), i10 = double((q >> 8) & 0xffu), i01 = double((q >> 16) & 0xffu),
+                     i11 = double(q >> 24);
+        const double gx = (1.0 - fy[k]) * (i10 - i00) + fy[k] * (i11 - i01);
+        const double gy = (1.0 - fx[k]) * (i01 - i00) + fx[k] * (i11 - i10);
+        const double p0 = w * (gx * Jp[0] + gy * Jp[3]);
+        const double p1 = w * (gx * Jp[1] + gy * Jp[4]);
+        const double p2 = w * (gx * Jp[2] + gy * Jp[5]);
+        // a = p A  (d r / d upsilon_h);   d r / d omega_h = -(a x X_h)
+        const double ax = p0 * c.A[0] + p1 * c.A[3] + p2 * c.A[6];
+        const double ay = p0 * c.A[1] + p1 * c.A[4] + p2 * c.A[7];
+        const double az = p0 * c.A[2] + p1 * c.A[5] + p2 * c.A[8];
         double row[15];
         row[0] = ax; row[1] = ay; row[2] = az;
         row[3] = -(ay * zh - az * yh);
         row[4] = -(az * xh - ax * zh);
         row[5] = -(ax * yh - ay * xh);
         // target pose: [-p | p x X_t]
-        row[6] = -px; row[7] = -py; row[8] = -pz;
-        row[9] = py * zt - pz * yt;
-        row[10] = pz * xt - px * zt;
-        row[11] = px * yt - py * xt;
+        row[6] = -p0; row[7] = -p1; row[8] = -p2;
+        row[9] = p1 * zt - p2 * yt;
+        row[10] = p2 * xt - p0 * zt;
+        row[11] = p0 * yt - p1 * xt;
         // affine (a_t, b_t)
-        row[12] = -w * ea * bk.w;
+        row[12] = -w * c.ea * Ih[k];
         row[13] = -w;
         // inverse distance: -(a . X_h) / rho
-        row[14] = -(ax * xh + ay * yh + az * zh) * irho;
-        const double rk = w * r[k];
-        a.res[int64_t(k) * n + i] = rk;
+        row[14] = -(ax * xh + ay * yh + az * zh) * c.irho;
+        const double rw = w * r[k];
+        a.res[int64_t(k) * n + i] = rw;
         double* Jk = a.J + (int64_t(k) * 15) * n + i;
 #pragma unroll
-        for (int c = 0; c < 15; ++c) Jk[int64_t(c) * n] = row[c];
+        for (int qq = 0; qq < 15; ++qq) Jk[int64_t(qq) * n] = row[qq];
         const double E = row[14];
 #pragma unroll
-        for (int c = 0; c < 14; ++c) acc[c] += E * row[c];
+        for (int qq = 0; qq < 14; ++qq) acc[qq] += E * row[qq];
         acc[14] += E * E;
-        acc[15] += E * rk;
+        acc[15] += E * rw;
       }
-      double2* o = reinterpret_cast<double2*>(a.orec + 16 * i);
+    }
+  }
+  if (WITH_J) {
+    // Schur record [obs][16]: transpose the warp's 32 x 16 values through shared
+    // memory (row stride 17) and store them as 16 coalesced 256 B runs.
+    double* rec = s_rec + warp * 32 * 17;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) o[c] = make_double2(acc[2 * c], acc[2 * c + 1]);
+    for (int q = 0; q < 16; ++q) rec[lane * 17 + q] = acc[q];
+    __syncwarp();
+    const int64_t base = int64_t(blockIdx.x) * kPhotoThreads + warp * 32;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int ob = 2 * j + (lane >> 4);
+      if (base + ob < a.n) a.orec[16 * (base + ob) + (lane & 15)] = rec[ob * 17 + (lane & 15)];
     }
   }
   const double bs = block_sum(cost, s_red);
   if (threadIdx.x == 0) a.block_cost[blockIdx.x] = bs;
+}
+
+template <bool WITH_J>
+void (*photo_kernel(int model))(const EvalArgs) {
+  switch (model) {
+    case PBA_CAM_PINHOLE: return k_eval_photo<WITH_J, PBA_CAM_PINHOLE>;
+    case PBA_CAM_DS: return k_eval_photo<WITH_J, PBA_CAM_DS>;
+    case PBA_CAM_KB4: return k_eval_photo<WITH_J, PBA_CAM_KB4>;
+    case PBA_CAM_EUCM: return k_eval_photo<WITH_J, PBA_CAM_EUCM>;
+  }
+  return k_eval_photo<WITH_J, -1>;
 }
 
 // -------------------------------------------------------------- geometric --
@@ -408,13 +497,24 @@ __global__ void k_unpermute(int64_t n, int planes, const int64_t* __restrict__ o
 
 }  // namespace
 
+// Upload-time conversion of the 8-bit keyframes (staged in `images_u8`, n_img
+// keyframes of pitch*height bytes) into the quad layout at keyframe `first`.
+pba_status launch_build_quads(Handle* h, const uint8_t* images_u8, int first, int n_img) {
+  const Sizes& z = h->sz;
+  const int64_t tot = int64_t(z.width) * z.height * n_img;
+  if (tot == 0) return PBA_OK;
+  PBA_LAUNCH(h, K_INIT_LM, k_build_quads, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, z.width, z.height, z.pitch,
+             int64_t(n_img), images_u8, h->quads.p + int64_t(first) * z.image_stride);
+  return PBA_OK;
+}
+
 pba_status launch_init_landmarks(Handle* h) {
   const Sizes& z = h->sz;
   if (z.n_lm == 0) return PBA_OK;
   const int photo = z.mode == PBA_MODE_PHOTOMETRIC;
   PBA_LAUNCH(h, K_INIT_LM, k_init_landmarks, dim3((z.n_lm + 127) / 128), dim3(128), 0, z.n_lm, photo, h->lm_host.p,
-             h->lm_uv.p, h->pose_calib.p, h->calib_model.p, h->intr.p, h->images.p, z.image_stride, z.width,
-             z.height, z.pitch, h->lm_pat.p, h->lm_ok.p);
+             h->lm_uv.p, h->pose_calib.p, h->calib_model.p, h->intr.p, h->quads.p, z.image_stride, z.width,
+             z.height, h->lm_pat.p, h->lm_ok.p);
   return PBA_OK;
 }
 
@@ -433,14 +533,15 @@ pba_status launch_evaluate(Handle* h, bool with_jacobian, const double* poses, c
   a.obs_lm = h->obs_lm.p; a.obs_edge = h->obs_edge.p; a.edge_h = h->edge_h.p; a.edge_t = h->edge_t.p;
   a.pose_calib = h->pose_calib.p; a.calib_model = h->calib_model.p; a.intr = h->intr.p; a.edge_T = h->edge_T.p;
   a.lm_pat = h->lm_pat.p; a.lm_ok = h->lm_ok.p; a.obs_uv = h->obs_uv.p;
-  a.images = h->images.p; a.image_stride = z.image_stride; a.width = z.width; a.height = z.height; a.pitch = z.pitch;
+  a.quads = h->quads.p; a.image_stride = z.image_stride; a.width = z.width; a.height = z.height; a.pitch = z.width;  // quad rows are packed
   a.rho = rho; a.use_huber = h->opt.use_huber; a.huber = h->opt.huber_parameter;
   a.res = h->res.p; a.J = h->J.p; a.orec = h->orec.p; a.block_cost = h->red_ws.p;
+  static_assert(kPhotoThreads == kEvalThreads, "block-cost workspace is sized for one CTA width");
   const int grid = eval_grid(z.n_obs);
   if (grid > 0) {
     if (photo) {
-      if (with_jacobian) { PBA_LAUNCH(h, K_RESJAC, k_eval_photo<true>, dim3(grid), dim3(kEvalThreads), 0, a); }
-      else { PBA_LAUNCH(h, K_COST, k_eval_photo<false>, dim3(grid), dim3(kEvalThreads), 0, a); }
+      if (with_jacobian) { PBA_LAUNCH(h, K_RESJAC, photo_kernel<true>(h->uniform_model), dim3(grid), dim3(kPhotoThreads), 0, a); }
+      else { PBA_LAUNCH(h, K_COST, photo_kernel<false>(h->uniform_model), dim3(grid), dim3(kPhotoThreads), 0, a); }
     } else {
       if (with_jacobian) { PBA_LAUNCH(h, K_RESJAC, k_eval_geom<true>, dim3(grid), dim3(kEvalThreads), 0, a); }
       else { PBA_LAUNCH(h, K_COST, k_eval_geom<false>, dim3(grid), dim3(kEvalThreads), 0, a); }

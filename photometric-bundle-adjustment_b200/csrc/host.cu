@@ -37,7 +37,8 @@ const char* const kKernelNames[K_NUM] = {
     "init_landmarks", "edge_prep",  "residual_jacobian", "cost_only",  "reduce_sum", "edge_gram",
     "landmark_gather", "landmark_scale", "schur_syrk", "rcs_reduce", "rcs_scale",  "cam_scale",
     "dense_fill",     "chol_panel", "chol_trsm",         "chol_syrk_dmma", "chol_solve", "pcg",
-    "backsub",        "model_cost", "retract",           "copy",       "unpermute",  "primitive"};
+    "band_cholesky",  "backsub",    "model_cost",        "retract",    "copy",       "unpermute",
+    "primitive"};
 
 pba_status map_cuda(cudaError_t e) {
   if (e == cudaSuccess) return PBA_OK;
@@ -222,6 +223,9 @@ pba_status create_impl(const pba_problem* p, const pba_options* o, int rank, int
   z.n_poses = p->n_poses; z.n_calib = p->n_calib;
   z.width = p->width; z.height = p->height; z.pitch = p->pitch;
   const int cd = z.cd;
+  h->uniform_model = p->n_calib > 0 ? p->calib_model[0] : -1;
+  for (int i = 1; i < p->n_calib; ++i)
+    if (p->calib_model[i] != p->calib_model[0]) h->uniform_model = -1;
 
   // ---- global layout: which parameter blocks survive Ceres' reduced program ----
   std::vector<uint8_t> used(p->n_poses, 0), is_target(p->n_poses, 0);
@@ -274,6 +278,7 @@ pba_status create_impl(const pba_problem* p, const pba_options* o, int rank, int
       h->blk_col[adj_ptr[a] + k] = adj[a][k];
       if (adj[a][k] == a) h->diag_blk[a] = int(adj_ptr[a] + k);
     }
+  for (int64_t b = 0; b < z.n_blocks; ++b) h->rcs_bandwidth = std::max(h->rcs_bandwidth, h->blk_col[b] - h->blk_row[b]);
   auto block_of = [&](int a, int b) -> int64_t {  // a <= b
     const auto it = std::lower_bound(adj[a].begin(), adj[a].end(), b);
     return adj_ptr[a] + (it - adj[a].begin());
@@ -466,6 +471,14 @@ pba_status create_impl(const pba_problem* p, const pba_options* o, int rank, int
   PBA_CUDA_OK(up(h->vec_sch_ptr, vsch_ptr)); PBA_CUDA_OK(up(h->vec_sch_src, vsch_src));
   PBA_CUDA_OK(up(h->row_ptr, row_ptr)); PBA_CUDA_OK(up(h->row_blk, row_blk)); PBA_CUDA_OK(up(h->row_col, row_col));
   PBA_CUDA_OK(up(h->row_trans, row_trans));
+  if (h->rcs_bandwidth <= band_max_bw(cd)) {
+    const int B = h->rcs_bandwidth + 1;
+    std::vector<int> col_blk(size_t(z.n_slots) * B, -1);
+    for (int64_t b = 0; b < z.n_blocks; ++b) col_blk[size_t(h->blk_row[b]) * B + (h->blk_col[b] - h->blk_row[b])] = int(b);
+    PBA_CUDA_OK(up(h->d_col_blk, col_blk));
+    PBA_CUDA_OK(cudaStreamSynchronize(s));
+    PBA_CUDA_OK(h->band_L.alloc(size_t(z.n_slots) * B * cd * cd));
+  }
   {
     std::vector<int> lm_host(n_lm);
     std::vector<double> lm_uv(size_t(2) * n_lm), rho(n_lm);
@@ -495,17 +508,27 @@ pba_status create_impl(const pba_problem* p, const pba_options* o, int rank, int
     PBA_CUDA_OK(cudaStreamSynchronize(s));
   }
   if (photo) {
-    z.image_stride = int64_t(p->pitch) * p->height;
-    PBA_CUDA_OK(h->images.alloc(size_t(z.image_stride) * p->n_poses));
-    if (p->image_ptrs) {
-      for (int i = 0; i < p->n_poses; ++i)
-        PBA_CUDA_OK(cudaMemcpyAsync(h->images.p + size_t(i) * z.image_stride, p->image_ptrs[i], z.image_stride, cudaMemcpyHostToDevice, s));
-    } else if (p->image_stride == z.image_stride) {
-      PBA_CUDA_OK(cudaMemcpyAsync(h->images.p, p->images, size_t(z.image_stride) * p->n_poses, cudaMemcpyHostToDevice, s));
-    } else {
-      for (int i = 0; i < p->n_poses; ++i)
-        PBA_CUDA_OK(cudaMemcpyAsync(h->images.p + size_t(i) * z.image_stride, p->images + size_t(i) * p->image_stride, z.image_stride, cudaMemcpyHostToDevice, s));
+    // keyframes go to the device as 8-bit rows (staged in batches) and are expanded
+    // there into the quad layout the evaluation kernels gather from
+    z.image_stride = int64_t(p->width) * p->height;  // pixels
+    const size_t img_bytes = size_t(p->pitch) * p->height;
+    PBA_CUDA_OK(h->quads.alloc(size_t(z.image_stride) * p->n_poses));
+    const int batch = std::max(1, std::min(p->n_poses, 256));
+    DevBuf<uint8_t> stage;
+    PBA_CUDA_OK(stage.alloc(img_bytes * batch));
+    for (int f0 = 0; f0 < p->n_poses; f0 += batch) {
+      const int cnt = std::min(batch, p->n_poses - f0);
+      if (!p->image_ptrs && p->image_stride == int64_t(img_bytes)) {
+        PBA_CUDA_OK(cudaMemcpyAsync(stage.p, p->images + size_t(f0) * img_bytes, img_bytes * cnt, cudaMemcpyHostToDevice, s));
+      } else {
+        for (int i = 0; i < cnt; ++i) {
+          const uint8_t* src = p->image_ptrs ? p->image_ptrs[f0 + i] : p->images + size_t(f0 + i) * p->image_stride;
+          PBA_CUDA_OK(cudaMemcpyAsync(stage.p + size_t(i) * img_bytes, src, img_bytes, cudaMemcpyHostToDevice, s));
+        }
+      }
+      if ((st = launch_build_quads(h, stage.p, f0, cnt)) != PBA_OK) return st;
     }
+    PBA_CUDA_OK(cudaStreamSynchronize(s));
   }
 
   // ---- work buffers ----
@@ -554,12 +577,17 @@ pba_status read_scalars(Handle* h) {
 
 int pick_solver(const Handle* h, int requested) {
   int s = requested == PBA_SOLVER_AUTO ? h->opt.solver : requested;
-  if (s == PBA_SOLVER_AUTO) s = h->sz.dim <= h->opt.cholesky_max_dim ? PBA_SOLVER_CHOLESKY : PBA_SOLVER_PCG;
+  const bool band_ok = h->rcs_bandwidth <= band_max_bw(h->sz.cd);
+  // AUTO: exact band factorisation when the covisibility is windowed, else dense
+  // DMMA Cholesky while it fits, else PCG
+  if (s == PBA_SOLVER_AUTO) s = band_ok ? PBA_SOLVER_BAND : (h->sz.dim <= h->opt.cholesky_max_dim ? PBA_SOLVER_CHOLESKY : PBA_SOLVER_PCG);
+  if (s == PBA_SOLVER_BAND && !band_ok) s = h->sz.dim <= h->opt.cholesky_max_dim ? PBA_SOLVER_CHOLESKY : PBA_SOLVER_PCG;
   return s;
 }
 
 pba_status solve_rcs(Handle* h, int solver) {
   h->last_solver = pick_solver(h, solver);
+  if (h->last_solver == PBA_SOLVER_BAND) return launch_band_rcs(h);
   return h->last_solver == PBA_SOLVER_CHOLESKY ? launch_cholesky_rcs(h) : launch_pcg_rcs(h);
 }
 
@@ -679,7 +707,7 @@ pba_status minimize_impl(Handle* h, pba_summary* sum) {
     ++n_lin; ++n_res;
     it.linear_solver_iterations = h->last_solver == PBA_SOLVER_PCG ? int(hs[S_PCG_ITERS]) : 1;
     const double model_cost_change = hs[S_MODEL];
-    const bool solved = !(h->last_solver == PBA_SOLVER_CHOLESKY && *chol_fail) && std::isfinite(model_cost_change) && std::isfinite(hs[S_STEP2]);
+    const bool solved = !(h->last_solver != PBA_SOLVER_PCG && *chol_fail) && std::isfinite(model_cost_change) && std::isfinite(hs[S_STEP2]);
     it.model_cost_change = model_cost_change;
     it.step_is_valid = solved && model_cost_change > 0.0;
     if (!it.step_is_valid) {
@@ -765,6 +793,7 @@ pba_status minimize_impl(Handle* h, pba_summary* sum) {
     sum->num_residuals = h->n_obs_global * z.R;
     sum->num_effective_parameters = int64_t(z.n_slots) * 6 + h->n_active_lm;
     for (int i = 0; i < z.n_poses; ++i) sum->num_effective_parameters += h->affine_active[i] ? 2 : 0;
+    sum->linear_solver = h->last_solver;
     sum->gpu_kernel_launches = std::accumulate(ks.launches, ks.launches + K_NUM, int64_t(0)) - launches0;
     sum->initial_cost = initial_cost;
     sum->final_cost = min_iteration_cost;
@@ -772,7 +801,7 @@ pba_status minimize_impl(Handle* h, pba_summary* sum) {
     sum->residual_evaluation_time_in_seconds = 1e-3 * ks.ms[K_COST];
     double lin = 0;
     for (int k : {K_EDGE_GRAM, K_LM_GATHER, K_LM_SCALE, K_SCHUR_SYRK, K_RCS_REDUCE, K_RCS_SCALE, K_CAM_SCALE, K_DENSE_FILL,
-                  K_CHOL_PANEL, K_CHOL_TRSM, K_CHOL_SYRK, K_CHOL_SOLVE, K_PCG, K_BACKSUB})
+                  K_CHOL_PANEL, K_CHOL_TRSM, K_CHOL_SYRK, K_CHOL_SOLVE, K_PCG, K_BAND_CHOL, K_BACKSUB})
       lin += ks.ms[k];
     sum->linear_solver_time_in_seconds = 1e-3 * lin;
     sum->minimizer_time_in_seconds = wall() - t_start;
@@ -990,7 +1019,7 @@ PBA_API pba_status pba_solve_rcs(pba_handle* hh, int32_t solver, double* y_cam, 
   pba_status st = solve_rcs(h, solver);
   if (st != PBA_OK) return st;
   if ((st = read_scalars(h)) != PBA_OK) return st;
-  if (h->last_solver == PBA_SOLVER_CHOLESKY && *reinterpret_cast<int*>(h->h_scalars + S_NUM)) return PBA_ERR_NUMERICAL_FAILURE;
+  if (h->last_solver != PBA_SOLVER_PCG && *reinterpret_cast<int*>(h->h_scalars + S_NUM)) return PBA_ERR_NUMERICAL_FAILURE;
   if (iterations) *iterations = h->last_solver == PBA_SOLVER_PCG ? int(h->h_scalars[S_PCG_ITERS]) : 1;
   if (y_cam && h->sz.dim) PBA_CUDA_OK(cudaMemcpy(y_cam, h->y_cam.p, sizeof(double) * h->sz.dim, cudaMemcpyDeviceToHost));
   return PBA_OK;
@@ -1018,7 +1047,7 @@ PBA_API pba_status pba_lm_iterate(pba_handle* hh, double radius, int32_t apply, 
   if (h->world > 1 && (st = allreduce_scalars(h, h->scalars.p + S_COST_C, 4, false)) != PBA_OK) return st;
   if ((st = read_scalars(h)) != PBA_OK) return st;
   const double* hs = h->h_scalars;
-  const bool chol_failed = h->last_solver == PBA_SOLVER_CHOLESKY && *reinterpret_cast<const int*>(hs + S_NUM);
+  const bool chol_failed = h->last_solver != PBA_SOLVER_PCG && *reinterpret_cast<const int*>(hs + S_NUM);
   pba_iteration it;
   memset(&it, 0, sizeof(it));
   it.cost = hs[S_COST];

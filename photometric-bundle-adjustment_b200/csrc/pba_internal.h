@@ -71,6 +71,7 @@ enum KernelId {
   K_CHOL_SYRK,   // DMMA trailing update
   K_CHOL_SOLVE,
   K_PCG,
+  K_BAND_CHOL,   // single-CTA block-banded Cholesky + solves
   K_BACKSUB,     // K6
   K_MODEL_COST,  // K8
   K_RETRACT,     // K7
@@ -137,14 +138,14 @@ struct Handle {
   DevBuf<double> intr;             // [n_calib*8]
   DevBuf<int> pose_calib, calib_model, d_slot;
   DevBuf<uint8_t> d_affine_active;
-  DevBuf<uint8_t> images;          // photometric: all keyframes
+  DevBuf<uint32_t> quads;          // photometric: all keyframes as 2x2-footprint words [n_poses][h][w]
   DevBuf<int> edge_h, edge_t;      // [E]
   DevBuf<int64_t> edge_ptr;        // [E+1]
   DevBuf<int> obs_lm, obs_edge;    // [n]
   DevBuf<double> obs_uv;           // geometric [2][n] SoA
   DevBuf<double> lm_uv;            // [n_lm*2] host pixel
   DevBuf<int> lm_host;             // [n_lm]
-  DevBuf<double> lm_pat;           // photometric [n_lm][8][4] (bx,by,bz,I_h); geometric [n_lm][4]
+  DevBuf<double> lm_pat;           // photometric SoA [8][4 = bx,by,bz,I_h][n_lm]; geometric [n_lm][4]
   DevBuf<uint8_t> lm_ok;           // [n_lm]
   DevBuf<int64_t> lm_ptr;          // [n_lm+1] landmark -> positions in sorted obs
   DevBuf<int64_t> lm_pos;          // [n]
@@ -216,6 +217,10 @@ struct Handle {
   int max_w_stride = 8;        // longest W row (doubles)
   int pcg_grid = 1;            // co-resident CTAs for the cooperative PCG kernel
   int last_solver = 0;
+  int rcs_bandwidth = 0;       // max (col - row) over the RCS blocks, in blocks
+  DevBuf<int> d_col_blk;       // [n_slots][bw+1] block index of (k, k+i) or -1 (band solver)
+  DevBuf<double> band_L;       // band factor [n_slots][bw+1][cd*cd]
+  int uniform_model = -1;      // PBA_CAM_* when every calibration uses the same model, else -1
 
   // NCCL
   void* nccl_comm = nullptr;
@@ -237,6 +242,7 @@ pba_status map_cuda(cudaError_t e);
 // -------------------------------------------------------------- launchers --
 // eval.cu
 pba_status launch_init_landmarks(Handle* h);
+pba_status launch_build_quads(Handle* h, const uint8_t* images_u8, int first, int n_img);
 pba_status launch_evaluate(Handle* h, bool with_jacobian, const double* poses, const double* affine,
                            const double* rho, int cost_slot);
 pba_status launch_model_cost(Handle* h);
@@ -250,6 +256,8 @@ pba_status launch_gradient_norms(Handle* h);
 // solve.cu
 pba_status launch_cholesky_rcs(Handle* h);
 pba_status launch_pcg_rcs(Handle* h);
+pba_status launch_band_rcs(Handle* h);
+int band_max_bw(int cd);
 pba_status dense_cholesky_solve(Handle* h, double* A, double* b, int ld, int* fail_dev);
 int dense_ld(int n);
 int pcg_max_grid(int device);

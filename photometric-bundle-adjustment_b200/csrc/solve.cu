@@ -11,6 +11,7 @@
 //     PCG, conjugate_gradients_solver.cc:63-249), run as ONE cooperative
 //     kernel so a solve costs one launch, not five per iteration.
 #include <cooperative_groups.h>
+#include <stdio.h>
 
 #include "launch.h"
 #include "pba_internal.h"
@@ -477,6 +478,375 @@ int pcg_max_grid(int device) {
   if (per_sm < 1) per_sm = 1;
   if (per_sm > 2) per_sm = 2;
   return sms * per_sm;
+}
+
+}  // namespace pba
+
+// ------------------------------------------------------ band Cholesky ------
+// Exact solve for block-banded reduced camera systems (windowed covisibility:
+// keyframe i only shares landmarks with i +- bw).  ONE CTA walks the block
+// columns; the active (bw+1) x (bw+1) block window of the trailing matrix lives
+// in shared memory as a ring (block (r,c) at [r % B][c % B]), so every column
+// costs a handful of __syncthreads phases and no global round trip.  The
+// forward substitution is fused into the factorisation; the backward
+// substitution streams the stored factor columns back with a register prefetch.
+// Replaces the sparse LDL^T of internal/ceres/eigensparse.cc:56-106 for this
+// structure.  Work is O(n bw^2 cd^3): 2,000 keyframes, bw = 12 -> ~1.3e8 FMAs.
+namespace pba {
+namespace {
+
+constexpr int kBandThreads = 256;
+
+template <int CD>
+__global__ void __launch_bounds__(kBandThreads) k_band_cholesky(int n_slots, int bw, const int* __restrict__ col_blk,
+                                                                 const double* __restrict__ S,
+                                                                 const double* __restrict__ rhs,
+                                                                 double* __restrict__ Lband, double* __restrict__ x,
+                                                                 int* __restrict__ fail) {
+  constexpr int BS = CD * CD;
+  constexpr int NT = kBandThreads;
+  extern __shared__ double sm[];
+  const int B = bw + 1;
+  double* W = sm;                       // [B][B][BS] ring of the trailing window
+  double* Cc = W + size_t(B) * B * BS;  // [B][BS] current block column (updates + original entries)
+  double* Lc = Cc + size_t(B) * BS;     // [B][BS] factor column: slot 0 = L_kk^-1, slots i = L_{k+i,k}
+  double* R = Lc + size_t(B) * BS;      // [B][CD] ring of the pending right-hand side (later: x window)
+  double* yk = R + size_t(B) * CD;      // [CD]
+  double* Lkk = yk + CD;                // [BS] diagonal factor (scratch)
+  double* idg = Lkk + BS;               // [CD] 1 / diag(L_kk)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < B * B * BS; i += NT) W[i] = 0.0;
+  for (int i = tid; i < B * CD; i += NT) R[i] = 0.0;
+
+  // Per-thread element ownership is independent of the column: element idx = tid + q*NT
+  // of the (bw+1) x BS column buffer <-> block i_q, entry e_q.
+  constexpr int PF = (20 * BS + NT - 1) / NT;  // columns of up to 20 blocks (band_max_bw)
+  int ei[PF], ee[PF], et[PF];
+#pragma unroll
+  for (int q = 0; q < PF; ++q) {
+    const int idx = tid + q * NT;
+    ei[q] = idx / BS;
+    ee[q] = idx % BS;
+    et[q] = (ee[q] % CD) * CD + ee[q] / CD;  // transposed entry
+  }
+  // Trailing-update pairs (i >= j >= 1) owned by this warp: p = warp, warp + 16, ...
+  constexpr int NW = NT / 32;
+  constexpr int MAXP = (19 * 20 / 2 + NW - 1) / NW;
+  int pi[MAXP], pj[MAXP];
+#pragma unroll
+  for (int q = 0; q < MAXP; ++q) {
+    int p = warp + q * NW, i = 1;
+    while (p >= i) { p -= i; ++i; }
+    pi[q] = i; pj[q] = 1 + p;
+  }
+
+  // Original entries of column k = row k of the upper block list, transposed; col_blk[k][i] =
+  // block index of (k, k+i) or -1.  Values are prefetched one column ahead and their block
+  // indices two columns ahead, so no global latency sits on the per-column critical path.
+  double pf[PF];
+  int tnext[PF];
+  double rpf = 0.0;
+  auto load_idx = [&](int kk) {
+#pragma unroll
+    for (int q = 0; q < PF; ++q) tnext[q] = (kk < n_slots && ei[q] <= bw) ? col_blk[kk * B + ei[q]] : -1;
+  };
+  auto load_val = [&](int kk) {
+#pragma unroll
+    for (int q = 0; q < PF; ++q) pf[q] = tnext[q] >= 0 ? S[size_t(tnext[q]) * BS + et[q]] : 0.0;
+    if (tid < CD) rpf = kk < n_slots ? rhs[kk * CD + tid] : 0.0;
+  };
+  load_idx(0);
+  load_val(0);
+  load_idx(1);
+  __syncthreads();
+
+#ifdef PBA_BAND_TIMING
+  long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long tt = clock64();
+#define BAND_TICK(i) { long long _n = clock64(); tacc[i] += _n - tt; tt = _n; }
+#else
+#define BAND_TICK(i)
+#endif
+  int kb = 0;  // k % B
+  for (int k = 0; k < n_slots; ++k) {
+    const int nb = min(bw, n_slots - 1 - k);  // blocks below the diagonal in this column
+    // A. column k <- accumulated updates of the ring + original entries
+#pragma unroll
+    for (int q = 0; q < PF; ++q) {
+      if (ei[q] <= nb) {
+        int rb = kb + ei[q];
+        rb = rb >= B ? rb - B : rb;
+        Cc[tid + q * NT] = W[(size_t(rb) * B + kb) * BS + ee[q]] + pf[q];
+      }
+    }
+    if (tid < CD) yk[tid] = R[kb * CD + tid] + rpf;
+    __syncthreads();
+    load_val(k + 1);  // uses the indices fetched during the previous column
+    load_idx(k + 2);
+    BAND_TICK(0)
+    // B. warp 0: Cholesky of the diagonal block in lane 0's registers, inverse of the
+    //    factor by columns across lanes, forward substitution y_k = L_kk^-1 (b_k + pending)
+    if (tid < 32) {
+      if (lane == 0) {
+        double L[CD][CD];
+#pragma unroll
+        for (int r = 0; r < CD; ++r)
+#pragma unroll
+          for (int c = 0; c <= r; ++c) L[r][c] = Cc[r * CD + c];
+#pragma unroll
+        for (int j = 0; j < CD; ++j) {
+          double d = L[j][j];
+          if (!(d > 0.0)) { *fail = 1; d = 1.0; }
+          const double inv = rsqrt(d);
+          L[j][j] = d * inv;
+          idg[j] = inv;
+#pragma unroll
+          for (int r = j + 1; r < CD; ++r) L[r][j] *= inv;
+#pragma unroll
+          for (int c = j + 1; c < CD; ++c)
+#pragma unroll
+            for (int r = c; r < CD; ++r) L[r][c] -= L[r][j] * L[c][j];
+        }
+#pragma unroll
+        for (int r = 0; r < CD; ++r)
+#pragma unroll
+          for (int c = 0; c <= r; ++c) Lkk[r * CD + c] = L[r][c];
+      }
+      __syncwarp();
+      if (lane < CD) {
+        // column `lane` of M = L_kk^-1 (lower triangular)
+        const int c = lane;
+        double m[CD];
+#pragma unroll
+        for (int r = 0; r < CD; ++r) {
+          double s = r == c ? 1.0 : 0.0;
+#pragma unroll
+          for (int q = 0; q < r; ++q) s -= (q >= c ? Lkk[r * CD + q] * m[q] : 0.0);
+          m[r] = r >= c ? s * idg[r] : 0.0;
+        }
+#pragma unroll
+        for (int r = 0; r < CD; ++r) Lc[r * CD + c] = m[r];
+      }
+      __syncwarp();
+      if (lane < CD) {
+        double s = 0.0;
+#pragma unroll
+        for (int c = 0; c < CD; ++c) s += Lc[lane * CD + c] * yk[c];
+        __syncwarp(0xffu >> (8 - CD));
+        yk[lane] = s;
+      }
+    }
+    __syncthreads();
+    BAND_TICK(1)
+    // C. L_ik = C_ik L_kk^-T = C_ik M^T.  CD = 8: one DMMA pair per block (this IS the
+    //    Cholesky, the one place the path uses the FP64 tensor cores); CD = 6: dot products.
+    if constexpr (CD == 8) {
+      const int fr = lane >> 2, fc = lane & 3;
+      for (int i = 1 + warp; i <= nb; i += NW) {
+        double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+        for (int k0 = 0; k0 < 8; k0 += 4)
+          dmma8x8x4(c0, c1, Cc[i * BS + fr * 8 + k0 + fc], Lc[fr * 8 + k0 + fc]);
+        *reinterpret_cast<double2*>(Lc + i * BS + fr * 8 + 2 * fc) = make_double2(c0, c1);
+      }
+    } else {
+      for (int idx = tid; idx < nb * BS; idx += NT) {
+        const int i = 1 + idx / BS, e = idx % BS, r = e / CD, c = e % CD;
+        const double* crow = Cc + i * BS + r * CD;
+        const double* mrow = Lc + c * CD;
+        double s = 0.0;
+#pragma unroll
+        for (int q = 0; q < CD; ++q) s += crow[q] * mrow[q];  // M is lower: mrow[q] = 0 for q > c
+        Lc[i * BS + e] = s;
+      }
+    }
+    __syncthreads();
+    BAND_TICK(2)
+    // D. store the factor column; pending rhs -= L_ik y_k; trailing window -= L_ik L_jk^T;
+    //    recycle ring row / column k (disjoint from the updated blocks)
+    {
+      double* Lk = Lband + size_t(k) * B * BS;
+#pragma unroll
+      for (int q = 0; q < PF; ++q)
+        if (ei[q] <= nb) Lk[tid + q * NT] = Lc[tid + q * NT];
+      if (tid < CD) x[k * CD + tid] = yk[tid];
+      if (tid < nb * CD) {
+        const int i = 1 + tid / CD, r = tid % CD;
+        double s = 0.0;
+#pragma unroll
+        for (int c = 0; c < CD; ++c) s += Lc[i * BS + r * CD + c] * yk[c];
+        int rb = kb + i;
+        rb = rb >= B ? rb - B : rb;
+        R[rb * CD + r] -= s;
+      }
+      BAND_TICK(5)
+      if constexpr (CD == 8) {
+        const int fr = lane >> 2, fc = lane & 3;
+        // the warp's pairs are independent: batches of 4 keep several loads / DMMAs in flight
+        constexpr int PB = 6;
+#pragma unroll 1
+        for (int q0 = 0; q0 < MAXP; q0 += PB) {
+          if (pi[q0] > nb) break;  // pairs are ordered by i: nothing further applies
+          double2 wv[PB];
+          double c0[PB], c1[PB], d0[PB], d1[PB];  // two independent accumulators per pair (k = 0..3 / 4..7)
+          double2* wp[PB];
+#pragma unroll
+          for (int u = 0; u < PB; ++u) {
+            const int q = q0 + u;
+            c0[u] = 0.0; c1[u] = 0.0; d0[u] = 0.0; d1[u] = 0.0;
+            const bool on = q < MAXP && pi[q < MAXP ? q : 0] <= nb;
+            const int ii = on ? pi[q] : 1, jj = on ? pj[q] : 1;
+            int ri = kb + ii, rj = kb + jj;
+            ri = ri >= B ? ri - B : ri;
+            rj = rj >= B ? rj - B : rj;
+            wp[u] = on ? reinterpret_cast<double2*>(W + (size_t(ri) * B + rj) * BS + fr * 8 + 2 * fc) : nullptr;
+            wv[u] = on ? *wp[u] : make_double2(0.0, 0.0);
+            dmma8x8x4(c0[u], c1[u], Lc[ii * BS + fr * 8 + fc], Lc[jj * BS + fr * 8 + fc]);
+            dmma8x8x4(d0[u], d1[u], Lc[ii * BS + fr * 8 + 4 + fc], Lc[jj * BS + fr * 8 + 4 + fc]);
+          }
+#pragma unroll
+          for (int u = 0; u < PB; ++u)
+            if (wp[u]) *wp[u] = make_double2(wv[u].x - (c0[u] + d0[u]), wv[u].y - (c1[u] + d1[u]));
+        }
+      } else {
+        constexpr int TS = CD / 2;
+        const int npairs = nb * (nb + 1) / 2;
+        for (int tix = tid; tix < npairs * 4; tix += NT) {
+          int p = tix >> 2, i = 1;
+          while (p >= i) { p -= i; ++i; }
+          const int j = 1 + p;
+          const int r0 = TS * ((tix >> 1) & 1), c0 = TS * (tix & 1);
+          double acc[TS][TS];
+#pragma unroll
+          for (int a = 0; a < TS; ++a)
+#pragma unroll
+            for (int b = 0; b < TS; ++b) acc[a][b] = 0.0;
+          const double* Li = Lc + i * BS + r0 * CD;
+          const double* Lj = Lc + j * BS + c0 * CD;
+#pragma unroll
+          for (int q = 0; q < CD; ++q) {
+            double av[TS], bv[TS];
+#pragma unroll
+            for (int a = 0; a < TS; ++a) { av[a] = Li[a * CD + q]; bv[a] = Lj[a * CD + q]; }
+#pragma unroll
+            for (int a = 0; a < TS; ++a)
+#pragma unroll
+              for (int b = 0; b < TS; ++b) acc[a][b] += av[a] * bv[b];
+          }
+          int ri = kb + i, rj = kb + j;
+          ri = ri >= B ? ri - B : ri;
+          rj = rj >= B ? rj - B : rj;
+          double* Wb = W + (size_t(ri) * B + rj) * BS;
+#pragma unroll
+          for (int a = 0; a < TS; ++a)
+#pragma unroll
+            for (int b = 0; b < TS; ++b) Wb[(r0 + a) * CD + c0 + b] -= acc[a][b];
+        }
+      }
+      BAND_TICK(3)
+      for (int idx = tid; idx < B * BS; idx += NT) {
+        const int o = idx / BS, e = idx % BS;
+        W[(size_t(kb) * B + o) * BS + e] = 0.0;
+        W[(size_t(o) * B + kb) * BS + e] = 0.0;
+      }
+      if (tid < CD) R[kb * CD + tid] = 0.0;
+    }
+    __syncthreads();
+    kb = kb + 1 == B ? 0 : kb + 1;
+    BAND_TICK(6)
+  }
+
+  // ---- backward substitution: x_k = M_k^T (y_k - sum_i L_{k+i,k}^T x_{k+i}) ----
+  // x window reuses the R ring; the next factor column is prefetched into registers.
+  double* X = R;
+  auto prefetch = [&](int kk) {
+    const double* Lk = Lband + size_t(kk) * B * BS;
+    const int nbk = min(bw, n_slots - 1 - kk);
+#pragma unroll
+    for (int q = 0; q < PF; ++q) pf[q] = ei[q] <= nbk ? Lk[tid + q * NT] : 0.0;
+    if (tid < CD) rpf = x[kk * CD + tid];
+  };
+  if (n_slots > 0) prefetch(n_slots - 1);
+  kb = n_slots > 0 ? (n_slots - 1) % B : 0;
+  for (int k = n_slots - 1; k >= 0; --k) {
+    const int nb = min(bw, n_slots - 1 - k);
+#pragma unroll
+    for (int q = 0; q < PF; ++q)
+      if (ei[q] <= nb) Lc[tid + q * NT] = pf[q];
+    if (tid < CD) yk[tid] = rpf;
+    __syncthreads();
+    if (k > 0) prefetch(k - 1);
+    if (tid < nb * CD) {
+      const int i = 1 + tid / CD, c = tid % CD;
+      int rb = kb + i;
+      rb = rb >= B ? rb - B : rb;
+      const double* xv = X + rb * CD;
+      double part = 0.0;
+#pragma unroll
+      for (int r = 0; r < CD; ++r) part += Lc[i * BS + r * CD + c] * xv[r];
+      Cc[tid] = part;  // [i-1][c]
+    }
+    __syncthreads();
+    if (tid < 32) {
+      double s = 0.0;
+      if (lane < CD) {
+        // two interleaved partial sums shorten the dependent chain
+        double s0 = yk[lane], s1 = 0.0;
+        int i = 0;
+        for (; i + 1 < nb; i += 2) { s0 -= Cc[i * CD + lane]; s1 -= Cc[(i + 1) * CD + lane]; }
+        if (i < nb) s0 -= Cc[i * CD + lane];
+        s = s0 + s1;
+      }
+      // x_c = sum_r M[r][c] s_r  (M lower)
+      double v = 0.0;
+#pragma unroll
+      for (int r = 0; r < CD; ++r) {
+        const double sr = __shfl_sync(0xffffffffu, s, r);
+        if (lane < CD) v += Lc[r * CD + lane] * sr;
+      }
+      if (lane < CD) { X[kb * CD + lane] = v; x[k * CD + lane] = v; }
+    }
+    __syncthreads();
+    kb = kb == 0 ? B - 1 : kb - 1;
+  }
+  BAND_TICK(4)
+#ifdef PBA_BAND_TIMING
+  if (tid == 0) printf("band timing (cycles/column): A %lld  B %lld  C %lld  D1(store) %lld D2(pairs) %lld D3(zero+sync) %lld | backward/col %lld\n", tacc[0] / n_slots, tacc[1] / n_slots, tacc[2] / n_slots, tacc[5] / n_slots, tacc[3] / n_slots, tacc[6] / n_slots, tacc[4] / n_slots);
+#endif
+}
+
+}  // namespace
+
+size_t band_smem_bytes(int cd, int bw) {
+  const size_t B = bw + 1, BS = size_t(cd) * cd;
+  return (B * B * BS + 2 * B * BS + B * cd + 2 * cd + BS) * sizeof(double);
+}
+
+// Largest half-bandwidth (in blocks) the shared-memory window supports.
+int band_max_bw(int cd) {
+  int bw = 0;
+  while (band_smem_bytes(cd, bw + 1) <= 200 * 1024 && (bw + 2) * cd * cd <= 20 * cd * cd) ++bw;
+  return bw;
+}
+
+pba_status launch_band_rcs(Handle* h) {
+  const Sizes& z = h->sz;
+  if (z.dim == 0) return PBA_OK;
+  const int bw = h->rcs_bandwidth;
+  const size_t smem = band_smem_bytes(z.cd, bw);
+  const double* S = h->rcs.p;
+  const double* rhs = S + z.n_blocks * z.cd * z.cd;
+  PBA_CUDA_OK(cudaMemsetAsync(h->chol_fail.p, 0, sizeof(int), h->stream));
+  if (z.cd == 8) {
+    PBA_CUDA_OK(cudaFuncSetAttribute(k_band_cholesky<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    PBA_LAUNCH(h, K_BAND_CHOL, k_band_cholesky<8>, dim3(1), dim3(kBandThreads), smem, z.n_slots, bw, h->d_col_blk.p, S, rhs,
+               h->band_L.p, h->y_cam.p, h->chol_fail.p);
+  } else {
+    PBA_CUDA_OK(cudaFuncSetAttribute(k_band_cholesky<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    PBA_LAUNCH(h, K_BAND_CHOL, k_band_cholesky<6>, dim3(1), dim3(kBandThreads), smem, z.n_slots, bw, h->d_col_blk.p, S, rhs,
+               h->band_L.p, h->y_cam.p, h->chol_fail.p);
+  }
+  return PBA_OK;
 }
 
 }  // namespace pba
