@@ -1,4 +1,4 @@
-// eval.cu — residual / Jacobian evaluation kernels (K0, K1, K2, K8).
+// eval.cu — residual / Jacobian evaluation kernels (K0, K1, K2).
 //
 // Replaces, for one shard of observations, Ceres' ProgramEvaluator::Evaluate
 // (internal/ceres/program_evaluator.h:139-286) together with the reference
@@ -20,6 +20,7 @@ constexpr int kEvalThreads = 128;
 
 struct EvalArgs {
   int64_t n;
+  int64_t ld;  // plane stride of res / J
   int n_lm;
   // structure
   const int* obs_lm;
@@ -44,8 +45,7 @@ struct EvalArgs {
   int use_huber;
   double huber;
   // outputs
-  double* res;
-  double* J;
+  double* J;   // interleaved planes [R][C+1][ld]: J row columns 0..C-1, column C = residual
   double* orec;
   double* block_cost;
 };
@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(kPhotoThreads, WITH_J ? 3 : 4) k_eval_photo(co
     if (WITH_J) {
       // ---- phase 2: recompute the warp with its projection Jacobian from registers
       //      (no loads), weight, stream the rows out ----
-      const int64_t n = a.n;
+      const int64_t n = a.ld;
 #pragma unroll 1
       for (int k = 0; k < 8; ++k) {
         const double xh = bx[k] * c.irho, yh = by[k] * c.irho, zh = bz[k] * c.irho;
@@ -319,8 +319,8 @@ __global__ void __launch_bounds__(kPhotoThreads, WITH_J ? 3 : 4) k_eval_photo(co
         // inverse distance: -(a . X_h) / rho
         row[14] = -(ax * xh + ay * yh + az * zh) * c.irho;
         const double rw = w * r[k];
-        a.res[int64_t(k) * n + i] = rw;
-        double* Jk = a.J + (int64_t(k) * 15) * n + i;
+        double* Jk = a.J + (int64_t(k) * 16) * n + i;  // planes [k][0..14] = J row, [k][15] = residual
+        Jk[15 * n] = rw;
 #pragma unroll
         for (int qq = 0; qq < 15; ++qq) Jk[int64_t(qq) * n] = row[qq];
         const double E = row[14];
@@ -395,7 +395,7 @@ __global__ void __launch_bounds__(kEvalThreads) k_eval_geom(const EvalArgs a) {
     double w;
     cost = huber(r0 * r0 + r1 * r1, a.use_huber, a.huber, &w);
     if (WITH_J) {
-      const int64_t n = a.n;
+      const int64_t n = a.ld;
       double acc[16];
 #pragma unroll
       for (int k = 0; k < 16; ++k) acc[k] = 0.0;
@@ -417,8 +417,8 @@ __global__ void __launch_bounds__(kEvalThreads) k_eval_geom(const EvalArgs a) {
         row[11] = px * yt - py * xt;
         row[12] = -(ax * xh + ay * yh + az * zh) * irho;
         const double rk = w * (k == 0 ? r0 : r1);
-        a.res[int64_t(k) * n + i] = rk;
-        double* Jk = a.J + (int64_t(k) * 13) * n + i;
+        double* Jk = a.J + (int64_t(k) * 14) * n + i;  // planes [k][0..12] = J row, [k][13] = residual
+        Jk[13 * n] = rk;
 #pragma unroll
         for (int c = 0; c < 13; ++c) Jk[int64_t(c) * n] = row[c];
         const double E = row[12];
@@ -452,47 +452,20 @@ __global__ void __launch_bounds__(1024) k_reduce_sum(const double* __restrict__ 
   }
 }
 
-// K8: model_cost_change = -(J d)^T (r + J d / 2) (trust_region_minimizer.cc:414-427),
-// with the unscaled Jacobian and the unscaled tangent step d.
-template <int R, int C>
-__global__ void __launch_bounds__(256) k_model_cost(int64_t n, const int* __restrict__ obs_lm,
-                                                     const int* __restrict__ obs_edge, const int* __restrict__ edge_h,
-                                                     const int* __restrict__ edge_t, const int* __restrict__ slot,
-                                                     const double* __restrict__ J, const double* __restrict__ res,
-                                                     const double* __restrict__ d_cam, const double* __restrict__ d_rho,
-                                                     double* __restrict__ block_out) {
-  __shared__ double s_red[8];
-  constexpr int CD = C - 7;  // 6 geometric, 8 photometric
-  const int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x;
-  double acc = 0.0;
-  if (i < n) {
-    const int e = obs_edge[i];
-    const int hs = slot[edge_h[e]], ts = slot[edge_t[e]];
-    double d[C];
-#pragma unroll
-    for (int c = 0; c < 6; ++c) d[c] = hs >= 0 ? d_cam[hs * CD + c] : 0.0;
-#pragma unroll
-    for (int c = 0; c < CD; ++c) d[6 + c] = ts >= 0 ? d_cam[ts * CD + c] : 0.0;
-    d[C - 1] = d_rho[obs_lm[i]];
-#pragma unroll
-    for (int k = 0; k < R; ++k) {
-      double m = 0.0;
-#pragma unroll
-      for (int c = 0; c < C; ++c) m += J[(int64_t(k) * C + c) * n + i] * d[c];
-      acc += -m * (res[int64_t(k) * n + i] + 0.5 * m);
-    }
-  }
-  const double bs = block_sum(acc, s_red);
-  if (threadIdx.x == 0) block_out[blockIdx.x] = bs;
-}
-
 // Test/diagnostic path: planes in edge order -> [obs][plane] in caller order.
-__global__ void k_unpermute(int64_t n, int planes, const int64_t* __restrict__ order,
+// which = 0: residuals [obs][R]; 1: Jacobians [obs][R][C]  (source planes [R][C+1][ld]).
+__global__ void k_unpermute(int64_t n, int64_t ld, int R, int C, int which, const int64_t* __restrict__ order,
                             const double* __restrict__ src, double* __restrict__ dst) {
   const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int64_t o = order[i];
-  for (int p = 0; p < planes; ++p) dst[o * planes + p] = src[int64_t(p) * n + i];
+  for (int k = 0; k < R; ++k) {
+    if (which == 0) {
+      dst[o * R + k] = src[(int64_t(k) * (C + 1) + C) * ld + i];
+    } else {
+      for (int c = 0; c < C; ++c) dst[(o * R + k) * C + c] = src[(int64_t(k) * (C + 1) + c) * ld + i];
+    }
+  }
 }
 
 }  // namespace
@@ -529,13 +502,13 @@ pba_status launch_evaluate(Handle* h, bool with_jacobian, const double* poses, c
                h->edge_t.p, poses, photo ? affine : nullptr, h->edge_T.p);
   }
   EvalArgs a;
-  a.n = z.n_obs; a.n_lm = z.n_lm;
+  a.n = z.n_obs; a.ld = z.ld; a.n_lm = z.n_lm;
   a.obs_lm = h->obs_lm.p; a.obs_edge = h->obs_edge.p; a.edge_h = h->edge_h.p; a.edge_t = h->edge_t.p;
   a.pose_calib = h->pose_calib.p; a.calib_model = h->calib_model.p; a.intr = h->intr.p; a.edge_T = h->edge_T.p;
   a.lm_pat = h->lm_pat.p; a.lm_ok = h->lm_ok.p; a.obs_uv = h->obs_uv.p;
   a.quads = h->quads.p; a.image_stride = z.image_stride; a.width = z.width; a.height = z.height; a.pitch = z.width;  // quad rows are packed
   a.rho = rho; a.use_huber = h->opt.use_huber; a.huber = h->opt.huber_parameter;
-  a.res = h->res.p; a.J = h->J.p; a.orec = h->orec.p; a.block_cost = h->red_ws.p;
+  a.J = h->J.p; a.orec = h->orec.p; a.block_cost = h->red_ws.p;
   static_assert(kPhotoThreads == kEvalThreads, "block-cost workspace is sized for one CTA width");
   const int grid = eval_grid(z.n_obs);
   if (grid > 0) {
@@ -551,29 +524,13 @@ pba_status launch_evaluate(Handle* h, bool with_jacobian, const double* poses, c
   return PBA_OK;
 }
 
-pba_status launch_model_cost(Handle* h) {
-  const Sizes& z = h->sz;
-  const int grid = int((z.n_obs + 255) / 256);
-  if (grid > 0) {
-    if (z.mode == PBA_MODE_PHOTOMETRIC) {
-      PBA_LAUNCH(h, K_MODEL_COST, (k_model_cost<8, 15>), dim3(grid), dim3(256), 0, z.n_obs, h->obs_lm.p, h->obs_edge.p,
-                 h->edge_h.p, h->edge_t.p, h->d_slot.p, h->J.p, h->res.p, h->d_cam.p, h->d_rho.p, h->red_ws.p);
-    } else {
-      PBA_LAUNCH(h, K_MODEL_COST, (k_model_cost<2, 13>), dim3(grid), dim3(256), 0, z.n_obs, h->obs_lm.p, h->obs_edge.p,
-                 h->edge_h.p, h->edge_t.p, h->d_slot.p, h->J.p, h->res.p, h->d_cam.p, h->d_rho.p, h->red_ws.p);
-    }
-  }
-  PBA_LAUNCH(h, K_REDUCE_SUM, k_reduce_sum, dim3(1), dim3(1024), 0, h->red_ws.p, int64_t(grid), h->scalars.p + S_MODEL);
-  return PBA_OK;
-}
-
-pba_status launch_unpermute(Handle* h, const double* src_planes, int planes, double* dst) {
+pba_status launch_unpermute(Handle* h, int which, double* dst) {
   const Sizes& z = h->sz;
   if (z.n_obs == 0) return PBA_OK;
   DevBuf<int64_t> order;
   PBA_CUDA_OK(order.upload(h->obs_order, h->stream));
-  PBA_LAUNCH(h, K_UNPERMUTE, k_unpermute, dim3(int((z.n_obs + 127) / 128)), dim3(128), 0, z.n_obs, planes, order.p,
-             src_planes, dst);
+  PBA_LAUNCH(h, K_UNPERMUTE, k_unpermute, dim3(int((z.n_obs + 127) / 128)), dim3(128), 0, z.n_obs, z.ld, z.R, z.C, which, order.p,
+             h->J.p, dst);
   PBA_CUDA_OK(cudaStreamSynchronize(h->stream));
   return PBA_OK;
 }

@@ -292,6 +292,7 @@ pba_status create_impl(const pba_problem* p, const pba_options* o, int rank, int
   z.n_lm = lm_hi - lm_lo;
   const int64_t obs_lo = p->lm_obs_ptr[lm_lo];
   z.n_obs = p->lm_obs_ptr[lm_hi] - obs_lo;
+  z.ld = (z.n_obs + 31) / 32 * 32;
   const int n_lm = z.n_lm;
   const int64_t n = z.n_obs;
 
@@ -538,18 +539,21 @@ pba_status create_impl(const pba_problem* p, const pba_options* o, int rank, int
   PBA_CUDA_OK(h->rho_c.alloc(n_lm)); PBA_CUDA_OK(h->rho_best.alloc(n_lm));
   PBA_CUDA_OK(h->lm_pat.alloc(size_t(n_lm) * (photo ? 32 : 4))); PBA_CUDA_OK(h->lm_ok.alloc(n_lm));
   PBA_CUDA_OK(h->edge_T.alloc(size_t(16) * z.n_edges));
-  PBA_CUDA_OK(h->res.alloc(nn * z.R)); PBA_CUDA_OK(h->J.alloc(nn * z.R * z.C)); PBA_CUDA_OK(h->orec.alloc(nn * 16));
+  PBA_CUDA_OK(h->J.alloc(size_t(z.ld) * z.R * (z.C + 1))); PBA_CUDA_OK(h->orec.alloc(nn * 16));
   PBA_CUDA_OK(h->W.alloc(size_t(w_total)));
+  if (w_total) PBA_CUDA_OK(cudaMemsetAsync(h->W.p, 0, sizeof(double) * size_t(w_total), s));  // unseen camera slots stay 0
   PBA_CUDA_OK(h->lm_c.alloc(n_lm)); PBA_CUDA_OK(h->lm_g.alloc(n_lm)); PBA_CUDA_OK(h->lm_scale.alloc(n_lm));
   PBA_CUDA_OK(h->lm_diag.alloc(n_lm)); PBA_CUDA_OK(h->lm_s2.alloc(n_lm)); PBA_CUDA_OK(h->lm_iete.alloc(n_lm));
   PBA_CUDA_OK(h->part_dir.alloc(size_t(z.n_chunks) * dir_stride)); PBA_CUDA_OK(h->part_sch.alloc(size_t(part_total)));
   PBA_CUDA_OK(h->rcs.alloc(size_t(z.n_blocks) * cd * cd + 3 * size_t(z.dim)));
+  PBA_CUDA_OK(h->rcs_B.alloc(size_t(z.n_blocks) * cd * cd + size_t(z.dim)));
   PBA_CUDA_OK(h->cam_scale.alloc(z.dim)); PBA_CUDA_OK(h->cam_diag.alloc(z.dim)); PBA_CUDA_OK(h->cam_D2.alloc(z.dim));
   PBA_CUDA_OK(h->y_cam.alloc(z.dim)); PBA_CUDA_OK(h->d_cam.alloc(z.dim)); PBA_CUDA_OK(h->d_rho.alloc(n_lm));
   PBA_CUDA_OK(h->blk_inv.alloc(size_t(z.n_slots) * cd * cd));
   h->pcg_grid = pcg_max_grid(h->device);
   PBA_CUDA_OK(h->pcg_ws.alloc(4 * size_t(z.dim) + 3 * size_t(h->pcg_grid) + 8));
-  const size_t red = std::max<size_t>(size_t(eval_grid(n)) + 8, 2 * ((size_t(p->n_poses) + n_lm + 255) / 256) + 8);
+  const size_t red = std::max<size_t>({size_t(eval_grid(n)) + 8, 2 * ((size_t(p->n_poses) + n_lm + 255) / 256) + 8,
+                                       size_t(n_lm + 127) / 128 + size_t(z.n_blocks + 127) / 128 + 8});
   PBA_CUDA_OK(h->red_ws.alloc(std::max<size_t>(red, (nn + 255) / 256 + 8)));
   PBA_CUDA_OK(h->scalars.alloc(S_NUM)); PBA_CUDA_OK(h->chol_fail.alloc(1));
   PBA_CUDA_OK(cudaMemsetAsync(h->scalars.p, 0, sizeof(double) * S_NUM, s));
@@ -695,7 +699,6 @@ pba_status minimize_impl(Handle* h, pba_summary* sum) {
     // ---- ComputeTrustRegionStep; the RCS for `radius` is already on the device ----
     if ((st = solve_rcs(h, PBA_SOLVER_AUTO)) != PBA_OK) return st;
     if ((st = launch_backsub(h)) != PBA_OK) return st;
-    if ((st = launch_model_cost(h)) != PBA_OK) return st;
     // speculative: candidate point and its cost (needed unless the step is invalid)
     if ((st = launch_retract(h)) != PBA_OK) return st;
     if ((st = launch_evaluate(h, false, h->poses_c.p, h->affine_c.p, h->rho_c.p, S_COST_C)) != PBA_OK) return st;
@@ -949,7 +952,7 @@ PBA_API pba_status pba_get_residuals(pba_handle* hh, double* residuals) {
   if (z.n_obs == 0) return PBA_OK;
   DevBuf<double> tmp;
   PBA_CUDA_OK(tmp.alloc(size_t(z.n_obs) * z.R));
-  pba_status st = launch_unpermute(h, h->res.p, z.R, tmp.p);
+  pba_status st = launch_unpermute(h, 0, tmp.p);
   if (st != PBA_OK) return st;
   PBA_CUDA_OK(cudaMemcpy(residuals, tmp.p, sizeof(double) * z.n_obs * z.R, cudaMemcpyDeviceToHost));
   return PBA_OK;
@@ -962,7 +965,7 @@ PBA_API pba_status pba_get_jacobians(pba_handle* hh, double* jacobians) {
   if (z.n_obs == 0) return PBA_OK;
   DevBuf<double> tmp;
   PBA_CUDA_OK(tmp.alloc(size_t(z.n_obs) * z.R * z.C));
-  pba_status st = launch_unpermute(h, h->J.p, z.R * z.C, tmp.p);
+  pba_status st = launch_unpermute(h, 1, tmp.p);
   if (st != PBA_OK) return st;
   PBA_CUDA_OK(cudaMemcpy(jacobians, tmp.p, sizeof(double) * z.n_obs * z.R * z.C, cudaMemcpyDeviceToHost));
   return PBA_OK;
@@ -1041,7 +1044,6 @@ PBA_API pba_status pba_lm_iterate(pba_handle* hh, double radius, int32_t apply, 
   if ((st = eval_jacobian_and_build(h, radius)) != PBA_OK) return st;
   if ((st = solve_rcs(h, PBA_SOLVER_AUTO)) != PBA_OK) return st;
   if ((st = launch_backsub(h)) != PBA_OK) return st;
-  if ((st = launch_model_cost(h)) != PBA_OK) return st;
   if ((st = launch_retract(h)) != PBA_OK) return st;
   if ((st = launch_evaluate(h, false, h->poses_c.p, h->affine_c.p, h->rho_c.p, S_COST_C)) != PBA_OK) return st;
   if (h->world > 1 && (st = allreduce_scalars(h, h->scalars.p + S_COST_C, 4, false)) != PBA_OK) return st;

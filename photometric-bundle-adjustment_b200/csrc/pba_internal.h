@@ -3,8 +3,8 @@
 //
 // HBM layout (all fp64 unless noted; n = local observations in EDGE ORDER,
 // i.e. sorted by (host pose, target pose, landmark)):
-//   res   [R][n]            residual planes (SoA: a warp of 32 consecutive
-//   J     [R*C][n]           observations writes 256 contiguous bytes per plane)
+//   J     [R][C+1][ld]      Jacobian planes, column C of each row = residual (SoA: a warp
+//                           of 32 consecutive observations writes 256 contiguous bytes per plane)
 //   orec  [n][16]           per-observation Schur record: E^T J_h (6) | E^T J_t
 //                           (cd) | E^T E | E^T r — AoS, one 128 B line each
 //   W     per host group g: [landmarks of g][8*(c_g+1)] dense rows
@@ -105,6 +105,7 @@ struct Sizes {
   int n_poses = 0, n_calib = 0;
   int n_lm = 0;         // local landmarks
   int64_t n_obs = 0;    // local observations
+  int64_t ld = 0;       // plane stride of res / J: n_obs rounded up to 32 (256 B aligned planes)
   int n_edges = 0;
   int n_chunks = 0;     // edge chunks (direct partials)
   int n_groups = 0;     // host groups
@@ -180,8 +181,7 @@ struct Handle {
 
   // ---- per-evaluation data ----
   DevBuf<double> edge_T;       // [E][16]
-  DevBuf<double> res;          // [R][n]
-  DevBuf<double> J;            // [R*C][n]
+  DevBuf<double> J;            // interleaved planes [R][C+1][ld]: Jacobian row columns + residual
   DevBuf<double> orec;         // [n][16]
   DevBuf<double> W;            // grouped landmark rows
   DevBuf<double> lm_c, lm_g;   // [n_lm] raw E^T E, E^T r
@@ -192,7 +192,8 @@ struct Handle {
   DevBuf<double> part_dir;     // direct partials
   DevBuf<double> part_sch;     // schur partials
   DevBuf<double> rcs;          // [n_blocks*cd*cd | rhs dim | diagB dim]  (one all-reduce buffer)
-  DevBuf<double> rcs_B;        // raw direct part (kept for model cost / diagnostics)
+  DevBuf<double> rcs_B;        // this rank's raw direct part B [n_blocks*cd*cd] + its gradient g_c [dim]
+                               // (camera part of the model cost change)
   DevBuf<double> cam_scale;    // [dim]
   DevBuf<double> cam_diag;     // [dim] frozen LM diagonal
   DevBuf<double> cam_D2;       // [dim] D^2 of the current solve
@@ -245,12 +246,12 @@ pba_status launch_init_landmarks(Handle* h);
 pba_status launch_build_quads(Handle* h, const uint8_t* images_u8, int first, int n_img);
 pba_status launch_evaluate(Handle* h, bool with_jacobian, const double* poses, const double* affine,
                            const double* rho, int cost_slot);
-pba_status launch_model_cost(Handle* h);
-pba_status launch_unpermute(Handle* h, const double* src_planes, int planes, double* dst_host_order_dev);
+pba_status launch_unpermute(Handle* h, int which, double* dst_host_order_dev);
 // schur.cu
 pba_status launch_post_jacobian(Handle* h);              // edge Gram + landmark gather (+ scales on first call)
 pba_status launch_build_rcs(Handle* h, double radius, bool refresh_diag);
-pba_status launch_backsub(Handle* h);
+pba_status launch_backsub(Handle* h);  // also leaves the model cost change in S_MODEL
+void launch_reduce_sum(Handle* h, const double* part, int64_t n, double* out);
 pba_status launch_retract(Handle* h);
 pba_status launch_gradient_norms(Handle* h);
 // solve.cu

@@ -23,91 +23,129 @@ namespace pba {
 namespace {
 
 // ------------------------------------------------------------ edge Gram ----
-// One CTA per edge chunk.  M = [J(0..C-1) | r] as a (32*R) x 16 tile in shared
-// memory per 32 observations; 12 row-groups x 10 upper 4x4 tiles of the 16x16
-// Gram matrix are accumulated in registers.
+// One CTA (3 warps) per edge chunk: G = M^T M for M = [J(0..C-1) | 0.. | r], a
+// (R * n_chunk) x 16 matrix.  The sum over M's rows is separable, so the CTA
+// streams ONE Jacobian row k at a time: 16 planes x 256 observations = sixteen
+// contiguous 2 KB runs per stage (long DRAM bursts; staging 32 observations of
+// all R rows instead reads 128 scattered 256 B pieces and ran at 31 % DRAM
+// utilisation).  Stages are copied with cp.async into a double buffer
+// (transposed: Mt[column][obs]) so the copy overlaps the previous stage's FMAs.
+// Warp w owns one 8x8 tile of the symmetric 16x16 Gram matrix ((0,0), (0,1),
+// (1,1)); lane l accumulates observations 2l, 2l+1 (+64 s) in an 8x8 register
+// block: 16 LDS.128 per 128 DFMA.  The 32 lane partials of a tile are combined
+// once per chunk with shuffles.  JR = interleaved planes [R][C+1][ld] (column C
+// of every row is the residual).
 template <int R, int C>
 struct GramCfg {
   static constexpr int CD = C - 7;
-  static constexpr int ROWS = 32 * R;
-  static constexpr int LD = 17;
-  static constexpr int TILE = ROWS * LD > 1920 ? ROWS * LD : 1920;
+  static constexpr int TOBS = 256;             // observations per stage
+  static constexpr int RS = TOBS + 2;          // padded row stride of Mt (even: LDS.128 stays aligned)
   static constexpr int DIR_STRIDE = 3 * CD * CD + 2 * CD;
 };
 
 template <int R, int C>
-__global__ void __launch_bounds__(128) k_edge_gram(int64_t n, const int* __restrict__ chunk_edge,
-                                                    const int64_t* __restrict__ chunk_begin,
-                                                    const int64_t* __restrict__ chunk_end,
-                                                    const int* __restrict__ edge_h, const int* __restrict__ edge_t,
-                                                    const int* __restrict__ slot, const double* __restrict__ J,
-                                                    const double* __restrict__ res, double* __restrict__ part_dir) {
+__global__ void __launch_bounds__(96) k_edge_gram(int64_t ld, const int* __restrict__ chunk_edge,
+                                                   const int64_t* __restrict__ chunk_begin,
+                                                   const int64_t* __restrict__ chunk_end,
+                                                   const int* __restrict__ edge_h, const int* __restrict__ edge_t,
+                                                   const int* __restrict__ slot, const double* __restrict__ JR,
+                                                   double* __restrict__ part_dir) {
   using Cfg = GramCfg<R, C>;
-  constexpr int CD = Cfg::CD, ROWS = Cfg::ROWS, LD = Cfg::LD;
-  __shared__ double M[Cfg::TILE];
-  __shared__ double G[256];
+  constexpr int CD = Cfg::CD, TOBS = Cfg::TOBS, RS = Cfg::RS, P = C + 1;
+  extern __shared__ __align__(16) double gram_sm[];  // Mt[2][16 * RS] double buffer + G[256]
+  double* G = gram_sm + 2 * 16 * RS;
   const int q = blockIdx.x;
   const int e = chunk_edge[q];
   const int64_t o0 = chunk_begin[q], o1 = chunk_end[q];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int g = warp * 3 + lane / 10;
-  const int tile = lane % 10;
-  const bool active = lane < 30;
-  // upper 4x4 tiles of a 4x4 tile grid: (0,0)(0,1)(0,2)(0,3)(1,1)(1,2)(1,3)(2,2)(2,3)(3,3)
-  const int ti = tile < 4 ? 0 : (tile < 7 ? 1 : (tile < 9 ? 2 : 3));
-  const int tj = tile < 4 ? tile : (tile < 7 ? tile - 3 : (tile < 9 ? tile - 5 : 3));
-  double acc[16];
+  const int ta = warp == 2 ? 8 : 0;   // first column of the tile's row block
+  const int tb = warp == 0 ? 0 : 8;   // first column of the tile's column block
+  const bool diag = ta == tb;
+  double acc[8][8];
 #pragma unroll
-  for (int x = 0; x < 16; ++x) acc[x] = 0.0;
+  for (int x = 0; x < 8; ++x)
+#pragma unroll
+    for (int y = 0; y < 8; ++y) acc[x][y] = 0.0;
+  // columns C..14 of M are structurally zero
+  for (int i = threadIdx.x; i < 2 * 16 * RS; i += 96) gram_sm[i] = 0.0;
+  __syncthreads();
 
-  for (int64_t base = o0; base < o1; base += 32) {
-    const int cnt = int(o1 - base < 32 ? o1 - base : 32);
-    __syncthreads();
-    for (int item = warp; item < 16 * R; item += 4) {
-      const int k = item >> 4, c = item & 15;
-      double v = 0.0;
-      if (lane < cnt) {
-        if (c < C) v = J[(int64_t(k) * C + c) * n + base + lane];
-        else if (c == 15) v = res[int64_t(k) * n + base + lane];
-      }
-      M[(k * 32 + lane) * LD + c] = v;
-    }
-    __syncthreads();
-    if (active) {
-      for (int kk = g; kk < ROWS; kk += 12) {
-        const double* row = M + kk * LD;
-        double a[4], b[4];
-#pragma unroll
-        for (int x = 0; x < 4; ++x) { a[x] = row[4 * ti + x]; b[x] = row[4 * tj + x]; }
-#pragma unroll
-        for (int x = 0; x < 4; ++x)
-#pragma unroll
-          for (int y = 0; y < 4; ++y) acc[4 * x + y] += a[x] * b[y];
+  const int n_t = int((o1 - o0 + TOBS - 1) / TOBS);  // obs tiles per row
+  const int n_stage = n_t * R;                       // stage s = (row k = s / n_t, tile s % n_t)
+  auto stage = [&](int st, int buf) {
+    const int k = st / n_t;
+    const int64_t base = o0 + int64_t(st % n_t) * TOBS;
+    const int cnt = int(o1 - base < TOBS ? o1 - base : TOBS);
+    double* Mt = gram_sm + buf * 16 * RS;
+    // items: (column cc, 32-obs slice j); warp takes every third
+    for (int item = warp; item < P * (TOBS / 32); item += 3) {
+      const int cc = item >> 3, j = item & 7;
+      const int c = cc < C ? cc : 15;
+      const int o = j * 32 + lane;
+      double* dst = Mt + c * RS + o;
+      if (o < cnt) {
+        const double* src = JR + (int64_t(k) * P + cc) * ld + base + o;
+        const unsigned sa = unsigned(__cvta_generic_to_shared(dst));
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(src));
+      } else {
+        *dst = 0.0;
       }
     }
-  }
-  __syncthreads();
-  if (active) {
+    asm volatile("cp.async.commit_group;\n" ::);
+  };
+
+  int buf = 0;
+  if (n_stage > 0) stage(0, 0);
+  for (int st = 0; st < n_stage; ++st) {
+    const bool more = st + 1 < n_stage;
+    if (more) stage(st + 1, buf ^ 1);
+    if (more) asm volatile("cp.async.wait_group 1;\n" ::);
+    else asm volatile("cp.async.wait_group 0;\n" ::);
+    __syncthreads();
+    // two base pointers per stage; every load below is [pointer + immediate]
+    const double2* pa = reinterpret_cast<const double2*>(gram_sm + buf * 16 * RS + ta * RS) + lane;
+    const double2* pb = reinterpret_cast<const double2*>(gram_sm + buf * 16 * RS + tb * RS) + lane;
 #pragma unroll
-    for (int x = 0; x < 16; ++x) M[(g * 10 + tile) * 16 + x] = acc[x];
+    for (int s = 0; s < TOBS / 64; ++s) {
+      double2 av[8], bv[8];
+#pragma unroll
+      for (int x = 0; x < 8; ++x) av[x] = pa[(x * RS + 64 * s) / 2];
+      if (diag) {
+#pragma unroll
+        for (int x = 0; x < 8; ++x) bv[x] = av[x];
+      } else {
+#pragma unroll
+        for (int x = 0; x < 8; ++x) bv[x] = pb[(x * RS + 64 * s) / 2];
+      }
+#pragma unroll
+      for (int x = 0; x < 8; ++x)
+#pragma unroll
+        for (int y = 0; y < 8; ++y) {
+          acc[x][y] = fma(av[x].x, bv[y].x, acc[x][y]);
+          acc[x][y] = fma(av[x].y, bv[y].y, acc[x][y]);
+        }
+    }
+    __syncthreads();  // everyone is done with `buf` before the next-but-one stage overwrites it
+    buf ^= 1;
   }
-  __syncthreads();
-  for (int idx = threadIdx.x; idx < 160; idx += 128) {
-    double s = 0.0;
-    for (int gg = 0; gg < 12; ++gg) s += M[(gg * 10 + idx / 16) * 16 + (idx & 15)];
-    const int tl = idx / 16;
-    const int a = tl < 4 ? 0 : (tl < 7 ? 1 : (tl < 9 ? 2 : 3));
-    const int b = tl < 4 ? tl : (tl < 7 ? tl - 3 : (tl < 9 ? tl - 5 : 3));
-    const int x = (idx & 15) >> 2, y = idx & 3;
-    G[(4 * a + x) * 16 + 4 * b + y] = s;
-    G[(4 * b + y) * 16 + 4 * a + x] = s;
-  }
+  // combine the 32 lane partials of the tile; lane l keeps entries 2l, 2l+1
+#pragma unroll
+  for (int x = 0; x < 8; ++x)
+#pragma unroll
+    for (int y = 0; y < 8; ++y) {
+      double v = acc[x][y];
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == ((x * 8 + y) >> 1)) {
+        G[(ta + x) * 16 + tb + y] = v;
+        G[(tb + y) * 16 + ta + x] = v;
+      }
+    }
   __syncthreads();
   // partial layout: [HH | HT (or its transpose when slot_h > slot_t) | TT | gh | gt]
   const int hs = slot[edge_h[e]], ts = slot[edge_t[e]];
   const bool trans = hs > ts;
   double* out = part_dir + int64_t(q) * Cfg::DIR_STRIDE;
-  for (int idx = threadIdx.x; idx < Cfg::DIR_STRIDE; idx += 128) {
+  for (int idx = threadIdx.x; idx < Cfg::DIR_STRIDE; idx += 96) {
     double v = 0.0;
     if (idx < CD * CD) {
       const int r = idx / CD, c = idx % CD;
@@ -132,7 +170,11 @@ __global__ void __launch_bounds__(128) k_edge_gram(int64_t n, const int* __restr
 
 // -------------------------------------------------------- landmark gather --
 // Per landmark: W row = [ F^T E per visible camera (8 wide each) | g_l c_l 0.. ],
-// c_l = sum E^T E, g_l = sum E^T r over the landmark's observations.
+// c_l = sum E^T E, g_l = sum E^T r over the landmark's observations.  A half-warp
+// per landmark: lane q owns element q of the 16-double Schur record, so each
+// record is one coalesced 128 B read and each camera slot one 64 B write.  Slots
+// of cameras that do not see the landmark are zeroed once in pba_create and never
+// written (the structure is static).
 __global__ void __launch_bounds__(128) k_lm_gather(int n_lm, int cd, const int64_t* __restrict__ lm_ptr,
                                                     const int64_t* __restrict__ lm_pos,
                                                     const int* __restrict__ obs_col,
@@ -141,38 +183,32 @@ __global__ void __launch_bounds__(128) k_lm_gather(int n_lm, int cd, const int64
                                                     const int* __restrict__ lm_w_stride,
                                                     const double* __restrict__ orec, double* __restrict__ W,
                                                     double* __restrict__ lm_c, double* __restrict__ lm_g) {
-  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  const int l = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+  const int q = threadIdx.x & 15;
   if (l >= n_lm) return;
   double* row = W + lm_w_off[l];
   const int stride = lm_w_stride[l];
-  for (int i = 0; i < stride; ++i) row[i] = 0.0;
-  double wh[6] = {0, 0, 0, 0, 0, 0};
-  double c = 0.0, g = 0.0;
+  double acc = 0.0;  // lanes 0-5: host columns, 14: c_l, 15: g_l
   for (int64_t k = lm_ptr[l]; k < lm_ptr[l + 1]; ++k) {
     const int64_t pos = lm_pos[k];
-    const double2* rec = reinterpret_cast<const double2*>(orec + 16 * pos);
-    double v[16];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { const double2 t = rec[i]; v[2 * i] = t.x; v[2 * i + 1] = t.y; }
-#pragma unroll
-    for (int i = 0; i < 6; ++i) wh[i] += v[i];
-    c += v[14];
-    g += v[15];
+    const double v = orec[16 * pos + q];
     const int col = obs_col[pos];
-    if (col >= 0) {
-      double* dst = row + 8 * col;
-      for (int i = 0; i < cd; ++i) dst[i] = v[6 + i];
+    if (q >= 6 && q < 6 + cd) {
+      if (col >= 0) row[8 * col + (q - 6)] = v;
+    } else {
+      acc += v;
     }
   }
   const int hc = lm_hostcol[l];
-  if (hc >= 0) {
-#pragma unroll
-    for (int i = 0; i < 6; ++i) row[8 * hc + i] = wh[i];
+  if (q < 6) {
+    if (hc >= 0) row[8 * hc + q] = acc;
+  } else if (q == 14) {
+    row[stride - 7] = acc;
+    lm_c[l] = acc;
+  } else if (q == 15) {
+    row[stride - 8] = acc;
+    lm_g[l] = acc;
   }
-  row[stride - 8] = g;
-  row[stride - 7] = c;
-  lm_c[l] = c;
-  lm_g[l] = g;
 }
 
 // Per landmark, per linear solve: Jacobi scale sigma_l (iteration 0 only),
@@ -300,7 +336,8 @@ __global__ void k_rcs_reduce(int cd, int64_t n_blocks, int n_slots, const int64_
                              const int64_t* __restrict__ vsch_src, const int* __restrict__ blk_row,
                              const int* __restrict__ blk_col, const double* __restrict__ part_dir,
                              const double* __restrict__ part_sch, double* __restrict__ S, double* __restrict__ rhs,
-                             double* __restrict__ diagB, double* __restrict__ gcam) {
+                             double* __restrict__ diagB, double* __restrict__ gcam, double* __restrict__ B_local,
+                             double* __restrict__ g_local) {
   const int64_t b = blockIdx.x;
   const int e = threadIdx.x;
   if (b < n_blocks) {
@@ -309,6 +346,7 @@ __global__ void k_rcs_reduce(int cd, int64_t n_blocks, int n_slots, const int64_
     for (int64_t k = dir_ptr[b]; k < dir_ptr[b + 1]; ++k) d += part_dir[dir_src[k] + e];
     for (int64_t k = sch_ptr[b]; k < sch_ptr[b + 1]; ++k) s += part_sch[sch_src[k] + e];
     S[b * cd * cd + e] = d - s;
+    B_local[b * cd * cd + e] = d;
     if (blk_row[b] == blk_col[b] && e / cd == e % cd) diagB[blk_row[b] * cd + e / cd] = d;
   } else {
     const int a = int(b - n_blocks);
@@ -318,6 +356,7 @@ __global__ void k_rcs_reduce(int cd, int64_t n_blocks, int n_slots, const int64_
     for (int64_t k = vsch_ptr[a]; k < vsch_ptr[a + 1]; ++k) s += part_sch[vsch_src[k] + e];
     rhs[a * cd + e] = d - s;
     gcam[a * cd + e] = d;
+    g_local[a * cd + e] = d;
   }
 }
 
@@ -357,30 +396,85 @@ __global__ void k_rcs_scale(int cd, int64_t n_blocks, int n_slots, const int* __
 // ------------------------------------------------------------- back-subst --
 // y_l = ete^-1 sigma_l (g_l - sum_a w_la . (sigma_a y_a))  (schur_eliminator_impl.h:309-375)
 // then the unscaled tangent step d_l = -sigma_l y_l.
+//
+// The same pass yields the landmark part of the model cost change
+//   -(J d)^T (r + J d / 2) = -d^T g - d^T H d / 2,   H = J^T J, g = J^T r (unscaled)
+// (trust_region_minimizer.cc:414-427) without touching J again:
+//   landmark l:  -d_l (g_l + t_l + c_l d_l / 2),  t_l = sum_a w_la . d_a
+// the camera part (-d_c.g_c - d_c^T B d_c / 2) comes from k_model_cost_cam.
 __global__ void __launch_bounds__(128) k_backsub(int n_lm, int cd, const int* __restrict__ lm_group,
                                                   const int* __restrict__ grp_cam_ptr, const int* __restrict__ grp_cams,
                                                   const int64_t* __restrict__ lm_w_off,
                                                   const int* __restrict__ lm_w_stride, const int64_t* __restrict__ lm_ptr,
                                                   const double* __restrict__ W, const double* __restrict__ lm_scale,
                                                   const double* __restrict__ lm_iete, const double* __restrict__ d_cam,
-                                                  double* __restrict__ d_rho) {
+                                                  double* __restrict__ d_rho, double* __restrict__ part_model) {
+  __shared__ double sm[4];
   const int l = blockIdx.x * blockDim.x + threadIdx.x;
-  if (l >= n_lm) return;
-  if (lm_ptr[l + 1] == lm_ptr[l]) { d_rho[l] = 0.0; return; }
-  const int g = lm_group[l];
-  const int c0 = grp_cam_ptr[g], c = grp_cam_ptr[g + 1] - c0;
-  const double* row = W + lm_w_off[l];
-  const int stride = lm_w_stride[l];
-  // d_cam = -sigma y  =>  sum_a w_la . (sigma_a y_a) = -sum_a w_la . d_a
-  double acc = row[stride - 8];  // g_l
-  for (int j = 0; j < c; ++j) {
-    const double* d = d_cam + grp_cams[c0 + j] * cd;
-    const double* w = row + 8 * j;
-    for (int i = 0; i < cd; ++i) acc += w[i] * d[i];
+  double mc = 0.0;
+  if (l < n_lm) {
+    if (lm_ptr[l + 1] == lm_ptr[l]) {
+      d_rho[l] = 0.0;
+    } else {
+      const int g = lm_group[l];
+      const int c0 = grp_cam_ptr[g], c = grp_cam_ptr[g + 1] - c0;
+      const double* row = W + lm_w_off[l];
+      const int stride = lm_w_stride[l];
+      // d_cam = -sigma y  =>  sum_a w_la . (sigma_a y_a) = -sum_a w_la . d_a
+      double t = 0.0;
+      for (int j = 0; j < c; ++j) {
+        const double* d = d_cam + grp_cams[c0 + j] * cd;
+        const double* w = row + 8 * j;
+        for (int i = 0; i < cd; ++i) t += w[i] * d[i];
+      }
+      const double gl = row[stride - 8], cl = row[stride - 7];
+      const double s = lm_scale[l];
+      const double y = lm_iete[l] * s * (gl + t);
+      const double dl = -s * y;
+      d_rho[l] = dl;
+      mc = -dl * (gl + t + 0.5 * cl * dl);
+    }
   }
-  const double s = lm_scale[l];
-  const double y = lm_iete[l] * s * acc;
-  d_rho[l] = -s * y;
+  for (int o = 16; o > 0; o >>= 1) mc += __shfl_down_sync(0xffffffffu, mc, o);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = mc;
+  __syncthreads();
+  if (threadIdx.x == 0) part_model[blockIdx.x] = sm[0] + sm[1] + sm[2] + sm[3];
+}
+
+// Camera part of the model cost change: one thread per RCS block of the raw (unscaled,
+// undamped, this rank's) direct part B:  -d_a^T B_ab d_b (x1/2 on the diagonal), plus
+// -d_a . g_a from the diagonal block's thread.
+__global__ void __launch_bounds__(128) k_model_cost_cam(int cd, int64_t n_blocks, const int* __restrict__ blk_row,
+                                                         const int* __restrict__ blk_col,
+                                                         const double* __restrict__ B_local,
+                                                         const double* __restrict__ g_local,
+                                                         const double* __restrict__ d_cam, double* __restrict__ part) {
+  __shared__ double sm[4];
+  const int64_t b = int64_t(blockIdx.x) * 128 + threadIdx.x;
+  double mc = 0.0;
+  if (b < n_blocks) {
+    const int a = blk_row[b], c = blk_col[b];
+    const double* Bb = B_local + b * cd * cd;
+    const double* da = d_cam + a * cd;
+    const double* dc = d_cam + c * cd;
+    double q = 0.0;
+    for (int i = 0; i < cd; ++i) {
+      double s = 0.0;
+      for (int j = 0; j < cd; ++j) s += Bb[i * cd + j] * dc[j];
+      q += da[i] * s;
+    }
+    if (a == c) {
+      double dg = 0.0;
+      for (int i = 0; i < cd; ++i) dg += da[i] * g_local[a * cd + i];
+      mc = -dg - 0.5 * q;
+    } else {
+      mc = -q;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) mc += __shfl_down_sync(0xffffffffu, mc, o);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = mc;
+  __syncthreads();
+  if (threadIdx.x == 0) part[blockIdx.x] = sm[0] + sm[1] + sm[2] + sm[3];
 }
 
 __global__ void k_cam_step(int dim, const double* __restrict__ y, const double* __restrict__ scale,
@@ -528,17 +622,21 @@ pba_status launch_post_jacobian(Handle* h) {
   const Sizes& z = h->sz;
   if (z.n_chunks > 0) {
     if (z.mode == PBA_MODE_PHOTOMETRIC) {
-      PBA_LAUNCH(h, K_EDGE_GRAM, k_edge_gram_photo, dim3(z.n_chunks), dim3(128), 0, z.n_obs, h->chunk_edge.p,
-                 h->chunk_begin.p, h->chunk_end.p, h->edge_h.p, h->edge_t.p, h->d_slot.p, h->J.p, h->res.p,
-                 h->part_dir.p);
+      constexpr size_t smem = (2 * 16 * GramCfg<8, 15>::RS + 256) * sizeof(double);
+      static bool attr = false;
+      if (!attr) { PBA_CUDA_OK(cudaFuncSetAttribute(k_edge_gram_photo, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))); attr = true; }
+      PBA_LAUNCH(h, K_EDGE_GRAM, k_edge_gram_photo, dim3(z.n_chunks), dim3(96), smem, z.ld, h->chunk_edge.p,
+                 h->chunk_begin.p, h->chunk_end.p, h->edge_h.p, h->edge_t.p, h->d_slot.p, h->J.p, h->part_dir.p);
     } else {
-      PBA_LAUNCH(h, K_EDGE_GRAM, k_edge_gram_geom, dim3(z.n_chunks), dim3(128), 0, z.n_obs, h->chunk_edge.p,
-                 h->chunk_begin.p, h->chunk_end.p, h->edge_h.p, h->edge_t.p, h->d_slot.p, h->J.p, h->res.p,
-                 h->part_dir.p);
+      constexpr size_t smem = (2 * 16 * GramCfg<2, 13>::RS + 256) * sizeof(double);
+      static bool attr = false;
+      if (!attr) { PBA_CUDA_OK(cudaFuncSetAttribute(k_edge_gram_geom, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))); attr = true; }
+      PBA_LAUNCH(h, K_EDGE_GRAM, k_edge_gram_geom, dim3(z.n_chunks), dim3(96), smem, z.ld, h->chunk_edge.p,
+                 h->chunk_begin.p, h->chunk_end.p, h->edge_h.p, h->edge_t.p, h->d_slot.p, h->J.p, h->part_dir.p);
     }
   }
   if (z.n_lm > 0) {
-    PBA_LAUNCH(h, K_LM_GATHER, k_lm_gather, dim3((z.n_lm + 127) / 128), dim3(128), 0, z.n_lm, z.cd, h->lm_ptr.p,
+    PBA_LAUNCH(h, K_LM_GATHER, k_lm_gather, dim3((z.n_lm + 7) / 8), dim3(128), 0, z.n_lm, z.cd, h->lm_ptr.p,
                h->lm_pos.p, h->obs_col.p, h->lm_hostcol.p, h->lm_w_off.p, h->lm_w_stride.p, h->orec.p, h->W.p,
                h->lm_c.p, h->lm_g.p);
   }
@@ -581,7 +679,7 @@ pba_status launch_build_rcs(Handle* h, double radius, bool refresh_diag) {
     PBA_LAUNCH(h, K_RCS_REDUCE, k_rcs_reduce, dim3((unsigned)grid), dim3(64), 0, z.cd, z.n_blocks, z.n_slots,
                h->blk_dir_ptr.p, h->blk_dir_src.p, h->blk_sch_ptr.p, h->blk_sch_src.p, h->vec_dir_ptr.p,
                h->vec_dir_src.p, h->vec_sch_ptr.p, h->vec_sch_src.p, h->d_blk_row.p, h->d_blk_col.p, h->part_dir.p,
-               h->part_sch.p, S, rhs, diagB, gcam);
+               h->part_sch.p, S, rhs, diagB, gcam, h->rcs_B.p, h->rcs_B.p + z.n_blocks * z.cd * z.cd);
   }
   if (h->world > 1) {
     pba_status st = allreduce_rcs(h);
@@ -600,18 +698,27 @@ pba_status launch_build_rcs(Handle* h, double radius, bool refresh_diag) {
   return PBA_OK;
 }
 
-// y_cam (scaled space) -> unscaled tangent steps for cameras and landmarks.
+// y_cam (scaled space) -> unscaled tangent steps for cameras and landmarks, and the
+// model cost change of that step (scalar S_MODEL; this rank's share when sharded).
 pba_status launch_backsub(Handle* h) {
   const Sizes& z = h->sz;
   if (z.dim > 0) {
     PBA_LAUNCH(h, K_BACKSUB, k_cam_step, dim3((z.dim + 255) / 256), dim3(256), 0, z.dim, h->y_cam.p, h->cam_scale.p,
                h->d_cam.p);
   }
-  if (z.n_lm > 0) {
-    PBA_LAUNCH(h, K_BACKSUB, k_backsub, dim3((z.n_lm + 127) / 128), dim3(128), 0, z.n_lm, z.cd, h->lm_group.p,
-               h->grp_cam_ptr.p, h->grp_cams.p, h->lm_w_off.p, h->lm_w_stride.p, h->lm_ptr.p, h->W.p, h->lm_scale.p,
-               h->lm_iete.p, h->d_cam.p, h->d_rho.p);
+  const int g_lm = (z.n_lm + 127) / 128;
+  const int g_cam = int((z.n_blocks + 127) / 128);
+  double* part = h->red_ws.p;
+  if (g_lm > 0) {
+    PBA_LAUNCH(h, K_BACKSUB, k_backsub, dim3(g_lm), dim3(128), 0, z.n_lm, z.cd, h->lm_group.p, h->grp_cam_ptr.p,
+               h->grp_cams.p, h->lm_w_off.p, h->lm_w_stride.p, h->lm_ptr.p, h->W.p, h->lm_scale.p, h->lm_iete.p,
+               h->d_cam.p, h->d_rho.p, part);
   }
+  if (g_cam > 0) {
+    PBA_LAUNCH(h, K_MODEL_COST, k_model_cost_cam, dim3(g_cam), dim3(128), 0, z.cd, z.n_blocks, h->d_blk_row.p,
+               h->d_blk_col.p, h->rcs_B.p, h->rcs_B.p + z.n_blocks * z.cd * z.cd, h->d_cam.p, part + g_lm);
+  }
+  launch_reduce_sum(h, part, int64_t(g_lm) + g_cam, h->scalars.p + S_MODEL);
   return PBA_OK;
 }
 
