@@ -287,7 +287,8 @@ def main():
             traffic = tj.get(key)
         except Exception:
             traffic = None
-    solver_used = "cholesky_dmma" if it["linear_solver_iterations"] == 1 and eng.kernel_stats().get("pcg") is None else "pcg"
+    solver_used = ("bcr (block cyclic reduction)" if "bcr" in stats else "band_cholesky" if "band_cholesky" in stats
+                   else "pcg" if "pcg" in stats else "dense_cholesky_dmma")
 
     # ---- end to end: the drop-in call with HOST buffers ----
     e2e = None

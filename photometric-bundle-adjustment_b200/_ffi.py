@@ -17,7 +17,7 @@ STATUS_NAMES = {0: "PBA_OK", 1: "PBA_ERR_INVALID_ARGUMENT", 2: "PBA_ERR_NO_DEVIC
 MODE_GEOMETRIC, MODE_PHOTOMETRIC = 0, 1
 CAM_PINHOLE, CAM_DS, CAM_KB4, CAM_EUCM = 0, 1, 2, 3
 CAM_NAMES = {"pinhole": CAM_PINHOLE, "ds": CAM_DS, "kb4": CAM_KB4, "eucm": CAM_EUCM}
-SOLVER_AUTO, SOLVER_CHOLESKY, SOLVER_PCG, SOLVER_BAND = 0, 1, 2, 3
+SOLVER_AUTO, SOLVER_CHOLESKY, SOLVER_PCG, SOLVER_BAND, SOLVER_BCR = 0, 1, 2, 3, 4
 CONVERGENCE, NO_CONVERGENCE, FAILURE = 0, 1, 2
 NCCL_ID_BYTES = 128
 

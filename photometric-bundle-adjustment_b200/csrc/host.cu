@@ -37,8 +37,8 @@ const char* const kKernelNames[K_NUM] = {
     "init_landmarks", "edge_prep",  "residual_jacobian", "cost_only",  "reduce_sum", "edge_gram",
     "landmark_gather", "landmark_scale", "schur_syrk", "rcs_reduce", "rcs_scale",  "cam_scale",
     "dense_fill",     "chol_panel", "chol_trsm",         "chol_syrk_dmma", "chol_solve", "pcg",
-    "band_cholesky",  "backsub",    "model_cost",        "retract",    "copy",       "unpermute",
-    "primitive"};
+    "band_cholesky",  "bcr",        "backsub",           "model_cost", "retract",    "copy",
+    "unpermute",      "primitive"};
 
 pba_status map_cuda(cudaError_t e) {
   if (e == cudaSuccess) return PBA_OK;
@@ -480,6 +480,7 @@ pba_status create_impl(const pba_problem* p, const pba_options* o, int rank, int
     PBA_CUDA_OK(cudaStreamSynchronize(s));
     PBA_CUDA_OK(h->band_L.alloc(size_t(z.n_slots) * B * cd * cd));
   }
+  if ((st = bcr_setup(h)) != PBA_OK) return st;
   {
     std::vector<int> lm_host(n_lm);
     std::vector<double> lm_uv(size_t(2) * n_lm), rho(n_lm);
@@ -582,15 +583,19 @@ pba_status read_scalars(Handle* h) {
 int pick_solver(const Handle* h, int requested) {
   int s = requested == PBA_SOLVER_AUTO ? h->opt.solver : requested;
   const bool band_ok = h->rcs_bandwidth <= band_max_bw(h->sz.cd);
-  // AUTO: exact band factorisation when the covisibility is windowed, else dense
-  // DMMA Cholesky while it fits, else PCG
-  if (s == PBA_SOLVER_AUTO) s = band_ok ? PBA_SOLVER_BAND : (h->sz.dim <= h->opt.cholesky_max_dim ? PBA_SOLVER_CHOLESKY : PBA_SOLVER_PCG);
-  if (s == PBA_SOLVER_BAND && !band_ok) s = h->sz.dim <= h->opt.cholesky_max_dim ? PBA_SOLVER_CHOLESKY : PBA_SOLVER_PCG;
+  const bool bcr_ok = h->bcr_m > 0;
+  const int general = h->sz.dim <= h->opt.cholesky_max_dim ? PBA_SOLVER_CHOLESKY : PBA_SOLVER_PCG;
+  // AUTO: exact solvers that exploit windowed covisibility first (parallel cyclic reduction,
+  // then the sequential band factorisation), else dense Cholesky while it fits, else PCG
+  if (s == PBA_SOLVER_AUTO) s = bcr_ok ? PBA_SOLVER_BCR : (band_ok ? PBA_SOLVER_BAND : general);
+  if (s == PBA_SOLVER_BCR && !bcr_ok) s = band_ok ? PBA_SOLVER_BAND : general;
+  if (s == PBA_SOLVER_BAND && !band_ok) s = general;
   return s;
 }
 
 pba_status solve_rcs(Handle* h, int solver) {
   h->last_solver = pick_solver(h, solver);
+  if (h->last_solver == PBA_SOLVER_BCR) return launch_bcr_rcs(h);
   if (h->last_solver == PBA_SOLVER_BAND) return launch_band_rcs(h);
   return h->last_solver == PBA_SOLVER_CHOLESKY ? launch_cholesky_rcs(h) : launch_pcg_rcs(h);
 }
@@ -804,7 +809,7 @@ pba_status minimize_impl(Handle* h, pba_summary* sum) {
     sum->residual_evaluation_time_in_seconds = 1e-3 * ks.ms[K_COST];
     double lin = 0;
     for (int k : {K_EDGE_GRAM, K_LM_GATHER, K_LM_SCALE, K_SCHUR_SYRK, K_RCS_REDUCE, K_RCS_SCALE, K_CAM_SCALE, K_DENSE_FILL,
-                  K_CHOL_PANEL, K_CHOL_TRSM, K_CHOL_SYRK, K_CHOL_SOLVE, K_PCG, K_BAND_CHOL, K_BACKSUB})
+                  K_CHOL_PANEL, K_CHOL_TRSM, K_CHOL_SYRK, K_CHOL_SOLVE, K_PCG, K_BAND_CHOL, K_BCR, K_BACKSUB})
       lin += ks.ms[k];
     sum->linear_solver_time_in_seconds = 1e-3 * lin;
     sum->minimizer_time_in_seconds = wall() - t_start;

@@ -72,6 +72,7 @@ enum KernelId {
   K_CHOL_SOLVE,
   K_PCG,
   K_BAND_CHOL,   // single-CTA block-banded Cholesky + solves
+  K_BCR,         // block cyclic reduction on super blocks
   K_BACKSUB,     // K6
   K_MODEL_COST,  // K8
   K_RETRACT,     // K7
@@ -221,6 +222,12 @@ struct Handle {
   int rcs_bandwidth = 0;       // max (col - row) over the RCS blocks, in blocks
   DevBuf<int> d_col_blk;       // [n_slots][bw+1] block index of (k, k+i) or -1 (band solver)
   DevBuf<double> band_L;       // band factor [n_slots][bw+1][cd*cd]
+  int bcr_m = 0;               // keyframes per BCR super block (0 = BCR not applicable)
+  int bcr_levels = 0;
+  std::vector<int> bcr_n;      // super blocks per level
+  std::vector<size_t> bcr_off; // 7 offsets per level into bcr_ws (A B b L U V y)
+  size_t bcr_x_off = 0;
+  DevBuf<double> bcr_ws;
   int uniform_model = -1;      // PBA_CAM_* when every calibration uses the same model, else -1
 
   // NCCL
@@ -258,6 +265,8 @@ pba_status launch_gradient_norms(Handle* h);
 pba_status launch_cholesky_rcs(Handle* h);
 pba_status launch_pcg_rcs(Handle* h);
 pba_status launch_band_rcs(Handle* h);
+pba_status launch_bcr_rcs(Handle* h);
+pba_status bcr_setup(Handle* h);
 int band_max_bw(int cd);
 pba_status dense_cholesky_solve(Handle* h, double* A, double* b, int ld, int* fail_dev);
 int dense_ld(int n);

@@ -178,6 +178,8 @@ def test_reduced_camera_system_parity(mode, model):
     assert rel(y_chol, y_ref) < 1e-8
     y_band, _ = eng.solve_rcs(pb.SOLVER_BAND)
     assert rel(y_band, y_ref) < 1e-8
+    y_bcr, _ = eng.solve_rcs(pb.SOLVER_BCR)
+    assert rel(y_bcr, y_ref) < 1e-8
     y_pcg, iters = eng.solve_rcs(pb.SOLVER_PCG)
     assert iters > 0
     assert rel(y_pcg, y_ref) < 1e-6
@@ -216,7 +218,7 @@ def test_lm_matches_oracle(mode, model, n_kf, n_pts):
     assert sg.gpu_kernel_launches > 0
 
 
-@pytest.mark.parametrize("solver", [pb.SOLVER_PCG, pb.SOLVER_BAND, pb.SOLVER_AUTO])
+@pytest.mark.parametrize("solver", [pb.SOLVER_PCG, pb.SOLVER_BAND, pb.SOLVER_BCR, pb.SOLVER_AUTO])
 @pytest.mark.parametrize("mode", [pb.MODE_GEOMETRIC, pb.MODE_PHOTOMETRIC])
 def test_lm_other_solvers_reach_same_cost(solver, mode):
     prob, _ = scene(mode, "pinhole", n_kf=30, n_pts=1500)
@@ -225,7 +227,7 @@ def test_lm_other_solvers_reach_same_cost(solver, mode):
     so = of.solve("oracle", po, of.default_options(huber_parameter=hub))
     pg = prob.copy()
     sg = pb.bundle_adjustment(pg, pb.BundleAdjustmentOptions(verbosity_level=0, huber_parameter=hub, solver=solver))
-    assert sg.linear_solver == (pb.SOLVER_BAND if solver == pb.SOLVER_AUTO else solver)
+    assert sg.linear_solver == (pb.SOLVER_BCR if solver == pb.SOLVER_AUTO else solver)
     assert abs(sg.final_cost - so.final_cost) <= RTOL_COST * so.final_cost
     assert np.abs(pg.poses - po.poses).max() < TOL_STATE
     assert np.abs(pg.inv_depth - po.inv_depth).max() < TOL_STATE

@@ -1,0 +1,81 @@
+"""Multi-rank path: landmark sharding (host logic, CPU/gloo, world_size 2) and the
+sharded LM solve with the NCCL all-reduce of the partial RCS (needs >= 2 GPUs)."""
+import json
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import oracle_ffi as of
+import pba_b200 as pb
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+WORKER = os.path.join(HERE, "multi_rank_worker.py")
+
+
+def free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def test_partition_landmarks_properties():
+    rng = np.random.default_rng(0)
+    for n_lm, world in ((1, 1), (7, 2), (1000, 4), (1000, 8), (5, 8)):
+        cnt = rng.integers(0, 12, size=n_lm)
+        ptr = np.r_[0, np.cumsum(cnt)].astype(np.int64)
+        b = pb.partition_landmarks(ptr, world)
+        assert b[0] == 0 and b[-1] == n_lm and len(b) == world + 1
+        assert all(b[i] <= b[i + 1] for i in range(world))
+        if n_lm >= 100:  # balanced by observation count
+            loads = [ptr[b[i + 1]] - ptr[b[i]] for i in range(world)]
+            assert max(loads) - min(loads) <= 24
+
+
+def test_two_rank_sharding_gloo(tmp_path):
+    """world_size 2 over gloo: shard costs / pose gradients all-reduce to the whole problem's."""
+    port = free_port()
+    procs = [subprocess.Popen([sys.executable, WORKER, "gloo", str(r), "2", str(tmp_path), str(pb.MODE_GEOMETRIC),
+                               str(port)]) for r in range(2)]
+    for p in procs:
+        assert p.wait(timeout=300) == 0
+    out = json.load(open(tmp_path / "gloo.json"))
+    prob, _ = pb.make_scene(pb.MODE_GEOMETRIC, 14, 900, "pinhole")
+    cost, r, J = of.evaluate("oracle", prob, True, 1.0, threads=2)
+    assert out["n_obs"] == prob.n_obs and out["n_lm"] == prob.n_landmarks
+    assert abs(out["cost"] - cost) <= 1e-12 * cost
+    g = np.zeros((prob.n_poses, 6))
+    for l in range(prob.n_landmarks):
+        for k in range(int(prob.lm_obs_ptr[l]), int(prob.lm_obs_ptr[l + 1])):
+            g[prob.lm_host[l]] += J[k][:, 0:6].T @ r[k]
+            g[prob.obs_target[k]] += J[k][:, 6:12].T @ r[k]
+    np.testing.assert_allclose(np.load(tmp_path / "gloo_grad.npy").reshape(-1, 6), g, rtol=1e-11, atol=1e-9)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", [pb.MODE_GEOMETRIC, pb.MODE_PHOTOMETRIC])
+def test_two_gpu_sharded_lm_matches_single_gpu(tmp_path, mode):
+    if pb.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    procs = [subprocess.Popen([sys.executable, WORKER, "gpu", str(r), "2", str(tmp_path), str(mode)]) for r in range(2)]
+    for p in procs:
+        assert p.wait(timeout=600) == 0
+    prob, _ = pb.make_scene(mode, 14, 900, "pinhole")
+    hub = 9.0 if mode == pb.MODE_PHOTOMETRIC else 1.0
+    ref = prob.copy()
+    s = pb.bundle_adjustment(ref, pb.BundleAdjustmentOptions(verbosity_level=0, huber_parameter=hub))
+    r0, r1 = np.load(tmp_path / "rank0.npz"), np.load(tmp_path / "rank1.npz")
+    for r in (r0, r1):  # every rank reports the global cost trace
+        assert int(r["iterations"]) == s.num_iterations
+        assert abs(float(r["cost0"]) - s.initial_cost) <= 1e-12 * s.initial_cost
+        assert abs(float(r["final_cost"]) - s.final_cost) <= 1e-9 * s.final_cost
+        np.testing.assert_allclose(r["costs"], [i["cost"] for i in s.iterations], rtol=1e-9)
+        assert np.abs(r["poses"] - ref.poses).max() < 1e-8
+    rho = np.r_[r0["rho"], r1["rho"]]
+    assert int(r0["first"]) == 0 and int(r1["first"]) == len(r0["rho"])
+    assert np.abs(rho - ref.inv_depth).max() < 1e-8
