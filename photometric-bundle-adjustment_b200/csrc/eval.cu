@@ -189,6 +189,7 @@ __device__ __forceinline__ double huber(double s, int use_huber, double a, doubl
 // slower — 7.7 ms vs 6.7 ms at 18M observations: 4x the load instructions for
 // the per-edge constants.)
 constexpr int kPhotoThreads = 128;
+constexpr size_t kPhotoSmemBytes = ((kPhotoThreads / 32) * 32 * 17 + 32 * kPhotoThreads) * sizeof(double) + 16 * kPhotoThreads * 4;
 
 struct PhotoCtx {
   double A[9], tr[3], ea, bb, in[8], irho;
@@ -207,9 +208,21 @@ __device__ __forceinline__ double quad_sample(uint32_t q, double fx, double fy) 
 template <bool WITH_J, int MODEL>
 __global__ void __launch_bounds__(kPhotoThreads, WITH_J ? 3 : 4) k_eval_photo(const EvalArgs a) {
   __shared__ double s_red[kPhotoThreads / 32];
-  __shared__ double s_rec[WITH_J ? (kPhotoThreads / 32) * 32 * 17 : 1];
-  const int64_t i = int64_t(blockIdx.x) * kPhotoThreads + threadIdx.x;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // Dynamic shared memory (K1 only, kPhotoSmemBytes = 57 KB > the 48 KB static limit):
+  //   s_rec  [4][32][17] doubles  Schur-record transposition
+  //   s_pat  [32][128] doubles    pass-1 -> pass-2 hand-over: bx by bz Ih per pixel
+  //   s_quad [8][128] u32, s_off [8][128] int
+  // [value][thread] layouts are conflict-free.  Keeping the hand-over in SHARED memory
+  // matters: as a per-thread local array it spills through L2 to HBM (ncu,
+  // profiles/r01b_*: 26.4 GB written per launch against 20.7 GB of outputs).
+  extern __shared__ __align__(16) unsigned char k1_sm[];
+  double* s_rec = reinterpret_cast<double*>(k1_sm);
+  double* s_pat = s_rec + (kPhotoThreads / 32) * 32 * 17;
+  uint32_t* s_quad = reinterpret_cast<uint32_t*>(s_pat + 32 * kPhotoThreads);
+  int* s_off = reinterpret_cast<int*>(s_quad + 8 * kPhotoThreads);
+  const int tid = threadIdx.x;
+  const int64_t i = int64_t(blockIdx.x) * kPhotoThreads + tid;
+  const int lane = tid & 31, warp = tid >> 5;
   double cost = 0.0;
   double acc[16];
 #pragma unroll
@@ -267,12 +280,11 @@ __global__ void __launch_bounds__(kPhotoThreads, WITH_J ? 3 : 4) k_eval_photo(co
     uint32_t quad[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) quad[k] = __ldg(img + off[k]);
-    double r[8];
     double s = 0.0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      r[k] = quad_sample(quad[k], fx[k], fy[k]) - (c.ea * Ih[k] + c.bb);
-      s += r[k] * r[k];
+      const double rk = quad_sample(quad[k], fx[k], fy[k]) - (c.ea * Ih[k] + c.bb);
+      s += rk * rk;
     }
     if (!ok) s = 0.0;  // invalid observation: r = 0, J = 0
     double w;
@@ -280,22 +292,40 @@ __global__ void __launch_bounds__(kPhotoThreads, WITH_J ? 3 : 4) k_eval_photo(co
     if (!ok) w = 0.0;
 
     if (WITH_J) {
-      // ---- phase 2: recompute the warp with its projection Jacobian from registers
-      //      (no loads), weight, stream the rows out ----
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        s_pat[(4 * k + 0) * kPhotoThreads + tid] = bx[k];
+        s_pat[(4 * k + 1) * kPhotoThreads + tid] = by[k];
+        s_pat[(4 * k + 2) * kPhotoThreads + tid] = bz[k];
+        s_pat[(4 * k + 3) * kPhotoThreads + tid] = Ih[k];
+        s_quad[k * kPhotoThreads + tid] = quad[k];
+        s_off[k * kPhotoThreads + tid] = off[k];
+      }
+      // ---- phase 2: one pixel at a time: recompute the warp with its projection Jacobian
+      //      (no global loads), weight, stream the row out ----
       const int64_t n = a.ld;
 #pragma unroll 1
       for (int k = 0; k < 8; ++k) {
-        const double xh = bx[k] * c.irho, yh = by[k] * c.irho, zh = bz[k] * c.irho;
+        const double bxk = s_pat[(4 * k + 0) * kPhotoThreads + tid], byk = s_pat[(4 * k + 1) * kPhotoThreads + tid];
+        const double bzk = s_pat[(4 * k + 2) * kPhotoThreads + tid], Ihk = s_pat[(4 * k + 3) * kPhotoThreads + tid];
+        const uint32_t q = s_quad[k * kPhotoThreads + tid];
+        const int ofk = s_off[k * kPhotoThreads + tid];
+        const double xh = bxk * c.irho, yh = byk * c.irho, zh = bzk * c.irho;
         const double xt = c.A[0] * xh + c.A[1] * yh + c.A[2] * zh + c.tr[0];
         const double yt = c.A[3] * xh + c.A[4] * yh + c.A[5] * zh + c.tr[1];
         const double zt = c.A[6] * xh + c.A[7] * yh + c.A[8] * zh + c.tr[2];
         double uv[2], Jp[6];
         cam_project<true>(c.model, c.in, xt, yt, zt, uv, Jp);
-        const uint32_t q = quad[k];
+        // same integer cell as pass 1 (a recomputed floor could differ by one ulp of u)
+        const int y0 = ofk / a.pitch, x0 = ofk - y0 * a.pitch;
+        const double fxk = ok ? uv[0] - x0 : 0.0, fyk = ok ? uv[1] - y0 : 0.0;
         const double i00 = double(q & 0xffu), i10 = double((q >> 8) & 0xffu), i01 = double((q >> 16) & 0xffu),
                      i11 = double(q >> 24);
-        const double gx = (1.0 - fy[k]) * (i10 - i00) + fy[k] * (i11 - i01);
-        const double gy = (1.0 - fx[k]) * (i01 - i00) + fx[k] * (i11 - i10);
+        const double I = (1.0 - fxk) * (1.0 - fyk) * i00 + fxk * (1.0 - fyk) * i10 + (1.0 - fxk) * fyk * i01 +
+                         fxk * fyk * i11;
+        const double rk = I - (c.ea * Ihk + c.bb);
+        const double gx = (1.0 - fyk) * (i10 - i00) + fyk * (i11 - i01);
+        const double gy = (1.0 - fxk) * (i01 - i00) + fxk * (i11 - i10);
         const double p0 = w * (gx * Jp[0] + gy * Jp[3]);
         const double p1 = w * (gx * Jp[1] + gy * Jp[4]);
         const double p2 = w * (gx * Jp[2] + gy * Jp[5]);
@@ -314,11 +344,11 @@ __global__ void __launch_bounds__(kPhotoThreads, WITH_J ? 3 : 4) k_eval_photo(co
         row[10] = p2 * xt - p0 * zt;
         row[11] = p0 * yt - p1 * xt;
         // affine (a_t, b_t)
-        row[12] = -w * c.ea * Ih[k];
+        row[12] = -w * c.ea * Ihk;
         row[13] = -w;
         // inverse distance: -(a . X_h) / rho
         row[14] = -(ax * xh + ay * yh + az * zh) * c.irho;
-        const double rw = w * r[k];
+        const double rw = w * rk;
         double* Jk = a.J + (int64_t(k) * 16) * n + i;  // planes [k][0..14] = J row, [k][15] = residual
         Jk[15 * n] = rw;
 #pragma unroll
@@ -513,7 +543,15 @@ pba_status launch_evaluate(Handle* h, bool with_jacobian, const double* poses, c
   const int grid = eval_grid(z.n_obs);
   if (grid > 0) {
     if (photo) {
-      if (with_jacobian) { PBA_LAUNCH(h, K_RESJAC, photo_kernel<true>(h->uniform_model), dim3(grid), dim3(kPhotoThreads), 0, a); }
+      if (with_jacobian) {
+        static bool attr = false;
+        if (!attr) {
+          for (int m = -1; m <= PBA_CAM_EUCM; ++m)
+            PBA_CUDA_OK(cudaFuncSetAttribute(photo_kernel<true>(m), cudaFuncAttributeMaxDynamicSharedMemorySize, int(kPhotoSmemBytes)));
+          attr = true;
+        }
+        PBA_LAUNCH(h, K_RESJAC, photo_kernel<true>(h->uniform_model), dim3(grid), dim3(kPhotoThreads), kPhotoSmemBytes, a);
+      }
       else { PBA_LAUNCH(h, K_COST, photo_kernel<false>(h->uniform_model), dim3(grid), dim3(kPhotoThreads), 0, a); }
     } else {
       if (with_jacobian) { PBA_LAUNCH(h, K_RESJAC, k_eval_geom<true>, dim3(grid), dim3(kEvalThreads), 0, a); }

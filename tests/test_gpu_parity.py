@@ -346,3 +346,39 @@ def test_lm_iterate_is_repeatable_and_matches_minimize_first_step():
     assert abs(a["cost_change"] - it1["cost_change"]) <= 1e-9 * abs(it1["cost_change"])
     assert abs(a["relative_decrease"] - it1["relative_decrease"]) <= 1e-9
     eng.close()
+
+
+# ------------------------------------------------------------- drop-in proof --
+def _dropin_lib():
+    import ctypes as C, os
+    base = os.path.join(os.path.dirname(of.REF_SO))
+    path = os.path.join(base, "libpba_dropin_v4.so" if of.REF_SO.endswith("_v4.so") else "libpba_dropin.so")
+    if not os.path.exists(path):
+        return None
+    lib = C.CDLL(path)
+    lib.pba_dropin_solve.argtypes = [C.POINTER(_ffi.pba_problem), C.POINTER(_ffi.pba_options), C.c_int,
+                                     C.POINTER(_ffi.pba_summary)]
+    return lib
+
+
+@pytest.mark.parametrize("model", ["pinhole", "ds", "kb4"])
+def test_reference_containers_drive_both_solvers(model):
+    """The reference's own Corners/Cameras/Landmarks/Calibration containers, built once, are
+    optimised (a) by the unmodified visnav::bundle_adjustment() and (b) through
+    include/visnav_b200/bundle_adjustment.h -> pba_solve -> CUDA: same argument list, same result."""
+    lib = _dropin_lib()
+    if lib is None:
+        pytest.skip("oracle/_ref/libpba_dropin.so not built on this box")
+    prob, _ = scene(pb.MODE_GEOMETRIC, model, n_kf=12, n_pts=600)
+    o = of.default_options()
+    a, b = prob.copy(), prob.copy()
+    s = pb.Summary()
+    pa, pbb = a.c, b.c
+    assert lib.pba_dropin_solve(C.byref(pa), C.byref(o), 0, None) == 0       # reference, Ceres on the CPU
+    assert lib.pba_dropin_solve(C.byref(pbb), C.byref(o), 1, C.byref(s.c)) == 0  # drop-in, CUDA engine
+    assert s.gpu_kernel_launches > 0
+    assert np.abs(a.poses - prob.poses).max() > 1e-4          # both actually moved
+    assert np.abs(b.poses - a.poses).max() < TOL_STATE
+    assert np.abs(b.inv_depth - a.inv_depth).max() < TOL_STATE
+    fixed = prob.pose_fixed.astype(bool)
+    assert np.array_equal(b.poses[fixed], prob.poses[fixed])
