@@ -245,14 +245,25 @@ def main():
     eng.set_stream(stream.cuda_stream)
 
     radius = 1e4
-    for _ in range(max(a.warmup, 3)):
+    clocks = ClockSampler(local_rank)
+    clocks.start()  # sampling spans warm-up + timed region (all under load)
+    t_w = time.time()
+    n_warm = max(a.warmup, 3)
+    for _ in range(n_warm):
         it = eng.lm_iterate(radius)
+    # keep the GPU loaded for >= 1 s before timing so nvidia-smi gets samples; every rank must
+    # run the same number of steps (each contains the all-reduce), so rank 0 decides
+    extra = torch.tensor([int(max(0.0, 1.0 - (time.time() - t_w)) / max((time.time() - t_w) / n_warm, 1e-4)) + 1],
+                         dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.broadcast(extra, 0)
+    for _ in range(int(extra.item())):
+        it = eng.lm_iterate(radius)
+    n_warm += int(extra.item())
     eng.reset_kernel_stats()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    clocks = ClockSampler(local_rank)
-    clocks.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
     for _ in range(a.steps):
@@ -337,7 +348,7 @@ def main():
     if rank == 0:
         line = {
             "metric": "lm_iterations_per_s", "value": value, "unit": "LM it/s", "n_gpus": world, "steps": a.steps,
-            "warmup": max(a.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "warmup": n_warm, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {
                 "workload": workload_name(a, prob.n_obs),
