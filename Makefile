@@ -9,7 +9,7 @@ CSRC    := $(PKG)/csrc
 NVCC    ?= /usr/local/cuda/bin/nvcc
 HOSTCXX ?= g++
 ARCH    := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS := -O3 -std=c++17 $(ARCH) -lineinfo -Xcompiler -fPIC,-O3,-fvisibility=hidden \
+NVFLAGS := -O3 -std=c++17 $(ARCH) -lineinfo -Xcompiler -fPIC,-O3,-fvisibility=hidden,-fopenmp \
            -Iinclude -I$(CSRC) --expt-relaxed-constexpr -Xptxas -v
 CU_SRCS := $(wildcard $(CSRC)/*.cu)
 CU_HDRS := $(wildcard $(CSRC)/*.h) $(wildcard $(CSRC)/*.cuh) include/pba.h
@@ -18,7 +18,7 @@ all: lib synth oracle ref
 
 lib: $(PKG)/libpba_b200.so
 $(PKG)/libpba_b200.so: $(CU_SRCS) $(CU_HDRS)
-	$(NVCC) $(NVFLAGS) -shared $(CU_SRCS) -o $@ -lcudart -ldl 2> $(PKG)/ptxas.log || (cat $(PKG)/ptxas.log; false)
+	$(NVCC) $(NVFLAGS) -shared $(CU_SRCS) -o $@ -lcudart -ldl -lgomp 2> $(PKG)/ptxas.log || (cat $(PKG)/ptxas.log; false)
 
 synth: $(PKG)/libpba_synth.so
 $(PKG)/libpba_synth.so: $(CSRC)/synth.cpp $(CSRC)/pba_math.h $(CSRC)/synth_scene.h include/pba.h include/pba_synth.h

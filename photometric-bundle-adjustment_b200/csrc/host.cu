@@ -183,13 +183,16 @@ pba_status validate(const pba_problem* p, const pba_options* o) {
     if (p->pose_calib[i] < 0 || p->pose_calib[i] >= p->n_calib) return PBA_ERR_INVALID_ARGUMENT;
   for (int i = 0; i < p->n_calib; ++i)
     if (p->calib_model[i] < 0 || p->calib_model[i] > PBA_CAM_EUCM) return PBA_ERR_UNSUPPORTED;  // from_data aborts (camera_models.h:469)
+  for (int l = 0; l < p->n_landmarks; ++l)  // offsets first: the parallel scan below indexes with them
+    if (p->lm_obs_ptr[l + 1] < p->lm_obs_ptr[l] || p->lm_obs_ptr[l + 1] > p->n_obs) return PBA_ERR_INVALID_ARGUMENT;
+  int bad = 0;
+#pragma omp parallel for schedule(static) reduction(| : bad)
   for (int l = 0; l < p->n_landmarks; ++l) {
-    if (p->lm_obs_ptr[l + 1] < p->lm_obs_ptr[l]) return PBA_ERR_INVALID_ARGUMENT;
-    if (p->lm_host[l] < 0 || p->lm_host[l] >= p->n_poses) return PBA_ERR_INVALID_ARGUMENT;
+    if (p->lm_host[l] < 0 || p->lm_host[l] >= p->n_poses) { bad |= 1; continue; }
     for (int64_t k = p->lm_obs_ptr[l]; k < p->lm_obs_ptr[l + 1]; ++k)
-      if (p->obs_target[k] < 0 || p->obs_target[k] >= p->n_poses || p->obs_target[k] == p->lm_host[l])
-        return PBA_ERR_INVALID_ARGUMENT;
+      if (p->obs_target[k] < 0 || p->obs_target[k] >= p->n_poses || p->obs_target[k] == p->lm_host[l]) bad |= 1;
   }
+  if (bad) return PBA_ERR_INVALID_ARGUMENT;
   if (p->mode == PBA_MODE_GEOMETRIC) {
     if (p->n_obs > 0 && !p->obs_uv) return PBA_ERR_INVALID_ARGUMENT;
   } else {
@@ -210,6 +213,14 @@ pba_status create_impl(const pba_problem* p, const pba_options* o, int rank, int
   if (o->device < 0 || o->device >= ndev) return PBA_ERR_INVALID_ARGUMENT;
   PBA_CUDA_OK(cudaSetDevice(o->device));
 
+  const bool timing = getenv("PBA_TIMING") != nullptr;
+  double t_mark = wall();
+  auto mark = [&](const char* what) {
+    if (!timing) return;
+    const double now = wall();
+    fprintf(stderr, "[pba_create] %-28s %8.1f ms\n", what, 1e3 * (now - t_mark));
+    t_mark = now;
+  };
   std::unique_ptr<Handle> hh(new Handle);
   Handle* h = hh.get();
   h->opt = *o;
@@ -227,6 +238,7 @@ pba_status create_impl(const pba_problem* p, const pba_options* o, int rank, int
   for (int i = 1; i < p->n_calib; ++i)
     if (p->calib_model[i] != p->calib_model[0]) h->uniform_model = -1;
 
+  mark("validate + device init");
   // ---- global layout: which parameter blocks survive Ceres' reduced program ----
   std::vector<uint8_t> used(p->n_poses, 0), is_target(p->n_poses, 0);
   for (int l = 0; l < p->n_landmarks; ++l) {
@@ -244,6 +256,7 @@ pba_status create_impl(const pba_problem* p, const pba_options* o, int rank, int
   z.dim = z.n_slots * cd;
   const std::vector<int>& slot = h->slot;
 
+  mark("active layout");
   // ---- global RCS block pattern: all camera pairs co-observing a landmark
   //      (schur_complement_solver.cc:261-297); identical on every rank ----
   std::vector<std::vector<int>> adj(z.n_slots);
@@ -284,6 +297,7 @@ pba_status create_impl(const pba_problem* p, const pba_options* o, int rank, int
     return adj_ptr[a] + (it - adj[a].begin());
   };
 
+  mark("RCS block pattern");
   // ---- local shard: landmarks ordered by host, observations by (host,target) edge ----
   std::vector<int> bounds;
   partition_landmarks(p->lm_obs_ptr, p->n_landmarks, world, bounds);
@@ -298,52 +312,128 @@ pba_status create_impl(const pba_problem* p, const pba_options* o, int rank, int
 
   h->lm_order.resize(n_lm);
   std::iota(h->lm_order.begin(), h->lm_order.end(), 0);
-  std::stable_sort(h->lm_order.begin(), h->lm_order.end(),
-                   [&](int a, int b) { return p->lm_host[lm_lo + a] < p->lm_host[lm_lo + b]; });
-
-  // lm-major arrays in internal landmark order
+  {
+    bool sorted = true;
+    for (int i = 1; i < n_lm && sorted; ++i) sorted = p->lm_host[lm_lo + i - 1] <= p->lm_host[lm_lo + i];
+    if (!sorted)
+      std::stable_sort(h->lm_order.begin(), h->lm_order.end(),
+                       [&](int a, int b) { return p->lm_host[lm_lo + a] < p->lm_host[lm_lo + b]; });
+  }
+  // lm-major observation index space k (internal landmark order); a host group's
+  // observations are contiguous in k, and the edge order only permutes inside a group
   std::vector<int64_t> lm_ptr(n_lm + 1, 0);
-  std::vector<int> k_lm(n), k_h(n), k_t(n);
-  std::vector<int64_t> k_orig(n);
+  for (int li = 0; li < n_lm; ++li) {
+    const int l = lm_lo + h->lm_order[li];
+    lm_ptr[li + 1] = lm_ptr[li] + (p->lm_obs_ptr[l + 1] - p->lm_obs_ptr[l]);
+  }
+  std::vector<int> grp_lm_ptr;  // host groups = runs of equal host
+  for (int li = 0; li < n_lm; ++li)
+    if (li == 0 || p->lm_host[lm_lo + h->lm_order[li]] != p->lm_host[lm_lo + h->lm_order[li - 1]]) grp_lm_ptr.push_back(li);
+  grp_lm_ptr.push_back(n_lm);
+  z.n_groups = int(grp_lm_ptr.size()) - 1;
+  const int G = z.n_groups;
+
+  // pass A (parallel over groups): distinct targets of every group, ascending, with counts
+  std::vector<std::vector<std::pair<int, int64_t>>> grp_tg(G);
+#pragma omp parallel
   {
-    int64_t k = 0;
-    for (int li = 0; li < n_lm; ++li) {
-      const int l = lm_lo + h->lm_order[li];
-      for (int64_t q = p->lm_obs_ptr[l]; q < p->lm_obs_ptr[l + 1]; ++q, ++k) {
-        k_lm[k] = li; k_h[k] = p->lm_host[l]; k_t[k] = p->obs_target[q]; k_orig[k] = q - obs_lo;
+    std::vector<int64_t> cnt(p->n_poses, 0);
+    std::vector<int> touched;
+#pragma omp for schedule(dynamic, 16)
+    for (int g = 0; g < G; ++g) {
+      touched.clear();
+      for (int li = grp_lm_ptr[g]; li < grp_lm_ptr[g + 1]; ++li) {
+        const int l = lm_lo + h->lm_order[li];
+        for (int64_t q = p->lm_obs_ptr[l]; q < p->lm_obs_ptr[l + 1]; ++q) {
+          const int t = p->obs_target[q];
+          if (cnt[t]++ == 0) touched.push_back(t);
+        }
       }
-      lm_ptr[li + 1] = k;
+      std::sort(touched.begin(), touched.end());
+      grp_tg[g].reserve(touched.size());
+      for (int t : touched) { grp_tg[g].emplace_back(t, cnt[t]); cnt[t] = 0; }
     }
   }
-  // stable LSD counting sort by (host, target)
-  std::vector<int64_t> perm(n), tmp(n);
-  {
-    std::vector<int64_t> cnt(p->n_poses + 1, 0);
-    for (int64_t k = 0; k < n; ++k) ++cnt[k_t[k] + 1];
-    for (int i = 0; i < p->n_poses; ++i) cnt[i + 1] += cnt[i];
-    for (int64_t k = 0; k < n; ++k) tmp[cnt[k_t[k]]++] = k;
-    std::fill(cnt.begin(), cnt.end(), 0);
-    for (int64_t k = 0; k < n; ++k) ++cnt[k_h[k] + 1];
-    for (int i = 0; i < p->n_poses; ++i) cnt[i + 1] += cnt[i];
-    for (int64_t i = 0; i < n; ++i) { const int64_t k = tmp[i]; perm[cnt[k_h[k]]++] = k; }
-  }
-  std::vector<int> obs_lm(n), obs_edge(n);
-  std::vector<int64_t> lm_pos(n);
-  std::vector<int> edge_h, edge_t;
+  // edges (serial prefix): edge e of group g = (host_g, target), observations contiguous
+  std::vector<int> edge_h, edge_t, grp_edge0(G + 1, 0);
   std::vector<int64_t> edge_ptr;
-  h->obs_order.resize(n);
-  for (int64_t i = 0; i < n; ++i) {
-    const int64_t k = perm[i];
-    if (i == 0 || k_h[k] != edge_h.back() || k_t[k] != edge_t.back()) {
-      edge_h.push_back(k_h[k]); edge_t.push_back(k_t[k]); edge_ptr.push_back(i);
+  for (int g = 0; g < G; ++g) {
+    const int host = p->lm_host[lm_lo + h->lm_order[grp_lm_ptr[g]]];
+    int64_t pos = lm_ptr[grp_lm_ptr[g]];
+    grp_edge0[g] = int(edge_h.size());
+    for (auto& tc : grp_tg[g]) {
+      edge_h.push_back(host); edge_t.push_back(tc.first); edge_ptr.push_back(pos);
+      pos += tc.second;
     }
-    obs_lm[i] = k_lm[k];
-    obs_edge[i] = int(edge_h.size()) - 1;
-    lm_pos[k] = i;
-    h->obs_order[i] = k_orig[k];
   }
+  grp_edge0[G] = int(edge_h.size());
   edge_ptr.push_back(n);
   z.n_edges = int(edge_h.size());
+
+  // host-group camera lists (slots, ascending) and buffer offsets (serial prefix, small)
+  std::vector<int> grp_cam_ptr(1, 0), grp_cams;
+  std::vector<int64_t> grp_w_off(G), grp_part_off(G);
+  int64_t w_total = 0, part_total = 0;
+  for (int g = 0; g < G; ++g) {
+    const int host = p->lm_host[lm_lo + h->lm_order[grp_lm_ptr[g]]];
+    const size_t c0 = grp_cams.size();
+    if (slot[host] >= 0) grp_cams.push_back(slot[host]);
+    for (auto& tc : grp_tg[g]) if (slot[tc.first] >= 0) grp_cams.push_back(slot[tc.first]);
+    std::sort(grp_cams.begin() + c0, grp_cams.end());
+    grp_cams.erase(std::unique(grp_cams.begin() + c0, grp_cams.end()), grp_cams.end());
+    const int c = int(grp_cams.size() - c0);
+    grp_cam_ptr.push_back(int(grp_cams.size()));
+    const int stride = 8 * (c + 1);
+    h->max_w_stride = std::max(h->max_w_stride, stride);
+    grp_w_off[g] = w_total;
+    grp_part_off[g] = part_total;
+    w_total += int64_t(grp_lm_ptr[g + 1] - grp_lm_ptr[g]) * stride;
+    part_total += int64_t(c) * (c + 1) / 2 * cd * cd + int64_t(c) * cd;
+  }
+  h->schur_tile_l = schur_tile_l(h->max_w_stride);
+
+  // pass B (parallel over groups): place every observation at its edge-order position
+  std::vector<int> obs_lm(n), obs_edge(n), obs_col(n, -1), lm_group(n_lm), lm_hostcol(n_lm, -1), lm_w_stride(n_lm);
+  std::vector<int64_t> lm_pos(n), lm_w_off(n_lm);
+  h->obs_order.resize(n);
+#pragma omp parallel
+  {
+    std::vector<int64_t> cursor(p->n_poses, 0);
+    std::vector<int> eidx(p->n_poses, 0), colt(p->n_poses, -1);
+#pragma omp for schedule(dynamic, 16)
+    for (int g = 0; g < G; ++g) {
+      const int li0 = grp_lm_ptr[g], li1 = grp_lm_ptr[g + 1];
+      const int host = p->lm_host[lm_lo + h->lm_order[li0]];
+      const int c0 = grp_cam_ptr[g], c = grp_cam_ptr[g + 1] - c0;
+      const int stride = 8 * (c + 1);
+      int64_t pos = lm_ptr[li0];
+      int e = grp_edge0[g];
+      for (auto& tc : grp_tg[g]) {
+        cursor[tc.first] = pos; eidx[tc.first] = e++;
+        pos += tc.second;
+        const int sl = slot[tc.first];
+        colt[tc.first] = sl >= 0 ? int(std::lower_bound(grp_cams.begin() + c0, grp_cams.begin() + c0 + c, sl) - (grp_cams.begin() + c0)) : -1;
+      }
+      const int hcol = slot[host] >= 0 ? int(std::lower_bound(grp_cams.begin() + c0, grp_cams.begin() + c0 + c, slot[host]) - (grp_cams.begin() + c0)) : -1;
+      for (int li = li0; li < li1; ++li) {
+        const int l = lm_lo + h->lm_order[li];
+        lm_group[li] = g;
+        lm_hostcol[li] = hcol;
+        lm_w_off[li] = grp_w_off[g] + int64_t(li - li0) * stride;
+        lm_w_stride[li] = stride;
+        int64_t k = lm_ptr[li];
+        for (int64_t q = p->lm_obs_ptr[l]; q < p->lm_obs_ptr[l + 1]; ++q, ++k) {
+          const int t = p->obs_target[q];
+          const int64_t at = cursor[t]++;
+          obs_lm[at] = li; obs_edge[at] = eidx[t]; obs_col[at] = colt[t];
+          lm_pos[k] = at;
+          h->obs_order[at] = q - obs_lo;
+        }
+      }
+    }
+  }
+  grp_tg.clear();
+  mark("edge ordering + host groups");
 
   // edge chunks (one CTA each in k_edge_gram)
   std::vector<int> chunk_edge;
@@ -353,52 +443,7 @@ pba_status create_impl(const pba_problem* p, const pba_options* o, int rank, int
       chunk_edge.push_back(e); chunk_begin.push_back(b); chunk_end.push_back(std::min<int64_t>(b + kChunkObs, edge_ptr[e + 1]));
     }
   z.n_chunks = int(chunk_edge.size());
-
-  // host groups and their camera lists
-  std::vector<int> grp_lm_ptr, grp_cam_ptr(1, 0), grp_cams, lm_group(n_lm), lm_hostcol(n_lm, -1), obs_col(n, -1);
-  std::vector<int64_t> grp_w_off, grp_part_off, lm_w_off(n_lm);
-  std::vector<int> lm_w_stride(n_lm);
-  int64_t w_total = 0, part_total = 0;
-  {
-    std::vector<int> col_of(z.n_slots, -1), cams;
-    int li = 0;
-    while (li < n_lm) {
-      const int host = p->lm_host[lm_lo + h->lm_order[li]];
-      int lj = li;
-      while (lj < n_lm && p->lm_host[lm_lo + h->lm_order[lj]] == host) ++lj;
-      const int g = int(grp_lm_ptr.size());
-      grp_lm_ptr.push_back(li);
-      cams.clear();
-      if (slot[host] >= 0) cams.push_back(slot[host]);
-      for (int64_t k = lm_ptr[li]; k < lm_ptr[lj]; ++k) if (slot[k_t[k]] >= 0) cams.push_back(slot[k_t[k]]);
-      std::sort(cams.begin(), cams.end());
-      cams.erase(std::unique(cams.begin(), cams.end()), cams.end());
-      const int c = int(cams.size());
-      for (int j = 0; j < c; ++j) col_of[cams[j]] = j;
-      const int stride = 8 * (c + 1);
-      h->max_w_stride = std::max(h->max_w_stride, stride);
-      grp_w_off.push_back(w_total);
-      grp_part_off.push_back(part_total);
-      for (int l = li; l < lj; ++l) {
-        lm_group[l] = g;
-        lm_hostcol[l] = slot[host] >= 0 ? col_of[slot[host]] : -1;
-        lm_w_off[l] = w_total + int64_t(l - li) * stride;
-        lm_w_stride[l] = stride;
-        for (int64_t k = lm_ptr[l]; k < lm_ptr[l + 1]; ++k)
-          obs_col[lm_pos[k]] = slot[k_t[k]] >= 0 ? col_of[slot[k_t[k]]] : -1;
-      }
-      w_total += int64_t(lj - li) * stride;
-      part_total += int64_t(c) * (c + 1) / 2 * cd * cd + int64_t(c) * cd;
-      grp_cams.insert(grp_cams.end(), cams.begin(), cams.end());
-      grp_cam_ptr.push_back(int(grp_cams.size()));
-      for (int j = 0; j < c; ++j) col_of[cams[j]] = -1;
-      li = lj;
-    }
-    grp_lm_ptr.push_back(n_lm);
-  }
-  z.n_groups = int(grp_w_off.size());
-  h->schur_tile_l = schur_tile_l(h->max_w_stride);
-
+  mark("chunks");
   // per-block source lists for the RCS reduction (static)
   const int dir_stride = 3 * cd * cd + 2 * cd;
   std::vector<int64_t> dir_ptr(z.n_blocks + 1, 0), sch_ptr(z.n_blocks + 1, 0), vdir_ptr(z.n_slots + 1, 0), vsch_ptr(z.n_slots + 1, 0);
@@ -450,6 +495,7 @@ pba_status create_impl(const pba_problem* p, const pba_options* o, int rank, int
     }
   }
 
+  mark("source lists + row CSR");
   // ---- upload static data ----
   cudaStream_t s = h->stream;
   auto up = [&](auto& buf, const auto& vec) { return buf.upload(vec, s); };
@@ -484,6 +530,7 @@ pba_status create_impl(const pba_problem* p, const pba_options* o, int rank, int
   {
     std::vector<int> lm_host(n_lm);
     std::vector<double> lm_uv(size_t(2) * n_lm), rho(n_lm);
+#pragma omp parallel for schedule(static)
     for (int li = 0; li < n_lm; ++li) {
       const int l = lm_lo + h->lm_order[li];
       lm_host[li] = p->lm_host[l];
@@ -493,6 +540,7 @@ pba_status create_impl(const pba_problem* p, const pba_options* o, int rank, int
     PBA_CUDA_OK(up(h->lm_host, lm_host)); PBA_CUDA_OK(up(h->lm_uv, lm_uv)); PBA_CUDA_OK(up(h->rho, rho));
     if (!photo) {
       std::vector<double> uv(size_t(2) * n);
+#pragma omp parallel for schedule(static)
       for (int64_t i = 0; i < n; ++i) {
         const int64_t q = obs_lo + h->obs_order[i];
         uv[i] = p->obs_uv[2 * q]; uv[n + i] = p->obs_uv[2 * q + 1];
@@ -509,6 +557,7 @@ pba_status create_impl(const pba_problem* p, const pba_options* o, int rank, int
     PBA_CUDA_OK(up(h->affine, aff));
     PBA_CUDA_OK(cudaStreamSynchronize(s));
   }
+  mark("upload structure");
   if (photo) {
     // keyframes go to the device as 8-bit rows (staged in batches) and are expanded
     // there into the quad layout the evaluation kernels gather from
@@ -533,6 +582,7 @@ pba_status create_impl(const pba_problem* p, const pba_options* o, int rank, int
     PBA_CUDA_OK(cudaStreamSynchronize(s));
   }
 
+  mark("upload images + quads");
   // ---- work buffers ----
   const size_t nn = size_t(n);
   PBA_CUDA_OK(h->poses_c.alloc(size_t(7) * p->n_poses)); PBA_CUDA_OK(h->poses_best.alloc(size_t(7) * p->n_poses));
@@ -564,9 +614,11 @@ pba_status create_impl(const pba_problem* p, const pba_options* o, int rank, int
     // k_schur_syrk needs > 48 KB of dynamic shared memory for wide groups
     schur_set_smem((size_t(h->schur_tile_l) * h->max_w_stride + h->schur_tile_l) * sizeof(double));
   }
+  mark("allocate work buffers");
   st = launch_init_landmarks(h);
   if (st != PBA_OK) return st;
   PBA_CUDA_OK(cudaStreamSynchronize(s));
+  mark("init landmarks");
   *out = hh.release();
   return PBA_OK;
 }
