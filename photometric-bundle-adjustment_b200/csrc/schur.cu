@@ -77,18 +77,21 @@ __global__ void __launch_bounds__(96) k_edge_gram(int64_t ld, const int* __restr
     const int64_t base = o0 + int64_t(st % n_t) * TOBS;
     const int cnt = int(o1 - base < TOBS ? o1 - base : TOBS);
     double* Mt = gram_sm + buf * 16 * RS;
-    // items: (column cc, 32-obs slice j); warp takes every third
-    for (int item = warp; item < P * (TOBS / 32); item += 3) {
-      const int cc = item >> 3, j = item & 7;
+    // warp w copies whole columns cc = w, w+3, ...: one address computation per column,
+    // then 8 x (32 observations) with immediate offsets (per-item address arithmetic was
+    // 2/3 of the kernel's instructions: 6.8 ms -> 4.6 ms at 18M observations)
+    const double* src = JR + (int64_t(k) * P + warp) * ld + base + lane;
+    for (int cc = warp; cc < P; cc += 3, src += 3 * ld) {
       const int c = cc < C ? cc : 15;
-      const int o = j * 32 + lane;
-      double* dst = Mt + c * RS + o;
-      if (o < cnt) {
-        const double* src = JR + (int64_t(k) * P + cc) * ld + base + o;
-        const unsigned sa = unsigned(__cvta_generic_to_shared(dst));
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(src));
-      } else {
-        *dst = 0.0;
+      double* dst = Mt + c * RS + lane;
+      const unsigned sa = unsigned(__cvta_generic_to_shared(dst));
+#pragma unroll
+      for (int j = 0; j < TOBS / 32; ++j) {
+        if (j * 32 + lane < cnt) {
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa + unsigned(j * 256)), "l"(src + j * 32));
+        } else {
+          dst[j * 32] = 0.0;
+        }
       }
     }
     asm volatile("cp.async.commit_group;\n" ::);
