@@ -22,6 +22,8 @@
 // The sequential band factorisation in solve.cu takes 8.3 ms for 2,000
 // keyframes on one SM; it also would not shrink when the landmarks are sharded
 // over GPUs (every rank solves the same RCS), capping multi-GPU scaling.
+#include <stdio.h>
+
 #include "launch.h"
 #include "pba_internal.h"
 
@@ -30,6 +32,12 @@ namespace pba {
 namespace {
 
 constexpr int kBcrThreads = 256;
+
+// shared-memory leading dimensions.  The product kernel (k_bcr_reduce) wants 16-byte aligned
+// rows (even) covering the 4-wide tiles; the factorisation kernels walk columns with one thread
+// per row, which is conflict-free only for an odd stride.
+__host__ __device__ inline int bcr_ld(int M) { return ((M + 3) / 4) * 4 + 2; }
+__host__ __device__ inline int bcr_ld_odd(int M) { return M + 1 + (M & 1); }
 
 // ---- CTA-level dense kernels on shared-memory matrices, blocked by NB = cd ----
 // All matrices are row-major with leading dimension ld.  The only serial piece is
@@ -176,22 +184,24 @@ __device__ void cta_trsm_lower(const double* L, int ld, const double* Dinv, doub
       for (int q = 0; q < NB; ++q) W[(j0 + q) * ldw + c] = o[q];
     }
     __syncthreads();
-    // rows below: W[i][c] -= L[i][j0..] . W[j0..][c]; items = (4-row strip, column)
-    const int n0 = j0 + NB, n = M - n0;
-    const int strips = (n + 3) / 4;
-    for (int t = tid; t < strips * ncols; t += kBcrThreads) {
-      const int st = t / ncols, c = t % ncols;
+    // rows below: W[i][c] -= L[i][j0..] . W[j0..][c].  Thread (c = tid % 128, g = tid / 128) owns
+    // column c and every other 4-row strip; the 8 pivot-row values stay in registers.
+    const int n0 = j0 + NB;
+    const int c = tid & 127, g = tid >> 7;
+    for (int cc = c; cc < ncols; cc += 128) {
       double w[NB];
 #pragma unroll
-      for (int q = 0; q < NB; ++q) w[q] = W[(j0 + q) * ldw + c];
+      for (int q = 0; q < NB; ++q) w[q] = W[(j0 + q) * ldw + cc];
+      for (int i0 = n0 + 4 * g; i0 < M; i0 += 8) {
 #pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        const int i = n0 + 4 * st + a;
-        if (i < M) {
-          double s = 0.0;
+        for (int a = 0; a < 4; ++a) {
+          const int i = i0 + a;
+          if (i < M) {
+            double s = 0.0;
 #pragma unroll
-          for (int q = 0; q < NB; ++q) s += L[i * ld + j0 + q] * w[q];
-          W[i * ldw + c] -= s;
+            for (int q = 0; q < NB; ++q) s += L[i * ld + j0 + q] * w[q];
+            W[i * ldw + cc] -= s;
+          }
         }
       }
     }
@@ -227,26 +237,33 @@ __device__ void cta_solve_lt(const double* L, int ld, const double* Dinv, double
   }
 }
 
-// out[r][c] = base[r][c] - sum_k X[k][r] Y[k][c]   (X, Y: M x M in shared memory, out/base global)
+// out[r][c] = base[r][c] - sum_k X[k][r] Y[k][c]   (X, Y: M x M in shared memory with an even
+// leading dimension -> 16-byte LDS; out/base global).  Only tile rows [tr0, tr1) are computed, so
+// several CTAs can split one product.  lower_only: X == Y, compute c <= r and mirror.
 __device__ void cta_xty_sub(const double* X, const double* Y, int ld, int M, double* __restrict__ out,
-                            const double* __restrict__ base, bool lower_only) {
+                            const double* __restrict__ base, bool lower_only, int tr0, int tr1) {
   const int T = (M + 3) / 4;
-  for (int t = threadIdx.x; t < T * T; t += kBcrThreads) {
-    const int tr = t / T, tc = t % T;
+  const int ntile = (tr1 - tr0) * T;
+  for (int t = threadIdx.x; t < ntile; t += kBcrThreads) {
+    const int tr = tr0 + t / T, tc = t % T;
     if (lower_only && tc > tr) continue;
     double acc[4][4];
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
       for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
-    const bool full = 4 * tr + 3 < M && 4 * tc + 3 < M;
+    // M is a multiple of cd (6 or 8); pad columns beyond M read finite junk only when M % 4 != 0,
+    // and those accumulators are never stored
+    const double* xp = X + 4 * tr;
+    const double* yp = Y + 4 * tc;
+#pragma unroll 2
     for (int k = 0; k < M; ++k) {
-      double xv[4], yv[4];
-#pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        xv[a] = (full || 4 * tr + a < M) ? X[k * ld + 4 * tr + a] : 0.0;
-        yv[a] = (full || 4 * tc + a < M) ? Y[k * ld + 4 * tc + a] : 0.0;
-      }
+      const double2 x0 = *reinterpret_cast<const double2*>(xp + k * ld);
+      const double2 x1 = *reinterpret_cast<const double2*>(xp + k * ld + 2);
+      const double2 y0 = *reinterpret_cast<const double2*>(yp + k * ld);
+      const double2 y1 = *reinterpret_cast<const double2*>(yp + k * ld + 2);
+      const double xv[4] = {x0.x, x0.y, x1.x, x1.y};
+      const double yv[4] = {y0.x, y0.y, y1.x, y1.y};
 #pragma unroll
       for (int a = 0; a < 4; ++a)
 #pragma unroll
@@ -266,11 +283,29 @@ __device__ void cta_xty_sub(const double* X, const double* Y, int ld, int M, dou
   }
 }
 
+// global (M x M, dense) -> shared (leading dimension ld), optionally transposed, with cp.async
+// (LDGSTS): every copy is in flight at once; call cta_load_wait() before reading.
 __device__ __forceinline__ void cta_load(double* dst, int ld, const double* __restrict__ src, int M, bool transpose) {
-  for (int i = threadIdx.x; i < M * M; i += kBcrThreads) {
-    const int r = i / M, c = i % M;
-    if (!transpose) dst[r * ld + c] = src[i];
-    else dst[c * ld + r] = src[i];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned d0 = unsigned(__cvta_generic_to_shared(dst));
+  for (int r = warp; r < M; r += kBcrThreads / 32) {
+    const double* s = src + int64_t(r) * M;
+    for (int c = lane; c < M; c += 32) {
+      const unsigned da = d0 + unsigned((transpose ? c * ld + r : r * ld + c) * 8);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(da), "l"(s + c));
+    }
+  }
+}
+__device__ __forceinline__ void cta_load_wait() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::);
+  __syncthreads();
+}
+__device__ __forceinline__ void cta_store(double* __restrict__ dst, const double* src, int ld, int M, bool lower_only) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int r = warp; r < M; r += kBcrThreads / 32) {
+    double* d = dst + int64_t(r) * M;
+#pragma unroll 4
+    for (int c = lane; c < M; c += 32) d[c] = (!lower_only || c <= r) ? src[r * ld + c] : 0.0;
   }
 }
 
@@ -318,48 +353,54 @@ __global__ void k_bcr_build(int cd, int m, int M, int64_t n_blocks, int n_slots,
   }
 }
 
-// Eliminate the odd super blocks of a level (one CTA each).
+// Eliminate the odd super blocks of a level.  TWO CTAs per block (blockIdx.y), each factoring
+// A_p itself (redundant, but the two triangular solves are the longer half of the work):
+//   y = 0:  L (stored), U = L^-1 B[p-1], y = L^-1 b[p]
+//   y = 1:  V = L^-1 B[p]^T  (only when block p + 1 exists)
 template <int NB>
 __global__ void __launch_bounds__(kBcrThreads) k_bcr_eliminate(int M, BcrLevel lv, int* __restrict__ fail) {
-  extern __shared__ double sm[];
-  const int ld = M + 1;                 // odd stride: conflict-free column walks
+  extern __shared__ __align__(16) double sm[];
+  const int ld = bcr_ld_odd(M);
   double* Ls = sm;                      // [M][ld]
   double* Ws = sm + M * ld;             // [M][ld]  right-hand sides (column M = y)
   double* Dinv = Ws + M * ld;           // [M/NB][NB*NB]
   const int q = blockIdx.x, p = 2 * q + 1;
+  const int part = blockIdx.y;
   const int tid = threadIdx.x;
+  if (part == 1 && p + 1 >= lv.n) return;
   cta_load(Ls, ld, lv.A + int64_t(p) * M * M, M, false);
-  // U = L^-1 B[p-1],  y = L^-1 b[p]: stage the right-hand sides while the factorisation runs
-  cta_load(Ws, ld, lv.B + int64_t(p - 1) * M * M, M, false);
-  for (int i = tid; i < M; i += kBcrThreads) Ws[i * ld + M] = lv.b[int64_t(p) * M + i];
-  __syncthreads();
-  cta_cholesky<NB>(Ls, M, ld, Dinv, fail);
-  double* Lg = lv.L + int64_t(q) * M * M;
-  for (int i = tid; i < M * M; i += kBcrThreads) Lg[i] = (i % M <= i / M) ? Ls[(i / M) * ld + i % M] : 0.0;
-  for (int i = tid; i < M * NB; i += kBcrThreads) lv.D[int64_t(q) * M * NB + i] = Dinv[i];
-  cta_trsm_lower<NB>(Ls, ld, Dinv, Ws, ld, M, M + 1);
-  double* Ug = lv.U + int64_t(q) * M * M;
-  for (int i = tid; i < M * M; i += kBcrThreads) Ug[i] = Ws[(i / M) * ld + i % M];
-  for (int i = tid; i < M; i += kBcrThreads) lv.y[int64_t(q) * M + i] = Ws[i * ld + M];
-  __syncthreads();
-  // V = L^-1 B[p]^T (when block p+1 exists)
-  if (p + 1 < lv.n) {
+  // the right-hand sides stream in while the factorisation runs
+  if (part == 0) {
+    cta_load(Ws, ld, lv.B + int64_t(p - 1) * M * M, M, false);
+    for (int i = tid; i < M; i += kBcrThreads) Ws[i * ld + M] = lv.b[int64_t(p) * M + i];
+  } else {
     cta_load(Ws, ld, lv.B + int64_t(p) * M * M, M, true);
-    __syncthreads();
+  }
+  cta_load_wait();
+  cta_cholesky<NB>(Ls, M, ld, Dinv, fail);
+  if (part == 0) {
+    cta_store(lv.L + int64_t(q) * M * M, Ls, ld, M, true);
+    for (int i = tid; i < M * NB; i += kBcrThreads) lv.D[int64_t(q) * M * NB + i] = Dinv[i];
+    cta_trsm_lower<NB>(Ls, ld, Dinv, Ws, ld, M, M + 1);
+    cta_store(lv.U + int64_t(q) * M * M, Ws, ld, M, false);
+    for (int i = tid; i < M; i += kBcrThreads) lv.y[int64_t(q) * M + i] = Ws[i * ld + M];
+  } else {
     cta_trsm_lower<NB>(Ls, ld, Dinv, Ws, ld, M, M);
-    double* Vg = lv.V + int64_t(q) * M * M;
-    for (int i = tid; i < M * M; i += kBcrThreads) Vg[i] = Ws[(i / M) * ld + i % M];
+    cta_store(lv.V + int64_t(q) * M * M, Ws, ld, M, false);
   }
 }
 
-// Even super blocks of a level -> next level (one CTA each):
-//   A' = A_e - V_{e-1}^T V_{e-1} - U_{e+1}^T U_{e+1};  b' likewise;  B' = -V_o^T U_o.
+// Even super blocks of a level -> next level.  THREE CTAs per block (blockIdx.y) so the
+// sparse upper levels still fill SMs:
+//   y = 0, 1:  A' = A_e - V_{e-1}^T V_{e-1} - U_{e+1}^T U_{e+1}  (tile rows split in halves; y = 0 also b')
+//   y = 2:     B' = -V_o^T U_o  (coupling across the eliminated block o = e + 1)
 __global__ void __launch_bounds__(kBcrThreads) k_bcr_reduce(int M, BcrLevel lv, BcrLevel nx) {
-  extern __shared__ double sm[];
-  const int ld = M + 1;
+  extern __shared__ __align__(16) double sm[];
+  const int ld = bcr_ld(M);
   double* Xs = sm;            // [M][ld]
   double* Ys = sm + M * ld;   // [M][ld]
   const int pe = blockIdx.x;  // position at the next level
+  const int part = blockIdx.y;
   const int p = 2 * pe;       // even position at this level
   const int tid = threadIdx.x;
   double* An = nx.A + int64_t(pe) * M * M;
@@ -368,36 +409,77 @@ __global__ void __launch_bounds__(kBcrThreads) k_bcr_reduce(int M, BcrLevel lv, 
   const double* Vl = has_l ? lv.V + int64_t((p - 1) / 2) * M * M : nullptr;
   const double* Ur = has_r ? lv.U + int64_t((p + 1) / 2) * M * M : nullptr;
   const double* Vr = has_r ? lv.V + int64_t((p + 1) / 2) * M * M : nullptr;
-  // b' (vector work first, straight from global)
-  for (int i = tid; i < M; i += kBcrThreads) {
-    double s = lv.b[int64_t(p) * M + i];
-    if (has_l) {
-      const double* y = lv.y + int64_t((p - 1) / 2) * M;
-      for (int k = 0; k < M; ++k) s -= Vl[int64_t(k) * M + i] * y[k];
+  const int T = (M + 3) / 4;
+  if (part == 2) {
+    if (p + 2 < lv.n) {
+      cta_load(Xs, ld, Ur, M, false);
+      cta_load(Ys, ld, Vr, M, false);
+      cta_load_wait();
+      cta_xty_sub(Ys, Xs, ld, M, nx.B + int64_t(pe) * M * M, nullptr, false, 0, T);
     }
-    if (has_r) {
-      const double* y = lv.y + int64_t((p + 1) / 2) * M;
-      for (int k = 0; k < M; ++k) s -= Ur[int64_t(k) * M + i] * y[k];
+    return;
+  }
+  if (part == 0) {
+    // b' (vector work, straight from global)
+    for (int i = tid; i < M; i += kBcrThreads) {
+      double s = lv.b[int64_t(p) * M + i];
+      if (has_l) {
+        const double* y = lv.y + int64_t((p - 1) / 2) * M;
+        for (int k = 0; k < M; ++k) s -= Vl[int64_t(k) * M + i] * y[k];
+      }
+      if (has_r) {
+        const double* y = lv.y + int64_t((p + 1) / 2) * M;
+        for (int k = 0; k < M; ++k) s -= Ur[int64_t(k) * M + i] * y[k];
+      }
+      nx.b[int64_t(pe) * M + i] = s;
     }
-    nx.b[int64_t(pe) * M + i] = s;
   }
-  // A' = A - Vl^T Vl
-  if (has_l) {
-    cta_load(Xs, ld, Vl, M, false);
-    __syncthreads();
-    cta_xty_sub(Xs, Xs, ld, M, An, Ae, true);
-  } else {
-    for (int i = tid; i < M * M; i += kBcrThreads) An[i] = Ae[i];
-  }
-  __syncthreads();
-  if (has_r) {
-    // A' -= Ur^T Ur ;  B'[pe] = A'[p+2][p] = -Vr^T Ur (needs block p + 2)
-    cta_load(Xs, ld, Ur, M, false);
-    const bool need_b = p + 2 < lv.n;
-    if (need_b) cta_load(Ys, ld, Vr, M, false);
-    __syncthreads();
-    cta_xty_sub(Xs, Xs, ld, M, An, An, true);
-    if (need_b) cta_xty_sub(Ys, Xs, ld, M, nx.B + int64_t(pe) * M * M, nullptr, false);
+  // the symmetric products are computed on the lower triangle: balance the two halves by area
+  const int split = int(0.7071 * T + 0.5);
+  const int tr0 = part == 0 ? 0 : split, tr1 = part == 0 ? split : T;
+  if (has_l) cta_load(Xs, ld, Vl, M, false);
+  if (has_r) cta_load(Ys, ld, Ur, M, false);
+  cta_load_wait();
+  // rows [4 tr0, 4 tr1) of the lower triangle (+ their mirror images); the two row ranges of
+  // the two CTAs write disjoint entries, and each entry is final after one pass
+  for (int t = tid; t < (tr1 - tr0) * T; t += kBcrThreads) {
+    const int tr = tr0 + t / T, tc = t % T;
+    if (tc > tr) continue;
+    double acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+    for (int pass = 0; pass < 2; ++pass) {
+      if (pass == 0 ? !has_l : !has_r) continue;
+      const double* Z = pass == 0 ? Xs : Ys;
+      const double* xp = Z + 4 * tr;
+      const double* yp = Z + 4 * tc;
+#pragma unroll 2
+      for (int k = 0; k < M; ++k) {
+        const double2 x0 = *reinterpret_cast<const double2*>(xp + k * ld);
+        const double2 x1 = *reinterpret_cast<const double2*>(xp + k * ld + 2);
+        const double2 y0 = *reinterpret_cast<const double2*>(yp + k * ld);
+        const double2 y1 = *reinterpret_cast<const double2*>(yp + k * ld + 2);
+        const double xv[4] = {x0.x, x0.y, x1.x, x1.y};
+        const double yv[4] = {y0.x, y0.y, y1.x, y1.y};
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) acc[a][b] += xv[a] * yv[b];
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int r = 4 * tr + a, c = 4 * tc + b;
+        if (r < M && c < M) {
+          const double v = Ae[int64_t(r) * M + c] - acc[a][b];
+          An[int64_t(r) * M + c] = v;
+          if (c < r) An[int64_t(c) * M + r] = v;
+        }
+      }
   }
 }
 
@@ -405,15 +487,15 @@ __global__ void __launch_bounds__(kBcrThreads) k_bcr_reduce(int M, BcrLevel lv, 
 template <int NB>
 __global__ void __launch_bounds__(kBcrThreads) k_bcr_top(int M, BcrLevel lv, double* __restrict__ x,
                                                           int* __restrict__ fail) {
-  extern __shared__ double sm[];
-  const int ld = M + 1;
+  extern __shared__ __align__(16) double sm[];
+  const int ld = bcr_ld_odd(M);
   double* Ls = sm;
   double* w = sm + M * ld;       // [M] as an M x 1 right-hand side (ldw = 1)
   double* Dinv = w + M;
   const int tid = threadIdx.x;
   cta_load(Ls, ld, lv.A, M, false);
   for (int i = tid; i < M; i += kBcrThreads) w[i] = lv.b[i];
-  __syncthreads();
+  cta_load_wait();
   cta_cholesky<NB>(Ls, M, ld, Dinv, fail);
   cta_trsm_lower<NB>(Ls, ld, Dinv, w, 1, M, 1);
   cta_solve_lt<NB>(Ls, ld, Dinv, w, M);
@@ -423,8 +505,8 @@ __global__ void __launch_bounds__(kBcrThreads) k_bcr_top(int M, BcrLevel lv, dou
 // Odd blocks of a level: x_o = L^-T (y_o - U x_{o-1} - V x_{o+1}); x indexed by ORIGINAL block (p << shift).
 template <int NB>
 __global__ void __launch_bounds__(kBcrThreads) k_bcr_backsub(int M, BcrLevel lv, int shift, double* __restrict__ x) {
-  extern __shared__ double sm[];
-  const int ld = M + 1;
+  extern __shared__ __align__(16) double sm[];
+  const int ld = bcr_ld_odd(M);
   double* Ls = sm;               // [M][ld]
   double* w = sm + M * ld;       // [M]
   double* xl = w + M;            // [M]
@@ -439,7 +521,7 @@ __global__ void __launch_bounds__(kBcrThreads) k_bcr_backsub(int M, BcrLevel lv,
   }
   cta_load(Ls, ld, lv.L + int64_t(q) * M * M, M, false);
   for (int i = tid; i < M * NB; i += kBcrThreads) Dinv[i] = lv.D[int64_t(q) * M * NB + i];
-  __syncthreads();
+  cta_load_wait();
   // w = y - U xl - V xr: one warp per row, lanes stride the columns (coalesced)
   const double* U = lv.U + int64_t(q) * M * M;
   const double* V = lv.V + int64_t(q) * M * M;
@@ -460,7 +542,7 @@ __global__ void __launch_bounds__(kBcrThreads) k_bcr_backsub(int M, BcrLevel lv,
 }  // namespace
 
 // two M x (M+1) matrices + vectors + the diagonal-block inverses
-size_t bcr_smem_bytes(int M, int cd) { return (size_t(2) * M * (M + 1) + 4 * size_t(M) + size_t(M) * cd) * sizeof(double); }
+size_t bcr_smem_bytes(int M, int cd) { return (size_t(2) * M * (bcr_ld(M) > bcr_ld_odd(M) ? bcr_ld(M) : bcr_ld_odd(M)) + 4 * size_t(M) + size_t(M) * cd + 8) * sizeof(double); }
 
 // Super-block size (in keyframes) for a given half-bandwidth, or 0 when BCR does not apply.
 int bcr_super_size(int cd, int bw, int n_slots) {
@@ -543,9 +625,9 @@ pba_status launch_bcr_rcs(Handle* h) {
   const bool c8 = z.cd == 8;
   for (int l = 0; l + 1 < nl; ++l) {
     BcrLevel lv = level(l), nx = level(l + 1);
-    if (c8) { PBA_LAUNCH(h, K_BCR, k_bcr_eliminate<8>, dim3(lv.n / 2), dim3(kBcrThreads), smem, M, lv, h->chol_fail.p); }
-    else { PBA_LAUNCH(h, K_BCR, k_bcr_eliminate<6>, dim3(lv.n / 2), dim3(kBcrThreads), smem, M, lv, h->chol_fail.p); }
-    PBA_LAUNCH(h, K_BCR, k_bcr_reduce, dim3(nx.n), dim3(kBcrThreads), smem, M, lv, nx);
+    if (c8) { PBA_LAUNCH(h, K_BCR, k_bcr_eliminate<8>, dim3(lv.n / 2, 2), dim3(kBcrThreads), smem, M, lv, h->chol_fail.p); }
+    else { PBA_LAUNCH(h, K_BCR, k_bcr_eliminate<6>, dim3(lv.n / 2, 2), dim3(kBcrThreads), smem, M, lv, h->chol_fail.p); }
+    PBA_LAUNCH(h, K_BCR, k_bcr_reduce, dim3(nx.n, 3), dim3(kBcrThreads), smem, M, lv, nx);
   }
   if (c8) { PBA_LAUNCH(h, K_BCR, k_bcr_top<8>, dim3(1), dim3(kBcrThreads), smem, M, level(nl - 1), x, h->chol_fail.p); }
   else { PBA_LAUNCH(h, K_BCR, k_bcr_top<6>, dim3(1), dim3(kBcrThreads), smem, M, level(nl - 1), x, h->chol_fail.p); }
