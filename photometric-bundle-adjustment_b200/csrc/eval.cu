@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(kPhotoThreads, WITH_J ? 3 : 4) k_eval_photo(co
       // ---- phase 2: one pixel at a time: recompute the warp with its projection Jacobian
       //      (no global loads), weight, stream the row out ----
       const int64_t n = a.ld;
-#pragma unroll 1
+#pragma unroll 2
       for (int k = 0; k < 8; ++k) {
         const double bxk = s_pat[(4 * k + 0) * kPhotoThreads + tid], byk = s_pat[(4 * k + 1) * kPhotoThreads + tid];
         const double bzk = s_pat[(4 * k + 2) * kPhotoThreads + tid], Ihk = s_pat[(4 * k + 3) * kPhotoThreads + tid];
