@@ -382,3 +382,22 @@ def test_reference_containers_drive_both_solvers(model):
     assert np.abs(b.inv_depth - a.inv_depth).max() < TOL_STATE
     fixed = prob.pose_fixed.astype(bool)
     assert np.array_equal(b.poses[fixed], prob.poses[fixed])
+
+
+@pytest.mark.parametrize("model", ["ds", "kb4"])
+def test_config3_shape_lm_matches_oracle(model):
+    """BASELINE config-3 shape at a size the CPU oracle finishes in seconds: fisheye model,
+    per-frame affine brightness, per-point inverse depth; several BCR levels on the GPU."""
+    prob, _ = pb.make_scene(pb.MODE_PHOTOMETRIC, 64, 12000, model)
+    po = prob.copy()
+    so = of.solve("oracle", po, of.default_options(huber_parameter=9.0, max_num_iterations=8))
+    pg = prob.copy()
+    sg = pb.bundle_adjustment(pg, pb.BundleAdjustmentOptions(verbosity_level=0, huber_parameter=9.0,
+                                                             max_num_iterations=8))
+    assert sg.linear_solver == pb.SOLVER_BCR
+    assert sg.num_iterations == so.num_iterations
+    assert abs(sg.final_cost - so.final_cost) <= RTOL_COST * so.final_cost
+    np.testing.assert_allclose([i["cost"] for i in sg.iterations], [i["cost"] for i in so.iterations], rtol=1e-6)
+    assert np.abs(pg.poses - po.poses).max() < TOL_STATE
+    assert np.abs(pg.inv_depth - po.inv_depth).max() < TOL_STATE
+    assert np.abs(pg.affine - po.affine).max() < 1e-4
