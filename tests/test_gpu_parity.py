@@ -401,3 +401,35 @@ def test_config3_shape_lm_matches_oracle(model):
     assert np.abs(pg.poses - po.poses).max() < TOL_STATE
     assert np.abs(pg.inv_depth - po.inv_depth).max() < TOL_STATE
     assert np.abs(pg.affine - po.affine).max() < 1e-4
+
+
+def _two_camera_problem(mode, models):
+    """Stereo-like rig: keyframes alternate between two calibrations (FrameCamId::cam_id 0 / 1)
+    with different camera models, like calib_cam.intrinsics[cam_id] in the reference."""
+    prob, _ = scene(mode, models[0], n_kf=10, n_pts=400)
+    other, _ = scene(mode, models[1], n_kf=10, n_pts=400)
+    intr = np.vstack([prob.intrinsics[0], other.intrinsics[0]])
+    cm = np.array([pb._ffi.CAM_NAMES[models[0]], pb._ffi.CAM_NAMES[models[1]]], np.int32)
+    pc = (np.arange(prob.n_poses) % 2).astype(np.int32)
+    return pb.Problem(mode, prob.poses, prob.pose_fixed, pc, cm, intr, prob.inv_depth, prob.lm_host, prob.lm_host_uv,
+                      prob.lm_obs_ptr, prob.obs_target, prob.obs_uv, prob.images, prob.affine)
+
+
+@pytest.mark.parametrize("mode", [pb.MODE_GEOMETRIC, pb.MODE_PHOTOMETRIC])
+@pytest.mark.parametrize("models", [("pinhole", "ds"), ("kb4", "eucm")])
+def test_mixed_camera_models(mode, models):
+    """Two calibrations with different models in one problem (runtime model dispatch).  Geometric
+    blocks evaluate the target with the HOST's model name and the target's intrinsic values
+    (reprojection.h:97-100, map_utils.h:363-364); photometric blocks use each camera's own model."""
+    prob = _two_camera_problem(mode, models)
+    hub = huber_for(mode)
+    cost_o, r_o, J_o = of.evaluate("oracle", prob, True, hub)
+    eng = pb.Engine(prob, pb.BundleAdjustmentOptions(verbosity_level=0, huber_parameter=hub))
+    cost = eng.evaluate(True)
+    assert abs(cost - cost_o) <= 1e-12 * abs(cost_o)
+    assert rel(eng.residuals(), r_o) < RTOL_RJ
+    assert rel(eng.jacobians(), J_o) < RTOL_RJ
+    eng.close()
+    if of.have_ref():  # and the oracle agrees with the real reference on this configuration
+        cost_r, r_r, J_r = of.evaluate("ref", prob, True, hub)
+        assert rel(r_o, r_r) < 1e-11 and rel(J_o, J_r) < 1e-11
