@@ -292,6 +292,53 @@ pba_status pba_se3_plus(int64_t n, const double* poses7, const double* delta6,
 pba_status pba_cholesky_solve(int32_t n, const double* A, const double* b,
                               double* x);
 
+/* ---- the callers either side of bundle_adjustment() ----
+ * optimize() (src/sfm.cpp:1883-1925) is followed by compute_projections()
+ * (src/sfm.cpp:1956-2008) + set_outlier_flags() (src/sfm.cpp:1928-1952) and
+ * remove_outlier_landmarks() (src/sfm.cpp:2029-2132); all of them go through
+ * Landmark::get_p() (include/visnav/common_types.h:205-217). */
+
+/* OutlierFlags (include/visnav/common_types.h:277-285), same bit values. */
+enum {
+  PBA_OUTLIER_NONE = 0,
+  PBA_OUTLIER_REPROJECTION_ERROR_HUGE = 1 << 0,
+  PBA_OUTLIER_REPROJECTION_ERROR_NORMAL = 1 << 1,
+  PBA_OUTLIER_CAMERA_DISTANCE = 1 << 2,
+  PBA_OUTLIER_Z_COORDINATE = 1 << 3
+};
+
+/* The four pangolin::Var thresholds of src/sfm.cpp:254-261 (defaults 40, 3,
+ * 0.1, 0.05 through pba_projection_thresholds_init). */
+typedef struct pba_projection_thresholds {
+  double reprojection_error_huge_pixel;
+  double reprojection_error_normal_pixel;
+  double camera_center_distance_meter;
+  double z_coordinate_meter;
+} pba_projection_thresholds;
+void pba_projection_thresholds_init(pba_projection_thresholds* t);
+
+/* Landmark::get_p for every landmark: p_w[l] = T_w_host * (normalize(unproject(z_h)) / inv_depth).
+ * p_w is HOST memory [n_landmarks*3].  Needs only the pose / intrinsics /
+ * landmark-host arrays of `p` (observations and images may be NULL). */
+pba_status pba_landmark_positions(const pba_problem* p, int32_t device, double* p_w);
+
+/* compute_projections() + set_outlier_flags() over the inlier observations of
+ * every landmark, and the keep/remove decision of remove_outlier_landmarks().
+ * Slot layout: landmark l owns slots [lm_obs_ptr[l] + l, lm_obs_ptr[l+1] + l + 1):
+ * first its host observation (obs.begin()), then its CSR observations in
+ * order; n_slots = n_obs + n_landmarks.  `p->obs_uv` must be set (corner
+ * positions), whatever `p->mode` is.  Each observation is projected with the
+ * model + intrinsics of the OBSERVING camera (src/sfm.cpp:1974).
+ * Outputs are HOST arrays, each optional (NULL = not wanted):
+ *   point_reprojected [n_slots*2], point_3d_c [n_slots*3],
+ *   reprojection_error [n_slots], outlier_flags [n_slots],
+ *   landmark_remove [n_landmarks] (1 = remove_outlier_landmarks would erase it),
+ *   any_severe_outliers [1] (src/sfm.cpp:2039-2051). */
+pba_status pba_compute_projections(const pba_problem* p, const pba_projection_thresholds* thresholds,
+                                   int32_t device, double* point_reprojected, double* point_3d_c,
+                                   double* reprojection_error, uint32_t* outlier_flags,
+                                   uint8_t* landmark_remove, int32_t* any_severe_outliers);
+
 #ifdef __cplusplus
 }
 #endif

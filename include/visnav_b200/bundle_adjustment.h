@@ -31,6 +31,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -57,78 +58,105 @@ struct PhotometricInputs {
   std::vector<double>* affine = nullptr;  // [2 * cameras.size()], may be null (zeros)
 };
 
+// The reference's map containers flattened into the SoA problem of include/pba.h
+// (one instance per call; `problem` points into the vectors held here).
+// Flattening rule = map_utils.h:327-375: cameras in `Cameras` iteration order,
+// landmarks in `Landmarks` iteration order (those with an empty `obs` skipped),
+// host = obs.begin(), then one observation per further `obs` entry.
+template <class CornersT, class CalibrationT, class CamerasT, class LandmarksT>
+struct FlatMap {
+  using FrameCamIdT = typename CamerasT::key_type;
+  using TrackIdT = typename LandmarksT::key_type;
+  using LandmarkT = typename LandmarksT::mapped_type;
+
+  std::vector<FrameCamIdT> pose_fcid;  // pose index -> FrameCamId
+  std::map<FrameCamIdT, int> pose_index;
+  std::vector<double> poses, intrinsics, inv_depth, host_uv, obs_uv;
+  std::vector<uint8_t> pose_fixed;
+  std::vector<int32_t> pose_calib, calib_model, lm_host, obs_target;
+  std::vector<int64_t> obs_ptr;
+  std::vector<LandmarkT*> lm_ref;     // landmark index -> the reference's Landmark
+  std::vector<TrackIdT> lm_track;     // landmark index -> TrackId
+  pba_problem problem;
+
+  template <class FixedSetT>
+  FlatMap(const CornersT& feature_corners, const FixedSetT& fixed_cameras, CalibrationT& calib_cam, CamerasT& cameras,
+          LandmarksT& landmarks)
+      : obs_ptr(1, 0) {
+    poses.reserve(cameras.size() * 7);
+    for (auto& kv : cameras) {
+      pose_index[kv.first] = int(pose_fixed.size());
+      pose_fcid.push_back(kv.first);
+      const double* T = kv.second.T_w_c.data();  // Sophus layout qx qy qz qw tx ty tz
+      poses.insert(poses.end(), T, T + 7);
+      pose_fixed.push_back(fixed_cameras.count(kv.first) > 0);
+      pose_calib.push_back(int32_t(kv.first.cam_id));
+    }
+    const int n_calib = int(calib_cam.intrinsics.size());
+    calib_model.resize(n_calib);
+    intrinsics.resize(size_t(n_calib) * 8);
+    for (int i = 0; i < n_calib; ++i) {
+      calib_model[i] = camera_model_id(calib_cam.intrinsics[i]->name());
+      std::memcpy(&intrinsics[size_t(i) * 8], calib_cam.intrinsics[i]->data(), 8 * sizeof(double));
+    }
+    for (auto& kv : landmarks) {
+      auto& lm = kv.second;
+      if (lm.obs.empty()) continue;
+      const auto host = lm.obs.begin();
+      const auto& zh = feature_corners.at(host->first).corners[host->second];
+      lm_ref.push_back(&lm);
+      lm_track.push_back(kv.first);
+      inv_depth.push_back(lm.inv_depth);
+      lm_host.push_back(pose_index.at(host->first));
+      host_uv.push_back(zh[0]);
+      host_uv.push_back(zh[1]);
+      for (auto it = std::next(lm.obs.begin()); it != lm.obs.end(); ++it) {
+        const auto& zt = feature_corners.at(it->first).corners[it->second];
+        obs_target.push_back(pose_index.at(it->first));
+        obs_uv.push_back(zt[0]);
+        obs_uv.push_back(zt[1]);
+      }
+      obs_ptr.push_back(int64_t(obs_target.size()));
+    }
+    std::memset(&problem, 0, sizeof(problem));
+    problem.mode = PBA_MODE_GEOMETRIC;
+    problem.n_poses = int32_t(pose_fixed.size());
+    problem.n_calib = n_calib;
+    problem.n_landmarks = int32_t(inv_depth.size());
+    problem.n_obs = int64_t(obs_target.size());
+    problem.poses = poses.data();
+    problem.pose_fixed = pose_fixed.data();
+    problem.pose_calib = pose_calib.data();
+    problem.calib_model = calib_model.data();
+    problem.intrinsics = intrinsics.data();
+    problem.inv_depth = inv_depth.data();
+    problem.lm_host = lm_host.data();
+    problem.lm_host_uv = host_uv.data();
+    problem.lm_obs_ptr = obs_ptr.data();
+    problem.obs_target = obs_target.data();
+    problem.obs_uv = obs_uv.data();
+  }
+  FlatMap(const FlatMap&) = delete;
+  FlatMap& operator=(const FlatMap&) = delete;
+
+  // In-place update of T_w_c / inv_depth, like Ceres through the raw parameter pointers.
+  void write_back(CamerasT& cameras) {
+    int i = 0;
+    for (auto& kv : cameras) std::memcpy(kv.second.T_w_c.data(), &poses[size_t(i++) * 7], 7 * sizeof(double));
+    for (size_t l = 0; l < lm_ref.size(); ++l) lm_ref[l]->inv_depth = inv_depth[l];
+  }
+};
+
 template <class CornersT, class OptionsT, class FixedSetT, class CalibrationT, class CamerasT, class LandmarksT>
 pba_status bundle_adjustment(const CornersT& feature_corners, const OptionsT& options, const FixedSetT& fixed_cameras,
                              CalibrationT& calib_cam, CamerasT& cameras, LandmarksT& landmarks,
                              pba_summary* summary = nullptr, const PhotometricInputs* photo = nullptr,
                              const pba_options* engine_options = nullptr) {
-  using FrameCamIdT = typename CamerasT::key_type;
-  // ---- flatten the containers into the SoA problem of include/pba.h ----
-  std::map<FrameCamIdT, int> pose_index;
-  std::vector<double> poses;
-  std::vector<uint8_t> pose_fixed;
-  std::vector<int32_t> pose_calib;
-  poses.reserve(cameras.size() * 7);
-  for (auto& kv : cameras) {
-    pose_index[kv.first] = int(pose_fixed.size());
-    const double* T = kv.second.T_w_c.data();  // Sophus layout qx qy qz qw tx ty tz
-    poses.insert(poses.end(), T, T + 7);
-    pose_fixed.push_back(fixed_cameras.count(kv.first) > 0);
-    pose_calib.push_back(int32_t(kv.first.cam_id));
-  }
-  const int n_calib = int(calib_cam.intrinsics.size());
-  std::vector<int32_t> calib_model(n_calib);
-  std::vector<double> intrinsics(size_t(n_calib) * 8);
-  for (int i = 0; i < n_calib; ++i) {
-    calib_model[i] = camera_model_id(calib_cam.intrinsics[i]->name());
-    std::memcpy(&intrinsics[size_t(i) * 8], calib_cam.intrinsics[i]->data(), 8 * sizeof(double));
-  }
-  std::vector<double> inv_depth, host_uv, obs_uv;
-  std::vector<int32_t> lm_host, obs_target;
-  std::vector<int64_t> obs_ptr(1, 0);
-  std::vector<typename LandmarksT::mapped_type*> lm_ref;
-  for (auto& kv : landmarks) {
-    auto& lm = kv.second;
-    if (lm.obs.empty()) continue;
-    const auto host = lm.obs.begin();
-    const auto& zh = feature_corners.at(host->first).corners[host->second];
-    lm_ref.push_back(&lm);
-    inv_depth.push_back(lm.inv_depth);
-    lm_host.push_back(pose_index.at(host->first));
-    host_uv.push_back(zh[0]);
-    host_uv.push_back(zh[1]);
-    for (auto it = std::next(lm.obs.begin()); it != lm.obs.end(); ++it) {
-      const auto& zt = feature_corners.at(it->first).corners[it->second];
-      obs_target.push_back(pose_index.at(it->first));
-      obs_uv.push_back(zt[0]);
-      obs_uv.push_back(zt[1]);
-    }
-    obs_ptr.push_back(int64_t(obs_target.size()));
-  }
-
-  pba_problem p;
-  std::memset(&p, 0, sizeof(p));
-  p.mode = photo ? PBA_MODE_PHOTOMETRIC : PBA_MODE_GEOMETRIC;
-  p.n_poses = int32_t(pose_fixed.size());
-  p.n_calib = n_calib;
-  p.n_landmarks = int32_t(inv_depth.size());
-  p.n_obs = int64_t(obs_target.size());
-  p.poses = poses.data();
-  p.pose_fixed = pose_fixed.data();
-  p.pose_calib = pose_calib.data();
-  p.calib_model = calib_model.data();
-  p.intrinsics = intrinsics.data();
-  p.inv_depth = inv_depth.data();
-  p.lm_host = lm_host.data();
-  p.lm_host_uv = host_uv.data();
-  p.lm_obs_ptr = obs_ptr.data();
-  p.obs_target = obs_target.data();
-  p.obs_uv = obs_uv.data();
-  // With the host = obs.begin() rule every host index is smaller than its targets;
-  // the geometric functor also evaluates the target with the host's model name.
-  for (int i = 0; i < n_calib; ++i) (void)i;
+  FlatMap<CornersT, CalibrationT, CamerasT, LandmarksT> flat(feature_corners, fixed_cameras, calib_cam, cameras, landmarks);
+  pba_problem& p = flat.problem;
   std::vector<double> zero_affine;
   if (photo) {
+    p.mode = PBA_MODE_PHOTOMETRIC;
     p.image_ptrs = photo->images.data();
     p.width = photo->width;
     p.height = photo->height;
@@ -155,10 +183,60 @@ pba_status bundle_adjustment(const CornersT& feature_corners, const OptionsT& op
     std::fprintf(stderr, "visnav_b200::bundle_adjustment: %s\n", pba_status_string(st));
     return st;
   }
-  // ---- write back in place, like Ceres does through the raw parameter pointers ----
-  int i = 0;
-  for (auto& kv : cameras) std::memcpy(kv.second.T_w_c.data(), &poses[size_t(i++) * 7], 7 * sizeof(double));
-  for (size_t l = 0; l < lm_ref.size(); ++l) lm_ref[l]->inv_depth = inv_depth[l];
+  flat.write_back(cameras);
+  return PBA_OK;
+}
+
+// Drop-in for the inlier half of compute_projections() (src/sfm.cpp:1956-1984)
+// including set_outlier_flags() (src/sfm.cpp:1928-1952): fills the reference's
+// `ImageProjections` / `TrackProjections` (common_types.h:288-316) from one GPU
+// pass.  `ProjectedLandmarkT` is the reference's ProjectedLandmark.  If
+// `tracks_to_remove` is given it receives the TrackIds remove_outlier_landmarks()
+// (src/sfm.cpp:2039-2091) would erase.  The already-rejected `outlier_obs`
+// (src/sfm.cpp:1986-2005, drawing only) stay with the caller.
+template <class ProjectedLandmarkT, class CornersT, class CalibrationT, class CamerasT, class LandmarksT,
+          class ImageProjectionsT, class TrackProjectionsT>
+pba_status compute_projections(const CornersT& feature_corners, CalibrationT& calib_cam, CamerasT& cameras,
+                               LandmarksT& landmarks, const pba_projection_thresholds& thresholds,
+                               ImageProjectionsT& image_projections, TrackProjectionsT& track_projections,
+                               std::vector<typename LandmarksT::key_type>* tracks_to_remove = nullptr,
+                               int device = 0) {
+  image_projections.clear();
+  track_projections.clear();
+  if (tracks_to_remove) tracks_to_remove->clear();
+  std::map<typename CamerasT::key_type, int> no_fixed;
+  FlatMap<CornersT, CalibrationT, CamerasT, LandmarksT> flat(feature_corners, no_fixed, calib_cam, cameras, landmarks);
+  const pba_problem& p = flat.problem;
+  const size_t ns = size_t(p.n_obs) + size_t(p.n_landmarks);
+  std::vector<double> repro(ns * 2), p3c(ns * 3), err(ns);
+  std::vector<uint32_t> flags(ns);
+  std::vector<uint8_t> remove(size_t(p.n_landmarks));
+  const pba_status st = pba_compute_projections(&p, &thresholds, device, repro.data(), p3c.data(), err.data(),
+                                                flags.data(), remove.data(), nullptr);
+  if (st != PBA_OK) {
+    std::fprintf(stderr, "visnav_b200::compute_projections: %s\n", pba_status_string(st));
+    return st;
+  }
+  for (int l = 0; l < p.n_landmarks; ++l) {
+    const int64_t base = p.lm_obs_ptr[l];
+    const int64_t cnt = p.lm_obs_ptr[l + 1] - base + 1;
+    for (int64_t k = 0; k < cnt; ++k) {
+      const size_t s = size_t(base + l + k);
+      const int pose = k == 0 ? p.lm_host[l] : p.obs_target[base + k - 1];
+      const double* z = k == 0 ? &flat.host_uv[size_t(l) * 2] : &flat.obs_uv[size_t(base + k - 1) * 2];
+      std::shared_ptr<ProjectedLandmarkT> proj(new ProjectedLandmarkT);
+      proj->track_id = flat.lm_track[l];
+      proj->point_measured[0] = z[0]; proj->point_measured[1] = z[1];
+      proj->point_reprojected[0] = repro[2 * s]; proj->point_reprojected[1] = repro[2 * s + 1];
+      proj->point_3d_c[0] = p3c[3 * s]; proj->point_3d_c[1] = p3c[3 * s + 1]; proj->point_3d_c[2] = p3c[3 * s + 2];
+      proj->reprojection_error = err[s];
+      proj->outlier_flags = flags[s];
+      const auto& fcid = flat.pose_fcid[pose];
+      image_projections[fcid].obs.push_back(proj);
+      track_projections[flat.lm_track[l]][fcid] = proj;
+    }
+    if (tracks_to_remove && remove[l]) tracks_to_remove->push_back(flat.lm_track[l]);
+  }
   return PBA_OK;
 }
 

@@ -1030,3 +1030,77 @@ ORACLE_API int pba_oracle_solve(pba_problem* p, const pba_options* opt, int num_
   }
   return PBA_OK;
 }
+
+// --------------------------------------------------------------------------
+// SURVEY.md §8(f)-2/3 restated: Landmark::get_p (common_types.h:205-217),
+// compute_projections (src/sfm.cpp:1956-1984, inlier observations),
+// set_outlier_flags (src/sfm.cpp:1928-1952) and the keep/remove decision of
+// remove_outlier_landmarks (src/sfm.cpp:2039-2091).  Slot layout as pba.h.
+static V3<double> landmark_point(const pba_problem* p, int l) {
+  const int h = p->lm_host[l];
+  const int c = p->pose_calib[h];
+  V3<double> b = unproject<double>(p->calib_model[c], p->intrinsics + 8 * c, p->lm_host_uv[2 * l], p->lm_host_uv[2 * l + 1]);
+  const double n = sqrt(b.x * b.x + b.y * b.y + b.z * b.z);  // Eigen normalize(): v /= norm
+  b = V3<double>{b.x / n, b.y / n, b.z / n};
+  const double rho = p->inv_depth[l];
+  const V3<double> X{b.x / rho, b.y / rho, b.z / rho};
+  return act(map_se3<double>(p->poses + 7 * h), X);
+}
+
+ORACLE_API int pba_oracle_landmark_positions(const pba_problem* p, double* p_w) {
+  for (int l = 0; l < p->n_landmarks; ++l) {
+    const V3<double> w = landmark_point(p, l);
+    p_w[3 * l] = w.x; p_w[3 * l + 1] = w.y; p_w[3 * l + 2] = w.z;
+  }
+  return 0;
+}
+
+ORACLE_API int pba_oracle_compute_projections(const pba_problem* p, const pba_projection_thresholds* thr,
+                                              double* point_reprojected, double* point_3d_c, double* reprojection_error,
+                                              uint32_t* outlier_flags, uint8_t* landmark_remove, int32_t* any_severe) {
+  const int64_t ns = p->n_obs + p->n_landmarks;
+  std::vector<uint32_t> fl(ns, 0);
+  bool severe = false;
+  for (int l = 0; l < p->n_landmarks; ++l) {
+    const V3<double> w = landmark_point(p, l);
+    const int64_t base = p->lm_obs_ptr[l];
+    const int64_t cnt = p->lm_obs_ptr[l + 1] - base + 1;
+    for (int64_t k = 0; k < cnt; ++k) {
+      const int64_t s = base + l + k;
+      const int pose = k == 0 ? p->lm_host[l] : p->obs_target[base + k - 1];
+      const double* z = k == 0 ? p->lm_host_uv + 2 * l : p->obs_uv + 2 * (base + k - 1);
+      const int c = p->pose_calib[pose];
+      const V3<double> pc = act(inverse(map_se3<double>(p->poses + 7 * pose)), w);
+      double uv[2];
+      project<double>(p->calib_model[c], p->intrinsics + 8 * c, pc, uv);
+      const double du = z[0] - uv[0], dv = z[1] - uv[1];
+      const double e = sqrt(du * du + dv * dv);
+      uint32_t f = PBA_OUTLIER_NONE;
+      if (e > thr->reprojection_error_huge_pixel) f |= PBA_OUTLIER_REPROJECTION_ERROR_HUGE;
+      if (e > thr->reprojection_error_normal_pixel) f |= PBA_OUTLIER_REPROJECTION_ERROR_NORMAL;
+      if (sqrt(pc.x * pc.x + pc.y * pc.y + pc.z * pc.z) < thr->camera_center_distance_meter) f |= PBA_OUTLIER_CAMERA_DISTANCE;
+      if (pc.z < thr->z_coordinate_meter) f |= PBA_OUTLIER_Z_COORDINATE;
+      fl[s] = f;
+      if (f & ~uint32_t(PBA_OUTLIER_REPROJECTION_ERROR_NORMAL)) severe = true;
+      if (point_reprojected) { point_reprojected[2 * s] = uv[0]; point_reprojected[2 * s + 1] = uv[1]; }
+      if (point_3d_c) { point_3d_c[3 * s] = pc.x; point_3d_c[3 * s + 1] = pc.y; point_3d_c[3 * s + 2] = pc.z; }
+      if (reprojection_error) reprojection_error[s] = e;
+    }
+  }
+  if (outlier_flags) memcpy(outlier_flags, fl.data(), sizeof(uint32_t) * ns);
+  if (any_severe) *any_severe = severe ? 1 : 0;
+  if (landmark_remove) {
+    for (int l = 0; l < p->n_landmarks; ++l) {
+      bool remove = false;
+      for (int64_t s = p->lm_obs_ptr[l] + l; s < p->lm_obs_ptr[l + 1] + l + 1 && !remove; ++s) {
+        const uint32_t f = fl[s];
+        if (f & PBA_OUTLIER_REPROJECTION_ERROR_HUGE) remove = true;
+        else if ((f & PBA_OUTLIER_REPROJECTION_ERROR_NORMAL) && !severe) remove = true;
+        else if (f & PBA_OUTLIER_CAMERA_DISTANCE) remove = true;
+        else if (f & PBA_OUTLIER_Z_COORDINATE) remove = true;
+      }
+      landmark_remove[l] = remove ? 1 : 0;
+    }
+  }
+  return 0;
+}

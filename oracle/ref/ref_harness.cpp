@@ -29,12 +29,14 @@
 
 #include <ceres/ceres.h>
 
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <map>
 #include <memory>
+#include <set>
 #include <string>
 #include <thread>
 #include <vector>
@@ -288,6 +290,55 @@ void fill_summary(const ceres::Solver::Summary& s, pba_summary* out) {
   }
 }
 
+// The reference's own map containers (common_types.h:160-230) filled from the
+// flat problem; FrameCamId(frame = pose index, cam = calibration index).
+struct RefMap {
+  visnav::Corners corners;
+  visnav::Cameras cameras;
+  visnav::Landmarks landmarks;
+  visnav::Calibration calib;
+  std::set<visnav::FrameCamId> fixed;
+  std::vector<visnav::FrameCamId> fcid;
+};
+
+int build_map(const pba_problem* p, RefMap* m) {
+  using namespace visnav;
+  int max_cam = 0;
+  for (int i = 0; i < p->n_poses; ++i) max_cam = std::max(max_cam, p->pose_calib[i]);
+  if (max_cam >= p->n_calib) return 2;
+  for (int i = 0; i < p->n_calib; ++i) {
+    m->calib.intrinsics.push_back(AbstractCamera<double>::from_data(
+        model_name(p->calib_model[i]), p->intrinsics + 8 * i));
+    m->calib.T_i_c.push_back(Sophus::SE3d());
+  }
+  m->fcid.resize(p->n_poses);
+  for (int i = 0; i < p->n_poses; ++i) {
+    m->fcid[i] = FrameCamId(i, size_t(p->pose_calib[i]));
+    Camera cam;
+    std::memcpy(cam.T_w_c.data(), p->poses + 7 * i, 7 * sizeof(double));
+    m->cameras[m->fcid[i]] = cam;
+    m->corners[m->fcid[i]];
+    if (p->pose_fixed && p->pose_fixed[i]) m->fixed.insert(m->fcid[i]);
+  }
+  for (int l = 0; l < p->n_landmarks; ++l) {
+    Landmark lm;
+    lm.inv_depth = p->inv_depth[l];
+    const int h = p->lm_host[l];
+    auto& hc = m->corners[m->fcid[h]].corners;
+    lm.obs[m->fcid[h]] = FeatureId(hc.size());
+    hc.emplace_back(p->lm_host_uv[2 * l], p->lm_host_uv[2 * l + 1]);
+    for (int64_t o = p->lm_obs_ptr[l]; o < p->lm_obs_ptr[l + 1]; ++o) {
+      const int t = p->obs_target[o];
+      if (!(m->fcid[h] < m->fcid[t])) return 3;  // host must be obs.begin()
+      auto& tc = m->corners[m->fcid[t]].corners;
+      lm.obs[m->fcid[t]] = FeatureId(tc.size());
+      tc.emplace_back(p->obs_uv[2 * o], p->obs_uv[2 * o + 1]);
+    }
+    m->landmarks[TrackId(l)] = lm;
+  }
+  return 0;
+}
+
 }  // namespace
 
 #define REF_API __attribute__((visibility("default")))
@@ -367,44 +418,14 @@ REF_API int pba_ref_solve(pba_problem* p, const pba_options* opt, int num_thread
   const bool photo = p->mode == PBA_MODE_PHOTOMETRIC;
   if (use_reference_entry && !photo) {
     using namespace visnav;
-    Corners corners;
-    Cameras cameras;
-    Landmarks landmarks;
-    Calibration calib;
-    std::set<FrameCamId> fixed;
-    int max_cam = 0;
-    for (int i = 0; i < p->n_poses; ++i) max_cam = std::max(max_cam, p->pose_calib[i]);
-    if (max_cam >= p->n_calib) return 2;
-    for (int i = 0; i < p->n_calib; ++i) {
-      calib.intrinsics.push_back(AbstractCamera<double>::from_data(
-          model_name(p->calib_model[i]), p->intrinsics + 8 * i));
-      calib.T_i_c.push_back(Sophus::SE3d());
-    }
-    std::vector<FrameCamId> fcid(p->n_poses);
-    for (int i = 0; i < p->n_poses; ++i) {
-      fcid[i] = FrameCamId(i, size_t(p->pose_calib[i]));
-      Camera cam;
-      std::memcpy(cam.T_w_c.data(), p->poses + 7 * i, 7 * sizeof(double));
-      cameras[fcid[i]] = cam;
-      corners[fcid[i]];
-      if (p->pose_fixed && p->pose_fixed[i]) fixed.insert(fcid[i]);
-    }
-    for (int l = 0; l < p->n_landmarks; ++l) {
-      Landmark lm;
-      lm.inv_depth = p->inv_depth[l];
-      const int h = p->lm_host[l];
-      auto& hc = corners[fcid[h]].corners;
-      lm.obs[fcid[h]] = FeatureId(hc.size());
-      hc.emplace_back(p->lm_host_uv[2 * l], p->lm_host_uv[2 * l + 1]);
-      for (int64_t o = p->lm_obs_ptr[l]; o < p->lm_obs_ptr[l + 1]; ++o) {
-        const int t = p->obs_target[o];
-        if (!(fcid[h] < fcid[t])) return 3;  // host must be obs.begin()
-        auto& tc = corners[fcid[t]].corners;
-        lm.obs[fcid[t]] = FeatureId(tc.size());
-        tc.emplace_back(p->obs_uv[2 * o], p->obs_uv[2 * o + 1]);
-      }
-      landmarks[TrackId(l)] = lm;
-    }
+    RefMap m;
+    if (int rc = build_map(p, &m)) return rc;
+    Corners& corners = m.corners;
+    Cameras& cameras = m.cameras;
+    Landmarks& landmarks = m.landmarks;
+    Calibration& calib = m.calib;
+    std::set<FrameCamId>& fixed = m.fixed;
+    std::vector<FrameCamId>& fcid = m.fcid;
     BundleAdjustmentOptions ba;
     ba.verbosity_level = opt->verbosity_level;
     ba.optimize_intrinsics = opt->optimize_intrinsics != 0;
@@ -498,6 +519,61 @@ REF_API int pba_ref_se3_plus(int64_t n, const double* poses7, const double* delt
 REF_API int pba_ref_se3_plus_jacobian(const double* pose7, double* J42) {
   Sophus::test::LocalParameterizationSE3 lp;
   lp.ComputeJacobian(pose7, J42);
+  return 0;
+}
+
+
+// SURVEY.md §8(f)-2/3.  Landmark::get_p (common_types.h:205-217), SE3::inverse
+// and AbstractCamera::project are the reference's own code, called on its own
+// containers.  compute_projections / set_outlier_flags themselves live in
+// src/sfm.cpp (GUI translation unit with pangolin::Var globals — unbuildable
+// here), so the loop of src/sfm.cpp:1960-1984 and the four tests of
+// src/sfm.cpp:1928-1952 are repeated around those calls.
+REF_API int pba_ref_landmark_positions(const pba_problem* p, double* p_w) {
+  RefMap m;
+  if (int rc = build_map(p, &m)) return rc;
+  for (int l = 0; l < p->n_landmarks; ++l) {
+    const Eigen::Vector3d w =
+        m.landmarks.at(visnav::TrackId(l)).get_p(m.cameras, m.calib, m.corners);
+    std::memcpy(p_w + 3 * l, w.data(), 3 * sizeof(double));
+  }
+  return 0;
+}
+
+REF_API int pba_ref_compute_projections(const pba_problem* p,
+                                        const pba_projection_thresholds* thr,
+                                        double* point_reprojected, double* point_3d_c,
+                                        double* reprojection_error,
+                                        uint32_t* outlier_flags) {
+  using namespace visnav;
+  RefMap m;
+  if (int rc = build_map(p, &m)) return rc;
+  for (int l = 0; l < p->n_landmarks; ++l) {
+    const Landmark& lm = m.landmarks.at(TrackId(l));
+    const int64_t base = p->lm_obs_ptr[l];
+    const int64_t cnt = p->lm_obs_ptr[l + 1] - base + 1;
+    for (int64_t k = 0; k < cnt; ++k) {
+      const int64_t s = base + l + k;
+      const int pose = k == 0 ? p->lm_host[l] : p->obs_target[base + k - 1];
+      const FrameCamId& fcid = m.fcid[pose];
+      const Eigen::Vector2d p_2d_corner =
+          m.corners.at(fcid).corners[lm.obs.at(fcid)];
+      const Eigen::Vector3d p_c = m.cameras.at(fcid).T_w_c.inverse() *
+                                  lm.get_p(m.cameras, m.calib, m.corners);
+      const Eigen::Vector2d p_2d_repoj =
+          m.calib.intrinsics.at(fcid.cam_id)->project(p_c);
+      const double e = (p_2d_corner - p_2d_repoj).norm();
+      uint32_t f = OutlierNone;
+      if (e > thr->reprojection_error_huge_pixel) f |= OutlierReprojectionErrorHuge;
+      if (e > thr->reprojection_error_normal_pixel) f |= OutlierReprojectionErrorNormal;
+      if (p_c.norm() < thr->camera_center_distance_meter) f |= OutlierCameraDistance;
+      if (p_c.z() < thr->z_coordinate_meter) f |= OutlierZCoordinate;
+      if (point_reprojected) std::memcpy(point_reprojected + 2 * s, p_2d_repoj.data(), 16);
+      if (point_3d_c) std::memcpy(point_3d_c + 3 * s, p_c.data(), 24);
+      if (reprojection_error) reprojection_error[s] = e;
+      if (outlier_flags) outlier_flags[s] = f;
+    }
+  }
   return 0;
 }
 

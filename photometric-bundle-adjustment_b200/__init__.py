@@ -12,6 +12,7 @@ from ._ffi import (CAM_DS, CAM_EUCM, CAM_KB4, CAM_PINHOLE, CONVERGENCE, FAILURE,
 from .calibration import Calibration, initialize_from_double_sphere, load_calibration, save_calibration
 from .engine import BundleAdjustmentOptions, Engine, Summary, bundle_adjustment, device_count
 from .problem import Problem, partition_landmarks
+from .projections import ProjectionThresholds, Projections, compute_projections, landmark_positions
 from .synth import make_scene
 
 __all__ = [
@@ -19,5 +20,6 @@ __all__ = [
     "BundleAdjustmentOptions", "Engine", "Summary", "bundle_adjustment", "device_count", "Problem",
     "partition_landmarks", "make_scene", "MODE_GEOMETRIC", "MODE_PHOTOMETRIC", "CAM_PINHOLE", "CAM_DS",
     "CAM_KB4", "CAM_EUCM", "SOLVER_AUTO", "SOLVER_CHOLESKY", "SOLVER_PCG", "SOLVER_BAND", "SOLVER_BCR", "CONVERGENCE", "NO_CONVERGENCE",
-    "FAILURE", "ExtensionMissing",
+    "FAILURE", "ExtensionMissing", "ProjectionThresholds", "Projections", "compute_projections",
+    "landmark_positions",
 ]

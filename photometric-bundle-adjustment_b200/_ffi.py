@@ -25,6 +25,7 @@ c_double_p = C.POINTER(C.c_double)
 c_u8_p = C.POINTER(C.c_uint8)
 c_i32_p = C.POINTER(C.c_int32)
 c_i64_p = C.POINTER(C.c_int64)
+c_u32_p = C.POINTER(C.c_uint32)
 
 
 class pba_problem(C.Structure):
@@ -84,6 +85,11 @@ class pba_summary(C.Structure):
     ]
 
 
+class pba_projection_thresholds(C.Structure):
+    _fields_ = [("reprojection_error_huge_pixel", C.c_double), ("reprojection_error_normal_pixel", C.c_double),
+                ("camera_center_distance_meter", C.c_double), ("z_coordinate_meter", C.c_double)]
+
+
 class pba_kernel_stat(C.Structure):
     _fields_ = [("name", C.c_char * 48), ("launches", C.c_int64), ("total_ms", C.c_double)]
 
@@ -115,7 +121,7 @@ PBA_SYMBOLS = [
     "pba_lm_iterate",
     "pba_set_state", "pba_get_state", "pba_get_sizes", "pba_reset_kernel_stats", "pba_get_kernel_stats",
     "pba_nccl_unique_id", "pba_comm_init", "pba_camera_project", "pba_camera_unproject", "pba_se3_plus",
-    "pba_cholesky_solve",
+    "pba_cholesky_solve", "pba_projection_thresholds_init", "pba_landmark_positions", "pba_compute_projections",
 ]
 
 _lib = None
@@ -172,11 +178,16 @@ def load_lib():
         "pba_camera_unproject": [C.c_int32, c_double_p, C.c_int64, c_double_p, c_double_p],
         "pba_se3_plus": [C.c_int64, c_double_p, c_double_p, c_double_p],
         "pba_cholesky_solve": [C.c_int32, c_double_p, c_double_p, c_double_p],
+        "pba_landmark_positions": [C.POINTER(pba_problem), C.c_int32, c_double_p],
+        "pba_compute_projections": [C.POINTER(pba_problem), C.POINTER(pba_projection_thresholds), C.c_int32,
+                                    c_double_p, c_double_p, c_double_p, c_u32_p, c_u8_p, c_i32_p],
     }
     for name, args in sigs.items():
         fn = getattr(lib, name)
         fn.argtypes = args
         fn.restype = C.c_int
+    lib.pba_projection_thresholds_init.argtypes = [C.POINTER(pba_projection_thresholds)]
+    lib.pba_projection_thresholds_init.restype = None
     lib.pba_destroy.argtypes = [H]
     lib.pba_destroy.restype = None
     lib.pba_get_kernel_stats.argtypes = [H, C.POINTER(pba_kernel_stat), C.c_int32]

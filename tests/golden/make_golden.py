@@ -81,5 +81,39 @@ def main():
         print(name, "obs", prob.n_obs, "cost %.6e -> %.6e in %d iterations" % (s.initial_cost, s.final_cost, s.num_iterations))
 
 
+def perturb_for_outliers(prob, seed):
+    """Push a few landmarks into each outlier class of src/sfm.cpp:1928-1952."""
+    rng = np.random.default_rng(seed)
+    idx = rng.permutation(prob.n_landmarks)
+    prob.inv_depth[idx[0:4]] *= 60.0     # a few cm from the host camera -> camera-distance / z flags
+    prob.inv_depth[idx[4:8]] *= -1.0     # behind the host -> z flag, huge reprojection error elsewhere
+    prob.inv_depth[idx[8:14]] *= 1.6     # moderate depth error -> "normal" reprojection error
+    prob._c = None
+    return prob
+
+
+def main_projections():
+    """projections_<model>.npz: the reference's Landmark::get_p / SE3::inverse /
+    AbstractCamera::project on its own containers (pba_ref_compute_projections),
+    at the default thresholds of src/sfm.cpp:254-261."""
+    assert of.have_ref(), "build oracle/_ref first (make ref)"
+    for k, model in enumerate(("pinhole", "ds", "kb4", "eucm")):
+        prob, _ = make_case(pb.MODE_GEOMETRIC, model)
+        prob = perturb_for_outliers(prob, 100 + k)
+        out = of.compute_projections("ref", prob)
+        p_w = of.landmark_positions("ref", prob)
+        name = "projections_%s.npz" % model
+        np.savez_compressed(
+            os.path.join(HERE, name), mode=prob.mode, poses=prob.poses, pose_fixed=prob.pose_fixed,
+            pose_calib=prob.pose_calib, calib_model=prob.calib_model, intrinsics=prob.intrinsics,
+            inv_depth=prob.inv_depth, lm_host=prob.lm_host, lm_host_uv=prob.lm_host_uv, lm_obs_ptr=prob.lm_obs_ptr,
+            obs_target=prob.obs_target, obs_uv=prob.obs_uv, ref_p_w=p_w, **{"ref_" + k2: v for k2, v in out.items()})
+        fl = out["outlier_flags"]
+        print(name, "slots", fl.size, "flag counts", [int(np.sum((fl >> b) & 1)) for b in range(4)])
+
+
 if __name__ == "__main__":
-    main()
+    if "--projections" in sys.argv:
+        main_projections()
+    else:
+        main()

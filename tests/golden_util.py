@@ -11,7 +11,11 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def golden_files():
-    return sorted(glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    return sorted(glob.glob(os.path.join(GOLDEN_DIR, "geom_*.npz")) + glob.glob(os.path.join(GOLDEN_DIR, "photo_*.npz")))
+
+
+def projection_files():
+    return sorted(glob.glob(os.path.join(GOLDEN_DIR, "projections_*.npz")))
 
 
 def load(path):

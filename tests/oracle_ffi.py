@@ -138,3 +138,45 @@ def build_rcs(prob, use_huber=True, huber=1.0, radius=1e4, threads=0):
     lib.pba_oracle_build_rcs(C.byref(pc), int(use_huber), float(huber), float(radius), threads, C.byref(dim),
                              _ffi.ptr(S, C.c_double), _ffi.ptr(rhs, C.c_double), _ffi.ptr(scale, C.c_double))
     return S, rhs, scale
+
+
+def landmark_positions(lib_kind, prob):
+    """Landmark::get_p for every landmark from the oracle port or the reference's own method."""
+    lib = oracle() if lib_kind == "oracle" else ref()
+    fn = lib.pba_oracle_landmark_positions if lib_kind == "oracle" else lib.pba_ref_landmark_positions
+    fn.argtypes = [C.POINTER(_ffi.pba_problem), _d]
+    out = np.zeros((prob.n_landmarks, 3))
+    pc = prob.c
+    rc = fn(C.byref(pc), _ffi.ptr(out, C.c_double))
+    assert rc == 0, rc
+    return out
+
+
+def compute_projections(lib_kind, prob, thresholds=None):
+    """compute_projections + set_outlier_flags (+ removal decision for the oracle port).
+    Returns a dict of flat arrays in the slot layout of include/pba.h."""
+    thresholds = thresholds or pba_b200.ProjectionThresholds()
+    t = thresholds.to_c()
+    nl, ns = prob.n_landmarks, prob.n_obs + prob.n_landmarks
+    out = dict(point_reprojected=np.zeros((ns, 2)), point_3d_c=np.zeros((ns, 3)), reprojection_error=np.zeros(ns),
+               outlier_flags=np.zeros(ns, np.uint32))
+    pc = prob.c
+    P, T = C.POINTER(_ffi.pba_problem), C.POINTER(_ffi.pba_projection_thresholds)
+    if lib_kind == "oracle":
+        fn = oracle().pba_oracle_compute_projections
+        fn.argtypes = [P, T, _d, _d, _d, _ffi.c_u32_p, _ffi.c_u8_p, _ffi.c_i32_p]
+        out["landmark_remove"] = np.zeros(nl, np.uint8)
+        severe = C.c_int32(0)
+        rc = fn(C.byref(pc), C.byref(t), _ffi.ptr(out["point_reprojected"], C.c_double),
+                _ffi.ptr(out["point_3d_c"], C.c_double), _ffi.ptr(out["reprojection_error"], C.c_double),
+                _ffi.ptr(out["outlier_flags"], C.c_uint32), _ffi.ptr(out["landmark_remove"], C.c_uint8),
+                C.byref(severe))
+        out["any_severe_outliers"] = bool(severe.value)
+    else:
+        fn = ref().pba_ref_compute_projections
+        fn.argtypes = [P, T, _d, _d, _d, _ffi.c_u32_p]
+        rc = fn(C.byref(pc), C.byref(t), _ffi.ptr(out["point_reprojected"], C.c_double),
+                _ffi.ptr(out["point_3d_c"], C.c_double), _ffi.ptr(out["reprojection_error"], C.c_double),
+                _ffi.ptr(out["outlier_flags"], C.c_uint32))
+    assert rc == 0, rc
+    return out
