@@ -274,7 +274,9 @@ int32_t pba_get_kernel_stats(pba_handle* h, pba_kernel_stat* out, int32_t cap);
 /* ---- multi-GPU: one process per GPU, NCCL all-reduce of the partial RCS ----
  * Rank 0 obtains an id (128 bytes), the caller broadcasts it by any means
  * (torch.distributed in bench.py), every rank calls pba_comm_init before
- * pba_build_rcs / pba_minimize. */
+ * pba_build_rcs / pba_minimize.  Communicators are cached per process and id:
+ * handles created later with the same id (and world/rank/device) reuse the
+ * first communicator, so only the first pba_comm_init pays ncclCommInitRank. */
 #define PBA_NCCL_ID_BYTES 128
 pba_status pba_nccl_unique_id(uint8_t id[PBA_NCCL_ID_BYTES]);
 pba_status pba_comm_init(pba_handle* h, const uint8_t id[PBA_NCCL_ID_BYTES]);

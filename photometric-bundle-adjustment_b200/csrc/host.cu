@@ -13,6 +13,7 @@
 //             host, every vector operation on the device.
 // pba_solve   is the drop-in for visnav::bundle_adjustment (map_utils.h:322).
 #include <dlfcn.h>
+#include <omp.h>
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
@@ -22,6 +23,7 @@
 #include <limits>
 #include <array>
 #include <memory>
+#include <mutex>
 #include <numeric>
 #include <string>
 #include <unordered_set>
@@ -124,7 +126,7 @@ constexpr int kNcclDouble = 8, kNcclSum = 0, kNcclMax = 2;
 }  // namespace
 
 Handle::~Handle() {
-  if (nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(nccl_comm);
+  // nccl_comm is owned by the process-wide cache (pba_comm_init), not by the handle
   if (h_scalars) cudaFreeHost(h_scalars);
   if (own_stream && stream) cudaStreamDestroy(stream);
 }
@@ -239,11 +241,24 @@ pba_status create_impl(const pba_problem* p, const pba_options* o, int rank, int
     if (p->calib_model[i] != p->calib_model[0]) h->uniform_model = -1;
 
   mark("validate + device init");
+  // One process per GPU shares the host cores: each rank takes its share of the OpenMP threads.
+  const int nthr = std::max(1, omp_get_num_procs() / std::max(1, world));
   // ---- global layout: which parameter blocks survive Ceres' reduced program ----
   std::vector<uint8_t> used(p->n_poses, 0), is_target(p->n_poses, 0);
-  for (int l = 0; l < p->n_landmarks; ++l) {
-    if (p->lm_obs_ptr[l + 1] > p->lm_obs_ptr[l]) { used[p->lm_host[l]] = 1; ++h->n_active_lm; }
-    for (int64_t k = p->lm_obs_ptr[l]; k < p->lm_obs_ptr[l + 1]; ++k) { used[p->obs_target[k]] = 1; is_target[p->obs_target[k]] = 1; }
+  {
+    int64_t n_active = 0;
+#pragma omp parallel num_threads(nthr) reduction(+ : n_active)
+    {
+      std::vector<uint8_t> u(p->n_poses, 0), t(p->n_poses, 0);
+#pragma omp for schedule(static)
+      for (int l = 0; l < p->n_landmarks; ++l) {
+        if (p->lm_obs_ptr[l + 1] > p->lm_obs_ptr[l]) { u[p->lm_host[l]] = 1; ++n_active; }
+        for (int64_t k = p->lm_obs_ptr[l]; k < p->lm_obs_ptr[l + 1]; ++k) { u[p->obs_target[k]] = 1; t[p->obs_target[k]] = 1; }
+      }
+#pragma omp critical
+      for (int i = 0; i < p->n_poses; ++i) { used[i] |= u[i]; is_target[i] |= t[i]; }
+    }
+    h->n_active_lm += n_active;
   }
   h->n_obs_global = p->n_obs;
   h->slot.assign(p->n_poses, -1);
@@ -261,20 +276,36 @@ pba_status create_impl(const pba_problem* p, const pba_options* o, int rank, int
   //      (schur_complement_solver.cc:261-297); identical on every rank ----
   std::vector<std::vector<int>> adj(z.n_slots);
   {
-    // many landmarks share a camera set: insert the pairs of each distinct set once
+    // many landmarks share a camera set: find the distinct sets (parallel scan, per-thread
+    // hash sets merged serially), then insert the pairs of each set once
     std::unordered_set<std::string> seen;
-    std::vector<int> cams;
-    for (int l = 0; l < p->n_landmarks; ++l) {
-      if (p->lm_obs_ptr[l + 1] == p->lm_obs_ptr[l]) continue;
-      cams.clear();
-      if (slot[p->lm_host[l]] >= 0) cams.push_back(slot[p->lm_host[l]]);
-      for (int64_t k = p->lm_obs_ptr[l]; k < p->lm_obs_ptr[l + 1]; ++k)
-        if (slot[p->obs_target[k]] >= 0) cams.push_back(slot[p->obs_target[k]]);
-      if (cams.empty()) continue;
-      std::sort(cams.begin(), cams.end());
-      if (!seen.emplace(reinterpret_cast<const char*>(cams.data()), cams.size() * sizeof(int)).second) continue;
-      for (size_t i = 0; i < cams.size(); ++i)
-        for (size_t j = i; j < cams.size(); ++j) adj[cams[i]].push_back(cams[j]);
+#pragma omp parallel num_threads(nthr)
+    {
+      std::unordered_set<std::string> mine;
+      std::vector<int> cams;
+      std::string last;
+#pragma omp for schedule(static)
+      for (int l = 0; l < p->n_landmarks; ++l) {
+        if (p->lm_obs_ptr[l + 1] == p->lm_obs_ptr[l]) continue;
+        cams.clear();
+        if (slot[p->lm_host[l]] >= 0) cams.push_back(slot[p->lm_host[l]]);
+        for (int64_t k = p->lm_obs_ptr[l]; k < p->lm_obs_ptr[l + 1]; ++k)
+          if (slot[p->obs_target[k]] >= 0) cams.push_back(slot[p->obs_target[k]]);
+        if (cams.empty()) continue;
+        std::sort(cams.begin(), cams.end());
+        const size_t bytes = cams.size() * sizeof(int);
+        if (last.size() == bytes && memcmp(last.data(), cams.data(), bytes) == 0) continue;  // same set as the previous landmark
+        last.assign(reinterpret_cast<const char*>(cams.data()), bytes);
+        mine.insert(last);
+      }
+#pragma omp critical
+      seen.insert(mine.begin(), mine.end());
+    }
+    for (const std::string& key : seen) {
+      const int* cams = reinterpret_cast<const int*>(key.data());
+      const size_t nc = key.size() / sizeof(int);
+      for (size_t i = 0; i < nc; ++i)
+        for (size_t j = i; j < nc; ++j) adj[cams[i]].push_back(cams[j]);
     }
     for (auto& v : adj) { std::sort(v.begin(), v.end()); v.erase(std::unique(v.begin(), v.end()), v.end()); }
   }
@@ -335,7 +366,7 @@ pba_status create_impl(const pba_problem* p, const pba_options* o, int rank, int
 
   // pass A (parallel over groups): distinct targets of every group, ascending, with counts
   std::vector<std::vector<std::pair<int, int64_t>>> grp_tg(G);
-#pragma omp parallel
+#pragma omp parallel num_threads(nthr)
   {
     std::vector<int64_t> cnt(p->n_poses, 0);
     std::vector<int> touched;
@@ -393,10 +424,12 @@ pba_status create_impl(const pba_problem* p, const pba_options* o, int rank, int
   h->schur_tile_l = schur_tile_l(h->max_w_stride);
 
   // pass B (parallel over groups): place every observation at its edge-order position
-  std::vector<int> obs_lm(n), obs_edge(n), obs_col(n, -1), lm_group(n_lm), lm_hostcol(n_lm, -1), lm_w_stride(n_lm);
-  std::vector<int64_t> lm_pos(n), lm_w_off(n_lm);
+  RawVec<int> obs_lm(n), obs_edge(n), obs_col(n);  // every entry is written in pass B
+  RawVec<int64_t> lm_pos(n);
+  std::vector<int> lm_group(n_lm), lm_hostcol(n_lm, -1), lm_w_stride(n_lm);
+  std::vector<int64_t> lm_w_off(n_lm);
   h->obs_order.resize(n);
-#pragma omp parallel
+#pragma omp parallel num_threads(nthr)
   {
     std::vector<int64_t> cursor(p->n_poses, 0);
     std::vector<int> eidx(p->n_poses, 0), colt(p->n_poses, -1);
@@ -1201,7 +1234,20 @@ PBA_API pba_status pba_comm_init(pba_handle* hh, const uint8_t id[PBA_NCCL_ID_BY
   PBA_CUDA_OK(cudaSetDevice(h->device));
   NcclId nid;
   memcpy(nid.b, id, PBA_NCCL_ID_BYTES);
-  if (g_nccl.CommInitRank(&h->nccl_comm, h->world, nid, h->rank) != 0) return PBA_ERR_NCCL;
+  // Communicators are cached per process, keyed by (id, world, rank, device): ncclCommInitRank
+  // costs seconds at 8 ranks, a solve milliseconds, so every later handle given the same id
+  // (the SfM loop calls optimize() again and again) reuses the first one.
+  static std::mutex mu;
+  static std::vector<std::pair<std::string, void*>> cache;
+  std::string key(reinterpret_cast<const char*>(id), PBA_NCCL_ID_BYTES);
+  key += "/" + std::to_string(h->world) + "/" + std::to_string(h->rank) + "/" + std::to_string(h->device);
+  std::lock_guard<std::mutex> lock(mu);
+  for (auto& kv : cache)
+    if (kv.first == key) { h->nccl_comm = kv.second; return PBA_OK; }
+  void* comm = nullptr;
+  if (g_nccl.CommInitRank(&comm, h->world, nid, h->rank) != 0) return PBA_ERR_NCCL;
+  cache.emplace_back(key, comm);
+  h->nccl_comm = comm;
   return PBA_OK;
 }
 

@@ -19,12 +19,30 @@
 #include <string>
 #include <vector>
 
+#include <memory>
+
 #include "pba.h"
 #include "pba_math.h"
 
 namespace pba {
 
 // ---------------------------------------------------------------- buffers --
+// Host array WITHOUT value-initialisation (std::vector zero-fills serially: ~0.1 s for the
+// observation-sized index arrays of pba_create, which are fully overwritten in parallel anyway).
+template <class T>
+struct RawVec {
+  std::unique_ptr<T[]> p;
+  size_t n = 0;
+  RawVec() {}
+  explicit RawVec(size_t count) { resize(count); }
+  void resize(size_t count) { p.reset(count ? new T[count] : nullptr); n = count; }
+  T& operator[](size_t i) { return p[i]; }
+  const T& operator[](size_t i) const { return p[i]; }
+  const T* data() const { return p.get(); }
+  size_t size() const { return n; }
+  bool empty() const { return n == 0; }
+};
+
 template <class T>
 struct DevBuf {
   T* p = nullptr;
@@ -44,7 +62,8 @@ struct DevBuf {
     if (count == 0) return cudaSuccess;
     return cudaMalloc(&p, count * sizeof(T));
   }
-  cudaError_t upload(const std::vector<T>& h, cudaStream_t s = 0) {
+  template <class V>
+  cudaError_t upload(const V& h, cudaStream_t s = 0) {  // std::vector<T> or RawVec<T>
     cudaError_t e = alloc(h.size());
     if (e != cudaSuccess || h.empty()) return e;
     return cudaMemcpyAsync(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, s);
@@ -128,7 +147,7 @@ struct Handle {
 
   // ---- host-side structure kept for state I/O and the LM driver ----
   std::vector<int> lm_order;      // internal landmark -> caller-local landmark (sorted by host)
-  std::vector<int64_t> obs_order; // sorted obs position -> caller-local obs index
+  RawVec<int64_t> obs_order;      // sorted obs position -> caller-local obs index
   std::vector<int> slot;          // pose -> RCS slot or -1
   std::vector<uint8_t> affine_active;
   std::vector<int> blk_row, blk_col;  // RCS block coordinates (slots), row <= col
