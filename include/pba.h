@@ -126,7 +126,7 @@ typedef struct pba_options {
   int32_t max_num_consecutive_invalid_steps; /* 5 */
   int32_t jacobi_scaling;             /* 1 */
   int32_t device;                     /* CUDA device ordinal, default 0 */
-  int32_t profile;                    /* 1 = bracket every kernel with CUDA events */
+  int32_t profile;                    /* 1 = bracket every kernel with CUDA events, 2 = only the residual/Jacobian kernel */
 } pba_options;
 
 /* One row of Ceres' Solver::Summary::iterations (include/ceres/iteration_callback.h). */
@@ -269,6 +269,8 @@ pba_status pba_get_sizes(pba_handle* h, int64_t* n_obs_local,
 
 /* Kernel accounting: every kernel launch is counted; durations need profile=1. */
 pba_status pba_reset_kernel_stats(pba_handle* h);
+/* Change pba_options.profile of a live handle (0 / 1 / 2). */
+pba_status pba_set_profile(pba_handle* h, int32_t level);
 int32_t pba_get_kernel_stats(pba_handle* h, pba_kernel_stat* out, int32_t cap);
 
 /* ---- multi-GPU: one process per GPU, NCCL all-reduce of the partial RCS ----

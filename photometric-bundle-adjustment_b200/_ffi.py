@@ -119,7 +119,7 @@ PBA_SYMBOLS = [
     "pba_create", "pba_destroy", "pba_set_stream", "pba_synchronize", "pba_evaluate", "pba_get_residuals",
     "pba_get_jacobians", "pba_build_rcs", "pba_get_rcs_dim", "pba_get_rcs", "pba_solve_rcs", "pba_minimize",
     "pba_lm_iterate",
-    "pba_set_state", "pba_get_state", "pba_get_sizes", "pba_reset_kernel_stats", "pba_get_kernel_stats",
+    "pba_set_state", "pba_get_state", "pba_get_sizes", "pba_reset_kernel_stats", "pba_set_profile", "pba_get_kernel_stats",
     "pba_nccl_unique_id", "pba_comm_init", "pba_camera_project", "pba_camera_unproject", "pba_se3_plus",
     "pba_cholesky_solve", "pba_projection_thresholds_init", "pba_landmark_positions", "pba_compute_projections",
 ]
@@ -172,6 +172,7 @@ def load_lib():
         "pba_get_state": [H, c_double_p, c_double_p, c_double_p],
         "pba_get_sizes": [H, c_i64_p, c_i32_p, c_i64_p],
         "pba_reset_kernel_stats": [H],
+        "pba_set_profile": [H, C.c_int32],
         "pba_nccl_unique_id": [c_u8_p],
         "pba_comm_init": [H, c_u8_p],
         "pba_camera_project": [C.c_int32, c_double_p, C.c_int64, c_double_p, c_double_p, c_double_p],

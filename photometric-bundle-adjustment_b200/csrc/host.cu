@@ -62,7 +62,8 @@ cudaEvent_t KernelStats::get_event() {
 }
 void KernelStats::begin(int id, cudaStream_t s) {
   ++launches[id];
-  if (!profile) return;
+  timing_now = profile == 1 || (profile == 2 && id == K_RESJAC);
+  if (!timing_now) return;
   Pending p;
   p.id = id;
   p.a = get_event();
@@ -71,7 +72,8 @@ void KernelStats::begin(int id, cudaStream_t s) {
   pending.push_back(p);
 }
 void KernelStats::end(cudaStream_t s) {
-  if (!profile) return;
+  if (!timing_now) return;
+  timing_now = false;
   cudaEventRecord(pending.back().b, s);
 }
 void KernelStats::resolve() {
@@ -227,7 +229,7 @@ pba_status create_impl(const pba_problem* p, const pba_options* o, int rank, int
   Handle* h = hh.get();
   h->opt = *o;
   h->rank = rank; h->world = world; h->device = o->device;
-  h->stats.profile = o->profile != 0;
+  h->stats.profile = o->profile;
   PBA_CUDA_OK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   h->own_stream = true;
   Sizes& z = h->sz;
@@ -1198,6 +1200,15 @@ PBA_API pba_status pba_reset_kernel_stats(pba_handle* hh) {
   if (!h) return PBA_ERR_INVALID_ARGUMENT;
   PBA_CUDA_OK(cudaStreamSynchronize(h->stream));
   h->stats.reset();
+  return PBA_OK;
+}
+
+PBA_API pba_status pba_set_profile(pba_handle* hh, int32_t level) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h || level < 0 || level > 2) return PBA_ERR_INVALID_ARGUMENT;
+  PBA_CUDA_OK(cudaStreamSynchronize(h->stream));
+  h->stats.resolve();
+  h->stats.profile = level;
   return PBA_OK;
 }
 

@@ -106,7 +106,8 @@ extern const char* const kKernelNames[K_NUM];
 struct KernelStats {
   int64_t launches[K_NUM] = {0};
   double ms[K_NUM] = {0};
-  bool profile = false;
+  int profile = 0;  // 0 none, 1 every kernel, 2 only K_RESJAC (the roofline kernel)
+  bool timing_now = false;
   // pending event pairs (resolved at synchronisation points)
   struct Pending { int id; cudaEvent_t a, b; };
   std::vector<Pending> pending;

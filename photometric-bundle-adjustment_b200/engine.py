@@ -34,7 +34,7 @@ class BundleAdjustmentOptions:
     parameter_tolerance: float = None
     initial_trust_region_radius: float = None
     device: int = 0
-    profile: bool = False
+    profile: int = 0  # 0 none, 1 CUDA events around every kernel, 2 only around the residual/Jacobian kernel
 
     def to_c(self):
         o = _ffi.pba_options()
@@ -182,6 +182,10 @@ class Engine:
 
     def reset_kernel_stats(self):
         _ffi.check(self.lib.pba_reset_kernel_stats(self._h))
+
+    def set_profile(self, level):
+        """0 none, 1 CUDA events around every kernel, 2 only around the residual/Jacobian kernel."""
+        _ffi.check(self.lib.pba_set_profile(self._h, int(level)))
 
     def kernel_stats(self):
         buf = (_ffi.pba_kernel_stat * 64)()
