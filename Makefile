@@ -10,7 +10,7 @@ NVCC    ?= /usr/local/cuda/bin/nvcc
 HOSTCXX ?= g++
 ARCH    := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS := -O3 -std=c++17 $(ARCH) -lineinfo -Xcompiler -fPIC,-O3,-fvisibility=hidden,-fopenmp \
-           -Iinclude -I$(CSRC) --expt-relaxed-constexpr -Xptxas -v
+           -Iinclude -I$(CSRC) --expt-relaxed-constexpr -Xptxas -v $(EXTRA)
 CU_SRCS := $(wildcard $(CSRC)/*.cu)
 CU_HDRS := $(wildcard $(CSRC)/*.h) $(wildcard $(CSRC)/*.cuh) include/pba.h
 

@@ -26,288 +26,11 @@
 
 #include "launch.h"
 #include "pba_internal.h"
+#include "bcr_dense.cuh"
 
 namespace pba {
 
 namespace {
-
-constexpr int kBcrThreads = 256;
-
-// shared-memory leading dimensions.  The product kernel (k_bcr_reduce) wants 16-byte aligned
-// rows (even) covering the 4-wide tiles; the factorisation kernels walk columns with one thread
-// per row, which is conflict-free only for an odd stride.
-__host__ __device__ inline int bcr_ld(int M) { return ((M + 3) / 4) * 4 + 2; }
-__host__ __device__ inline int bcr_ld_odd(int M) { return M + 1 + (M & 1); }
-
-// ---- CTA-level dense kernels on shared-memory matrices, blocked by NB = cd ----
-// All matrices are row-major with leading dimension ld.  The only serial piece is
-// the NB x NB diagonal-block factorisation (warp 0); everything else is
-// register-tiled, synchronised twice per block column.
-
-// Factor the NB x NB block at D (lower Cholesky, in place) and write the inverse
-// of the factor to Di [NB*NB] (lower).  Executed by warp 0; ends with __syncwarp.
-template <int NB>
-__device__ __forceinline__ void warp_factor_diag(double* D, int ld, double* Di, int* fail) {
-  const int lane = threadIdx.x & 31;
-  __shared__ double s_l[NB * NB];
-  __shared__ double s_id[NB];
-  if (lane == 0) {
-    double L[NB][NB];
-#pragma unroll
-    for (int r = 0; r < NB; ++r)
-#pragma unroll
-      for (int c = 0; c <= r; ++c) L[r][c] = D[r * ld + c];
-#pragma unroll
-    for (int j = 0; j < NB; ++j) {
-      double d = L[j][j];
-      if (!(d > 0.0)) { *fail = 1; d = 1.0; }
-      const double inv = rsqrt(d);
-      L[j][j] = d * inv;
-      s_id[j] = inv;
-#pragma unroll
-      for (int r = j + 1; r < NB; ++r) L[r][j] *= inv;
-#pragma unroll
-      for (int c = j + 1; c < NB; ++c)
-#pragma unroll
-        for (int r = c; r < NB; ++r) L[r][c] -= L[r][j] * L[c][j];
-    }
-#pragma unroll
-    for (int r = 0; r < NB; ++r)
-#pragma unroll
-      for (int c = 0; c < NB; ++c) {
-        const double v = c <= r ? L[r][c] : 0.0;
-        s_l[r * NB + c] = v;
-        D[r * ld + c] = v;
-      }
-  }
-  __syncwarp();
-  if (lane < NB) {
-    const int c = lane;  // column c of the inverse
-    double m[NB];
-#pragma unroll
-    for (int r = 0; r < NB; ++r) {
-      double s = r == c ? 1.0 : 0.0;
-#pragma unroll
-      for (int q = 0; q < r; ++q) s -= (q >= c ? s_l[r * NB + q] * m[q] : 0.0);
-      m[r] = r >= c ? s * s_id[r] : 0.0;
-    }
-#pragma unroll
-    for (int r = 0; r < NB; ++r) Di[r * NB + c] = m[r];
-  }
-  __syncwarp();
-}
-
-// A <- lower Cholesky factor of A (strict upper triangle untouched); Dinv[J] = inverse
-// of the J-th diagonal block of the factor.
-template <int NB>
-__device__ void cta_cholesky(double* A, int M, int ld, double* Dinv, int* fail) {
-  const int tid = threadIdx.x;
-  const int nbk = M / NB;
-  for (int J = 0; J < nbk; ++J) {
-    const int j0 = J * NB;
-    double* Di = Dinv + J * NB * NB;
-    if (tid < 32) warp_factor_diag<NB>(A + j0 * ld + j0, ld, Di, fail);
-    __syncthreads();
-    // panel: rows below the diagonal block  <-  row * L_D^-T = row * Di^T
-    for (int i = j0 + NB + tid; i < M; i += kBcrThreads) {
-      double v[NB], o[NB];
-#pragma unroll
-      for (int q = 0; q < NB; ++q) v[q] = A[i * ld + j0 + q];
-#pragma unroll
-      for (int c = 0; c < NB; ++c) {
-        double s = 0.0;
-#pragma unroll
-        for (int q = 0; q <= c; ++q) s += v[q] * Di[c * NB + q];
-        o[c] = s;
-      }
-#pragma unroll
-      for (int q = 0; q < NB; ++q) A[i * ld + j0 + q] = o[q];
-    }
-    __syncthreads();
-    // trailing lower triangle -= panel panel^T, 4x4 register tiles
-    const int n0 = j0 + NB, n = M - n0;
-    const int T = (n + 3) / 4;
-    for (int t = tid; t < T * T; t += kBcrThreads) {
-      const int tr = t / T, tc = t % T;
-      if (tc > tr) continue;
-      double acc[4][4];
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
-#pragma unroll
-      for (int q = 0; q < NB; ++q) {
-        double x[4], y[4];
-#pragma unroll
-        for (int a = 0; a < 4; ++a) {
-          const int r = n0 + 4 * tr + a, c = n0 + 4 * tc + a;
-          x[a] = r < M ? A[r * ld + j0 + q] : 0.0;
-          y[a] = c < M ? A[c * ld + j0 + q] : 0.0;
-        }
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-          for (int b = 0; b < 4; ++b) acc[a][b] += x[a] * y[b];
-      }
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          const int r = n0 + 4 * tr + a, c = n0 + 4 * tc + b;
-          if (r < M && c <= r) A[r * ld + c] -= acc[a][b];
-        }
-    }
-    __syncthreads();
-  }
-}
-
-// W (M x ncols, shared) <- L^-1 W, blocked forward substitution.
-template <int NB>
-__device__ void cta_trsm_lower(const double* L, int ld, const double* Dinv, double* W, int ldw, int M, int ncols) {
-  const int tid = threadIdx.x;
-  const int nbk = M / NB;
-  for (int J = 0; J < nbk; ++J) {
-    const int j0 = J * NB;
-    const double* Di = Dinv + J * NB * NB;
-    for (int c = tid; c < ncols; c += kBcrThreads) {
-      double v[NB], o[NB];
-#pragma unroll
-      for (int q = 0; q < NB; ++q) v[q] = W[(j0 + q) * ldw + c];
-#pragma unroll
-      for (int r = 0; r < NB; ++r) {
-        double s = 0.0;
-#pragma unroll
-        for (int q = 0; q <= r; ++q) s += Di[r * NB + q] * v[q];
-        o[r] = s;
-      }
-#pragma unroll
-      for (int q = 0; q < NB; ++q) W[(j0 + q) * ldw + c] = o[q];
-    }
-    __syncthreads();
-    // rows below: W[i][c] -= L[i][j0..] . W[j0..][c].  Thread (c = tid % 128, g = tid / 128) owns
-    // column c and every other 4-row strip; the 8 pivot-row values stay in registers.
-    const int n0 = j0 + NB;
-    const int c = tid & 127, g = tid >> 7;
-    for (int cc = c; cc < ncols; cc += 128) {
-      double w[NB];
-#pragma unroll
-      for (int q = 0; q < NB; ++q) w[q] = W[(j0 + q) * ldw + cc];
-      for (int i0 = n0 + 4 * g; i0 < M; i0 += 8) {
-#pragma unroll
-        for (int a = 0; a < 4; ++a) {
-          const int i = i0 + a;
-          if (i < M) {
-            double s = 0.0;
-#pragma unroll
-            for (int q = 0; q < NB; ++q) s += L[i * ld + j0 + q] * w[q];
-            W[i * ldw + cc] -= s;
-          }
-        }
-      }
-    }
-    __syncthreads();
-  }
-}
-
-// w (M, shared) <- L^-T w, blocked backward substitution.
-template <int NB>
-__device__ void cta_solve_lt(const double* L, int ld, const double* Dinv, double* w, int M) {
-  const int tid = threadIdx.x;
-  const int nbk = M / NB;
-  for (int J = nbk - 1; J >= 0; --J) {
-    const int j0 = J * NB;
-    const double* Di = Dinv + J * NB * NB;
-    if (tid < 32) {
-      double v = 0.0;
-      if (tid < NB) {
-#pragma unroll
-        for (int q = 0; q < NB; ++q) v += Di[q * NB + tid] * w[j0 + q];  // Di^T w_J
-      }
-      __syncwarp();
-      if (tid < NB) w[j0 + tid] = v;
-    }
-    __syncthreads();
-    for (int k = tid; k < j0; k += kBcrThreads) {
-      double s = 0.0;
-#pragma unroll
-      for (int q = 0; q < NB; ++q) s += L[(j0 + q) * ld + k] * w[j0 + q];
-      w[k] -= s;
-    }
-    __syncthreads();
-  }
-}
-
-// out[r][c] = base[r][c] - sum_k X[k][r] Y[k][c]   (X, Y: M x M in shared memory with an even
-// leading dimension -> 16-byte LDS; out/base global).  Only tile rows [tr0, tr1) are computed, so
-// several CTAs can split one product.  lower_only: X == Y, compute c <= r and mirror.
-__device__ void cta_xty_sub(const double* X, const double* Y, int ld, int M, double* __restrict__ out,
-                            const double* __restrict__ base, bool lower_only, int tr0, int tr1) {
-  const int T = (M + 3) / 4;
-  const int ntile = (tr1 - tr0) * T;
-  for (int t = threadIdx.x; t < ntile; t += kBcrThreads) {
-    const int tr = tr0 + t / T, tc = t % T;
-    if (lower_only && tc > tr) continue;
-    double acc[4][4];
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-      for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
-    // M is a multiple of cd (6 or 8); pad columns beyond M read finite junk only when M % 4 != 0,
-    // and those accumulators are never stored
-    const double* xp = X + 4 * tr;
-    const double* yp = Y + 4 * tc;
-#pragma unroll 2
-    for (int k = 0; k < M; ++k) {
-      const double2 x0 = *reinterpret_cast<const double2*>(xp + k * ld);
-      const double2 x1 = *reinterpret_cast<const double2*>(xp + k * ld + 2);
-      const double2 y0 = *reinterpret_cast<const double2*>(yp + k * ld);
-      const double2 y1 = *reinterpret_cast<const double2*>(yp + k * ld + 2);
-      const double xv[4] = {x0.x, x0.y, x1.x, x1.y};
-      const double yv[4] = {y0.x, y0.y, y1.x, y1.y};
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b] += xv[a] * yv[b];
-    }
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        const int r = 4 * tr + a, c = 4 * tc + b;
-        if (r < M && c < M) {
-          const double v = (base ? base[int64_t(r) * M + c] : 0.0) - acc[a][b];
-          out[int64_t(r) * M + c] = v;
-          if (lower_only && c < r) out[int64_t(c) * M + r] = v;
-        }
-      }
-  }
-}
-
-// global (M x M, dense) -> shared (leading dimension ld), optionally transposed, with cp.async
-// (LDGSTS): every copy is in flight at once; call cta_load_wait() before reading.
-__device__ __forceinline__ void cta_load(double* dst, int ld, const double* __restrict__ src, int M, bool transpose) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const unsigned d0 = unsigned(__cvta_generic_to_shared(dst));
-  for (int r = warp; r < M; r += kBcrThreads / 32) {
-    const double* s = src + int64_t(r) * M;
-    for (int c = lane; c < M; c += 32) {
-      const unsigned da = d0 + unsigned((transpose ? c * ld + r : r * ld + c) * 8);
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(da), "l"(s + c));
-    }
-  }
-}
-__device__ __forceinline__ void cta_load_wait() {
-  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::);
-  __syncthreads();
-}
-__device__ __forceinline__ void cta_store(double* __restrict__ dst, const double* src, int ld, int M, bool lower_only) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int r = warp; r < M; r += kBcrThreads / 32) {
-    double* d = dst + int64_t(r) * M;
-#pragma unroll 4
-    for (int c = lane; c < M; c += 32) d[c] = (!lower_only || c <= r) ? src[r * ld + c] : 0.0;
-  }
-}
 
 struct BcrLevel {
   int n;            // super blocks at this level
@@ -353,48 +76,144 @@ __global__ void k_bcr_build(int cd, int m, int M, int64_t n_blocks, int n_slots,
   }
 }
 
-// Eliminate the odd super blocks of a level.  TWO CTAs per block (blockIdx.y), each factoring
-// A_p itself (redundant, but the two triangular solves are the longer half of the work):
-//   y = 0:  L (stored), U = L^-1 B[p-1], y = L^-1 b[p]
-//   y = 1:  V = L^-1 B[p]^T  (only when block p + 1 exists)
+// Eliminate the odd super blocks of a level, in two launches so that neither has a long chain:
+//   k_bcr_factor  one CTA per odd block:  A_p = L L^T (L and the inverses of its diagonal blocks stored)
+//   k_bcr_solve   kSolveCols right-hand-side columns per CTA of  [U | V | y] = L^-1 [B[p-1] | B[p]^T | b[p]]
+// (the triangular solves are independent per column: at the sparse upper levels they spread over
+// up to 12 SMs per block instead of queueing behind the factorisation on one).
 template <int NB>
-__global__ void __launch_bounds__(kBcrThreads) k_bcr_eliminate(int M, BcrLevel lv, int* __restrict__ fail) {
+__global__ void __launch_bounds__(kBcrThreads) k_bcr_factor(int M, BcrLevel lv, int* __restrict__ fail) {
   extern __shared__ __align__(16) double sm[];
   const int ld = bcr_ld_odd(M);
   double* Ls = sm;                      // [M][ld]
-  double* Ws = sm + M * ld;             // [M][ld]  right-hand sides (column M = y)
-  double* Dinv = Ws + M * ld;           // [M/NB][NB*NB]
+  double* Dinv = Ls + M * ld;           // [M/NB][NB*NB]
+  double* Pt = Dinv + M * NB;           // [NB][bcr_ldp(M)]  Cholesky panel scratch
   const int q = blockIdx.x, p = 2 * q + 1;
-  const int part = blockIdx.y;
   const int tid = threadIdx.x;
-  if (part == 1 && p + 1 >= lv.n) return;
+  BCR_STAMP(0);
   cta_load(Ls, ld, lv.A + int64_t(p) * M * M, M, false);
-  // the right-hand sides stream in while the factorisation runs
-  if (part == 0) {
-    cta_load(Ws, ld, lv.B + int64_t(p - 1) * M * M, M, false);
-    for (int i = tid; i < M; i += kBcrThreads) Ws[i * ld + M] = lv.b[int64_t(p) * M + i];
-  } else {
-    cta_load(Ws, ld, lv.B + int64_t(p) * M * M, M, true);
-  }
   cta_load_wait();
-  cta_cholesky<NB>(Ls, M, ld, Dinv, fail);
-  if (part == 0) {
-    cta_store(lv.L + int64_t(q) * M * M, Ls, ld, M, true);
-    for (int i = tid; i < M * NB; i += kBcrThreads) lv.D[int64_t(q) * M * NB + i] = Dinv[i];
-    cta_trsm_lower<NB>(Ls, ld, Dinv, Ws, ld, M, M + 1);
-    cta_store(lv.U + int64_t(q) * M * M, Ws, ld, M, false);
-    for (int i = tid; i < M; i += kBcrThreads) lv.y[int64_t(q) * M + i] = Ws[i * ld + M];
-  } else {
-    cta_trsm_lower<NB>(Ls, ld, Dinv, Ws, ld, M, M);
-    cta_store(lv.V + int64_t(q) * M * M, Ws, ld, M, false);
-  }
+  BCR_STAMP(1);
+  cta_cholesky<NB>(Ls, M, ld, Dinv, Pt, fail);
+  BCR_STAMP(2);
+  cta_store(lv.L + int64_t(q) * M * M, Ls, ld, M, true);
+  for (int i = tid; i < M * NB; i += kBcrThreads) lv.D[int64_t(q) * M * NB + i] = Dinv[i];
+  BCR_STAMP(3);
 }
 
-// Even super blocks of a level -> next level.  THREE CTAs per block (blockIdx.y) so the
-// sparse upper levels still fill SMs:
-//   y = 0, 1:  A' = A_e - V_{e-1}^T V_{e-1} - U_{e+1}^T U_{e+1}  (tile rows split in halves; y = 0 also b')
-//   y = 2:     B' = -V_o^T U_o  (coupling across the eliminated block o = e + 1)
+// kSolveCols columns per CTA: 16 at the sparse upper levels (12 CTAs per block, short chains),
+// 32 while there are more blocks than SMs can hold at 12 CTAs each.
+template <int NB, int kSolveCols>
+__global__ void __launch_bounds__(kBcrThreads) k_bcr_solve(int M, BcrLevel lv) {
+  extern __shared__ __align__(16) double sm[];
+  const int ld = bcr_ld_odd(M);
+  constexpr int ldw = kSolveCols + 1;
+  double* Ls = sm;                      // [M][ld]
+  double* Dinv = Ls + M * ld;           // [M/NB][NB*NB]
+  double* Ws = Dinv + M * NB;           // [M][ldw]
+  const int q = blockIdx.x, p = 2 * q + 1;
+  const int col0 = blockIdx.y * kSolveCols;  // first column of [U | V | y] handled here
+  const int tid = threadIdx.x;
+  const bool has_v = p + 1 < lv.n;
+  const int ncols_all = 2 * M + 1;
+  if (col0 >= ncols_all) return;
+  // a slice entirely inside V of a block without right neighbour has nothing to do
+  if (!has_v && col0 >= M && col0 + kSolveCols <= 2 * M) return;
+  BCR_STAMP(4);
+  cta_load(Ls, ld, lv.L + int64_t(q) * M * M, M, false);
+  for (int i = tid; i < M * NB; i += kBcrThreads) Dinv[i] = lv.D[int64_t(q) * M * NB + i];
+  {
+    const double* Bl = lv.B + int64_t(p - 1) * M * M;
+    const double* Br = has_v ? lv.B + int64_t(p) * M * M : nullptr;
+    const double* bp = lv.b + int64_t(p) * M;
+    // U columns are contiguous along c, V columns (B[p]^T) along i: index the threads accordingly
+    for (int e = tid; e < M * kSolveCols; e += kBcrThreads) {
+      const int cU = e % kSolveCols, iU = e / kSolveCols;  // c fastest
+      const int iV = e % M, cV = e / M;                    // i fastest
+      const int colU = col0 + cU, colV = col0 + cV;
+      if (colU < M) Ws[iU * ldw + cU] = Bl[int64_t(iU) * M + colU];
+      if (colV >= M && colV < 2 * M) Ws[iV * ldw + cV] = has_v ? Br[int64_t(colV - M) * M + iV] : 0.0;
+      if (colU == 2 * M) Ws[iU * ldw + cU] = bp[iU];
+      if (colU > 2 * M) Ws[iU * ldw + cU] = 0.0;
+    }
+  }
+  cta_load_wait();
+  BCR_STAMP(5);
+  // forward substitution: thread (c, g) owns column c and the rows i = g (mod 16) of every update
+  const int c = tid % kSolveCols, g = tid / kSolveCols;
+  constexpr int kGroups = kBcrThreads / kSolveCols;
+  const int nbk = M / NB;
+  for (int J = 0; J < nbk; ++J) {
+    const int j0 = J * NB, n0 = j0 + NB;
+    const double* Di = Dinv + J * NB * NB;
+    if (g == 0) {
+      double v[NB], o[NB];
+#pragma unroll
+      for (int k = 0; k < NB; ++k) v[k] = Ws[(j0 + k) * ldw + c];
+#pragma unroll
+      for (int r = 0; r < NB; ++r) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k <= r; ++k) t += Di[r * NB + k] * v[k];
+        o[r] = t;
+      }
+#pragma unroll
+      for (int k = 0; k < NB; ++k) Ws[(j0 + k) * ldw + c] = o[k];
+    }
+    __syncthreads();
+    if (n0 + g < M) {
+      double w[NB];
+#pragma unroll
+      for (int k = 0; k < NB; ++k) w[k] = Ws[(j0 + k) * ldw + c];
+      for (int i = n0 + g; i < M; i += 2 * kGroups) {
+        const int i2 = i + kGroups;
+        const bool two = i2 < M;
+        const int ib = two ? i2 : i;
+        double la[NB], lb[NB];
+#pragma unroll
+        for (int k = 0; k < NB; ++k) { la[k] = Ls[i * ld + j0 + k]; lb[k] = Ls[ib * ld + j0 + k]; }
+        double sa = Ws[i * ldw + c], sb = Ws[ib * ldw + c];
+#pragma unroll
+        for (int k = 0; k < NB; ++k) { sa -= la[k] * w[k]; sb -= lb[k] * w[k]; }
+        Ws[i * ldw + c] = sa;
+        if (two) Ws[i2 * ldw + c] = sb;
+      }
+    }
+    __syncthreads();
+  }
+  BCR_STAMP(6);
+  {
+    double* Uq = lv.U + int64_t(q) * M * M;
+    double* Vq = lv.V + int64_t(q) * M * M;
+    double* yq = lv.y + int64_t(q) * M;
+    for (int e = tid; e < M * kSolveCols; e += kBcrThreads) {
+      const int cc = e % kSolveCols, i = e / kSolveCols;
+      const int col = col0 + cc;
+      const double v = Ws[i * ldw + cc];
+      if (col < M) Uq[int64_t(i) * M + col] = v;
+      else if (col < 2 * M) { if (has_v) Vq[int64_t(i) * M + (col - M)] = v; }
+      else if (col == 2 * M) yq[i] = v;
+    }
+  }
+  BCR_STAMP(7);
+}
+
+// Even super blocks of a level -> next level.  Nine CTAs per block (blockIdx.y) so the
+// sparse upper levels still fill SMs and every CTA's dependent chain is short:
+//   y in [0, 4):  A' = A_e - V_{e-1}^T V_{e-1} - U_{e+1}^T U_{e+1}: the lower-triangle 4x4 tiles,
+//                 enumerated without holes, a quarter each; the k range of every tile is split over
+//                 four thread groups and reduced through shared memory
+//   y in [4, 8):  B' = -V_o^T U_o (coupling across the eliminated block o = e + 1), a quarter of
+//                 the tiles each, k split over two thread groups
+//   y == 8:       b' = b_e - V_{e-1}^T y_{e-1} - U_{e+1}^T y_{e+1}
+// SPLIT = true is the latency-optimised form above (9 CTAs per block).  With more blocks than
+// SMs the redundant operand loads of the 9 parts dominate instead, so the dense lower levels run
+// SPLIT = false: one CTA for A' (every thread a tile, full k range), one for B', one for b'.
+template <bool SPLIT>
 __global__ void __launch_bounds__(kBcrThreads) k_bcr_reduce(int M, BcrLevel lv, BcrLevel nx) {
+  constexpr int kPartsA = SPLIT ? 4 : 1, kPartsB = SPLIT ? 4 : 1;
+  constexpr int kGroupsA = SPLIT ? 4 : 1, kGroupsB = SPLIT ? 2 : 1;   // k-range split inside a CTA
+  constexpr int kSlotsA = kBcrThreads / kGroupsA, kSlotsB = kBcrThreads / kGroupsB;
   extern __shared__ __align__(16) double sm[];
   const int ld = bcr_ld(M);
   double* Xs = sm;            // [M][ld]
@@ -410,77 +229,140 @@ __global__ void __launch_bounds__(kBcrThreads) k_bcr_reduce(int M, BcrLevel lv, 
   const double* Ur = has_r ? lv.U + int64_t((p + 1) / 2) * M * M : nullptr;
   const double* Vr = has_r ? lv.V + int64_t((p + 1) / 2) * M * M : nullptr;
   const int T = (M + 3) / 4;
-  if (part == 2) {
-    if (p + 2 < lv.n) {
-      cta_load(Xs, ld, Ur, M, false);
-      cta_load(Ys, ld, Vr, M, false);
-      cta_load_wait();
-      cta_xty_sub(Ys, Xs, ld, M, nx.B + int64_t(pe) * M * M, nullptr, false, 0, T);
+  BCR_STAMP(8);
+  if (part == kPartsA + kPartsB) {
+    // b': thread (i, half) accumulates one of the two products for row i; coalesced over i
+    double* red = sm;
+    const int i = tid % 128, half = tid / 128;
+    double s = 0.0;
+    if (i < M && (half == 0 ? has_l : has_r)) {
+      const double* Z = half == 0 ? Vl : Ur;
+      const double* y = lv.y + int64_t(half == 0 ? (p - 1) / 2 : (p + 1) / 2) * M;
+#pragma unroll 8
+      for (int k = 0; k < M; ++k) s += Z[int64_t(k) * M + i] * y[k];
+    }
+    red[tid] = s;
+    __syncthreads();
+    if (tid < M) nx.b[int64_t(pe) * M + tid] = lv.b[int64_t(p) * M + tid] - red[tid] - red[128 + tid];
+    return;
+  }
+  if (part >= kPartsA) {
+    if (p + 2 >= lv.n) return;
+    // B' = -Vr^T Ur: tiles [t0, t1) of the T x T grid
+    const int nt = T * T, per = (nt + kPartsB - 1) / kPartsB;
+    const int t0 = (part - kPartsA) * per, t1 = min(nt, t0 + per);
+    cta_load(Xs, ld, Ur, M, false);
+    cta_load(Ys, ld, Vr, M, false);
+    cta_load_wait();
+    const int g = tid / kSlotsB, ul = tid % kSlotsB;
+    double* red = sm;  // [kSlotsB][16] partial tiles of group 1 (the operands are dead by then)
+    double* Bn = nx.B + int64_t(pe) * M * M;
+    for (int base = t0; base < t1; base += kSlotsB) {  // uniform trip count
+      const int t = base + ul;
+      const bool live = t < t1;
+      const int tr = live ? t / T : 0, tc = live ? t % T : 0;
+      double acc[4][4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+      if (live) tile_xty(Ys, Xs, ld, tr, tc, (M * g) / kGroupsB, (M * (g + 1)) / kGroupsB, acc);
+      if (kGroupsB > 1) {
+        __syncthreads();  // every read of Xs / Ys of this round is done
+        if (g == 1) {
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) red[ul * 16 + 4 * a + b] = acc[a][b];
+        }
+        __syncthreads();
+      }
+      if (g == 0 && live) {
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            const int r = 4 * tr + a, c = 4 * tc + b;
+            if (r < M && c < M)
+              Bn[int64_t(r) * M + c] = -(acc[a][b] + (kGroupsB > 1 ? red[ul * 16 + 4 * a + b] : 0.0));
+          }
+      }
+      if (kGroupsB > 1 && base + kSlotsB < t1) {  // another round: the partials overwrote the operands
+        __syncthreads();
+        cta_load(Xs, ld, Ur, M, false);
+        cta_load(Ys, ld, Vr, M, false);
+        cta_load_wait();
+      }
     }
     return;
   }
-  if (part == 0) {
-    // b' (vector work, straight from global)
-    for (int i = tid; i < M; i += kBcrThreads) {
-      double s = lv.b[int64_t(p) * M + i];
-      if (has_l) {
-        const double* y = lv.y + int64_t((p - 1) / 2) * M;
-        for (int k = 0; k < M; ++k) s -= Vl[int64_t(k) * M + i] * y[k];
-      }
-      if (has_r) {
-        const double* y = lv.y + int64_t((p + 1) / 2) * M;
-        for (int k = 0; k < M; ++k) s -= Ur[int64_t(k) * M + i] * y[k];
-      }
-      nx.b[int64_t(pe) * M + i] = s;
-    }
-  }
-  // the symmetric products are computed on the lower triangle: balance the two halves by area
-  const int split = int(0.7071 * T + 0.5);
-  const int tr0 = part == 0 ? 0 : split, tr1 = part == 0 ? split : T;
+  // A': lower-triangle tiles u = tr (tr + 1) / 2 + tc, tc <= tr
+  const int nt = T * (T + 1) / 2, per = (nt + kPartsA - 1) / kPartsA;
+  const int u0 = part * per, u1 = min(nt, u0 + per);
+  BCR_STAMP(9);
   if (has_l) cta_load(Xs, ld, Vl, M, false);
   if (has_r) cta_load(Ys, ld, Ur, M, false);
   cta_load_wait();
-  // rows [4 tr0, 4 tr1) of the lower triangle (+ their mirror images); the two row ranges of
-  // the two CTAs write disjoint entries, and each entry is final after one pass
-  for (int t = tid; t < (tr1 - tr0) * T; t += kBcrThreads) {
-    const int tr = tr0 + t / T, tc = t % T;
-    if (tc > tr) continue;
+  BCR_STAMP(10);
+  const int g = tid / kSlotsA, ul = tid % kSlotsA;
+  double* red = sm;  // [kGroupsA - 1][kSlotsA][16]
+  for (int base = u0; base < u1; base += kSlotsA) {  // uniform trip count
+    const int u = base + ul;
+    const bool live = u < u1;
+    int tr = 0, tc = 0;
+    if (live) {
+      tr = int((sqrtf(8.0f * float(u) + 1.0f) - 1.0f) * 0.5f);
+      while (tr * (tr + 1) / 2 > u) --tr;
+      while ((tr + 1) * (tr + 2) / 2 <= u) ++tr;
+      tc = u - tr * (tr + 1) / 2;
+    }
     double acc[4][4];
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
       for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
-    for (int pass = 0; pass < 2; ++pass) {
-      if (pass == 0 ? !has_l : !has_r) continue;
-      const double* Z = pass == 0 ? Xs : Ys;
-      const double* xp = Z + 4 * tr;
-      const double* yp = Z + 4 * tc;
-#pragma unroll 2
-      for (int k = 0; k < M; ++k) {
-        const double2 x0 = *reinterpret_cast<const double2*>(xp + k * ld);
-        const double2 x1 = *reinterpret_cast<const double2*>(xp + k * ld + 2);
-        const double2 y0 = *reinterpret_cast<const double2*>(yp + k * ld);
-        const double2 y1 = *reinterpret_cast<const double2*>(yp + k * ld + 2);
-        const double xv[4] = {x0.x, x0.y, x1.x, x1.y};
-        const double yv[4] = {y0.x, y0.y, y1.x, y1.y};
+    if (live) {
+      const int k0 = (M * g) / kGroupsA, k1 = (M * (g + 1)) / kGroupsA;
+      if (has_l) tile_xty(Xs, Xs, ld, tr, tc, k0, k1, acc);
+      if (has_r) tile_xty(Ys, Ys, ld, tr, tc, k0, k1, acc);
+    }
+    if (kGroupsA > 1) {
+      __syncthreads();  // every read of Xs / Ys of this round is done
+      if (g > 0) {
 #pragma unroll
         for (int a = 0; a < 4; ++a)
 #pragma unroll
-          for (int b = 0; b < 4; ++b) acc[a][b] += xv[a] * yv[b];
+          for (int b = 0; b < 4; ++b) red[((g - 1) * kSlotsA + ul) * 16 + 4 * a + b] = acc[a][b];
       }
+      __syncthreads();
     }
+    if (g == 0 && live) {
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+      for (int a = 0; a < 4; ++a)
 #pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        const int r = 4 * tr + a, c = 4 * tc + b;
-        if (r < M && c < M) {
-          const double v = Ae[int64_t(r) * M + c] - acc[a][b];
-          An[int64_t(r) * M + c] = v;
-          if (c < r) An[int64_t(c) * M + r] = v;
+        for (int b = 0; b < 4; ++b) {
+          const int r = 4 * tr + a, c = 4 * tc + b;
+          if (r < M && c <= r) {
+            double sum = acc[a][b];
+            if (kGroupsA > 1) {
+              const int e = ul * 16 + 4 * a + b;
+#pragma unroll
+              for (int gg = 0; gg < kGroupsA - 1; ++gg) sum += red[gg * kSlotsA * 16 + e];
+            }
+            const double v = Ae[int64_t(r) * M + c] - sum;
+            An[int64_t(r) * M + c] = v;
+            if (c < r) An[int64_t(c) * M + r] = v;
+          }
         }
-      }
+    }
+    if (kGroupsA > 1 && base + kSlotsA < u1) {
+      __syncthreads();
+      if (has_l) cta_load(Xs, ld, Vl, M, false);
+      if (has_r) cta_load(Ys, ld, Ur, M, false);
+      cta_load_wait();
+    }
   }
+  BCR_STAMP(11);
 }
 
 // Last remaining block: x = A^-1 b (the survivor is always original block 0).
@@ -492,63 +374,100 @@ __global__ void __launch_bounds__(kBcrThreads) k_bcr_top(int M, BcrLevel lv, dou
   double* Ls = sm;
   double* w = sm + M * ld;       // [M] as an M x 1 right-hand side (ldw = 1)
   double* Dinv = w + M;
+  double* Pt = Dinv + M * NB;
   const int tid = threadIdx.x;
   cta_load(Ls, ld, lv.A, M, false);
   for (int i = tid; i < M; i += kBcrThreads) w[i] = lv.b[i];
   cta_load_wait();
-  cta_cholesky<NB>(Ls, M, ld, Dinv, fail);
+  cta_cholesky<NB>(Ls, M, ld, Dinv, Pt, fail);
   cta_trsm_lower<NB>(Ls, ld, Dinv, w, 1, M, 1);
   cta_solve_lt<NB>(Ls, ld, Dinv, w, M);
   for (int i = tid; i < M; i += kBcrThreads) x[i] = w[i];
 }
 
 // Odd blocks of a level: x_o = L^-T (y_o - U x_{o-1} - V x_{o+1}); x indexed by ORIGINAL block (p << shift).
-template <int NB>
+// UVS: U and V are staged in shared memory next to L (all three copies in flight at once);
+// otherwise (three M x M matrices do not fit) their rows are read from global memory.
+template <int NB, bool UVS>
 __global__ void __launch_bounds__(kBcrThreads) k_bcr_backsub(int M, BcrLevel lv, int shift, double* __restrict__ x) {
   extern __shared__ __align__(16) double sm[];
   const int ld = bcr_ld_odd(M);
-  double* Ls = sm;               // [M][ld]
-  double* w = sm + M * ld;       // [M]
+  double* Ls = sm;                               // [M][ld]
+  double* Us = Ls + M * ld;                      // [M][ld]  (UVS only)
+  double* Vs = Us + M * ld;                      // [M][ld]  (UVS only)
+  double* w = UVS ? Vs + M * ld : Ls + M * ld;   // [M]
   double* xl = w + M;            // [M]
   double* xr = xl + M;           // [M]
   double* Dinv = xr + M;         // [M/NB][NB*NB]
   const int q = blockIdx.x, p = 2 * q + 1;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x;
   const bool has_r = p + 1 < lv.n;
+  const double* U = lv.U + int64_t(q) * M * M;
+  const double* V = lv.V + int64_t(q) * M * M;
+  BCR_STAMP(16);
   for (int i = tid; i < M; i += kBcrThreads) {
     xl[i] = x[(int64_t(p - 1) << shift) * M + i];
     xr[i] = has_r ? x[(int64_t(p + 1) << shift) * M + i] : 0.0;
   }
   cta_load(Ls, ld, lv.L + int64_t(q) * M * M, M, false);
+  if (UVS) {
+    cta_load(Us, ld, U, M, false);
+    if (has_r) cta_load(Vs, ld, V, M, false);
+  }
   for (int i = tid; i < M * NB; i += kBcrThreads) Dinv[i] = lv.D[int64_t(q) * M * NB + i];
   cta_load_wait();
-  // w = y - U xl - V xr: one warp per row, lanes stride the columns (coalesced)
-  const double* U = lv.U + int64_t(q) * M * M;
-  const double* V = lv.V + int64_t(q) * M * M;
-  for (int r = warp; r < M; r += kBcrThreads / 32) {
-    double s = 0.0;
-    for (int c = lane; c < M; c += 32) {
-      s += U[int64_t(r) * M + c] * xl[c];
-      if (has_r) s += V[int64_t(r) * M + c] * xr[c];
+  BCR_STAMP(17);
+  // w = y - U xl - V xr: thread (r, half) walks half of row r of U and V (odd ld: conflict-free
+  // in shared memory; from global the 128-byte lines stay in L1 across the walk), one shuffle
+  // joins the halves.  M <= 128.
+  {
+    const int r = tid >> 1, hf = tid & 1;
+    const int c0 = hf ? M / 2 : 0, c1 = hf ? M : M / 2;
+    double a0 = 0.0, a1 = 0.0;
+    if (r < M) {
+      const double* ur = UVS ? Us + r * ld : U + int64_t(r) * M;
+      const double* vr = UVS ? Vs + r * ld : V + int64_t(r) * M;
+#pragma unroll 4
+      for (int c = c0; c < c1; ++c) a0 += ur[c] * xl[c];
+      if (has_r) {
+#pragma unroll 4
+        for (int c = c0; c < c1; ++c) a1 += vr[c] * xr[c];
+      }
     }
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) w[r] = lv.y[int64_t(q) * M + r] - s;
+    a0 += a1;
+    a0 += __shfl_xor_sync(0xffffffffu, a0, 1);
+    if (hf == 0 && r < M) w[r] = lv.y[int64_t(q) * M + r] - a0;
   }
   __syncthreads();
+  BCR_STAMP(18);
   cta_solve_lt<NB>(Ls, ld, Dinv, w, M);
+  BCR_STAMP(19);
   for (int i = tid; i < M; i += kBcrThreads) x[(int64_t(p) << shift) * M + i] = w[i];
 }
 
 }  // namespace
 
+constexpr size_t kBcrSmemCap = 220 * 1024;
+
+// per-kernel footprints (smaller than the two-matrix maximum so that two CTAs share an SM)
+static size_t bcr_factor_smem(int M, int cd) {
+  return (size_t(M) * bcr_ld_odd(M) + size_t(M) * cd + size_t(cd) * bcr_ldp(M) + 8) * sizeof(double);
+}
+static size_t bcr_backsub_smem(int M, int cd, bool uvs) {
+  return (size_t(uvs ? 3 : 1) * M * bcr_ld_odd(M) + 3 * size_t(M) + size_t(M) * cd + 8) * sizeof(double);
+}
+static size_t bcr_solve_smem(int M, int cd, int cols) {
+  return (size_t(M) * bcr_ld_odd(M) + size_t(M) * cd + size_t(M) * (cols + 1) + 8) * sizeof(double);
+}
+
 // two M x (M+1) matrices + vectors + the diagonal-block inverses
-size_t bcr_smem_bytes(int M, int cd) { return (size_t(2) * M * (bcr_ld(M) > bcr_ld_odd(M) ? bcr_ld(M) : bcr_ld_odd(M)) + 4 * size_t(M) + size_t(M) * cd + 8) * sizeof(double); }
+size_t bcr_smem_bytes(int M, int cd) { return (size_t(2) * M * (bcr_ld(M) > bcr_ld_odd(M) ? bcr_ld(M) : bcr_ld_odd(M)) + 4 * size_t(M) + size_t(M) * cd + size_t(cd) * bcr_ldp(M) + 8) * sizeof(double); }
 
 // Super-block size (in keyframes) for a given half-bandwidth, or 0 when BCR does not apply.
 int bcr_super_size(int cd, int bw, int n_slots) {
   const int m = bw < 1 ? 1 : bw;
   const int M = m * cd;
-  if (bcr_smem_bytes(M, cd) > 220 * 1024) return 0;  // two M x (M+1) fp64 matrices must fit shared memory
+  if (bcr_smem_bytes(M, cd) > kBcrSmemCap) return 0;  // two M x (M+1) fp64 matrices must fit shared memory
   if (n_slots < 2 * m) return 0;  // fewer than two super blocks: nothing to reduce
   return m;
 }
@@ -586,15 +505,24 @@ pba_status bcr_setup(Handle* h) {
   h->bcr_x_off = total;
   const int smem = int(bcr_smem_bytes(M, z.cd));
   if (z.cd == 8) {
-    PBA_CUDA_OK(cudaFuncSetAttribute(k_bcr_eliminate<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    PBA_CUDA_OK(cudaFuncSetAttribute(k_bcr_factor<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    PBA_CUDA_OK(cudaFuncSetAttribute(k_bcr_solve<8, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    PBA_CUDA_OK(cudaFuncSetAttribute(k_bcr_solve<8, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     PBA_CUDA_OK(cudaFuncSetAttribute(k_bcr_top<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    PBA_CUDA_OK(cudaFuncSetAttribute(k_bcr_backsub<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    PBA_CUDA_OK(cudaFuncSetAttribute(k_bcr_backsub<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if (bcr_backsub_smem(M, z.cd, true) <= kBcrSmemCap)
+      PBA_CUDA_OK(cudaFuncSetAttribute(k_bcr_backsub<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bcr_backsub_smem(M, z.cd, true))));
   } else {
-    PBA_CUDA_OK(cudaFuncSetAttribute(k_bcr_eliminate<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    PBA_CUDA_OK(cudaFuncSetAttribute(k_bcr_factor<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    PBA_CUDA_OK(cudaFuncSetAttribute(k_bcr_solve<6, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    PBA_CUDA_OK(cudaFuncSetAttribute(k_bcr_solve<6, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     PBA_CUDA_OK(cudaFuncSetAttribute(k_bcr_top<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    PBA_CUDA_OK(cudaFuncSetAttribute(k_bcr_backsub<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    PBA_CUDA_OK(cudaFuncSetAttribute(k_bcr_backsub<6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if (bcr_backsub_smem(M, z.cd, true) <= kBcrSmemCap)
+      PBA_CUDA_OK(cudaFuncSetAttribute(k_bcr_backsub<6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bcr_backsub_smem(M, z.cd, true))));
   }
-  PBA_CUDA_OK(cudaFuncSetAttribute(k_bcr_reduce, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  PBA_CUDA_OK(cudaFuncSetAttribute(k_bcr_reduce<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  PBA_CUDA_OK(cudaFuncSetAttribute(k_bcr_reduce<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   return PBA_OK;
 }
 
@@ -625,18 +553,51 @@ pba_status launch_bcr_rcs(Handle* h) {
   const bool c8 = z.cd == 8;
   for (int l = 0; l + 1 < nl; ++l) {
     BcrLevel lv = level(l), nx = level(l + 1);
-    if (c8) { PBA_LAUNCH(h, K_BCR, k_bcr_eliminate<8>, dim3(lv.n / 2, 2), dim3(kBcrThreads), smem, M, lv, h->chol_fail.p); }
-    else { PBA_LAUNCH(h, K_BCR, k_bcr_eliminate<6>, dim3(lv.n / 2, 2), dim3(kBcrThreads), smem, M, lv, h->chol_fail.p); }
-    PBA_LAUNCH(h, K_BCR, k_bcr_reduce, dim3(nx.n, 3), dim3(kBcrThreads), smem, M, lv, nx);
+    const int n_odd = lv.n / 2;
+    const bool wide = n_odd > 24;  // 12 CTAs per block would exceed two CTAs per SM
+    const int sc = wide ? 32 : 16;
+    const dim3 gs(n_odd, (2 * M + 1 + sc - 1) / sc);
+    const size_t smem_f = bcr_factor_smem(M, z.cd), smem_s = bcr_solve_smem(M, z.cd, sc);
+    if (c8) {
+      PBA_LAUNCH(h, K_BCR, k_bcr_factor<8>, dim3(n_odd), dim3(kBcrThreads), smem_f, M, lv, h->chol_fail.p);
+      if (wide) { PBA_LAUNCH(h, K_BCR, (k_bcr_solve<8, 32>), gs, dim3(kBcrThreads), smem_s, M, lv); }
+      else { PBA_LAUNCH(h, K_BCR, (k_bcr_solve<8, 16>), gs, dim3(kBcrThreads), smem_s, M, lv); }
+    } else {
+      PBA_LAUNCH(h, K_BCR, k_bcr_factor<6>, dim3(n_odd), dim3(kBcrThreads), smem_f, M, lv, h->chol_fail.p);
+      if (wide) { PBA_LAUNCH(h, K_BCR, (k_bcr_solve<6, 32>), gs, dim3(kBcrThreads), smem_s, M, lv); }
+      else { PBA_LAUNCH(h, K_BCR, (k_bcr_solve<6, 16>), gs, dim3(kBcrThreads), smem_s, M, lv); }
+    }
+    if (nx.n > 40) { PBA_LAUNCH(h, K_BCR, k_bcr_reduce<false>, dim3(nx.n, 3), dim3(kBcrThreads), smem, M, lv, nx); }
+    else { PBA_LAUNCH(h, K_BCR, k_bcr_reduce<true>, dim3(nx.n, 9), dim3(kBcrThreads), smem, M, lv, nx); }
   }
   if (c8) { PBA_LAUNCH(h, K_BCR, k_bcr_top<8>, dim3(1), dim3(kBcrThreads), smem, M, level(nl - 1), x, h->chol_fail.p); }
   else { PBA_LAUNCH(h, K_BCR, k_bcr_top<6>, dim3(1), dim3(kBcrThreads), smem, M, level(nl - 1), x, h->chol_fail.p); }
   for (int l = nl - 2; l >= 0; --l) {
     BcrLevel lv = level(l);
-    if (c8) { PBA_LAUNCH(h, K_BCR, k_bcr_backsub<8>, dim3(lv.n / 2), dim3(kBcrThreads), smem, M, lv, l, x); }
-    else { PBA_LAUNCH(h, K_BCR, k_bcr_backsub<6>, dim3(lv.n / 2), dim3(kBcrThreads), smem, M, lv, l, x); }
+    const bool uvs = bcr_backsub_smem(M, z.cd, true) <= kBcrSmemCap;
+    const size_t smem_b = bcr_backsub_smem(M, z.cd, uvs);
+    if (c8) {
+      if (uvs) { PBA_LAUNCH(h, K_BCR, (k_bcr_backsub<8, true>), dim3(lv.n / 2), dim3(kBcrThreads), smem_b, M, lv, l, x); }
+      else { PBA_LAUNCH(h, K_BCR, (k_bcr_backsub<8, false>), dim3(lv.n / 2), dim3(kBcrThreads), smem_b, M, lv, l, x); }
+    } else {
+      if (uvs) { PBA_LAUNCH(h, K_BCR, (k_bcr_backsub<6, true>), dim3(lv.n / 2), dim3(kBcrThreads), smem_b, M, lv, l, x); }
+      else { PBA_LAUNCH(h, K_BCR, (k_bcr_backsub<6, false>), dim3(lv.n / 2), dim3(kBcrThreads), smem_b, M, lv, l, x); }
+    }
   }
   PBA_CUDA_OK(cudaMemcpyAsync(h->y_cam.p, x, sizeof(double) * z.dim, cudaMemcpyDeviceToDevice, h->stream));
+#ifdef PBA_BCR_TIMING
+  {
+    static int calls = 0;
+    if (++calls == 5) {
+      cudaStreamSynchronize(h->stream);
+      long long t[32];
+      cudaMemcpyFromSymbol(t, g_bcr_t, sizeof(t));
+      auto us = [&](int a, int b) { return double(t[b] - t[a]) / 1965.0; };
+      fprintf(stderr, "[bcr] M=%d levels=%d | factor: load %.1f chol %.1f storeL %.1f | solve: load %.1f trsm %.1f store %.1f | reduce: b' %.1f load %.1f gemm %.1f | backsub: load %.1f matvec %.1f solve %.1f (us, last launch of each kernel, CTA 0)\n",
+              M, nl, us(0, 1), us(1, 2), us(2, 3), us(4, 5), us(5, 6), us(6, 7), us(8, 9), us(9, 10), us(10, 11), us(16, 17), us(17, 18), us(18, 19));
+    }
+  }
+#endif
   return PBA_OK;
 }
 
