@@ -206,7 +206,7 @@ pba_status validate(const pba_problem* p, const pba_options* o) {
   return PBA_OK;
 }
 
-constexpr int kChunkObs = 512;
+constexpr int kChunkObs = 1024;
 
 pba_status create_impl(const pba_problem* p, const pba_options* o, int rank, int world, Handle** out) {
   pba_status st = validate(p, o);

@@ -29,19 +29,29 @@ namespace {
 // contiguous 2 KB runs per stage (long DRAM bursts; staging 32 observations of
 // all R rows instead reads 128 scattered 256 B pieces and ran at 31 % DRAM
 // utilisation).  Stages are copied with cp.async into a double buffer
-// (transposed: Mt[column][obs]) so the copy overlaps the previous stage's FMAs.
-// Warp w owns one 8x8 tile of the symmetric 16x16 Gram matrix ((0,0), (0,1),
-// (1,1)); lane l accumulates observations 2l, 2l+1 (+64 s) in an 8x8 register
-// block: 16 LDS.128 per 128 DFMA.  The 32 lane partials of a tile are combined
-// once per chunk with shuffles.  JR = interleaved planes [R][C+1][ld] (column C
-// of every row is the residual).
-constexpr int kGramStages = 2;  // 3 stages measured slower (5.2 vs 4.6 ms): shared memory caps the SM at 2 CTAs either way
+// (transposed: Mt[column][obs]) so the copy overlaps the previous stage's math.
+// The products run on the FP64 tensor cores: one mma.sync.m8n8k4 (DMMA) adds four
+// observations to an 8x8 tile of G, and because G = M^T M the A fragment
+// (column-of-M x observation) and the B fragment (observation x column-of-M) of a
+// column block are the SAME register, so a k-step of all three upper tiles costs
+// 2 LDS.64 + 3 DMMA per lane (the scalar 8x8 register-tile version needed
+// 16 LDS.128 + 128 DFMA per 64 observations and was issue-bound at 32 % of the
+// FP64 pipe: 4.6 ms for 18 M observations).  Warp w takes k-steps w, w+3, ...;
+// the three warps' fragments are summed through shared memory once per chunk.
+// JR = interleaved planes [R][C+1][ld] (column C of every row is the residual).
+constexpr int kGramStages = 2;  // measured: 3 x 256 -> 4.45 ms, 4 x 128 -> 4.22 ms, 2 x 256 -> 4.09 ms
+
+__device__ __forceinline__ void gram_dmma(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c[0]), "+d"(c[1])
+               : "d"(a), "d"(b));
+}
 
 template <int R, int C>
 struct GramCfg {
   static constexpr int CD = C - 7;
   static constexpr int TOBS = 256;             // observations per stage
-  static constexpr int RS = TOBS + 2;          // padded row stride of Mt (even: LDS.128 stays aligned)
+  static constexpr int RS = TOBS + 4;          // row stride of Mt: = 4 (mod 16) doubles -> conflict-free fragment loads
   static constexpr int DIR_STRIDE = 3 * CD * CD + 2 * CD;
 };
 
@@ -60,39 +70,53 @@ __global__ void __launch_bounds__(96) k_edge_gram(int64_t ld, const int* __restr
   const int e = chunk_edge[q];
   const int64_t o0 = chunk_begin[q], o1 = chunk_end[q];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int ta = warp == 2 ? 8 : 0;   // first column of the tile's row block
-  const int tb = warp == 0 ? 0 : 8;   // first column of the tile's column block
-  const bool diag = ta == tb;
-  double acc[8][8];
-#pragma unroll
-  for (int x = 0; x < 8; ++x)
-#pragma unroll
-    for (int y = 0; y < 8; ++y) acc[x][y] = 0.0;
-  // columns C..14 of M are structurally zero
-  for (int i = threadIdx.x; i < kGramStages * 16 * RS; i += 96) gram_sm[i] = 0.0;
-  __syncthreads();
+  const int fr = lane >> 2, fo = lane & 3;  // fragment coordinates: column of M (within a block), observation
+  // upper tiles (0,0), (0,1), (1,1) of G; two accumulator sets keep six independent DMMA chains in flight
+  double c00[2][2] = {{0.0, 0.0}, {0.0, 0.0}}, c01[2][2] = {{0.0, 0.0}, {0.0, 0.0}}, c11[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+  // columns C..14 of M are structurally zero (nothing to do for the photometric 15-column rows)
+  if (C < 15) {
+    for (int i = threadIdx.x; i < kGramStages * (15 - C) * RS; i += 96) {
+      const int b = i / ((15 - C) * RS), j = i % ((15 - C) * RS);
+      gram_sm[b * 16 * RS + C * RS + j] = 0.0;
+    }
+    __syncthreads();
+  }
 
-  const int n_t = int((o1 - o0 + TOBS - 1) / TOBS);  // obs tiles per row
-  const int n_stage = n_t * R;                       // stage s = (row k = s / n_t, tile s % n_t)
+  // Stages start at an EVEN observation (o0 rounded down) so that every lane copies an aligned
+  // pair with one 16-byte cp.async (half the LDGSTS instructions: the 8-byte version was
+  // MIO-throttled); the observation before o0, if any, and everything from o1 on are zero-filled.
+  const int64_t o0al = o0 & ~int64_t(1);
+  const int n_t = int((o1 - o0al + TOBS - 1) / TOBS);  // obs tiles per row
+  const int n_stage = n_t * R;                         // stage s = (row k = s / n_t, tile s % n_t)
   auto stage = [&](int st, int buf) {
     const int k = st / n_t;
-    const int64_t base = o0 + int64_t(st % n_t) * TOBS;
-    const int cnt = int(o1 - base < TOBS ? o1 - base : TOBS);
+    const int64_t base = o0al + int64_t(st % n_t) * TOBS;
+    const int lo = int(o0 - base > 0 ? o0 - base : 0);             // first valid observation (0 or 1)
+    const int hi = int(o1 - base < TOBS ? o1 - base : TOBS);       // one past the last valid observation
     double* Mt = gram_sm + buf * 16 * RS;
     // warp w copies whole columns cc = w, w+3, ...: one address computation per column,
-    // then 8 x (32 observations) with immediate offsets (per-item address arithmetic was
-    // 2/3 of the kernel's instructions: 6.8 ms -> 4.6 ms at 18M observations)
-    const double* src = JR + (int64_t(k) * P + warp) * ld + base + lane;
+    // then 4 x (32 pairs) with immediate offsets
+    const double* src = JR + (int64_t(k) * P + warp) * ld + base + 2 * lane;
     for (int cc = warp; cc < P; cc += 3, src += 3 * ld) {
       const int c = cc < C ? cc : 15;
-      double* dst = Mt + c * RS + lane;
+      double* dst = Mt + c * RS + 2 * lane;
       const unsigned sa = unsigned(__cvta_generic_to_shared(dst));
 #pragma unroll
-      for (int j = 0; j < TOBS / 32; ++j) {
-        if (j * 32 + lane < cnt) {
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa + unsigned(j * 256)), "l"(src + j * 32));
+      for (int j = 0; j < TOBS / 64; ++j) {
+        const int a = j * 64 + 2 * lane;
+        if (a >= lo && a + 1 < hi) {
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa + unsigned(j * 512)), "l"(src + j * 64));
         } else {
-          dst[j * 32] = 0.0;
+          if (a >= lo && a < hi) {
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa + unsigned(j * 512)), "l"(src + j * 64));
+          } else {
+            dst[j * 64] = 0.0;
+          }
+          if (a + 1 >= lo && a + 1 < hi) {
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa + unsigned(j * 512 + 8)), "l"(src + j * 64 + 1));
+          } else {
+            dst[j * 64 + 1] = 0.0;
+          }
         }
       }
     }
@@ -113,44 +137,43 @@ __global__ void __launch_bounds__(96) k_edge_gram(int64_t ld, const int* __restr
     else asm volatile("cp.async.commit_group;\n" ::);
     asm volatile("cp.async.wait_group %0;\n" ::"n"(kGramStages - 1));
     __syncthreads();
-    // two base pointers per stage; every load below is [pointer + immediate]
-    const double2* pa = reinterpret_cast<const double2*>(gram_sm + buf * 16 * RS + ta * RS) + lane;
-    const double2* pb = reinterpret_cast<const double2*>(gram_sm + buf * 16 * RS + tb * RS) + lane;
-#pragma unroll
-    for (int s = 0; s < TOBS / 64; ++s) {
-      double2 av[8], bv[8];
-#pragma unroll
-      for (int x = 0; x < 8; ++x) av[x] = pa[(x * RS + 64 * s) / 2];
-      if (diag) {
-#pragma unroll
-        for (int x = 0; x < 8; ++x) bv[x] = av[x];
-      } else {
-#pragma unroll
-        for (int x = 0; x < 8; ++x) bv[x] = pb[(x * RS + 64 * s) / 2];
-      }
-#pragma unroll
-      for (int x = 0; x < 8; ++x)
-#pragma unroll
-        for (int y = 0; y < 8; ++y) {
-          acc[x][y] = fma(av[x].x, bv[y].x, acc[x][y]);
-          acc[x][y] = fma(av[x].y, bv[y].y, acc[x][y]);
-        }
+    const int64_t base = o0al + int64_t(st % n_t) * TOBS;
+    const int cnt = int(o1 - base < TOBS ? o1 - base : TOBS);
+    const int nk = (cnt + 3) >> 2;  // k-steps of four observations (head and tail are zero-filled)
+    const double* m0 = gram_sm + buf * 16 * RS + fr * RS + fo;  // column block 0; block 1 = + 8 RS
+    int ks = warp;
+    for (; ks + 3 < nk; ks += 6) {
+      const double f0 = m0[4 * ks], f1 = m0[8 * RS + 4 * ks];
+      const double g0 = m0[4 * ks + 12], g1 = m0[8 * RS + 4 * ks + 12];
+      gram_dmma(c00[0], f0, f0); gram_dmma(c01[0], f0, f1); gram_dmma(c11[0], f1, f1);
+      gram_dmma(c00[1], g0, g0); gram_dmma(c01[1], g0, g1); gram_dmma(c11[1], g1, g1);
+    }
+    if (ks < nk) {
+      const double f0 = m0[4 * ks], f1 = m0[8 * RS + 4 * ks];
+      gram_dmma(c00[0], f0, f0); gram_dmma(c01[0], f0, f1); gram_dmma(c11[0], f1, f1);
     }
     __syncthreads();  // everyone is done with `buf` before a later stage overwrites it
     buf = buf + 1 == kGramStages ? 0 : buf + 1;
   }
-  // combine the 32 lane partials of the tile; lane l keeps entries 2l, 2l+1
+  // sum the three warps' fragments: lane holds C[lane / 4][2 (lane % 4) + {0, 1}] of each tile
+  {
+    double* scratch = gram_sm;  // [3 warps][3 tiles][64]; the ring is dead after the last barrier
 #pragma unroll
-  for (int x = 0; x < 8; ++x)
-#pragma unroll
-    for (int y = 0; y < 8; ++y) {
-      double v = acc[x][y];
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane == ((x * 8 + y) >> 1)) {
-        G[(ta + x) * 16 + tb + y] = v;
-        G[(tb + y) * 16 + ta + x] = v;
-      }
+    for (int j = 0; j < 2; ++j) {
+      const int e = fr * 8 + 2 * fo + j;
+      scratch[(warp * 3 + 0) * 64 + e] = c00[0][j] + c00[1][j];
+      scratch[(warp * 3 + 1) * 64 + e] = c01[0][j] + c01[1][j];
+      scratch[(warp * 3 + 2) * 64 + e] = c11[0][j] + c11[1][j];
     }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 192; i += 96) {
+      const int t = i >> 6, e = i & 63, r = e >> 3, c = e & 7;
+      const double v = scratch[t * 64 + e] + scratch[(3 + t) * 64 + e] + scratch[(6 + t) * 64 + e];
+      const int ta = t == 2 ? 8 : 0, tb = t == 0 ? 0 : 8;
+      G[(ta + r) * 16 + tb + c] = v;
+      if (t == 1) G[(tb + c) * 16 + ta + r] = v;
+    }
+  }
   __syncthreads();
   // partial layout: [HH | HT (or its transpose when slot_h > slot_t) | TT | gh | gt]
   const int hs = slot[edge_h[e]], ts = slot[edge_t[e]];
