@@ -647,7 +647,7 @@ pba_status create_impl(const pba_problem* p, const pba_options* o, int rank, int
   PBA_CUDA_OK(cudaMallocHost(&h->h_scalars, sizeof(double) * (S_NUM + 2)));
   if (h->max_w_stride > 0) {
     // k_schur_syrk needs > 48 KB of dynamic shared memory for wide groups
-    schur_set_smem((size_t(h->schur_tile_l) * h->max_w_stride + h->schur_tile_l) * sizeof(double));
+    schur_set_smem(2 * (size_t(h->schur_tile_l) * (h->max_w_stride + 4) + h->schur_tile_l) * sizeof(double));
   }
   mark("allocate work buffers");
   st = launch_init_landmarks(h);

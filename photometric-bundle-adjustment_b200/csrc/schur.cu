@@ -15,6 +15,8 @@
 //   k_schur_syrk   per host group:                W^T diag(sigma^2/ete) W
 //   k_rcs_reduce   per RCS block:                 sum of its partial blocks
 // (the per-block source lists are static and built once in pba_create).
+#include <type_traits>
+
 #include "launch.h"
 #include "pba_internal.h"
 
@@ -268,8 +270,15 @@ __global__ void k_lm_scale(int n_lm, int init_scale, int jacobi, int refresh_dia
 // ------------------------------------------------------------ Schur SYRK ---
 // One CTA per host group: partial = W^T diag(s2) W over the group's landmarks,
 // as cd x cd blocks for camera pairs (i <= j) plus the vectors W^T (s2 g).
-// Landmark rows are staged in shared memory 'tile_l' at a time; each thread
-// owns up to two 4x4 register tiles per pass.
+// Landmark rows are staged in shared memory 'tile_l' at a time.  The products
+// run on the FP64 tensor cores: a k-step is four landmarks, an 8x8 output tile
+// one camera pair (or camera x the (g_l, c_l) block for the vectors), so a
+// tile-step costs 2 LDS.64 + DMUL + DMMA per lane (the scalar 4x4 register
+// tiles needed 8 LDS.64 per 16 DFMA and ran at a third of the FP64 peak).
+// Warp w owns tiles w, w+8, ... (<= kSyrkTiles per pass) with static accumulators.
+constexpr int kSyrkTiles = 12;
+__host__ __device__ inline int syrk_row_stride(int stride) { return stride + 4; }  // = 4 or 12 (mod 16): conflict-free fragments
+
 __global__ void __launch_bounds__(256) k_schur_syrk(int cd, int tile_l, const int* __restrict__ grp_lm_ptr,
                                                      const int* __restrict__ grp_cam_ptr,
                                                      const int64_t* __restrict__ grp_w_off,
@@ -282,81 +291,206 @@ __global__ void __launch_bounds__(256) k_schur_syrk(int cd, int tile_l, const in
   const int c = grp_cam_ptr[g + 1] - grp_cam_ptr[g];
   if (c == 0) return;
   const int stride = 8 * (c + 1);
+  const int ss = syrk_row_stride(stride);
   const double* Wg = W + grp_w_off[g];
   double* out = part_sch + grp_part_off[g];
   const int P = c * (c + 1) / 2;
-  const int T = 4 * P + 2 * c;
-  double* s_s2 = sm + size_t(tile_l) * stride;
+  const int n_tiles = P + c;  // camera pairs (i <= j), then camera i x the (g_l, c_l, 0..) block
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int fr = lane >> 2, fo = lane & 3;  // fragment coordinates: column within the block, landmark of the k-step
 
-  for (int t0 = 0; t0 < T; t0 += 512) {
-    int ci[2], cj[2], ok[2];
-    double acc[2][16];
+  for (int t0 = 0; t0 < n_tiles; t0 += 8 * kSyrkTiles) {
+    int oi[kSyrkTiles], oj[kSyrkTiles];
+    double acc[kSyrkTiles][2];
 #pragma unroll
-    for (int b = 0; b < 2; ++b) {
-      const int t = t0 + b * 256 + threadIdx.x;
-      ok[b] = t < T;
-      ci[b] = 0; cj[b] = 0;
-      if (ok[b]) {
-        if (t < 4 * P) {
-          int p = t >> 2, i = 0;
+    for (int tt = 0; tt < kSyrkTiles; ++tt) {
+      const int t = t0 + warp + 8 * tt;
+      oi[tt] = -1; oj[tt] = 0;
+      if (t < n_tiles) {
+        int i, j;
+        if (t < P) {
+          int p = t; i = 0;
           while (p >= c - i) { p -= c - i; ++i; }
-          ci[b] = 8 * i + 4 * ((t & 3) >> 1);
-          cj[b] = 8 * (i + p) + 4 * (t & 1);
+          j = i + p;
         } else {
-          const int v = t - 4 * P;
-          ci[b] = 8 * (v >> 1) + 4 * (v & 1);
-          cj[b] = 8 * c;
+          i = t - P; j = c;
         }
+        oi[tt] = 8 * i + fr; oj[tt] = 8 * j + fr;
       }
-#pragma unroll
-      for (int x = 0; x < 16; ++x) acc[b][x] = 0.0;
+      acc[tt][0] = 0.0; acc[tt][1] = 0.0;
     }
-    for (int lb = l0; lb < l1; lb += tile_l) {
+    // double-buffered cp.async staging: tile lb + tile_l streams in while tile lb is multiplied
+    const int buf_doubles = tile_l * ss + tile_l;
+    auto stage = [&](int lb, int buf) {
       const int cnt = l1 - lb < tile_l ? l1 - lb : tile_l;
-      __syncthreads();
       const double* src = Wg + size_t(lb - l0) * stride;
-      for (int i = threadIdx.x; i < cnt * stride; i += 256) sm[i] = src[i];
-      for (int i = threadIdx.x; i < cnt; i += 256) s_s2[i] = lm_s2[lb + i];
+      double* dst = sm + buf * buf_doubles;
+      const int cpr = stride >> 1;  // 16-byte chunks per row (rows are 64-byte aligned on both sides)
+      for (int i = threadIdx.x; i < cnt * cpr; i += 256) {
+        const int l = i / cpr, x = i - l * cpr;
+        const unsigned da = unsigned(__cvta_generic_to_shared(dst + l * ss + 2 * x));
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(da), "l"(src + size_t(l) * stride + 2 * x));
+      }
+      for (int i = threadIdx.x; i < cnt; i += 256) {
+        const unsigned da = unsigned(__cvta_generic_to_shared(dst + tile_l * ss + i));
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(da), "l"(lm_s2 + lb + i));
+      }
+      asm volatile("cp.async.commit_group;\n" ::);
+    };
+    __syncthreads();  // the previous pass is done with both buffers
+    stage(l0, 0);
+    int buf = 0;
+    for (int lb = l0; lb < l1; lb += tile_l, buf ^= 1) {
+      const int cnt = l1 - lb < tile_l ? l1 - lb : tile_l;
+      if (lb + tile_l < l1) {
+        stage(lb + tile_l, buf ^ 1);
+        asm volatile("cp.async.wait_group 1;\n" ::);
+      } else {
+        asm volatile("cp.async.wait_group 0;\n" ::);
+      }
       __syncthreads();
+      const double* tile = sm + buf * buf_doubles;
+      const double* s_s2 = tile + tile_l * ss;
+      for (int k0 = 0; k0 < cnt; k0 += 4) {
+        const int l = k0 + fo;
+        const bool lv = l < cnt;
+        const double* row = tile + l * ss;
+        const double s2 = lv ? s_s2[l] : 0.0;
 #pragma unroll
-      for (int b = 0; b < 2; ++b) {
-        if (!ok[b]) continue;
-        for (int l = 0; l < cnt; ++l) {
-          const double* row = sm + size_t(l) * stride;
-          const double s2 = s_s2[l];
-          double a[4], bb[4];
-#pragma unroll
-          for (int x = 0; x < 4; ++x) { a[x] = s2 * row[ci[b] + x]; bb[x] = row[cj[b] + x]; }
-#pragma unroll
-          for (int x = 0; x < 4; ++x)
-#pragma unroll
-            for (int y = 0; y < 4; ++y) acc[b][4 * x + y] += a[x] * bb[y];
+        for (int tt = 0; tt < kSyrkTiles; ++tt) {
+          if (oi[tt] < 0) continue;  // warp-uniform
+          const double a = lv ? s2 * row[oi[tt]] : 0.0;
+          const double bq = lv ? row[oj[tt]] : 0.0;
+          gram_dmma(acc[tt], a, bq);
         }
       }
+      __syncthreads();  // everyone is done with `buf` before the next pass restages it
     }
+    // lane holds C[fr][2 fo + {0, 1}] of every tile
 #pragma unroll
-    for (int b = 0; b < 2; ++b) {
-      if (!ok[b]) continue;
-      const int t = t0 + b * 256 + threadIdx.x;
-      if (t < 4 * P) {
-        const int p = t >> 2;
-        const int r0 = 4 * ((t & 3) >> 1), c0 = 4 * (t & 1);
-        double* blk = out + size_t(p) * cd * cd;
+    for (int tt = 0; tt < kSyrkTiles; ++tt) {
+      const int t = t0 + warp + 8 * tt;
+      if (t >= n_tiles) continue;
+      if (t < P) {
+        double* blk = out + size_t(t) * cd * cd;
 #pragma unroll
-        for (int x = 0; x < 4; ++x)
-#pragma unroll
-          for (int y = 0; y < 4; ++y)
-            if (r0 + x < cd && c0 + y < cd) blk[(r0 + x) * cd + c0 + y] = acc[b][4 * x + y];
+        for (int jj = 0; jj < 2; ++jj)
+          if (fr < cd && 2 * fo + jj < cd) blk[fr * cd + 2 * fo + jj] = acc[tt][jj];
       } else {
-        const int v = t - 4 * P;
-        double* vec = out + size_t(P) * cd * cd + size_t(v >> 1) * cd;
-        const int r0 = 4 * (v & 1);
-#pragma unroll
-        for (int x = 0; x < 4; ++x)
-          if (r0 + x < cd) vec[r0 + x] = acc[b][4 * x];
+        double* vec = out + size_t(P) * cd * cd + size_t(t - P) * cd;
+        if (fo == 0 && fr < cd) vec[fr] = acc[tt][0];
       }
     }
   }
+}
+
+// Row-paired variant for groups of at most kSyrkRowsMaxC cameras (windowed covisibility): warp w
+// owns tile rows w and c-1-w of the upper triangle (c + 3 tiles together, vector tile included),
+// keeps the two scaled A fragments of a k-step in registers and loads only the B fragment per
+// tile: 1 LDS.64 per DMMA instead of 2, which is what bounds the generic kernel above.
+constexpr int kSyrkRowsMaxC = 12;
+constexpr int kSyrkRowTiles = kSyrkRowsMaxC + 1;   // tiles of the longest row (row 0: j = 0..c)
+constexpr int kSyrkRowTilesB = kSyrkRowsMaxC / 2 + 2;  // second row of a warp: ib >= c / 2, so at most c / 2 + 2 tiles
+
+__global__ void __launch_bounds__(256) k_schur_syrk_rows(int cd, int tile_l, const int* __restrict__ grp_lm_ptr,
+                                                          const int* __restrict__ grp_cam_ptr,
+                                                          const int64_t* __restrict__ grp_w_off,
+                                                          const int64_t* __restrict__ grp_part_off,
+                                                          const double* __restrict__ W, const double* __restrict__ lm_s2,
+                                                          double* __restrict__ part_sch) {
+  extern __shared__ double sm[];
+  const int g = blockIdx.x;
+  const int l0 = grp_lm_ptr[g], l1 = grp_lm_ptr[g + 1];
+  const int c = grp_cam_ptr[g + 1] - grp_cam_ptr[g];
+  if (c == 0) return;
+  const int stride = 8 * (c + 1);
+  const int ss = syrk_row_stride(stride);
+  const double* Wg = W + grp_w_off[g];
+  double* out = part_sch + grp_part_off[g];
+  const int P = c * (c + 1) / 2;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int fr = lane >> 2, fo = lane & 3;
+  // rows of this warp: ia = pw (tiles j = ia..c), ib = c - 1 - pw (tiles j = ib..c) when distinct.
+  // Only ceil(c / 2) of the 8 warps have rows; odd CTAs rotate the assignment by two warps so that
+  // two co-resident CTAs load the four SM sub-partitions (warp % 4) evenly.
+  const int pw = (warp + ((blockIdx.x & 1) ? 6 : 0)) & 7;
+  const int ia = pw, ib = c - 1 - pw;
+  const bool has_a = ia < c && ia <= ib, has_b = ib > ia;
+  // accumulators: row a uses slots [0, c - ia], row b uses slots [0, c - ib] of its own array; both
+  // lengths are bounded by kSyrkRowTiles and the unused slots are skipped with warp-uniform tests
+  double acca[kSyrkRowTiles][2], accb[kSyrkRowTilesB][2];
+#pragma unroll
+  for (int t = 0; t < kSyrkRowTiles; ++t) acca[t][0] = acca[t][1] = 0.0;
+#pragma unroll
+  for (int t = 0; t < kSyrkRowTilesB; ++t) accb[t][0] = accb[t][1] = 0.0;
+  const int na = has_a ? c - ia + 1 : 0, nb = has_b ? c - ib + 1 : 0;
+
+  const int buf_doubles = tile_l * ss + tile_l;
+  auto stage = [&](int lb, int buf) {
+    const int cnt = l1 - lb < tile_l ? l1 - lb : tile_l;
+    const double* src = Wg + size_t(lb - l0) * stride;
+    double* dst = sm + buf * buf_doubles;
+    const int cpr = stride >> 1;
+    for (int i = threadIdx.x; i < cnt * cpr; i += 256) {
+      const int l = i / cpr, x = i - l * cpr;
+      const unsigned da = unsigned(__cvta_generic_to_shared(dst + l * ss + 2 * x));
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(da), "l"(src + size_t(l) * stride + 2 * x));
+    }
+    for (int i = threadIdx.x; i < cnt; i += 256) {
+      const unsigned da = unsigned(__cvta_generic_to_shared(dst + tile_l * ss + i));
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(da), "l"(lm_s2 + lb + i));
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
+  };
+  stage(l0, 0);
+  int buf = 0;
+  for (int lb = l0; lb < l1; lb += tile_l, buf ^= 1) {
+    const int cnt = l1 - lb < tile_l ? l1 - lb : tile_l;
+    if (lb + tile_l < l1) {
+      stage(lb + tile_l, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;\n" ::);
+    } else {
+      asm volatile("cp.async.wait_group 0;\n" ::);
+    }
+    __syncthreads();
+    const double* tile = sm + buf * buf_doubles;
+    const double* s_s2 = tile + tile_l * ss;
+    if (has_a) {
+      for (int k0 = 0; k0 < cnt; k0 += 4) {
+        const int l = k0 + fo;
+        const bool lv = l < cnt;
+        const double* row = tile + l * ss + fr;
+        const double s2 = lv ? s_s2[l] : 0.0;
+        const double fa = lv ? s2 * row[8 * ia] : 0.0;
+        const double fb = (lv && has_b) ? s2 * row[8 * ib] : 0.0;
+#pragma unroll
+        for (int t = 0; t < kSyrkRowTiles; ++t) {
+          if (t < na) gram_dmma(acca[t], fa, lv ? row[8 * (ia + t)] : 0.0);
+          if (t < kSyrkRowTilesB && t < nb) gram_dmma(accb[t < kSyrkRowTilesB ? t : 0], fb, lv ? row[8 * (ib + t)] : 0.0);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // lane holds C[fr][2 fo + {0, 1}] of every tile; pair (i, j) is block i c - i (i - 1) / 2 + (j - i)
+  auto store_row = [&](int i, int n, auto& acc, auto ntile) {
+    const int p0 = i * c - i * (i - 1) / 2;
+#pragma unroll
+    for (int t = 0; t < decltype(ntile)::value; ++t) {
+      if (t >= n) continue;
+      if (i + t < c) {
+        double* blk = out + size_t(p0 + t) * cd * cd;
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj)
+          if (fr < cd && 2 * fo + jj < cd) blk[fr * cd + 2 * fo + jj] = acc[t][jj];
+      } else {
+        double* vec = out + size_t(P) * cd * cd + size_t(i) * cd;
+        if (fo == 0 && fr < cd) vec[fr] = acc[t][0];
+      }
+    }
+  };
+  if (has_a) store_row(ia, na, acca, std::integral_constant<int, kSyrkRowTiles>());
+  if (has_b) store_row(ib, nb, accb, std::integral_constant<int, kSyrkRowTilesB>());
 }
 
 // ------------------------------------------------------------ RCS reduce ---
@@ -678,12 +812,15 @@ pba_status launch_post_jacobian(Handle* h) {
 }
 
 void schur_set_smem(size_t bytes) {
-  if (bytes > 48 * 1024) cudaFuncSetAttribute(k_schur_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
+  if (bytes > 48 * 1024) {
+    cudaFuncSetAttribute(k_schur_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
+    cudaFuncSetAttribute(k_schur_syrk_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
+  }
 }
 
 int schur_tile_l(int max_stride) {
   int t = 32;
-  while (t > 1 && size_t(t) * (max_stride + 1) * sizeof(double) > 160 * 1024) t >>= 1;
+  while (t > 1 && 2 * size_t(t) * (syrk_row_stride(max_stride) + 1) * sizeof(double) > 160 * 1024) t >>= 1;
   return t;
 }
 
@@ -700,9 +837,14 @@ pba_status launch_build_rcs(Handle* h, double radius, bool refresh_diag) {
   }
   if (z.n_groups > 0) {
     const int tile_l = h->schur_tile_l;
-    const size_t smem = (size_t(tile_l) * h->max_w_stride + tile_l) * sizeof(double);
-    PBA_LAUNCH(h, K_SCHUR_SYRK, k_schur_syrk, dim3(z.n_groups), dim3(256), smem, z.cd, tile_l, h->grp_lm_ptr.p,
-               h->grp_cam_ptr.p, h->grp_w_off.p, h->grp_part_off.p, h->W.p, h->lm_s2.p, h->part_sch.p);
+    const size_t smem = 2 * (size_t(tile_l) * syrk_row_stride(h->max_w_stride) + tile_l) * sizeof(double);
+    if (h->max_w_stride <= 8 * (kSyrkRowsMaxC + 1)) {
+      PBA_LAUNCH(h, K_SCHUR_SYRK, k_schur_syrk_rows, dim3(z.n_groups), dim3(256), smem, z.cd, tile_l, h->grp_lm_ptr.p,
+                 h->grp_cam_ptr.p, h->grp_w_off.p, h->grp_part_off.p, h->W.p, h->lm_s2.p, h->part_sch.p);
+    } else {
+      PBA_LAUNCH(h, K_SCHUR_SYRK, k_schur_syrk, dim3(z.n_groups), dim3(256), smem, z.cd, tile_l, h->grp_lm_ptr.p,
+                 h->grp_cam_ptr.p, h->grp_w_off.p, h->grp_part_off.p, h->W.p, h->lm_s2.p, h->part_sch.p);
+    }
   }
   double* S = h->rcs.p;
   double* rhs = S + z.n_blocks * z.cd * z.cd;
