@@ -467,7 +467,7 @@ size_t bcr_smem_bytes(int M, int cd) { return (size_t(2) * M * (bcr_ld(M) > bcr_
 int bcr_super_size(int cd, int bw, int n_slots) {
   const int m = bw < 1 ? 1 : bw;
   const int M = m * cd;
-  if (bcr_smem_bytes(M, cd) > kBcrSmemCap) return 0;  // two M x (M+1) fp64 matrices must fit shared memory
+  if (bcr_smem_bytes(M, cd) > kBcrSmemCap || m > bcr_max_blocks(cd) || M > 128) return 0;  // two M x (M+1) fp64 matrices must fit shared memory
   if (n_slots < 2 * m) return 0;  // fewer than two super blocks: nothing to reduce
   return m;
 }

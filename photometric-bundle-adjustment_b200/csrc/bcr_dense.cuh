@@ -85,6 +85,8 @@ __device__ __forceinline__ void thread_factor_diag(double* D, int ld, double* Di
 
 // Shared scratch of cta_cholesky: the current panel, transposed (Pt[q][i - n0], q < NB).
 __host__ __device__ inline int bcr_ldp(int M) { return ((M + 3) / 4) * 4 + 4; }
+// largest M / NB cta_cholesky's static tile ownership covers
+__host__ __device__ inline int bcr_max_blocks(int NB) { return NB == 8 ? 15 : 19; }
 
 // A <- lower Cholesky factor of A (strict upper triangle untouched); Dinv[J] = inverse
 // of the J-th diagonal block of the factor.  Pt: NB * bcr_ldp(M) doubles of scratch.
@@ -92,7 +94,9 @@ template <int NB>
 __device__ void cta_cholesky(double* __restrict__ A, int M, int ld, double* __restrict__ Dinv, double* __restrict__ Pt,
                              int* fail) {
   constexpr int TS = NB / 2;  // tile size: tiles never straddle a block column
-  constexpr int kTiles = 2;   // tiles per thread: T (T + 1) / 2 <= 2 * 256  <=>  M / NB <= 15
+  // tiles per thread: T (T + 1) / 2 <= kTiles * 256 with T = 2 M / NB.  The shared-memory cap of
+  // bcr_super_size() bounds M / NB by 14 (NB = 8) and 19 (NB = 6); see kBcrMaxBlocks.
+  constexpr int kTiles = NB == 8 ? 2 : 3;
   const int tid = threadIdx.x;
   const int nbk = M / NB;
   const int T = 2 * nbk;

@@ -186,6 +186,27 @@ def test_reduced_camera_system_parity(mode, model):
     eng.close()
 
 
+@pytest.mark.parametrize("mode", [pb.MODE_GEOMETRIC, pb.MODE_PHOTOMETRIC])
+def test_reduced_camera_system_parity_wide_windows(mode):
+    """Landmarks seen by 15-18 keyframes: host groups with up to 17 cameras (the generic Schur
+    product kernel, not the row-paired one for <= 12) and a half-bandwidth too wide for the
+    band / BCR solvers' shared-memory blocks (dense Cholesky / PCG take over)."""
+    prob, _ = scene(mode, "pinhole", n_kf=40, n_pts=1200, min_len=15, max_len=18)
+    assert np.diff(prob.lm_obs_ptr).max() >= 15
+    hub = huber_for(mode)
+    S_o, rhs_o, _ = of.build_rcs(prob, True, hub, radius=1e4)
+    eng = pb.Engine(prob, pb.BundleAdjustmentOptions(huber_parameter=hub))
+    eng.evaluate(True)
+    eng.build_rcs(1e4)
+    S, rhs = eng.rcs()
+    assert rel(S, S_o) < 1e-10
+    assert rel(rhs, rhs_o) < 1e-10
+    y_ref = np.linalg.solve(S_o, rhs_o)
+    y, _ = eng.solve_rcs(pb.SOLVER_AUTO)
+    assert rel(y, y_ref) < 1e-8
+    eng.close()
+
+
 # ------------------------------------------------------------------ LM run --
 @pytest.mark.parametrize("mode,model,n_kf,n_pts", [
     (pb.MODE_GEOMETRIC, "pinhole", 10, 400),
