@@ -225,14 +225,28 @@ __global__ void __launch_bounds__(128) k_lm_gather(int n_lm, int cd, const int64
   double* row = W + lm_w_off[l];
   const int stride = lm_w_stride[l];
   double acc = 0.0;  // lanes 0-5: host columns, 14: c_l, 15: g_l
-  for (int64_t k = lm_ptr[l]; k < lm_ptr[l + 1]; ++k) {
-    const int64_t pos = lm_pos[k];
-    const double v = orec[16 * pos + q];
-    const int col = obs_col[pos];
-    if (q >= 6 && q < 6 + cd) {
-      if (col >= 0) row[8 * col + (q - 6)] = v;
-    } else {
-      acc += v;
+  // observations four at a time: the position loads, then the record loads, are independent
+  // (one dependent pair per observation kept the kernel latency-bound at 55 % of HBM)
+  const int64_t k1 = lm_ptr[l + 1];
+  for (int64_t k = lm_ptr[l]; k < k1; k += 4) {
+    int64_t pos[4];
+    double v[4];
+    int col[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) pos[j] = k + j < k1 ? lm_pos[k + j] : -1;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      v[j] = pos[j] >= 0 ? orec[16 * pos[j] + q] : 0.0;
+      col[j] = pos[j] >= 0 ? obs_col[pos[j]] : -1;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (pos[j] < 0) continue;
+      if (q >= 6 && q < 6 + cd) {
+        if (col[j] >= 0) row[8 * col[j] + (q - 6)] = v[j];
+      } else {
+        acc += v[j];
+      }
     }
   }
   const int hc = lm_hostcol[l];
