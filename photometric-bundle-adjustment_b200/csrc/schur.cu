@@ -584,43 +584,58 @@ __global__ void k_rcs_scale(int cd, int64_t n_blocks, int n_slots, const int* __
 // (trust_region_minimizer.cc:414-427) without touching J again:
 //   landmark l:  -d_l (g_l + t_l + c_l d_l / 2),  t_l = sum_a w_la . d_a
 // the camera part (-d_c.g_c - d_c^T B d_c / 2) comes from k_model_cost_cam.
-__global__ void __launch_bounds__(128) k_backsub(int n_lm, int cd, const int* __restrict__ lm_group,
+// A half-warp per landmark (lanes stride the landmark's row of W: coalesced, all loads
+// independent), 128 landmarks per CTA so the model-cost partials keep one slot per 128 landmarks.
+__global__ void __launch_bounds__(256) k_backsub(int n_lm, int cd, const int* __restrict__ lm_group,
                                                   const int* __restrict__ grp_cam_ptr, const int* __restrict__ grp_cams,
                                                   const int64_t* __restrict__ lm_w_off,
                                                   const int* __restrict__ lm_w_stride, const int64_t* __restrict__ lm_ptr,
                                                   const double* __restrict__ W, const double* __restrict__ lm_scale,
                                                   const double* __restrict__ lm_iete, const double* __restrict__ d_cam,
                                                   double* __restrict__ d_rho, double* __restrict__ part_model) {
-  __shared__ double sm[4];
-  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ double sm[8];
+  const int hw = threadIdx.x >> 4, q = threadIdx.x & 15;
   double mc = 0.0;
-  if (l < n_lm) {
-    if (lm_ptr[l + 1] == lm_ptr[l]) {
-      d_rho[l] = 0.0;
-    } else {
+  for (int it = 0; it < 8; ++it) {
+    const int l = blockIdx.x * 128 + it * 16 + hw;
+    const bool live = l < n_lm && lm_ptr[l + 1] > lm_ptr[l];
+    const double* row = nullptr;
+    int stride = 0;
+    // d_cam = -sigma y  =>  sum_a w_la . (sigma_a y_a) = -sum_a w_la . d_a
+    double t = 0.0;
+    if (live) {
       const int g = lm_group[l];
       const int c0 = grp_cam_ptr[g], c = grp_cam_ptr[g + 1] - c0;
-      const double* row = W + lm_w_off[l];
-      const int stride = lm_w_stride[l];
-      // d_cam = -sigma y  =>  sum_a w_la . (sigma_a y_a) = -sum_a w_la . d_a
-      double t = 0.0;
-      for (int j = 0; j < c; ++j) {
-        const double* d = d_cam + grp_cams[c0 + j] * cd;
-        const double* w = row + 8 * j;
-        for (int i = 0; i < cd; ++i) t += w[i] * d[i];
+      row = W + lm_w_off[l];
+      stride = lm_w_stride[l];
+#pragma unroll 4
+      for (int e = q; e < 8 * c; e += 16) {
+        const int j = e >> 3, i = e & 7;
+        if (i < cd) t += row[e] * d_cam[grp_cams[c0 + j] * cd + i];
       }
-      const double gl = row[stride - 8], cl = row[stride - 7];
-      const double s = lm_scale[l];
-      const double y = lm_iete[l] * s * (gl + t);
-      const double dl = -s * y;
-      d_rho[l] = dl;
-      mc = -dl * (gl + t + 0.5 * cl * dl);
+    }
+    for (int o = 8; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (q == 0 && l < n_lm) {
+      if (!live) {
+        d_rho[l] = 0.0;
+      } else {
+        const double gl = row[stride - 8], cl = row[stride - 7];
+        const double s = lm_scale[l];
+        const double y = lm_iete[l] * s * (gl + t);
+        const double dl = -s * y;
+        d_rho[l] = dl;
+        mc += -dl * (gl + t + 0.5 * cl * dl);
+      }
     }
   }
   for (int o = 16; o > 0; o >>= 1) mc += __shfl_down_sync(0xffffffffu, mc, o);
   if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = mc;
   __syncthreads();
-  if (threadIdx.x == 0) part_model[blockIdx.x] = sm[0] + sm[1] + sm[2] + sm[3];
+  if (threadIdx.x == 0) {
+    double v = 0.0;
+    for (int i = 0; i < 8; ++i) v += sm[i];
+    part_model[blockIdx.x] = v;
+  }
 }
 
 // Camera part of the model cost change: one thread per RCS block of the raw (unscaled,
@@ -900,7 +915,7 @@ pba_status launch_backsub(Handle* h) {
   const int g_cam = int((z.n_blocks + 127) / 128);
   double* part = h->red_ws.p;
   if (g_lm > 0) {
-    PBA_LAUNCH(h, K_BACKSUB, k_backsub, dim3(g_lm), dim3(128), 0, z.n_lm, z.cd, h->lm_group.p, h->grp_cam_ptr.p,
+    PBA_LAUNCH(h, K_BACKSUB, k_backsub, dim3(g_lm), dim3(256), 0, z.n_lm, z.cd, h->lm_group.p, h->grp_cam_ptr.p,
                h->grp_cams.p, h->lm_w_off.p, h->lm_w_stride.p, h->lm_ptr.p, h->W.p, h->lm_scale.p, h->lm_iete.p,
                h->d_cam.p, h->d_rho.p, part);
   }
