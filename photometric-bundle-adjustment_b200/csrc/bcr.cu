@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(kBcrThreads) k_bcr_solve(int M, BcrLevel lv) {
   // a slice entirely inside V of a block without right neighbour has nothing to do
   if (!has_v && col0 >= M && col0 + kSolveCols <= 2 * M) return;
   BCR_STAMP(4);
-  cta_load(Ls, ld, lv.L + int64_t(q) * M * M, M, false);
+  cta_load(Ls, ld, lv.L + int64_t(q) * M * M, M, false, true);
   for (int i = tid; i < M * NB; i += kBcrThreads) Dinv[i] = lv.D[int64_t(q) * M * NB + i];
   {
     const double* Bl = lv.B + int64_t(p - 1) * M * M;
@@ -409,7 +409,7 @@ __global__ void __launch_bounds__(kBcrThreads) k_bcr_backsub(int M, BcrLevel lv,
     xl[i] = x[(int64_t(p - 1) << shift) * M + i];
     xr[i] = has_r ? x[(int64_t(p + 1) << shift) * M + i] : 0.0;
   }
-  cta_load(Ls, ld, lv.L + int64_t(q) * M * M, M, false);
+  cta_load(Ls, ld, lv.L + int64_t(q) * M * M, M, false, true);
   if (UVS) {
     cta_load(Us, ld, U, M, false);
     if (has_r) cta_load(Vs, ld, V, M, false);
@@ -503,6 +503,9 @@ pba_status bcr_setup(Handle* h) {
   for (size_t l = 0; l < ns.size(); ++l)
     for (size_t o : {offA[l], offB[l], offb[l], offL[l], offU[l], offV[l], offy[l], offD[l]}) h->bcr_off.push_back(o);
   h->bcr_x_off = total;
+  // level 0 is rebuilt from the RCS blocks by k_bcr_build before every solve; the block pattern is
+  // static, so the entries it never writes are zeroed here once (A and B of level 0 are contiguous)
+  PBA_CUDA_OK(cudaMemsetAsync(h->bcr_ws.p + offA[0], 0, sizeof(double) * (size_t(S) * M * M + size_t(S > 1 ? S - 1 : 0) * M * M), h->stream));
   const int smem = int(bcr_smem_bytes(M, z.cd));
   if (z.cd == 8) {
     PBA_CUDA_OK(cudaFuncSetAttribute(k_bcr_factor<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -544,8 +547,7 @@ pba_status launch_bcr_rcs(Handle* h) {
   const double* rhs = Sblk + z.n_blocks * z.cd * z.cd;
   double* x = ws + h->bcr_x_off;
   PBA_CUDA_OK(cudaMemsetAsync(h->chol_fail.p, 0, sizeof(int), h->stream));
-  BcrLevel l0 = level(0);
-  PBA_CUDA_OK(cudaMemsetAsync(l0.A, 0, sizeof(double) * (size_t(S) * M * M + size_t(S > 1 ? S - 1 : 0) * M * M), h->stream));
+  BcrLevel l0 = level(0);  // entries outside the static block pattern were zeroed once in bcr_setup
   PBA_LAUNCH(h, K_BCR, k_bcr_build, dim3((unsigned)(z.n_blocks + S)), dim3(64), 0, z.cd, m, M, z.n_blocks, z.n_slots,
              h->d_blk_row.p, h->d_blk_col.p, Sblk, rhs, S, l0.A, l0.B, l0.b);
   const size_t smem = bcr_smem_bytes(M, z.cd);

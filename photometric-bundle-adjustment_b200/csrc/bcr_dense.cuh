@@ -308,12 +308,14 @@ __device__ __forceinline__ void tile_xty(const double* X, const double* Y, int l
 
 // global (M x M, dense) -> shared (leading dimension ld), optionally transposed, with cp.async
 // (LDGSTS): every copy is in flight at once; call cta_load_wait() before reading.
-__device__ __forceinline__ void cta_load(double* dst, int ld, const double* __restrict__ src, int M, bool transpose) {
+__device__ __forceinline__ void cta_load(double* dst, int ld, const double* __restrict__ src, int M, bool transpose,
+                                         bool lower_only = false) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned d0 = unsigned(__cvta_generic_to_shared(dst));
   for (int r = warp; r < M; r += kBcrThreads / 32) {
     const double* s = src + int64_t(r) * M;
-    for (int c = lane; c < M; c += 32) {
+    const int cend = lower_only ? r + 1 : M;  // a Cholesky factor: the strict upper triangle is never read
+    for (int c = lane; c < cend; c += 32) {
       const unsigned da = d0 + unsigned((transpose ? c * ld + r : r * ld + c) * 8);
       asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(da), "l"(s + c));
     }
