@@ -282,6 +282,9 @@ def main():
     # per-kernel breakdown: same step, every kernel bracketed (not part of the timed region)
     n_prof = min(a.steps, 5)
     eng.set_profile(1)
+    eng.lm_iterate(radius)  # re-align the ranks (the all-reduce's event time includes waiting for the slowest)
+    if world > 1:
+        dist.barrier()
     eng.reset_kernel_stats()
     for _ in range(n_prof):
         eng.lm_iterate(radius)
