@@ -52,9 +52,16 @@ struct EvalArgs {
 
 // K0: per-edge relative pose A = R_t^T R_h, t = R_t^T (t_h - t_t) and the
 // target's affine brightness (exp(a), b).
+//
+// edge_M (Jacobian evaluations of the photometric residual only): with the right-multiplied
+// local parameterisation X_t = exp(-d_t) T_rel exp(d_h) P, and exp(-d_t) T_rel =
+// T_rel exp(-Ad(T_rel^-1) d_t), so every Jacobian row satisfies
+//     d r / d d_t = (d r / d d_h) M,   M = -Ad(T_rel^-1) = [[-A^T, A^T [t]x], [0, -A^T]]
+// — one 6x6 matrix per EDGE.  K1 therefore does not store the six target-pose planes, and the
+// Gram kernel derives the (h,t) and (t,t) blocks from the (h,h) block.
 __global__ void k_edge_prep(int n_edges, const int* __restrict__ edge_h, const int* __restrict__ edge_t,
                             const double* __restrict__ poses, const double* __restrict__ affine,
-                            double* __restrict__ edge_T) {
+                            double* __restrict__ edge_T, double* __restrict__ edge_M) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n_edges) return;
   const double* Th = poses + 7 * edge_h[e];
@@ -76,6 +83,22 @@ __global__ void k_edge_prep(int n_edges, const int* __restrict__ edge_h, const i
   }
   o[14] = 0.0;
   o[15] = 0.0;
+  if (edge_M) {
+    double* m = edge_M + 36 * e;
+    const double tx = o[9], ty = o[10], tz = o[11];
+    // S = [t]x
+    const double S[9] = {0.0, -tz, ty, tz, 0.0, -tx, -ty, tx, 0.0};
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) {
+        const double at = o[3 * j + i];  // (A^T)[i][j]
+        double as = 0.0;                 // (A^T S)[i][j]
+        for (int k = 0; k < 3; ++k) as += o[3 * k + i] * S[3 * k + j];
+        m[6 * i + j] = -at;
+        m[6 * i + 3 + j] = as;
+        m[6 * (3 + i) + j] = 0.0;
+        m[6 * (3 + i) + 3 + j] = -at;
+      }
+  }
 }
 
 // 2x2 bilinear footprints: quad(x,y) = I(x,y) | I(x+1,y)<<8 | I(x,y+1)<<16 | I(x+1,y+1)<<24
@@ -351,8 +374,10 @@ __global__ void __launch_bounds__(kPhotoThreads, WITH_J ? 3 : 4) k_eval_photo(co
         const double rw = w * rk;
         double* Jk = a.J + (int64_t(k) * 16) * n + i;  // planes [k][0..14] = J row, [k][15] = residual
         Jk[15 * n] = rw;
+        // planes 6..11 (target pose) are NOT stored: they are row[0..5] x M of the edge (k_edge_prep)
 #pragma unroll
-        for (int qq = 0; qq < 15; ++qq) Jk[int64_t(qq) * n] = row[qq];
+        for (int qq = 0; qq < 15; ++qq)
+          if (qq < 6 || qq >= 12) Jk[int64_t(qq) * n] = row[qq];
         const double E = row[14];
 #pragma unroll
         for (int qq = 0; qq < 14; ++qq) acc[qq] += E * row[qq];
@@ -484,8 +509,10 @@ __global__ void __launch_bounds__(1024) k_reduce_sum(const double* __restrict__ 
 
 // Test/diagnostic path: planes in edge order -> [obs][plane] in caller order.
 // which = 0: residuals [obs][R]; 1: Jacobians [obs][R][C]  (source planes [R][C+1][ld]).
+// edge_M != nullptr (photometric): the target-pose columns 6..11 are rebuilt as (columns 0..5) x M.
 __global__ void k_unpermute(int64_t n, int64_t ld, int R, int C, int which, const int64_t* __restrict__ order,
-                            const double* __restrict__ src, double* __restrict__ dst) {
+                            const double* __restrict__ src, const int* __restrict__ obs_edge,
+                            const double* __restrict__ edge_M, double* __restrict__ dst) {
   const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int64_t o = order[i];
@@ -493,7 +520,17 @@ __global__ void k_unpermute(int64_t n, int64_t ld, int R, int C, int which, cons
     if (which == 0) {
       dst[o * R + k] = src[(int64_t(k) * (C + 1) + C) * ld + i];
     } else {
-      for (int c = 0; c < C; ++c) dst[(o * R + k) * C + c] = src[(int64_t(k) * (C + 1) + c) * ld + i];
+      for (int c = 0; c < C; ++c) {
+        double v;
+        if (edge_M && c >= 6 && c < 12) {
+          const double* m = edge_M + 36 * int64_t(obs_edge[i]);
+          v = 0.0;
+          for (int q = 0; q < 6; ++q) v += src[(int64_t(k) * (C + 1) + q) * ld + i] * m[6 * q + (c - 6)];
+        } else {
+          v = src[(int64_t(k) * (C + 1) + c) * ld + i];
+        }
+        dst[(o * R + k) * C + c] = v;
+      }
     }
   }
 }
@@ -529,7 +566,8 @@ pba_status launch_evaluate(Handle* h, bool with_jacobian, const double* poses, c
   const bool photo = z.mode == PBA_MODE_PHOTOMETRIC;
   if (z.n_edges > 0) {
     PBA_LAUNCH(h, K_EDGE_PREP, k_edge_prep, dim3((z.n_edges + 127) / 128), dim3(128), 0, z.n_edges, h->edge_h.p,
-               h->edge_t.p, poses, photo ? affine : nullptr, h->edge_T.p);
+               h->edge_t.p, poses, photo ? affine : nullptr, h->edge_T.p,
+               photo && with_jacobian ? h->edge_M.p : nullptr);
   }
   EvalArgs a;
   a.n = z.n_obs; a.ld = z.ld; a.n_lm = z.n_lm;
@@ -568,7 +606,7 @@ pba_status launch_unpermute(Handle* h, int which, double* dst) {
   DevBuf<int64_t> order;
   PBA_CUDA_OK(order.upload(h->obs_order, h->stream));
   PBA_LAUNCH(h, K_UNPERMUTE, k_unpermute, dim3(int((z.n_obs + 127) / 128)), dim3(128), 0, z.n_obs, z.ld, z.R, z.C, which, order.p,
-             h->J.p, dst);
+             h->J.p, h->obs_edge.p, z.mode == PBA_MODE_PHOTOMETRIC ? h->edge_M.p : nullptr, dst);
   PBA_CUDA_OK(cudaStreamSynchronize(h->stream));
   return PBA_OK;
 }

@@ -202,6 +202,7 @@ struct Handle {
 
   // ---- per-evaluation data ----
   DevBuf<double> edge_T;       // [E][16]
+  DevBuf<double> edge_M;       // [E][36] photometric: target-pose Jacobian columns = host-pose columns x M (adjoint)
   DevBuf<double> J;            // interleaved planes [R][C+1][ld]: Jacobian row columns + residual
   DevBuf<double> orec;         // [n][16]
   DevBuf<double> W;            // grouped landmark rows

@@ -63,11 +63,17 @@ __global__ void __launch_bounds__(96) k_edge_gram(int64_t ld, const int* __restr
                                                    const int64_t* __restrict__ chunk_end,
                                                    const int* __restrict__ edge_h, const int* __restrict__ edge_t,
                                                    const int* __restrict__ slot, const double* __restrict__ JR,
-                                                   double* __restrict__ part_dir) {
+                                                   const double* __restrict__ edge_M, double* __restrict__ part_dir) {
   using Cfg = GramCfg<R, C>;
   constexpr int CD = Cfg::CD, TOBS = Cfg::TOBS, RS = Cfg::RS, P = C + 1;
-  extern __shared__ __align__(16) double gram_sm[];  // Mt[kGramStages][16 * RS] ring + G[256]
-  double* G = gram_sm + kGramStages * 16 * RS;
+  // Photometric rows (RED): K1 stores only the host-pose, affine and residual planes — the
+  // target-pose columns are (host-pose columns) x M with one 6x6 M per edge (eval.cu,
+  // k_edge_prep) — so M's matrix here is [J_h(6) J_a(2) | r]: 9 staged planes instead of 16, two
+  // DMMAs per k-step instead of three, and the 15-column Gram matrix is E^T G9 E at the end.
+  constexpr bool RED = R == 8;
+  constexpr int NR = RED ? 9 : 16;  // staged rows of Mt
+  extern __shared__ __align__(16) double gram_sm[];  // Mt[kGramStages][NR * RS] ring + G[256]
+  double* G = gram_sm + kGramStages * NR * RS;
   const int q = blockIdx.x;
   const int e = chunk_edge[q];
   const int64_t o0 = chunk_begin[q], o1 = chunk_end[q];
@@ -76,10 +82,10 @@ __global__ void __launch_bounds__(96) k_edge_gram(int64_t ld, const int* __restr
   // upper tiles (0,0), (0,1), (1,1) of G; two accumulator sets keep six independent DMMA chains in flight
   double c00[2][2] = {{0.0, 0.0}, {0.0, 0.0}}, c01[2][2] = {{0.0, 0.0}, {0.0, 0.0}}, c11[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
   // columns C..14 of M are structurally zero (nothing to do for the photometric 15-column rows)
-  if (C < 15) {
+  if (!RED && C < 15) {
     for (int i = threadIdx.x; i < kGramStages * (15 - C) * RS; i += 96) {
       const int b = i / ((15 - C) * RS), j = i % ((15 - C) * RS);
-      gram_sm[b * 16 * RS + C * RS + j] = 0.0;
+      gram_sm[b * NR * RS + C * RS + j] = 0.0;
     }
     __syncthreads();
   }
@@ -95,12 +101,14 @@ __global__ void __launch_bounds__(96) k_edge_gram(int64_t ld, const int* __restr
     const int64_t base = o0al + int64_t(st % n_t) * TOBS;
     const int lo = int(o0 - base > 0 ? o0 - base : 0);             // first valid observation (0 or 1)
     const int hi = int(o1 - base < TOBS ? o1 - base : TOBS);       // one past the last valid observation
-    double* Mt = gram_sm + buf * 16 * RS;
+    double* Mt = gram_sm + buf * NR * RS;
     // warp w copies whole columns cc = w, w+3, ...: one address computation per column,
     // then 4 x (32 pairs) with immediate offsets
-    const double* src = JR + (int64_t(k) * P + warp) * ld + base + 2 * lane;
-    for (int cc = warp; cc < P; cc += 3, src += 3 * ld) {
-      const int c = cc < C ? cc : 15;
+    for (int cc = warp; cc < (RED ? 9 : P); cc += 3) {
+      // RED: staged row cc <- plane 0..5 (host pose), 12, 13 (affine), 15 (residual)
+      const int sp = RED ? (cc < 6 ? cc : (cc < 8 ? cc + 6 : 15)) : cc;
+      const int c = RED ? cc : (cc < C ? cc : 15);
+      const double* src = JR + (int64_t(k) * P + sp) * ld + base + 2 * lane;
       double* dst = Mt + c * RS + 2 * lane;
       const unsigned sa = unsigned(__cvta_generic_to_shared(dst));
 #pragma unroll
@@ -142,17 +150,34 @@ __global__ void __launch_bounds__(96) k_edge_gram(int64_t ld, const int* __restr
     const int64_t base = o0al + int64_t(st % n_t) * TOBS;
     const int cnt = int(o1 - base < TOBS ? o1 - base : TOBS);
     const int nk = (cnt + 3) >> 2;  // k-steps of four observations (head and tail are zero-filled)
-    const double* m0 = gram_sm + buf * 16 * RS + fr * RS + fo;  // column block 0; block 1 = + 8 RS
+    const double* m0 = gram_sm + buf * NR * RS + fr * RS + fo;  // column block 0; block 1 = + 8 RS
     int ks = warp;
-    for (; ks + 3 < nk; ks += 6) {
-      const double f0 = m0[4 * ks], f1 = m0[8 * RS + 4 * ks];
-      const double g0 = m0[4 * ks + 12], g1 = m0[8 * RS + 4 * ks + 12];
-      gram_dmma(c00[0], f0, f0); gram_dmma(c01[0], f0, f1); gram_dmma(c11[0], f1, f1);
-      gram_dmma(c00[1], g0, g0); gram_dmma(c01[1], g0, g1); gram_dmma(c11[1], g1, g1);
-    }
-    if (ks < nk) {
-      const double f0 = m0[4 * ks], f1 = m0[8 * RS + 4 * ks];
-      gram_dmma(c00[0], f0, f0); gram_dmma(c01[0], f0, f1); gram_dmma(c11[0], f1, f1);
+    if (RED) {
+      // block 1 has one non-zero column (the residual, staged row 8): lanes of fragment row 0 carry it
+      const double* m8 = gram_sm + buf * NR * RS + 8 * RS + fo;
+      for (; ks + 3 < nk; ks += 6) {
+        const double f0 = m0[4 * ks], g0 = m0[4 * ks + 12];
+        const double r0 = m8[4 * ks], r1 = m8[4 * ks + 12];
+        const double f1 = fr == 0 ? r0 : 0.0, g1 = fr == 0 ? r1 : 0.0;
+        gram_dmma(c00[0], f0, f0); gram_dmma(c01[0], f0, f1);
+        gram_dmma(c00[1], g0, g0); gram_dmma(c01[1], g0, g1);
+      }
+      if (ks < nk) {
+        const double f0 = m0[4 * ks];
+        const double r0 = m8[4 * ks];
+        gram_dmma(c00[0], f0, f0); gram_dmma(c01[0], f0, fr == 0 ? r0 : 0.0);
+      }
+    } else {
+      for (; ks + 3 < nk; ks += 6) {
+        const double f0 = m0[4 * ks], f1 = m0[8 * RS + 4 * ks];
+        const double g0 = m0[4 * ks + 12], g1 = m0[8 * RS + 4 * ks + 12];
+        gram_dmma(c00[0], f0, f0); gram_dmma(c01[0], f0, f1); gram_dmma(c11[0], f1, f1);
+        gram_dmma(c00[1], g0, g0); gram_dmma(c01[1], g0, g1); gram_dmma(c11[1], g1, g1);
+      }
+      if (ks < nk) {
+        const double f0 = m0[4 * ks], f1 = m0[8 * RS + 4 * ks];
+        gram_dmma(c00[0], f0, f0); gram_dmma(c01[0], f0, f1); gram_dmma(c11[0], f1, f1);
+      }
     }
     __syncthreads();  // everyone is done with `buf` before a later stage overwrites it
     buf = buf + 1 == kGramStages ? 0 : buf + 1;
@@ -168,12 +193,54 @@ __global__ void __launch_bounds__(96) k_edge_gram(int64_t ld, const int* __restr
       scratch[(warp * 3 + 2) * 64 + e] = c11[0][j] + c11[1][j];
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 192; i += 96) {
-      const int t = i >> 6, e = i & 63, r = e >> 3, c = e & 7;
-      const double v = scratch[t * 64 + e] + scratch[(3 + t) * 64 + e] + scratch[(6 + t) * 64 + e];
-      const int ta = t == 2 ? 8 : 0, tb = t == 0 ? 0 : 8;
-      G[(ta + r) * 16 + tb + c] = v;
-      if (t == 1) G[(tb + c) * 16 + ta + r] = v;
+    if (!RED) {
+      for (int i = threadIdx.x; i < 192; i += 96) {
+        const int t = i >> 6, e = i & 63, r = e >> 3, c = e & 7;
+        const double v = scratch[t * 64 + e] + scratch[(3 + t) * 64 + e] + scratch[(6 + t) * 64 + e];
+        const int ta = t == 2 ? 8 : 0, tb = t == 0 ? 0 : 8;
+        G[(ta + r) * 16 + tb + c] = v;
+        if (t == 1) G[(tb + c) * 16 + ta + r] = v;
+      }
+    } else {
+      // G9 (9x9, symmetric; [8][8] = r^T r is not needed), E (9x16) and T1 = G9 E behind the scratch
+      double* G9 = gram_sm + 9 * 64;
+      double* E = G9 + 81;
+      double* T1 = E + 9 * 16;
+      for (int i = threadIdx.x; i < 81; i += 96) {
+        const int r = i / 9, c = i % 9;
+        double v = 0.0;
+        if (r < 8 && c < 8) { const int e = r * 8 + c; v = scratch[e] + scratch[3 * 64 + e] + scratch[6 * 64 + e]; }
+        else if (r < 8) { const int e = r * 8; v = scratch[64 + e] + scratch[4 * 64 + e] + scratch[7 * 64 + e]; }
+        else if (c < 8) { const int e = c * 8; v = scratch[64 + e] + scratch[4 * 64 + e] + scratch[7 * 64 + e]; }
+        G9[i] = v;
+      }
+      // columns of the full row: h(0..5) | t pose (6..11) = h x M | affine (12, 13) | rho (14, unused) | r (15)
+      const double* Me = edge_M + 36 * int64_t(e);
+      for (int i = threadIdx.x; i < 9 * 16; i += 96) {
+        const int r = i >> 4, c = i & 15;
+        double v = 0.0;
+        if (c < 6) v = r == c ? 1.0 : 0.0;
+        else if (c < 12) v = r < 6 ? Me[6 * r + (c - 6)] : 0.0;
+        else if (c < 14) v = r == 6 + (c - 12) ? 1.0 : 0.0;
+        else if (c == 15) v = r == 8 ? 1.0 : 0.0;
+        E[i] = v;
+      }
+      __syncthreads();
+      for (int i = threadIdx.x; i < 9 * 16; i += 96) {
+        const int r = i >> 4, c = i & 15;
+        double v = 0.0;
+#pragma unroll
+        for (int m = 0; m < 9; ++m) v += G9[r * 9 + m] * E[m * 16 + c];
+        T1[i] = v;
+      }
+      __syncthreads();
+      for (int i = threadIdx.x; i < 256; i += 96) {
+        const int a = i >> 4, b = i & 15;
+        double v = 0.0;
+#pragma unroll
+        for (int m = 0; m < 9; ++m) v += E[m * 16 + a] * T1[m * 16 + b];
+        G[i] = v;
+      }
     }
   }
   __syncthreads();
@@ -819,17 +886,17 @@ pba_status launch_post_jacobian(Handle* h) {
   const Sizes& z = h->sz;
   if (z.n_chunks > 0) {
     if (z.mode == PBA_MODE_PHOTOMETRIC) {
-      constexpr size_t smem = (kGramStages * 16 * GramCfg<8, 15>::RS + 256) * sizeof(double);
+      constexpr size_t smem = (kGramStages * 9 * GramCfg<8, 15>::RS + 256) * sizeof(double);
       static bool attr = false;
       if (!attr) { PBA_CUDA_OK(cudaFuncSetAttribute(k_edge_gram_photo, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))); attr = true; }
       PBA_LAUNCH(h, K_EDGE_GRAM, k_edge_gram_photo, dim3(z.n_chunks), dim3(96), smem, z.ld, h->chunk_edge.p,
-                 h->chunk_begin.p, h->chunk_end.p, h->edge_h.p, h->edge_t.p, h->d_slot.p, h->J.p, h->part_dir.p);
+                 h->chunk_begin.p, h->chunk_end.p, h->edge_h.p, h->edge_t.p, h->d_slot.p, h->J.p, h->edge_M.p, h->part_dir.p);
     } else {
       constexpr size_t smem = (kGramStages * 16 * GramCfg<2, 13>::RS + 256) * sizeof(double);
       static bool attr = false;
       if (!attr) { PBA_CUDA_OK(cudaFuncSetAttribute(k_edge_gram_geom, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))); attr = true; }
       PBA_LAUNCH(h, K_EDGE_GRAM, k_edge_gram_geom, dim3(z.n_chunks), dim3(96), smem, z.ld, h->chunk_edge.p,
-                 h->chunk_begin.p, h->chunk_end.p, h->edge_h.p, h->edge_t.p, h->d_slot.p, h->J.p, h->part_dir.p);
+                 h->chunk_begin.p, h->chunk_end.p, h->edge_h.p, h->edge_t.p, h->d_slot.p, h->J.p, nullptr, h->part_dir.p);
     }
   }
   if (z.n_lm > 0) {
