@@ -915,7 +915,7 @@ void schur_set_smem(size_t bytes) {
 }
 
 int schur_tile_l(int max_stride) {
-  int t = 32;
+  int t = 64;
   while (t > 1 && 2 * size_t(t) * (syrk_row_stride(max_stride) + 1) * sizeof(double) > 160 * 1024) t >>= 1;
   return t;
 }
