@@ -30,6 +30,7 @@
 #include <ceres/ceres.h>
 
 #include <algorithm>
+#include <bitset>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -574,6 +575,70 @@ REF_API int pba_ref_compute_projections(const pba_problem* p,
       if (outlier_flags) outlier_flags[s] = f;
     }
   }
+  return 0;
+}
+
+// the map archive.  save_map_file / load_map_file are the reference's own
+// functions (include/visnav/map_utils.h:58-116, cereal binary); the containers come from the flat
+// problem plus deterministic filler for the fields bundle adjustment does not touch (corner
+// angles, descriptors, matches, feature tracks, one outlier track / outlier observation).
+REF_API int pba_ref_save_map(const pba_problem* p, const char* path) {
+  using namespace visnav;
+  RefMap m;
+  if (int rc = build_map(p, &m)) return rc;
+  Matches matches;
+  FeatureTracks tracks, outlier_tracks;
+  for (auto& kv : m.corners) {
+    KeypointsData& kd = kv.second;
+    const size_t n = kd.corners.size();
+    kd.corner_angles.resize(n);
+    kd.corner_descriptors.resize(n);
+    for (size_t i = 0; i < n; ++i) {
+      kd.corner_angles[i] = 0.001 * double(i) - 0.5 * double(kv.first.frame_id);
+      std::bitset<256> d;
+      for (int b = 0; b < 256; ++b) d[b] = ((i * 2654435761u + size_t(kv.first.frame_id) * 40503u + b * 7919u) >> 7) & 1u;
+      kd.corner_descriptors[i] = d;
+    }
+  }
+  for (int i = 0; i + 1 < p->n_poses; ++i) {
+    MatchData md;
+    md.T_i_j = m.cameras.at(m.fcid[i]).T_w_c.inverse() * m.cameras.at(m.fcid[i + 1]).T_w_c;
+    const int n = int(std::min(m.corners.at(m.fcid[i]).corners.size(), m.corners.at(m.fcid[i + 1]).corners.size()));
+    for (int k = 0; k < std::min(n, 7); ++k) md.matches.emplace_back(k, n - 1 - k);
+    for (int k = 0; k < std::min(n, 4); ++k) md.inliers.emplace_back(k, n - 1 - k);
+    matches[std::make_pair(m.fcid[i], m.fcid[i + 1])] = md;
+  }
+  for (auto& kv : m.landmarks) tracks[kv.first] = kv.second.obs;
+  if (!m.landmarks.empty()) {
+    auto best = m.landmarks.begin();
+    for (auto it = m.landmarks.begin(); it != m.landmarks.end(); ++it)
+      if (it->second.obs.size() > best->second.obs.size()) best = it;
+    Landmark& first = best->second;  // the landmark with the most observations
+    outlier_tracks[TrackId(1000000)] = first.obs;
+    if (first.obs.size() > 2) {  // move the last observation to outlier_obs
+      auto last = std::prev(first.obs.end());
+      first.outlier_obs[last->first] = last->second;
+      first.obs.erase(last);
+    }
+  }
+  save_map_file(path, m.corners, matches, tracks, outlier_tracks, m.cameras, m.landmarks);
+  return 0;
+}
+
+// load_map_file(in) -> save_map_file(out): what the reference understood of a file it did not write
+REF_API int pba_ref_map_roundtrip(const char* in_path, const char* out_path, int64_t* counts) {
+  using namespace visnav;
+  Corners corners;
+  Matches matches;
+  FeatureTracks tracks, outlier_tracks;
+  Cameras cameras;
+  Landmarks landmarks;
+  load_map_file(in_path, corners, matches, tracks, outlier_tracks, cameras, landmarks);
+  if (counts) {
+    counts[0] = int64_t(corners.size()); counts[1] = int64_t(matches.size()); counts[2] = int64_t(tracks.size());
+    counts[3] = int64_t(outlier_tracks.size()); counts[4] = int64_t(cameras.size()); counts[5] = int64_t(landmarks.size());
+  }
+  save_map_file(out_path, corners, matches, tracks, outlier_tracks, cameras, landmarks);
   return 0;
 }
 

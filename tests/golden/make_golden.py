@@ -112,8 +112,26 @@ def main_projections():
         print(name, "slots", fl.size, "flag counts", [int(np.sum((fl >> b) & 1)) for b in range(4)])
 
 
+def main_map():
+    """map_geom_ds.cereal: the reference's own save_map_file (include/visnav/map_utils.h:58-86, cereal
+    binary) on containers built from the geom_ds fixture (+ deterministic filler, oracle/ref/ref_harness.cpp)."""
+    import ctypes as C
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import golden_util as gu
+    assert of.have_ref(), "build oracle/_ref first (make ref)"
+    prob, _ = gu.load(os.path.join(HERE, "geom_ds.npz"))
+    lib = of.ref()
+    lib.pba_ref_save_map.argtypes = [C.POINTER(pb._ffi.pba_problem), C.c_char_p]
+    pc = prob.c
+    out = os.path.join(HERE, "map_geom_ds.cereal")
+    assert lib.pba_ref_save_map(C.byref(pc), out.encode()) == 0
+    print("map_geom_ds.cereal", os.path.getsize(out), "bytes")
+
+
 if __name__ == "__main__":
-    if "--projections" in sys.argv:
+    if "--map" in sys.argv:
+        main_map()
+    elif "--projections" in sys.argv:
         main_projections()
     else:
         main()
