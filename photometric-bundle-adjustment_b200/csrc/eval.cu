@@ -212,7 +212,7 @@ __device__ __forceinline__ double huber(double s, int use_huber, double a, doubl
 // slower — 7.7 ms vs 6.7 ms at 18M observations: 4x the load instructions for
 // the per-edge constants.)
 constexpr int kPhotoThreads = 128;
-constexpr size_t kPhotoSmemBytes = ((kPhotoThreads / 32) * 32 * 17 + 32 * kPhotoThreads) * sizeof(double) + 16 * kPhotoThreads * 4;
+constexpr size_t kPhotoSmemBytes = 32 * kPhotoThreads * sizeof(double) + 16 * kPhotoThreads * 4;
 
 struct PhotoCtx {
   double A[9], tr[3], ea, bb, in[8], irho;
@@ -232,16 +232,17 @@ template <bool WITH_J, int MODEL>
 __global__ void __launch_bounds__(kPhotoThreads, WITH_J ? 3 : 4) k_eval_photo(const EvalArgs a) {
   __shared__ double s_red[kPhotoThreads / 32];
   // Dynamic shared memory (K1 only, kPhotoSmemBytes = 57 KB > the 48 KB static limit):
-  //   s_rec  [4][32][17] doubles  Schur-record transposition
-  //   s_pat  [32][128] doubles    pass-1 -> pass-2 hand-over: bx by bz Ih per pixel
+  //   s_pat  [4 warps][32 values][32 lanes] doubles  pass-1 -> pass-2 hand-over: bx by bz Ih per pixel
+  //   s_rec  [4 warps][32][17] doubles  Schur-record transposition, ALIASED on the warp's own s_pat
+  //          block (dead once the warp has left the pixel loop)
   //   s_quad [8][128] u32, s_off [8][128] int
   // [value][thread] layouts are conflict-free.  Keeping the hand-over in SHARED memory
   // matters: as a per-thread local array it spills through L2 to HBM (ncu,
   // profiles/r01b_*: 26.4 GB written per launch against 20.7 GB of outputs).
   extern __shared__ __align__(16) unsigned char k1_sm[];
-  double* s_rec = reinterpret_cast<double*>(k1_sm);
-  double* s_pat = s_rec + (kPhotoThreads / 32) * 32 * 17;
-  uint32_t* s_quad = reinterpret_cast<uint32_t*>(s_pat + 32 * kPhotoThreads);
+  double* s_pat = reinterpret_cast<double*>(k1_sm) + (threadIdx.x >> 5) * 1024 + (threadIdx.x & 31);  // + 32 * value
+  double* s_rec = reinterpret_cast<double*>(k1_sm) + (threadIdx.x >> 5) * 1024;
+  uint32_t* s_quad = reinterpret_cast<uint32_t*>(reinterpret_cast<double*>(k1_sm) + 32 * kPhotoThreads);
   int* s_off = reinterpret_cast<int*>(s_quad + 8 * kPhotoThreads);
   const int tid = threadIdx.x;
   const int64_t i = int64_t(blockIdx.x) * kPhotoThreads + tid;
@@ -317,10 +318,10 @@ __global__ void __launch_bounds__(kPhotoThreads, WITH_J ? 3 : 4) k_eval_photo(co
     if (WITH_J) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        s_pat[(4 * k + 0) * kPhotoThreads + tid] = bx[k];
-        s_pat[(4 * k + 1) * kPhotoThreads + tid] = by[k];
-        s_pat[(4 * k + 2) * kPhotoThreads + tid] = bz[k];
-        s_pat[(4 * k + 3) * kPhotoThreads + tid] = Ih[k];
+        s_pat[(4 * k + 0) * 32] = bx[k];
+        s_pat[(4 * k + 1) * 32] = by[k];
+        s_pat[(4 * k + 2) * 32] = bz[k];
+        s_pat[(4 * k + 3) * 32] = Ih[k];
         s_quad[k * kPhotoThreads + tid] = quad[k];
         s_off[k * kPhotoThreads + tid] = off[k];
       }
@@ -329,8 +330,8 @@ __global__ void __launch_bounds__(kPhotoThreads, WITH_J ? 3 : 4) k_eval_photo(co
       const int64_t n = a.ld;
 #pragma unroll 2
       for (int k = 0; k < 8; ++k) {
-        const double bxk = s_pat[(4 * k + 0) * kPhotoThreads + tid], byk = s_pat[(4 * k + 1) * kPhotoThreads + tid];
-        const double bzk = s_pat[(4 * k + 2) * kPhotoThreads + tid], Ihk = s_pat[(4 * k + 3) * kPhotoThreads + tid];
+        const double bxk = s_pat[(4 * k + 0) * 32], byk = s_pat[(4 * k + 1) * 32];
+        const double bzk = s_pat[(4 * k + 2) * 32], Ihk = s_pat[(4 * k + 3) * 32];
         const uint32_t q = s_quad[k * kPhotoThreads + tid];
         const int ofk = s_off[k * kPhotoThreads + tid];
         const double xh = bxk * c.irho, yh = byk * c.irho, zh = bzk * c.irho;
@@ -361,11 +362,7 @@ __global__ void __launch_bounds__(kPhotoThreads, WITH_J ? 3 : 4) k_eval_photo(co
         row[3] = -(ay * zh - az * yh);
         row[4] = -(az * xh - ax * zh);
         row[5] = -(ax * yh - ay * xh);
-        // target pose: [-p | p x X_t]
-        row[6] = -p0; row[7] = -p1; row[8] = -p2;
-        row[9] = p1 * zt - p2 * yt;
-        row[10] = p2 * xt - p0 * zt;
-        row[11] = p0 * yt - p1 * xt;
+        // target pose [-p | p x X_t] = row[0..5] x M of the edge: neither stored nor formed here
         // affine (a_t, b_t)
         row[12] = -w * c.ea * Ihk;
         row[13] = -w;
@@ -380,16 +377,32 @@ __global__ void __launch_bounds__(kPhotoThreads, WITH_J ? 3 : 4) k_eval_photo(co
           if (qq < 6 || qq >= 12) Jk[int64_t(qq) * n] = row[qq];
         const double E = row[14];
 #pragma unroll
-        for (int qq = 0; qq < 14; ++qq) acc[qq] += E * row[qq];
+        for (int qq = 0; qq < 14; ++qq)
+          if (qq < 6 || qq >= 12) acc[qq] += E * row[qq];
         acc[14] += E * E;
         acc[15] += E * rw;
+      }
+      // target-pose part of the Schur record, (E^T J_h) M with M = [[-A^T, A^T [t]x], [0, -A^T]]:
+      // u = A v_upsilon, E^T J_t = [-u | u x t - A v_omega]
+      {
+        const double u0 = c.A[0] * acc[0] + c.A[1] * acc[1] + c.A[2] * acc[2];
+        const double u1 = c.A[3] * acc[0] + c.A[4] * acc[1] + c.A[5] * acc[2];
+        const double u2 = c.A[6] * acc[0] + c.A[7] * acc[1] + c.A[8] * acc[2];
+        const double w0 = c.A[0] * acc[3] + c.A[1] * acc[4] + c.A[2] * acc[5];
+        const double w1 = c.A[3] * acc[3] + c.A[4] * acc[4] + c.A[5] * acc[5];
+        const double w2 = c.A[6] * acc[3] + c.A[7] * acc[4] + c.A[8] * acc[5];
+        acc[6] = -u0; acc[7] = -u1; acc[8] = -u2;
+        acc[9] = (u1 * c.tr[2] - u2 * c.tr[1]) - w0;
+        acc[10] = (u2 * c.tr[0] - u0 * c.tr[2]) - w1;
+        acc[11] = (u0 * c.tr[1] - u1 * c.tr[0]) - w2;
       }
     }
   }
   if (WITH_J) {
     // Schur record [obs][16]: transpose the warp's 32 x 16 values through shared
     // memory (row stride 17) and store them as 16 coalesced 256 B runs.
-    double* rec = s_rec + warp * 32 * 17;
+    __syncwarp();  // the warp is done with its s_pat block, which s_rec aliases
+    double* rec = s_rec;
 #pragma unroll
     for (int q = 0; q < 16; ++q) rec[lane * 17 + q] = acc[q];
     __syncwarp();
