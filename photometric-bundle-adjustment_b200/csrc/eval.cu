@@ -369,12 +369,13 @@ __global__ void __launch_bounds__(kPhotoThreads, WITH_J ? 3 : 4) k_eval_photo(co
         // inverse distance: -(a . X_h) / rho
         row[14] = -(ax * xh + ay * yh + az * zh) * c.irho;
         const double rw = w * rk;
-        double* Jk = a.J + (int64_t(k) * 16) * n + i;  // planes [k][0..14] = J row, [k][15] = residual
-        Jk[15 * n] = rw;
-        // planes 6..11 (target pose) are NOT stored: they are row[0..5] x M of the edge (k_edge_prep)
+        // kPhotoPlanes planes per row: columns 6..11 (target pose) are NOT stored, they are
+        // row[0..5] x M of the edge (k_edge_prep); photo_plane() compacts the rest, residual last
+        double* Jk = a.J + (int64_t(k) * kPhotoPlanes) * n + i;
+        Jk[int64_t(photo_plane(15)) * n] = rw;
 #pragma unroll
         for (int qq = 0; qq < 15; ++qq)
-          if (qq < 6 || qq >= 12) Jk[int64_t(qq) * n] = row[qq];
+          if (qq < 6 || qq >= 12) Jk[int64_t(photo_plane(qq)) * n] = row[qq];
         const double E = row[14];
 #pragma unroll
         for (int qq = 0; qq < 14; ++qq)
@@ -529,18 +530,19 @@ __global__ void k_unpermute(int64_t n, int64_t ld, int R, int C, int which, cons
   const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int64_t o = order[i];
+  const int P = edge_M ? kPhotoPlanes : C + 1;  // planes per row
   for (int k = 0; k < R; ++k) {
     if (which == 0) {
-      dst[o * R + k] = src[(int64_t(k) * (C + 1) + C) * ld + i];
+      dst[o * R + k] = src[(int64_t(k) * P + (edge_M ? photo_plane(C) : C)) * ld + i];
     } else {
       for (int c = 0; c < C; ++c) {
         double v;
         if (edge_M && c >= 6 && c < 12) {
           const double* m = edge_M + 36 * int64_t(obs_edge[i]);
           v = 0.0;
-          for (int q = 0; q < 6; ++q) v += src[(int64_t(k) * (C + 1) + q) * ld + i] * m[6 * q + (c - 6)];
+          for (int q = 0; q < 6; ++q) v += src[(int64_t(k) * P + q) * ld + i] * m[6 * q + (c - 6)];
         } else {
-          v = src[(int64_t(k) * (C + 1) + c) * ld + i];
+          v = src[(int64_t(k) * P + (edge_M ? photo_plane(c) : c)) * ld + i];
         }
         dst[(o * R + k) * C + c] = v;
       }
@@ -548,7 +550,27 @@ __global__ void k_unpermute(int64_t n, int64_t ld, int R, int C, int which, cons
   }
 }
 
+// Set-up: obs_edge[i] = e and obs_col[i] = edge_col[e] for the observations [edge_ptr[e], edge_ptr[e+1]) of edge e.
+__global__ void k_expand_edges(int n_edges, const int64_t* __restrict__ edge_ptr, const int* __restrict__ edge_col,
+                               int* __restrict__ obs_edge, int* __restrict__ obs_col) {
+  const int e = blockIdx.x;
+  if (e >= n_edges) return;
+  const int col = edge_col[e];
+  for (int64_t i = edge_ptr[e] + threadIdx.x; i < edge_ptr[e + 1]; i += blockDim.x) {
+    obs_edge[i] = e;
+    obs_col[i] = col;
+  }
+}
+
 }  // namespace
+
+pba_status launch_expand_edges(Handle* h, const int* edge_col_dev) {
+  const Sizes& z = h->sz;
+  if (z.n_edges == 0) return PBA_OK;
+  PBA_LAUNCH(h, K_INIT_LM, k_expand_edges, dim3(z.n_edges), dim3(128), 0, z.n_edges, h->edge_ptr.p, edge_col_dev,
+             h->obs_edge.p, h->obs_col.p);
+  return PBA_OK;
+}
 
 // Upload-time conversion of the 8-bit keyframes (staged in `images_u8`, n_img
 // keyframes of pitch*height bytes) into the quad layout at keyframe `first`.

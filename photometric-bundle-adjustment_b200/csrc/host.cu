@@ -426,7 +426,8 @@ pba_status create_impl(const pba_problem* p, const pba_options* o, int rank, int
   h->schur_tile_l = schur_tile_l(h->max_w_stride);
 
   // pass B (parallel over groups): place every observation at its edge-order position
-  RawVec<int> obs_lm(n), obs_edge(n), obs_col(n);  // every entry is written in pass B
+  RawVec<int> obs_lm(n);  // every entry is written in pass B
+  std::vector<int> edge_col(z.n_edges, -1);  // W column of an edge's target; obs_edge / obs_col are expanded on the device
   RawVec<int64_t> lm_pos(n);
   std::vector<int> lm_group(n_lm), lm_hostcol(n_lm, -1), lm_w_stride(n_lm);
   std::vector<int64_t> lm_w_off(n_lm);
@@ -434,7 +435,6 @@ pba_status create_impl(const pba_problem* p, const pba_options* o, int rank, int
 #pragma omp parallel num_threads(nthr)
   {
     std::vector<int64_t> cursor(p->n_poses, 0);
-    std::vector<int> eidx(p->n_poses, 0), colt(p->n_poses, -1);
 #pragma omp for schedule(dynamic, 16)
     for (int g = 0; g < G; ++g) {
       const int li0 = grp_lm_ptr[g], li1 = grp_lm_ptr[g + 1];
@@ -444,10 +444,10 @@ pba_status create_impl(const pba_problem* p, const pba_options* o, int rank, int
       int64_t pos = lm_ptr[li0];
       int e = grp_edge0[g];
       for (auto& tc : grp_tg[g]) {
-        cursor[tc.first] = pos; eidx[tc.first] = e++;
+        cursor[tc.first] = pos;
         pos += tc.second;
         const int sl = slot[tc.first];
-        colt[tc.first] = sl >= 0 ? int(std::lower_bound(grp_cams.begin() + c0, grp_cams.begin() + c0 + c, sl) - (grp_cams.begin() + c0)) : -1;
+        edge_col[e++] = sl >= 0 ? int(std::lower_bound(grp_cams.begin() + c0, grp_cams.begin() + c0 + c, sl) - (grp_cams.begin() + c0)) : -1;
       }
       const int hcol = slot[host] >= 0 ? int(std::lower_bound(grp_cams.begin() + c0, grp_cams.begin() + c0 + c, slot[host]) - (grp_cams.begin() + c0)) : -1;
       for (int li = li0; li < li1; ++li) {
@@ -460,7 +460,7 @@ pba_status create_impl(const pba_problem* p, const pba_options* o, int rank, int
         for (int64_t q = p->lm_obs_ptr[l]; q < p->lm_obs_ptr[l + 1]; ++q, ++k) {
           const int t = p->obs_target[q];
           const int64_t at = cursor[t]++;
-          obs_lm[at] = li; obs_edge[at] = eidx[t]; obs_col[at] = colt[t];
+          obs_lm[at] = li;
           lm_pos[k] = at;
           h->obs_order[at] = q - obs_lo;
         }
@@ -539,9 +539,17 @@ pba_status create_impl(const pba_problem* p, const pba_options* o, int rank, int
   PBA_CUDA_OK(up(h->intr, intr)); PBA_CUDA_OK(up(h->pose_calib, pose_calib)); PBA_CUDA_OK(up(h->calib_model, calib_model));
   PBA_CUDA_OK(up(h->d_slot, h->slot)); PBA_CUDA_OK(up(h->d_affine_active, h->affine_active));
   PBA_CUDA_OK(up(h->edge_h, edge_h)); PBA_CUDA_OK(up(h->edge_t, edge_t)); PBA_CUDA_OK(up(h->edge_ptr, edge_ptr));
-  PBA_CUDA_OK(up(h->obs_lm, obs_lm)); PBA_CUDA_OK(up(h->obs_edge, obs_edge));
+  PBA_CUDA_OK(up(h->obs_lm, obs_lm));
   PBA_CUDA_OK(up(h->lm_ptr, lm_ptr)); PBA_CUDA_OK(up(h->lm_pos, lm_pos));
-  PBA_CUDA_OK(up(h->lm_group, lm_group)); PBA_CUDA_OK(up(h->obs_col, obs_col)); PBA_CUDA_OK(up(h->lm_hostcol, lm_hostcol));
+  PBA_CUDA_OK(up(h->lm_group, lm_group)); PBA_CUDA_OK(up(h->lm_hostcol, lm_hostcol));
+  {
+    // per-observation edge index and W column: constant along an edge, so expanded from the edge table on the device
+    DevBuf<int> d_edge_col;
+    PBA_CUDA_OK(up(d_edge_col, edge_col));
+    PBA_CUDA_OK(h->obs_edge.alloc(size_t(n))); PBA_CUDA_OK(h->obs_col.alloc(size_t(n)));
+    if ((st = launch_expand_edges(h, d_edge_col.p)) != PBA_OK) return st;
+    PBA_CUDA_OK(cudaStreamSynchronize(s));  // d_edge_col goes out of scope
+  }
   PBA_CUDA_OK(up(h->chunk_edge, chunk_edge)); PBA_CUDA_OK(up(h->chunk_begin, chunk_begin)); PBA_CUDA_OK(up(h->chunk_end, chunk_end));
   PBA_CUDA_OK(up(h->grp_lm_ptr, grp_lm_ptr)); PBA_CUDA_OK(up(h->grp_cam_ptr, grp_cam_ptr)); PBA_CUDA_OK(up(h->grp_cams, grp_cams));
   PBA_CUDA_OK(up(h->grp_w_off, grp_w_off)); PBA_CUDA_OK(up(h->grp_part_off, grp_part_off));
@@ -626,7 +634,7 @@ pba_status create_impl(const pba_problem* p, const pba_options* o, int rank, int
   PBA_CUDA_OK(h->lm_pat.alloc(size_t(n_lm) * (photo ? 32 : 4))); PBA_CUDA_OK(h->lm_ok.alloc(n_lm));
   PBA_CUDA_OK(h->edge_T.alloc(size_t(16) * z.n_edges));
   if (photo) PBA_CUDA_OK(h->edge_M.alloc(size_t(36) * z.n_edges));
-  PBA_CUDA_OK(h->J.alloc(size_t(z.ld) * z.R * (z.C + 1))); PBA_CUDA_OK(h->orec.alloc(nn * 16));
+  PBA_CUDA_OK(h->J.alloc(size_t(z.ld) * z.R * (photo ? kPhotoPlanes : z.C + 1))); PBA_CUDA_OK(h->orec.alloc(nn * 16));
   PBA_CUDA_OK(h->W.alloc(size_t(w_total)));
   if (w_total) PBA_CUDA_OK(cudaMemsetAsync(h->W.p, 0, sizeof(double) * size_t(w_total), s));  // unseen camera slots stay 0
   PBA_CUDA_OK(h->lm_c.alloc(n_lm)); PBA_CUDA_OK(h->lm_g.alloc(n_lm)); PBA_CUDA_OK(h->lm_scale.alloc(n_lm));

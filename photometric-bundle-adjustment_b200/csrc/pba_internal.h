@@ -120,6 +120,12 @@ struct KernelStats {
   ~KernelStats();
 };
 
+// Photometric Jacobian planes: the six target-pose columns are never stored (eval.cu), so a row has
+// kPhotoPlanes = 10 planes: columns 0..5 (host pose) -> 0..5, 12, 13 (affine) -> 6, 7, 14 (inverse
+// distance) -> 8, 15 (residual) -> 9.
+constexpr int kPhotoPlanes = 10;
+__host__ __device__ inline int photo_plane(int c) { return c < 6 ? c : c - 6; }
+
 // ------------------------------------------------------------- the handle --
 struct Sizes {
   int mode = 0, R = 2, C = 13, cd = 6;  // residuals/obs, local columns/obs, RCS block dim
@@ -275,6 +281,7 @@ pba_status launch_build_quads(Handle* h, const uint8_t* images_u8, int first, in
 pba_status launch_evaluate(Handle* h, bool with_jacobian, const double* poses, const double* affine,
                            const double* rho, int cost_slot);
 pba_status launch_unpermute(Handle* h, int which, double* dst_host_order_dev);
+pba_status launch_expand_edges(Handle* h, const int* edge_col_dev);  // fills obs_edge / obs_col from edge_ptr
 // schur.cu
 pba_status launch_post_jacobian(Handle* h);              // edge Gram + landmark gather (+ scales on first call)
 pba_status launch_build_rcs(Handle* h, double radius, bool refresh_diag);

@@ -105,10 +105,10 @@ __global__ void __launch_bounds__(96) k_edge_gram(int64_t ld, const int* __restr
     // warp w copies whole columns cc = w, w+3, ...: one address computation per column,
     // then 4 x (32 pairs) with immediate offsets
     for (int cc = warp; cc < (RED ? 9 : P); cc += 3) {
-      // RED: staged row cc <- plane 0..5 (host pose), 12, 13 (affine), 15 (residual)
-      const int sp = RED ? (cc < 6 ? cc : (cc < 8 ? cc + 6 : 15)) : cc;
+      // RED: staged row cc <- stored plane 0..5 (host pose), 6, 7 (affine), 9 (residual); plane 8 (rho) is skipped
+      const int sp = RED ? (cc < 8 ? cc : kPhotoPlanes - 1) : cc;
       const int c = RED ? cc : (cc < C ? cc : 15);
-      const double* src = JR + (int64_t(k) * P + sp) * ld + base + 2 * lane;
+      const double* src = JR + (int64_t(k) * (RED ? kPhotoPlanes : P) + sp) * ld + base + 2 * lane;
       double* dst = Mt + c * RS + 2 * lane;
       const unsigned sa = unsigned(__cvta_generic_to_shared(dst));
 #pragma unroll
