@@ -205,6 +205,10 @@ pba_status pba_solve(pba_problem* problem, const pba_options* options,
 pba_status pba_create(const pba_problem* problem, const pba_options* options,
                       int32_t rank, int32_t world_size, pba_handle** out);
 void pba_destroy(pba_handle* h);
+/* A destroyed handle's device memory stays in a per-process cache of large chunks and is reused by the
+ * next pba_create / pba_solve (allocating and freeing tens of GB costs more than a solve).  This returns
+ * the cached chunks to the driver. */
+void pba_trim_device_cache(void);
 
 /* Use an existing stream (a cudaStream_t, e.g. torch's current stream) so the
  * caller can bracket work with its own CUDA events.  NULL = library stream. */

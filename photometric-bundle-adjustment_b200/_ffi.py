@@ -116,7 +116,7 @@ def ptr(a, ctype):
 # Every symbol include/pba.h declares (checked by tests/test_abi.py).
 PBA_SYMBOLS = [
     "pba_abi_version", "pba_status_string", "pba_device_count", "pba_options_init", "pba_solve",
-    "pba_create", "pba_destroy", "pba_set_stream", "pba_synchronize", "pba_evaluate", "pba_get_residuals",
+    "pba_create", "pba_destroy", "pba_trim_device_cache", "pba_set_stream", "pba_synchronize", "pba_evaluate", "pba_get_residuals",
     "pba_get_jacobians", "pba_build_rcs", "pba_get_rcs_dim", "pba_get_rcs", "pba_solve_rcs", "pba_minimize",
     "pba_lm_iterate",
     "pba_set_state", "pba_get_state", "pba_get_sizes", "pba_reset_kernel_stats", "pba_set_profile", "pba_get_kernel_stats",
@@ -191,6 +191,8 @@ def load_lib():
     lib.pba_projection_thresholds_init.restype = None
     lib.pba_destroy.argtypes = [H]
     lib.pba_destroy.restype = None
+    lib.pba_trim_device_cache.argtypes = []
+    lib.pba_trim_device_cache.restype = None
     lib.pba_get_kernel_stats.argtypes = [H, C.POINTER(pba_kernel_stat), C.c_int32]
     lib.pba_get_kernel_stats.restype = C.c_int32
     lib.pba_synth_render_gpu.argtypes = [C.POINTER(pba_synth_params), C.c_int, C.c_int, C.c_int, c_u8_p]

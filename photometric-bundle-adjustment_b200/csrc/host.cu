@@ -129,8 +129,82 @@ constexpr int kNcclDouble = 8, kNcclSum = 0, kNcclMax = 2;
 
 Handle::~Handle() {
   // nccl_comm is owned by the process-wide cache (pba_comm_init), not by the handle
+  if (stream) cudaStreamSynchronize(stream);  // nothing may still run on memory that goes back to the cache
   if (h_scalars) cudaFreeHost(h_scalars);
   if (own_stream && stream) cudaStreamDestroy(stream);
+}
+
+// ---- device arena + per-process chunk cache ----
+namespace {
+constexpr size_t kArenaChunk = size_t(1) << 30;
+std::mutex g_cache_mu;
+struct CachedChunk { int device; DeviceArena::Chunk c; };
+std::vector<CachedChunk> g_chunk_cache;
+}  // namespace
+
+DeviceArena*& current_arena() {
+  static thread_local DeviceArena* a = nullptr;
+  return a;
+}
+
+void* DeviceArena::alloc(size_t bytes, cudaError_t* err) {
+  *err = cudaSuccess;
+  bytes = (bytes + 255) & ~size_t(255);
+  if (!chunks.empty() && used + bytes <= chunks.back().bytes) {
+    void* r = chunks.back().p + used;
+    used += bytes;
+    return r;
+  }
+  Chunk c{nullptr, 0};
+  {
+    std::lock_guard<std::mutex> lock(g_cache_mu);
+    int best = -1;  // smallest cached chunk of this device that fits
+    for (int i = 0; i < int(g_chunk_cache.size()); ++i)
+      if (g_chunk_cache[i].device == device && g_chunk_cache[i].c.bytes >= bytes &&
+          (best < 0 || g_chunk_cache[i].c.bytes < g_chunk_cache[best].c.bytes)) best = i;
+    if (best >= 0) {
+      c = g_chunk_cache[best].c;
+      g_chunk_cache.erase(g_chunk_cache.begin() + best);
+    }
+  }
+  if (!c.p) {
+    const size_t want = bytes > kArenaChunk ? bytes : kArenaChunk;
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, want);
+    if (e != cudaSuccess) {  // give cached chunks that did not fit back to the driver and retry
+      cudaGetLastError();
+      trim_device_cache();
+      e = cudaMalloc(&q, want);
+    }
+    if (e != cudaSuccess) { *err = e; return nullptr; }
+    c.p = static_cast<char*>(q);
+    c.bytes = want;
+  }
+  chunks.push_back(c);
+  used = bytes;
+  return c.p;
+}
+
+void DeviceArena::release_to_cache() {
+  std::lock_guard<std::mutex> lock(g_cache_mu);
+  for (const Chunk& c : chunks) g_chunk_cache.push_back({device, c});
+  chunks.clear();
+  used = 0;
+}
+
+void trim_device_cache() {
+  std::vector<CachedChunk> all;
+  {
+    std::lock_guard<std::mutex> lock(g_cache_mu);
+    all.swap(g_chunk_cache);
+  }
+  int cur = 0;
+  cudaGetDevice(&cur);
+  for (const CachedChunk& cc : all) {
+    cudaSetDevice(cc.device);
+    cudaFree(cc.c.p);
+  }
+  cudaSetDevice(cur);
 }
 
 pba_status allreduce_rcs(Handle* h) {
@@ -229,6 +303,8 @@ pba_status create_impl(const pba_problem* p, const pba_options* o, int rank, int
   Handle* h = hh.get();
   h->opt = *o;
   h->rank = rank; h->world = world; h->device = o->device;
+  h->arena.device = o->device;
+  ArenaScope arena_scope(&h->arena);  // every DevBuf allocated below lives in the handle's arena
   h->stats.profile = o->profile;
   PBA_CUDA_OK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   h->own_stream = true;
@@ -1008,6 +1084,8 @@ PBA_API void pba_destroy(pba_handle* hh) {
   cudaStreamSynchronize(h->stream);
   delete h;
 }
+
+PBA_API void pba_trim_device_cache(void) { trim_device_cache(); }
 
 PBA_API pba_status pba_set_stream(pba_handle* hh, void* cuda_stream) {
   Handle* h = reinterpret_cast<Handle*>(hh);

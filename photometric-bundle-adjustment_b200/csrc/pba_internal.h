@@ -43,23 +43,57 @@ struct RawVec {
   bool empty() const { return n == 0; }
 };
 
+// Device memory of a handle comes from an arena of large chunks (a handle makes ~80 allocations;
+// cudaMalloc / cudaFree of tens of GB cost 0.2-0.8 s on a fresh box, more than the 20 LM iterations
+// of a solve).  When the handle dies its chunks go to a per-process cache and the next handle
+// (the SfM loop calls optimize() again and again) takes them back without touching the driver;
+// pba_trim_device_cache() returns them.  Memory from the cache is NOT zeroed.
+struct DeviceArena {
+  struct Chunk { char* p; size_t bytes; };
+  std::vector<Chunk> chunks;
+  size_t used = 0;  // bytes used in chunks.back()
+  int device = 0;
+  void* alloc(size_t bytes, cudaError_t* err);
+  void release_to_cache();
+  DeviceArena() {}
+  DeviceArena(const DeviceArena&) = delete;
+  DeviceArena& operator=(const DeviceArena&) = delete;
+  ~DeviceArena() { release_to_cache(); }
+};
+// Set (per thread) while pba_create builds a handle: DevBuf allocations then come from its arena.
+DeviceArena*& current_arena();
+struct ArenaScope {
+  DeviceArena* prev;
+  explicit ArenaScope(DeviceArena* a) : prev(current_arena()) { current_arena() = a; }
+  ~ArenaScope() { current_arena() = prev; }
+};
+void trim_device_cache();
+
 template <class T>
 struct DevBuf {
   T* p = nullptr;
   size_t n = 0;
+  bool owned = true;  // false: the memory belongs to a DeviceArena
   DevBuf() {}
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
   ~DevBuf() { release(); }
   void release() {
-    if (p) cudaFree(p);
+    if (p && owned) cudaFree(p);
     p = nullptr;
     n = 0;
+    owned = true;
   }
   cudaError_t alloc(size_t count) {
     release();
     n = count;
     if (count == 0) return cudaSuccess;
+    if (DeviceArena* a = current_arena()) {
+      cudaError_t e = cudaSuccess;
+      p = static_cast<T*>(a->alloc(count * sizeof(T), &e));
+      owned = false;
+      return e;
+    }
     return cudaMalloc(&p, count * sizeof(T));
   }
   template <class V>
@@ -143,6 +177,7 @@ struct Sizes {
 };
 
 struct Handle {
+  DeviceArena arena;  // first member: destroyed last, after every DevBuf below
   pba_options opt;
   Sizes sz;
   int rank = 0, world = 1;
