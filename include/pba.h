@@ -54,7 +54,8 @@ enum { PBA_CAM_PINHOLE = 0, PBA_CAM_DS = 1, PBA_CAM_KB4 = 2, PBA_CAM_EUCM = 3 };
 /* RCS solvers: dense tiled Cholesky (FP64 tensor cores), block-Jacobi PCG, and two exact
  * solvers for block-banded systems (windowed covisibility): BAND = sequential block-banded
  * Cholesky on one SM, BCR = parallel block cyclic reduction on dense super blocks.
- * AUTO = BCR when applicable, else BAND, else CHOLESKY while dim <= cholesky_max_dim, else PCG. */
+ * AUTO = BCR when applicable (BAND for chains of <= 64 free keyframes), else BAND, else CHOLESKY while
+ * dim <= cholesky_max_dim, else PCG. */
 enum { PBA_SOLVER_AUTO = 0, PBA_SOLVER_CHOLESKY = 1, PBA_SOLVER_PCG = 2, PBA_SOLVER_BAND = 3, PBA_SOLVER_BCR = 4 };
 
 /* Ceres termination types (include/ceres/types.h) kept so reports line up. */
