@@ -465,20 +465,25 @@ __global__ void __launch_bounds__(256) k_schur_syrk(int cd, int tile_l, const in
   }
 }
 
-// Row-paired variant for groups of at most kSyrkRowsMaxC cameras (windowed covisibility): warp w
-// owns tile rows w and c-1-w of the upper triangle (c + 3 tiles together, vector tile included),
-// keeps the two scaled A fragments of a k-step in registers and loads only the B fragment per
-// tile: 1 LDS.64 per DMMA instead of 2, which is what bounds the generic kernel above.
+// Row-paired variant for groups of at most kSyrkRowsMaxC cameras (windowed covisibility).  The tile
+// rows i and c-1-i of the upper triangle (c + 3 tiles together, vector tile included) form a pair;
+// TWO warps share a pair, one taking its even and one its odd tiles, so a group of 12 cameras keeps
+// 12 warps busy with ~8 accumulator tiles each (one warp per pair: 6 of 8 warps busy, 121 registers,
+// DMMA pipe 46 % busy with `barrier` / `short_scoreboard` on top of the stall list).  A warp keeps the
+// two scaled A fragments of a k-step in registers and loads only the B fragment per tile: 1 LDS.64
+// per DMMA instead of 2, which is what bounds the generic kernel above.
 constexpr int kSyrkRowsMaxC = 12;
-constexpr int kSyrkRowTiles = kSyrkRowsMaxC + 1;   // tiles of the longest row (row 0: j = 0..c)
-constexpr int kSyrkRowTilesB = kSyrkRowsMaxC / 2 + 2;  // second row of a warp: ib >= c / 2, so at most c / 2 + 2 tiles
+constexpr int kSyrkRowsThreads = 32 * 2 * ((kSyrkRowsMaxC + 1) / 2);                  // 384
+constexpr int kSyrkRowTiles = (kSyrkRowsMaxC + 1 + 1) / 2;      // half of the longest row (row 0: j = 0..c)
+constexpr int kSyrkRowTilesB = (kSyrkRowsMaxC / 2 + 2 + 1) / 2; // half of the second row (ib >= c / 2: at most c / 2 + 2 tiles)
 
-__global__ void __launch_bounds__(256) k_schur_syrk_rows(int cd, int tile_l, const int* __restrict__ grp_lm_ptr,
-                                                          const int* __restrict__ grp_cam_ptr,
-                                                          const int64_t* __restrict__ grp_w_off,
-                                                          const int64_t* __restrict__ grp_part_off,
-                                                          const double* __restrict__ W, const double* __restrict__ lm_s2,
-                                                          double* __restrict__ part_sch) {
+__global__ void __launch_bounds__(kSyrkRowsThreads) k_schur_syrk_rows(int cd, int tile_l, const int* __restrict__ grp_lm_ptr,
+                                                                       const int* __restrict__ grp_cam_ptr,
+                                                                       const int64_t* __restrict__ grp_w_off,
+                                                                       const int64_t* __restrict__ grp_part_off,
+                                                                       const double* __restrict__ W,
+                                                                       const double* __restrict__ lm_s2,
+                                                                       double* __restrict__ part_sch) {
   extern __shared__ double sm[];
   const int g = blockIdx.x;
   const int l0 = grp_lm_ptr[g], l1 = grp_lm_ptr[g + 1];
@@ -491,20 +496,19 @@ __global__ void __launch_bounds__(256) k_schur_syrk_rows(int cd, int tile_l, con
   const int P = c * (c + 1) / 2;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int fr = lane >> 2, fo = lane & 3;
-  // rows of this warp: ia = pw (tiles j = ia..c), ib = c - 1 - pw (tiles j = ib..c) when distinct.
-  // Only ceil(c / 2) of the 8 warps have rows; odd CTAs rotate the assignment by two warps so that
-  // two co-resident CTAs load the four SM sub-partitions (warp % 4) evenly.
-  const int pw = (warp + ((blockIdx.x & 1) ? 6 : 0)) & 7;
+  // pair pw: rows ia = pw (tiles j = ia..c) and ib = c - 1 - pw (tiles j = ib..c) when distinct;
+  // this warp takes the tiles t of each row with t % 2 == half
+  const int pw = warp >> 1, half = warp & 1;
   const int ia = pw, ib = c - 1 - pw;
   const bool has_a = ia < c && ia <= ib, has_b = ib > ia;
-  // accumulators: row a uses slots [0, c - ia], row b uses slots [0, c - ib] of its own array; both
-  // lengths are bounded by kSyrkRowTiles and the unused slots are skipped with warp-uniform tests
   double acca[kSyrkRowTiles][2], accb[kSyrkRowTilesB][2];
 #pragma unroll
   for (int t = 0; t < kSyrkRowTiles; ++t) acca[t][0] = acca[t][1] = 0.0;
 #pragma unroll
   for (int t = 0; t < kSyrkRowTilesB; ++t) accb[t][0] = accb[t][1] = 0.0;
-  const int na = has_a ? c - ia + 1 : 0, nb = has_b ? c - ib + 1 : 0;
+  // tiles of row a / b owned by this warp: t = half, half + 2, ...
+  const int na_full = has_a ? c - ia + 1 : 0, nb_full = has_b ? c - ib + 1 : 0;
+  const int na = (na_full - half + 1) / 2, nb = (nb_full - half + 1) / 2;
 
   const int buf_doubles = tile_l * ss + tile_l;
   auto stage = [&](int lb, int buf) {
@@ -512,12 +516,12 @@ __global__ void __launch_bounds__(256) k_schur_syrk_rows(int cd, int tile_l, con
     const double* src = Wg + size_t(lb - l0) * stride;
     double* dst = sm + buf * buf_doubles;
     const int cpr = stride >> 1;
-    for (int i = threadIdx.x; i < cnt * cpr; i += 256) {
+    for (int i = threadIdx.x; i < cnt * cpr; i += kSyrkRowsThreads) {
       const int l = i / cpr, x = i - l * cpr;
       const unsigned da = unsigned(__cvta_generic_to_shared(dst + l * ss + 2 * x));
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(da), "l"(src + size_t(l) * stride + 2 * x));
     }
-    for (int i = threadIdx.x; i < cnt; i += 256) {
+    for (int i = threadIdx.x; i < cnt; i += kSyrkRowsThreads) {
       const unsigned da = unsigned(__cvta_generic_to_shared(dst + tile_l * ss + i));
       asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(da), "l"(lm_s2 + lb + i));
     }
@@ -544,10 +548,12 @@ __global__ void __launch_bounds__(256) k_schur_syrk_rows(int cd, int tile_l, con
         const double s2 = lv ? s_s2[l] : 0.0;
         const double fa = lv ? s2 * row[8 * ia] : 0.0;
         const double fb = (lv && has_b) ? s2 * row[8 * ib] : 0.0;
+        const double* ra = row + 8 * (ia + half);
+        const double* rb = row + 8 * (ib + half);
 #pragma unroll
         for (int t = 0; t < kSyrkRowTiles; ++t) {
-          if (t < na) gram_dmma(acca[t], fa, lv ? row[8 * (ia + t)] : 0.0);
-          if (t < kSyrkRowTilesB && t < nb) gram_dmma(accb[t < kSyrkRowTilesB ? t : 0], fb, lv ? row[8 * (ib + t)] : 0.0);
+          if (t < na) gram_dmma(acca[t], fa, lv ? ra[16 * t] : 0.0);
+          if (t < kSyrkRowTilesB && t < nb) gram_dmma(accb[t < kSyrkRowTilesB ? t : 0], fb, lv ? rb[16 * t] : 0.0);
         }
       }
     }
@@ -559,8 +565,9 @@ __global__ void __launch_bounds__(256) k_schur_syrk_rows(int cd, int tile_l, con
 #pragma unroll
     for (int t = 0; t < decltype(ntile)::value; ++t) {
       if (t >= n) continue;
-      if (i + t < c) {
-        double* blk = out + size_t(p0 + t) * cd * cd;
+      const int jt = half + 2 * t;  // tile index within the row: column block i + jt
+      if (i + jt < c) {
+        double* blk = out + size_t(p0 + jt) * cd * cd;
 #pragma unroll
         for (int jj = 0; jj < 2; ++jj)
           if (fr < cd && 2 * fo + jj < cd) blk[fr * cd + 2 * fo + jj] = acc[t][jj];
@@ -935,7 +942,7 @@ pba_status launch_build_rcs(Handle* h, double radius, bool refresh_diag) {
     const int tile_l = h->schur_tile_l;
     const size_t smem = 2 * (size_t(tile_l) * syrk_row_stride(h->max_w_stride) + tile_l) * sizeof(double);
     if (h->max_w_stride <= 8 * (kSyrkRowsMaxC + 1)) {
-      PBA_LAUNCH(h, K_SCHUR_SYRK, k_schur_syrk_rows, dim3(z.n_groups), dim3(256), smem, z.cd, tile_l, h->grp_lm_ptr.p,
+      PBA_LAUNCH(h, K_SCHUR_SYRK, k_schur_syrk_rows, dim3(z.n_groups), dim3(kSyrkRowsThreads), smem, z.cd, tile_l, h->grp_lm_ptr.p,
                  h->grp_cam_ptr.p, h->grp_w_off.p, h->grp_part_off.p, h->W.p, h->lm_s2.p, h->part_sch.p);
     } else {
       PBA_LAUNCH(h, K_SCHUR_SYRK, k_schur_syrk, dim3(z.n_groups), dim3(256), smem, z.cd, tile_l, h->grp_lm_ptr.p,
