@@ -42,8 +42,9 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 # §8(d) it is reported against its OWN compulsory bytes: 1,088 - 8 rows x 6 columns x 8 B + 128 B = 832
 # (ncu DRAM traffic: 875 B/obs, profiles/k1_traffic.json).  The figure without the Schur record (704) and the
 # materialised one (1,088) are kept next to it for comparability.
-K1_BYTES_PER_OBS = {1: 832, 0: 256}
-K1_BYTES_PER_OBS_JR_ONLY = {1: 704, 0: 256}
+# (geometric: 256 - 2 rows x 6 columns x 8 B = 160, + 128 B Schur record = 288)
+K1_BYTES_PER_OBS = {1: 832, 0: 288}
+K1_BYTES_PER_OBS_JR_ONLY = {1: 704, 0: 160}
 K1_BYTES_PER_OBS_MATERIALISED = {1: 1088, 0: 256}
 
 
@@ -380,7 +381,7 @@ def main():
                 "step": "one full LM iteration (pba_lm_iterate): J+r eval, Schur/RCS build, solve, back-substitution, "
                         "model cost, candidate cost; state not advanced",
                 "l2": "inputs larger than L2: stored Jacobian planes %.1f GB + images %.2f GB per GPU vs 126 MB L2" %
-                      (n_obs_local * 8 * 10 * 8 / 1e9 if a.mode == 1 else n_obs_local * 2 * 14 * 8 / 1e9,
+                      (n_obs_local * 8 * 10 * 8 / 1e9 if a.mode == 1 else n_obs_local * 2 * 8 * 8 / 1e9,
                        (prob.images.nbytes if prob.images is not None else 0) / 1e9),
                 "rcs_solver": solver_used, "partition": "landmarks by observation count, %d shard(s)" % world,
                 "scene_s": t_scene, "create_s": t_create,

@@ -53,7 +53,7 @@ struct EvalArgs {
 // K0: per-edge relative pose A = R_t^T R_h, t = R_t^T (t_h - t_t) and the
 // target's affine brightness (exp(a), b).
 //
-// edge_M (Jacobian evaluations of the photometric residual only): with the right-multiplied
+// edge_M (Jacobian evaluations only): with the right-multiplied
 // local parameterisation X_t = exp(-d_t) T_rel exp(d_h) P, and exp(-d_t) T_rel =
 // T_rel exp(-Ad(T_rel^-1) d_t), so every Jacobian row satisfies
 //     d r / d d_t = (d r / d d_h) M,   M = -Ad(T_rel^-1) = [[-A^T, A^T [t]x], [0, -A^T]]
@@ -370,12 +370,12 @@ __global__ void __launch_bounds__(kPhotoThreads, WITH_J ? 3 : 4) k_eval_photo(co
         row[14] = -(ax * xh + ay * yh + az * zh) * c.irho;
         const double rw = w * rk;
         // kPhotoPlanes planes per row: columns 6..11 (target pose) are NOT stored, they are
-        // row[0..5] x M of the edge (k_edge_prep); photo_plane() compacts the rest, residual last
+        // row[0..5] x M of the edge (k_edge_prep); stored_plane() compacts the rest, residual last
         double* Jk = a.J + (int64_t(k) * kPhotoPlanes) * n + i;
-        Jk[int64_t(photo_plane(15)) * n] = rw;
+        Jk[int64_t(stored_plane(15)) * n] = rw;
 #pragma unroll
         for (int qq = 0; qq < 15; ++qq)
-          if (qq < 6 || qq >= 12) Jk[int64_t(photo_plane(qq)) * n] = row[qq];
+          if (qq < 6 || qq >= 12) Jk[int64_t(stored_plane(qq)) * n] = row[qq];
         const double E = row[14];
 #pragma unroll
         for (int qq = 0; qq < 14; ++qq)
@@ -480,21 +480,33 @@ __global__ void __launch_bounds__(kEvalThreads) k_eval_geom(const EvalArgs a) {
         row[3] = -(ay * zh - az * yh);
         row[4] = -(az * xh - ax * zh);
         row[5] = -(ax * yh - ay * xh);
-        row[6] = -px; row[7] = -py; row[8] = -pz;
-        row[9] = py * zt - pz * yt;
-        row[10] = pz * xt - px * zt;
-        row[11] = px * yt - py * xt;
+        // target pose [-p | p x X_t] = row[0..5] x M of the edge (k_edge_prep): neither stored nor formed
         row[12] = -(ax * xh + ay * yh + az * zh) * irho;
         const double rk = w * (k == 0 ? r0 : r1);
-        double* Jk = a.J + (int64_t(k) * 14) * n + i;  // planes [k][0..12] = J row, [k][13] = residual
-        Jk[13 * n] = rk;
+        // kGeomPlanes planes per row: host pose 0..5, inverse distance 6, residual 7
+        double* Jk = a.J + (int64_t(k) * kGeomPlanes) * n + i;
+        Jk[int64_t(stored_plane(13)) * n] = rk;
+        Jk[int64_t(stored_plane(12)) * n] = row[12];
 #pragma unroll
-        for (int c = 0; c < 13; ++c) Jk[int64_t(c) * n] = row[c];
+        for (int c = 0; c < 6; ++c) Jk[int64_t(c) * n] = row[c];
         const double E = row[12];
 #pragma unroll
-        for (int c = 0; c < 12; ++c) acc[c] += E * row[c];
+        for (int c = 0; c < 6; ++c) acc[c] += E * row[c];
         acc[14] += E * E;
         acc[15] += E * rk;
+      }
+      // target-pose part of the Schur record, (E^T J_h) M: u = A v_upsilon, E^T J_t = [-u | u x t - A v_omega]
+      {
+        const double u0 = A[0] * acc[0] + A[1] * acc[1] + A[2] * acc[2];
+        const double u1 = A[3] * acc[0] + A[4] * acc[1] + A[5] * acc[2];
+        const double u2 = A[6] * acc[0] + A[7] * acc[1] + A[8] * acc[2];
+        const double w0 = A[0] * acc[3] + A[1] * acc[4] + A[2] * acc[5];
+        const double w1 = A[3] * acc[3] + A[4] * acc[4] + A[5] * acc[5];
+        const double w2 = A[6] * acc[3] + A[7] * acc[4] + A[8] * acc[5];
+        acc[6] = -u0; acc[7] = -u1; acc[8] = -u2;
+        acc[9] = (u1 * T[11] - u2 * T[10]) - w0;
+        acc[10] = (u2 * T[9] - u0 * T[11]) - w1;
+        acc[11] = (u0 * T[10] - u1 * T[9]) - w2;
       }
       double2* o = reinterpret_cast<double2*>(a.orec + 16 * i);
 #pragma unroll
@@ -530,10 +542,10 @@ __global__ void k_unpermute(int64_t n, int64_t ld, int R, int C, int which, cons
   const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int64_t o = order[i];
-  const int P = edge_M ? kPhotoPlanes : C + 1;  // planes per row
+  const int P = edge_M ? C + 1 - 6 : C + 1;  // planes per row
   for (int k = 0; k < R; ++k) {
     if (which == 0) {
-      dst[o * R + k] = src[(int64_t(k) * P + (edge_M ? photo_plane(C) : C)) * ld + i];
+      dst[o * R + k] = src[(int64_t(k) * P + (edge_M ? stored_plane(C) : C)) * ld + i];
     } else {
       for (int c = 0; c < C; ++c) {
         double v;
@@ -542,7 +554,7 @@ __global__ void k_unpermute(int64_t n, int64_t ld, int R, int C, int which, cons
           v = 0.0;
           for (int q = 0; q < 6; ++q) v += src[(int64_t(k) * P + q) * ld + i] * m[6 * q + (c - 6)];
         } else {
-          v = src[(int64_t(k) * P + (edge_M ? photo_plane(c) : c)) * ld + i];
+          v = src[(int64_t(k) * P + (edge_M ? stored_plane(c) : c)) * ld + i];
         }
         dst[(o * R + k) * C + c] = v;
       }
@@ -602,7 +614,7 @@ pba_status launch_evaluate(Handle* h, bool with_jacobian, const double* poses, c
   if (z.n_edges > 0) {
     PBA_LAUNCH(h, K_EDGE_PREP, k_edge_prep, dim3((z.n_edges + 127) / 128), dim3(128), 0, z.n_edges, h->edge_h.p,
                h->edge_t.p, poses, photo ? affine : nullptr, h->edge_T.p,
-               photo && with_jacobian ? h->edge_M.p : nullptr);
+               with_jacobian ? h->edge_M.p : nullptr);
   }
   EvalArgs a;
   a.n = z.n_obs; a.ld = z.ld; a.n_lm = z.n_lm;
@@ -641,7 +653,7 @@ pba_status launch_unpermute(Handle* h, int which, double* dst) {
   DevBuf<int64_t> order;
   PBA_CUDA_OK(order.upload(h->obs_order, h->stream));
   PBA_LAUNCH(h, K_UNPERMUTE, k_unpermute, dim3(int((z.n_obs + 127) / 128)), dim3(128), 0, z.n_obs, z.ld, z.R, z.C, which, order.p,
-             h->J.p, h->obs_edge.p, z.mode == PBA_MODE_PHOTOMETRIC ? h->edge_M.p : nullptr, dst);
+             h->J.p, h->obs_edge.p, h->edge_M.p, dst);
   PBA_CUDA_OK(cudaStreamSynchronize(h->stream));
   return PBA_OK;
 }

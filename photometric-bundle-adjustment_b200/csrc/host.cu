@@ -709,8 +709,8 @@ pba_status create_impl(const pba_problem* p, const pba_options* o, int rank, int
   PBA_CUDA_OK(h->rho_c.alloc(n_lm)); PBA_CUDA_OK(h->rho_best.alloc(n_lm));
   PBA_CUDA_OK(h->lm_pat.alloc(size_t(n_lm) * (photo ? 32 : 4))); PBA_CUDA_OK(h->lm_ok.alloc(n_lm));
   PBA_CUDA_OK(h->edge_T.alloc(size_t(16) * z.n_edges));
-  if (photo) PBA_CUDA_OK(h->edge_M.alloc(size_t(36) * z.n_edges));
-  PBA_CUDA_OK(h->J.alloc(size_t(z.ld) * z.R * (photo ? kPhotoPlanes : z.C + 1))); PBA_CUDA_OK(h->orec.alloc(nn * 16));
+  PBA_CUDA_OK(h->edge_M.alloc(size_t(36) * z.n_edges));
+  PBA_CUDA_OK(h->J.alloc(size_t(z.ld) * z.R * (z.C + 1 - 6))); PBA_CUDA_OK(h->orec.alloc(nn * 16));  // stored planes: pba_internal.h
   PBA_CUDA_OK(h->W.alloc(size_t(w_total)));
   if (w_total) PBA_CUDA_OK(cudaMemsetAsync(h->W.p, 0, sizeof(double) * size_t(w_total), s));  // unseen camera slots stay 0
   PBA_CUDA_OK(h->lm_c.alloc(n_lm)); PBA_CUDA_OK(h->lm_g.alloc(n_lm)); PBA_CUDA_OK(h->lm_scale.alloc(n_lm));

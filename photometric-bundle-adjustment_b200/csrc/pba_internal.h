@@ -154,11 +154,13 @@ struct KernelStats {
   ~KernelStats();
 };
 
-// Photometric Jacobian planes: the six target-pose columns are never stored (eval.cu), so a row has
-// kPhotoPlanes = 10 planes: columns 0..5 (host pose) -> 0..5, 12, 13 (affine) -> 6, 7, 14 (inverse
-// distance) -> 8, 15 (residual) -> 9.
+// Stored Jacobian planes: the six target-pose columns of a row are never stored (eval.cu: they are
+// the host-pose columns x a per-edge adjoint), so a row of C columns + residual has C + 1 - 6 planes:
+// columns 0..5 (host pose) -> planes 0..5, every later column c (affine, inverse distance) and the
+// residual (c = C) -> plane c - 6.  Photometric: 10 planes per row, geometric: 8.
 constexpr int kPhotoPlanes = 10;
-__host__ __device__ inline int photo_plane(int c) { return c < 6 ? c : c - 6; }
+constexpr int kGeomPlanes = 8;
+__host__ __device__ inline int stored_plane(int c) { return c < 6 ? c : c - 6; }
 
 // ------------------------------------------------------------- the handle --
 struct Sizes {

@@ -66,11 +66,13 @@ __global__ void __launch_bounds__(96) k_edge_gram(int64_t ld, const int* __restr
                                                    const double* __restrict__ edge_M, double* __restrict__ part_dir) {
   using Cfg = GramCfg<R, C>;
   constexpr int CD = Cfg::CD, TOBS = Cfg::TOBS, RS = Cfg::RS, P = C + 1;
-  // Photometric rows (RED): K1 stores only the host-pose, affine and residual planes — the
-  // target-pose columns are (host-pose columns) x M with one 6x6 M per edge (eval.cu,
-  // k_edge_prep) — so M's matrix here is [J_h(6) J_a(2) | r]: 9 staged planes instead of 16, two
-  // DMMAs per k-step instead of three, and the 15-column Gram matrix is E^T G9 E at the end.
-  constexpr bool RED = R == 8;
+  // K1 stores only the host-pose, affine, inverse-distance and residual planes — the target-pose
+  // columns are (host-pose columns) x M with one 6x6 M per edge (eval.cu, k_edge_prep) — so the
+  // matrix staged here is [J_h(6) J_a(NAFF) 0.. | r]: 9 rows instead of 16, two DMMAs per k-step
+  // instead of three, and the full Gram matrix is E^T G9 E at the end.
+  constexpr bool RED = true;
+  constexpr int NAFF = C - 13;      // affine columns: 2 photometric, 0 geometric
+  constexpr int PL = C + 1 - 6;     // stored planes per row (pba_internal.h: stored_plane)
   constexpr int NR = RED ? 9 : 16;  // staged rows of Mt
   extern __shared__ __align__(16) double gram_sm[];  // Mt[kGramStages][NR * RS] ring + G[256]
   double* G = gram_sm + kGramStages * NR * RS;
@@ -82,10 +84,10 @@ __global__ void __launch_bounds__(96) k_edge_gram(int64_t ld, const int* __restr
   // upper tiles (0,0), (0,1), (1,1) of G; two accumulator sets keep six independent DMMA chains in flight
   double c00[2][2] = {{0.0, 0.0}, {0.0, 0.0}}, c01[2][2] = {{0.0, 0.0}, {0.0, 0.0}}, c11[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
   // columns C..14 of M are structurally zero (nothing to do for the photometric 15-column rows)
-  if (!RED && C < 15) {
-    for (int i = threadIdx.x; i < kGramStages * (15 - C) * RS; i += 96) {
-      const int b = i / ((15 - C) * RS), j = i % ((15 - C) * RS);
-      gram_sm[b * NR * RS + C * RS + j] = 0.0;
+  if (NAFF < 2) {  // staged rows 6 + NAFF .. 7 have no source plane
+    for (int i = threadIdx.x; i < kGramStages * (2 - NAFF) * RS; i += 96) {
+      const int b = i / ((2 - NAFF) * RS), j = i % ((2 - NAFF) * RS);
+      gram_sm[b * NR * RS + (6 + NAFF) * RS + j] = 0.0;
     }
     __syncthreads();
   }
@@ -104,11 +106,13 @@ __global__ void __launch_bounds__(96) k_edge_gram(int64_t ld, const int* __restr
     double* Mt = gram_sm + buf * NR * RS;
     // warp w copies whole columns cc = w, w+3, ...: one address computation per column,
     // then 4 x (32 pairs) with immediate offsets
-    for (int cc = warp; cc < (RED ? 9 : P); cc += 3) {
-      // RED: staged row cc <- stored plane 0..5 (host pose), 6, 7 (affine), 9 (residual); plane 8 (rho) is skipped
-      const int sp = RED ? (cc < 8 ? cc : kPhotoPlanes - 1) : cc;
-      const int c = RED ? cc : (cc < C ? cc : 15);
-      const double* src = JR + (int64_t(k) * (RED ? kPhotoPlanes : P) + sp) * ld + base + 2 * lane;
+    for (int cc = warp; cc < 9; cc += 3) {
+      // staged row cc <- stored plane 0..5 (host pose), 6.. (affine), PL - 1 (residual); the
+      // inverse-distance plane is skipped, rows without a source plane stay zero
+      if (cc >= 6 + NAFF && cc < 8) continue;
+      const int sp = cc < 8 ? cc : PL - 1;
+      const int c = cc;
+      const double* src = JR + (int64_t(k) * PL + sp) * ld + base + 2 * lane;
       double* dst = Mt + c * RS + 2 * lane;
       const unsigned sa = unsigned(__cvta_generic_to_shared(dst));
 #pragma unroll
@@ -221,7 +225,7 @@ __global__ void __launch_bounds__(96) k_edge_gram(int64_t ld, const int* __restr
         double v = 0.0;
         if (c < 6) v = r == c ? 1.0 : 0.0;
         else if (c < 12) v = r < 6 ? Me[6 * r + (c - 6)] : 0.0;
-        else if (c < 14) v = r == 6 + (c - 12) ? 1.0 : 0.0;
+        else if (c < 14) v = (c - 12 < NAFF && r == 6 + (c - 12)) ? 1.0 : 0.0;
         else if (c == 15) v = r == 8 ? 1.0 : 0.0;
         E[i] = v;
       }
@@ -899,11 +903,11 @@ pba_status launch_post_jacobian(Handle* h) {
       PBA_LAUNCH(h, K_EDGE_GRAM, k_edge_gram_photo, dim3(z.n_chunks), dim3(96), smem, z.ld, h->chunk_edge.p,
                  h->chunk_begin.p, h->chunk_end.p, h->edge_h.p, h->edge_t.p, h->d_slot.p, h->J.p, h->edge_M.p, h->part_dir.p);
     } else {
-      constexpr size_t smem = (kGramStages * 16 * GramCfg<2, 13>::RS + 256) * sizeof(double);
+      constexpr size_t smem = (kGramStages * 9 * GramCfg<2, 13>::RS + 256) * sizeof(double);
       static bool attr = false;
       if (!attr) { PBA_CUDA_OK(cudaFuncSetAttribute(k_edge_gram_geom, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))); attr = true; }
       PBA_LAUNCH(h, K_EDGE_GRAM, k_edge_gram_geom, dim3(z.n_chunks), dim3(96), smem, z.ld, h->chunk_edge.p,
-                 h->chunk_begin.p, h->chunk_end.p, h->edge_h.p, h->edge_t.p, h->d_slot.p, h->J.p, nullptr, h->part_dir.p);
+                 h->chunk_begin.p, h->chunk_end.p, h->edge_h.p, h->edge_t.p, h->d_slot.p, h->J.p, h->edge_M.p, h->part_dir.p);
     }
   }
   if (z.n_lm > 0) {
