@@ -533,6 +533,24 @@ __global__ void __launch_bounds__(1024) k_reduce_sum(const double* __restrict__ 
   }
 }
 
+// Long reductions (one partial per 128 observations: 140 k at config 4) go through kReduceMid
+// CTAs first, each summing a fixed contiguous slice (one CTA alone took 37 us per reduction).
+__global__ void __launch_bounds__(256) k_reduce_mid(const double* __restrict__ part, int64_t n, double* __restrict__ mid) {
+  __shared__ double s[8];
+  const int64_t per = (n + gridDim.x - 1) / gridDim.x;
+  const int64_t i0 = per * blockIdx.x, i1 = i0 + per < n ? i0 + per : n;
+  double v = 0.0;
+  for (int64_t i = i0 + threadIdx.x; i < i1; i += 256) v += part[i];
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < 8; ++i) t += s[i];
+    mid[blockIdx.x] = t;
+  }
+}
+
 // Test/diagnostic path: planes in edge order -> [obs][plane] in caller order.
 // which = 0: residuals [obs][R]; 1: Jacobians [obs][R][C]  (source planes [R][C+1][ld]).
 // edge_M != nullptr (photometric): the target-pose columns 6..11 are rebuilt as (columns 0..5) x M.
@@ -643,7 +661,7 @@ pba_status launch_evaluate(Handle* h, bool with_jacobian, const double* poses, c
       else { PBA_LAUNCH(h, K_COST, k_eval_geom<false>, dim3(grid), dim3(kEvalThreads), 0, a); }
     }
   }
-  PBA_LAUNCH(h, K_REDUCE_SUM, k_reduce_sum, dim3(1), dim3(1024), 0, h->red_ws.p, int64_t(grid), h->scalars.p + cost_slot);
+  launch_reduce_sum(h, h->red_ws.p, int64_t(grid), h->scalars.p + cost_slot);
   return PBA_OK;
 }
 
@@ -660,7 +678,12 @@ pba_status launch_unpermute(Handle* h, int which, double* dst) {
 
 void launch_reduce_sum(Handle* h, const double* part, int64_t n, double* out) {
   h->stats.begin(K_REDUCE_SUM, h->stream);
-  k_reduce_sum<<<1, 1024, 0, h->stream>>>(part, n, out);
+  if (n > 4096) {
+    k_reduce_mid<<<kReduceMid, 256, 0, h->stream>>>(part, n, h->red_mid.p);
+    k_reduce_sum<<<1, 1024, 0, h->stream>>>(h->red_mid.p, kReduceMid, out);
+  } else {
+    k_reduce_sum<<<1, 1024, 0, h->stream>>>(part, n, out);
+  }
   h->stats.end(h->stream);
 }
 

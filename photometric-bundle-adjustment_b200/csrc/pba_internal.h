@@ -158,6 +158,7 @@ struct KernelStats {
 // the host-pose columns x a per-edge adjoint), so a row of C columns + residual has C + 1 - 6 planes:
 // columns 0..5 (host pose) -> planes 0..5, every later column c (affine, inverse distance) and the
 // residual (c = C) -> plane c - 6.  Photometric: 10 planes per row, geometric: 8.
+constexpr int kReduceMid = 64;  // CTAs of the first stage of a long scalar reduction
 constexpr int kPhotoPlanes = 10;
 constexpr int kGeomPlanes = 8;
 __host__ __device__ inline int stored_plane(int c) { return c < 6 ? c : c - 6; }
@@ -269,6 +270,7 @@ struct Handle {
   DevBuf<double> pcg_ws;       // PCG vectors
   DevBuf<double> blk_inv;      // block-Jacobi inverses [n_slots*cd*cd]
   DevBuf<double> red_ws;       // reduction workspace
+  DevBuf<double> red_mid;      // [kReduceMid] first-stage sums of the long reductions
   DevBuf<double> scalars;      // small device scalar bank
   double* h_scalars = nullptr; // pinned mirror
 
