@@ -16,9 +16,16 @@ CU_HDRS := $(wildcard $(CSRC)/*.h) $(wildcard $(CSRC)/*.cuh) include/pba.h
 
 all: lib synth oracle ref
 
+# one object per translation unit (no relocatable device code is needed), so `make -j` compiles them in
+# parallel; the per-file ptxas reports are concatenated into $(PKG)/ptxas.log
+CU_OBJS := $(patsubst $(CSRC)/%.cu,build/%.o,$(CU_SRCS))
 lib: $(PKG)/libpba_b200.so
-$(PKG)/libpba_b200.so: $(CU_SRCS) $(CU_HDRS)
-	$(NVCC) $(NVFLAGS) -shared $(CU_SRCS) -o $@ -lcudart -ldl -lgomp 2> $(PKG)/ptxas.log || (cat $(PKG)/ptxas.log; false)
+build/%.o: $(CSRC)/%.cu $(CU_HDRS)
+	@mkdir -p build
+	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> build/$*.ptxas.log || (cat build/$*.ptxas.log; false)
+$(PKG)/libpba_b200.so: $(CU_OBJS)
+	$(NVCC) $(ARCH) -shared $(CU_OBJS) -o $@ -lcudart -ldl -lgomp
+	@cat build/*.ptxas.log > $(PKG)/ptxas.log
 
 synth: $(PKG)/libpba_synth.so
 $(PKG)/libpba_synth.so: $(CSRC)/synth.cpp $(CSRC)/pba_math.h $(CSRC)/synth_scene.h include/pba.h include/pba_synth.h
@@ -32,5 +39,6 @@ ref:
 	@if [ -d /root/reference ]; then $(MAKE) -C oracle/ref both; else echo "no /root/reference: using prebuilt oracle/_ref if present"; fi
 
 clean:
+	rm -rf build
 	rm -f $(PKG)/libpba_b200.so $(PKG)/libpba_synth.so oracle/libpba_oracle.so
 .PHONY: all lib synth oracle ref clean

@@ -157,7 +157,7 @@ typedef struct pba_summary {
   int32_t num_linear_solves;
   int32_t rcs_dim;           /* reduced camera system dimension */
   int32_t linear_solver;     /* PBA_SOLVER_* actually used */
-  int32_t reserved_;
+  int32_t num_inexact_linear_solves; /* PCG solves that stopped above pcg_tolerance (treated as invalid steps) */
   int64_t rcs_blocks;        /* stored upper-triangular blocks */
   int64_t num_residual_blocks;
   int64_t num_residuals;
@@ -227,7 +227,9 @@ pba_status pba_evaluate(pba_handle* h, int32_t with_jacobian, double* cost);
  * CALLER'S observation order (local shard): residuals [n_obs*R], jacobians
  * [n_obs*R*C] row-major per block with columns (host pose 6 | target pose 6 |
  * [affine 2] | rho 1), robustified like residual_block.cc:166-196.
- * Columns of constant (fixed) poses are zero. */
+ * These are the cost function's local Jacobians (what the reference's AutoDiff + local
+ * parameterisation produce for the block): columns of constant (fixed) poses are NOT zeroed here;
+ * constness is applied when the reduced camera system is assembled. */
 pba_status pba_get_residuals(pba_handle* h, double* residuals);
 pba_status pba_get_jacobians(pba_handle* h, double* jacobians);
 

@@ -73,7 +73,7 @@ class pba_summary(C.Structure):
         ("termination_type", C.c_int32), ("num_iterations", C.c_int32), ("num_successful_steps", C.c_int32),
         ("num_unsuccessful_steps", C.c_int32), ("num_residual_evaluations", C.c_int32),
         ("num_jacobian_evaluations", C.c_int32), ("num_linear_solves", C.c_int32), ("rcs_dim", C.c_int32),
-        ("linear_solver", C.c_int32), ("reserved_", C.c_int32),
+        ("linear_solver", C.c_int32), ("num_inexact_linear_solves", C.c_int32),
         ("rcs_blocks", C.c_int64), ("num_residual_blocks", C.c_int64), ("num_residuals", C.c_int64),
         ("num_effective_parameters", C.c_int64), ("gpu_kernel_launches", C.c_int64),
         ("initial_cost", C.c_double), ("final_cost", C.c_double), ("setup_time_in_seconds", C.c_double),

@@ -506,26 +506,6 @@ pba_status bcr_setup(Handle* h) {
   // level 0 is rebuilt from the RCS blocks by k_bcr_build before every solve; the block pattern is
   // static, so the entries it never writes are zeroed here once (A and B of level 0 are contiguous)
   PBA_CUDA_OK(cudaMemsetAsync(h->bcr_ws.p + offA[0], 0, sizeof(double) * (size_t(S) * M * M + size_t(S > 1 ? S - 1 : 0) * M * M), h->stream));
-  const int smem = int(bcr_smem_bytes(M, z.cd));
-  if (z.cd == 8) {
-    PBA_CUDA_OK(cudaFuncSetAttribute(k_bcr_factor<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    PBA_CUDA_OK(cudaFuncSetAttribute(k_bcr_solve<8, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    PBA_CUDA_OK(cudaFuncSetAttribute(k_bcr_solve<8, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    PBA_CUDA_OK(cudaFuncSetAttribute(k_bcr_top<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    PBA_CUDA_OK(cudaFuncSetAttribute(k_bcr_backsub<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    if (bcr_backsub_smem(M, z.cd, true) <= kBcrSmemCap)
-      PBA_CUDA_OK(cudaFuncSetAttribute(k_bcr_backsub<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bcr_backsub_smem(M, z.cd, true))));
-  } else {
-    PBA_CUDA_OK(cudaFuncSetAttribute(k_bcr_factor<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    PBA_CUDA_OK(cudaFuncSetAttribute(k_bcr_solve<6, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    PBA_CUDA_OK(cudaFuncSetAttribute(k_bcr_solve<6, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    PBA_CUDA_OK(cudaFuncSetAttribute(k_bcr_top<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    PBA_CUDA_OK(cudaFuncSetAttribute(k_bcr_backsub<6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    if (bcr_backsub_smem(M, z.cd, true) <= kBcrSmemCap)
-      PBA_CUDA_OK(cudaFuncSetAttribute(k_bcr_backsub<6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bcr_backsub_smem(M, z.cd, true))));
-  }
-  PBA_CUDA_OK(cudaFuncSetAttribute(k_bcr_reduce<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  PBA_CUDA_OK(cudaFuncSetAttribute(k_bcr_reduce<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   return PBA_OK;
 }
 

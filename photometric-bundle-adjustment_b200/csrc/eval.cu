@@ -316,6 +316,10 @@ __global__ void __launch_bounds__(kPhotoThreads, WITH_J ? 3 : 4) k_eval_photo(co
     if (!ok) w = 0.0;
 
     if (WITH_J) {
+      // invalid observation: the block is exactly zero.  Multiplying by w = 0 is not enough — a failed
+      // projection can be Inf / NaN (z_t = 0, rho = 0) and 0 * NaN = NaN would reach the normal
+      // equations — so pass 2 runs on a harmless point instead (X_h = 0, X_t = (0, 0, 1)).
+      if (!ok) c.irho = 0.0;
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         s_pat[(4 * k + 0) * 32] = bx[k];
@@ -339,7 +343,7 @@ __global__ void __launch_bounds__(kPhotoThreads, WITH_J ? 3 : 4) k_eval_photo(co
         const double yt = c.A[3] * xh + c.A[4] * yh + c.A[5] * zh + c.tr[1];
         const double zt = c.A[6] * xh + c.A[7] * yh + c.A[8] * zh + c.tr[2];
         double uv[2], Jp[6];
-        cam_project<true>(c.model, c.in, xt, yt, zt, uv, Jp);
+        cam_project<true>(c.model, c.in, ok ? xt : 0.0, ok ? yt : 0.0, ok ? zt : 1.0, uv, Jp);
         // same integer cell as pass 1 (a recomputed floor could differ by one ulp of u)
         const int y0 = ofk / a.pitch, x0 = ofk - y0 * a.pitch;
         const double fxk = ok ? uv[0] - x0 : 0.0, fyk = ok ? uv[1] - y0 : 0.0;
@@ -647,12 +651,6 @@ pba_status launch_evaluate(Handle* h, bool with_jacobian, const double* poses, c
   if (grid > 0) {
     if (photo) {
       if (with_jacobian) {
-        static bool attr = false;
-        if (!attr) {
-          for (int m = -1; m <= PBA_CAM_EUCM; ++m)
-            PBA_CUDA_OK(cudaFuncSetAttribute(photo_kernel<true>(m), cudaFuncAttributeMaxDynamicSharedMemorySize, int(kPhotoSmemBytes)));
-          attr = true;
-        }
         PBA_LAUNCH(h, K_RESJAC, photo_kernel<true>(h->uniform_model), dim3(grid), dim3(kPhotoThreads), kPhotoSmemBytes, a);
       }
       else { PBA_LAUNCH(h, K_COST, photo_kernel<false>(h->uniform_model), dim3(grid), dim3(kPhotoThreads), 0, a); }

@@ -192,6 +192,14 @@ void DeviceArena::release_to_cache() {
   used = 0;
 }
 
+void DeviceArena::rewind(const Mark& m) {
+  if (chunks.size() > m.n_chunks) {
+    std::lock_guard<std::mutex> lock(g_cache_mu);
+    while (chunks.size() > m.n_chunks) { g_chunk_cache.push_back({device, chunks.back()}); chunks.pop_back(); }
+  }
+  used = m.used;
+}
+
 void trim_device_cache() {
   std::vector<CachedChunk> all;
   {
@@ -205,6 +213,24 @@ void trim_device_cache() {
     cudaFree(cc.c.p);
   }
   cudaSetDevice(cur);
+}
+
+// (kernel, device) -> largest dynamic shared memory size opted into so far (launch.h)
+cudaError_t ensure_dynamic_smem(const void* kernel, size_t bytes, int device) {
+  struct Entry { const void* k; int dev; size_t bytes; };
+  static std::mutex mu;
+  static std::vector<Entry> table;
+  std::lock_guard<std::mutex> lock(mu);
+  for (Entry& e : table)
+    if (e.k == kernel && e.dev == device) {
+      if (e.bytes >= bytes) return cudaSuccess;
+      const cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
+      if (err == cudaSuccess) e.bytes = bytes;
+      return err;
+    }
+  const cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
+  if (err == cudaSuccess) table.push_back({kernel, device, bytes});
+  return err;
 }
 
 pba_status allreduce_rcs(Handle* h) {
@@ -620,11 +646,14 @@ pba_status create_impl(const pba_problem* p, const pba_options* o, int rank, int
   PBA_CUDA_OK(up(h->lm_group, lm_group)); PBA_CUDA_OK(up(h->lm_hostcol, lm_hostcol));
   {
     // per-observation edge index and W column: constant along an edge, so expanded from the edge table on the device
+    PBA_CUDA_OK(h->obs_edge.alloc(size_t(n))); PBA_CUDA_OK(h->obs_col.alloc(size_t(n)));
+    const DeviceArena::Mark tmp_mark = h->arena.mark();  // d_edge_col is a set-up temporary
     DevBuf<int> d_edge_col;
     PBA_CUDA_OK(up(d_edge_col, edge_col));
-    PBA_CUDA_OK(h->obs_edge.alloc(size_t(n))); PBA_CUDA_OK(h->obs_col.alloc(size_t(n)));
     if ((st = launch_expand_edges(h, d_edge_col.p)) != PBA_OK) return st;
-    PBA_CUDA_OK(cudaStreamSynchronize(s));  // d_edge_col goes out of scope
+    PBA_CUDA_OK(cudaStreamSynchronize(s));
+    d_edge_col.release();
+    h->arena.rewind(tmp_mark);
   }
   PBA_CUDA_OK(up(h->chunk_edge, chunk_edge)); PBA_CUDA_OK(up(h->chunk_begin, chunk_begin)); PBA_CUDA_OK(up(h->chunk_end, chunk_end));
   PBA_CUDA_OK(up(h->grp_lm_ptr, grp_lm_ptr)); PBA_CUDA_OK(up(h->grp_cam_ptr, grp_cam_ptr)); PBA_CUDA_OK(up(h->grp_cams, grp_cams));
@@ -684,6 +713,7 @@ pba_status create_impl(const pba_problem* p, const pba_options* o, int rank, int
     const size_t img_bytes = size_t(p->pitch) * p->height;
     PBA_CUDA_OK(h->quads.alloc(size_t(z.image_stride) * p->n_poses));
     const int batch = std::max(1, std::min(p->n_poses, 256));
+    const DeviceArena::Mark tmp_mark = h->arena.mark();  // the staging buffer is handed back below
     DevBuf<uint8_t> stage;
     PBA_CUDA_OK(stage.alloc(img_bytes * batch));
     for (int f0 = 0; f0 < p->n_poses; f0 += batch) {
@@ -699,6 +729,8 @@ pba_status create_impl(const pba_problem* p, const pba_options* o, int rank, int
       if ((st = launch_build_quads(h, stage.p, f0, cnt)) != PBA_OK) return st;
     }
     PBA_CUDA_OK(cudaStreamSynchronize(s));
+    stage.release();
+    h->arena.rewind(tmp_mark);
   }
 
   mark("upload images + quads");
@@ -731,10 +763,6 @@ pba_status create_impl(const pba_problem* p, const pba_options* o, int rank, int
   PBA_CUDA_OK(cudaMemsetAsync(h->scalars.p, 0, sizeof(double) * S_NUM, s));
   PBA_CUDA_OK(cudaMemsetAsync(h->chol_fail.p, 0, sizeof(int), s));
   PBA_CUDA_OK(cudaMallocHost(&h->h_scalars, sizeof(double) * (S_NUM + 2)));
-  if (h->max_w_stride > 0) {
-    // k_schur_syrk needs > 48 KB of dynamic shared memory for wide groups
-    schur_set_smem(2 * (size_t(h->schur_tile_l) * (h->max_w_stride + 4) + h->schur_tile_l) * sizeof(double));
-  }
   mark("allocate work buffers");
   st = launch_init_landmarks(h);
   if (st != PBA_OK) return st;
@@ -822,7 +850,7 @@ pba_status minimize_impl(Handle* h, pba_summary* sum) {
   int termination = PBA_NO_CONVERGENCE;
   char message[256] = "";
   int num_successful = 0, num_unsuccessful = 0, consecutive_invalid = 0;
-  int n_jac = 0, n_res = 0, n_lin = 0;
+  int n_jac = 0, n_res = 0, n_lin = 0, n_inexact = 0;
   pba_status st;
   double* hs = h->h_scalars;
   const int* chol_fail = reinterpret_cast<const int*>(hs + S_NUM);
@@ -891,7 +919,13 @@ pba_status minimize_impl(Handle* h, pba_summary* sum) {
     ++n_lin; ++n_res;
     it.linear_solver_iterations = h->last_solver == PBA_SOLVER_PCG ? int(hs[S_PCG_ITERS]) : 1;
     const double model_cost_change = hs[S_MODEL];
-    const bool solved = !(h->last_solver != PBA_SOLVER_PCG && *chol_fail) && std::isfinite(model_cost_change) && std::isfinite(hs[S_STEP2]);
+    // A direct solver fails on a non-positive pivot; the iterative one when it stops short of its
+    // tolerance: the reference's SPARSE_SCHUR solve is exact, so a truncated PCG step is treated as a
+    // linear-solver failure (invalid step: the radius shrinks, which also improves the conditioning).
+    const bool pcg_short = h->last_solver == PBA_SOLVER_PCG && !(hs[S_PCG_RES] <= opt.pcg_tolerance);
+    if (pcg_short) ++n_inexact;
+    const bool solved = !(h->last_solver != PBA_SOLVER_PCG && *chol_fail) && !pcg_short && std::isfinite(model_cost_change) &&
+                        std::isfinite(hs[S_STEP2]);
     it.model_cost_change = model_cost_change;
     it.step_is_valid = solved && model_cost_change > 0.0;
     if (!it.step_is_valid) {
@@ -978,6 +1012,7 @@ pba_status minimize_impl(Handle* h, pba_summary* sum) {
     sum->num_effective_parameters = int64_t(z.n_slots) * 6 + h->n_active_lm;
     for (int i = 0; i < z.n_poses; ++i) sum->num_effective_parameters += h->affine_active[i] ? 2 : 0;
     sum->linear_solver = h->last_solver;
+    sum->num_inexact_linear_solves = n_inexact;
     sum->gpu_kernel_launches = std::accumulate(ks.launches, ks.launches + K_NUM, int64_t(0)) - launches0;
     sum->initial_cost = initial_cost;
     sum->final_cost = min_iteration_cost;
@@ -990,7 +1025,10 @@ pba_status minimize_impl(Handle* h, pba_summary* sum) {
     sum->linear_solver_time_in_seconds = 1e-3 * lin;
     sum->minimizer_time_in_seconds = wall() - t_start;
     sum->total_time_in_seconds = sum->minimizer_time_in_seconds;
-    snprintf(sum->message, sizeof(sum->message), "%s", message);
+    if (n_inexact > 0)
+      snprintf(sum->message, sizeof(sum->message), "%.180s [%d PCG solve(s) stopped above pcg_tolerance]", message, n_inexact);
+    else
+      snprintf(sum->message, sizeof(sum->message), "%s", message);
   }
   return PBA_OK;
 }

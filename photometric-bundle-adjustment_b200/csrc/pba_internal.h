@@ -55,6 +55,11 @@ struct DeviceArena {
   int device = 0;
   void* alloc(size_t bytes, cudaError_t* err);
   void release_to_cache();
+  // Stack discipline for set-up temporaries (image staging, per-edge tables): everything allocated
+  // after mark() is handed back by rewind(); the caller guarantees the stream is done with it.
+  struct Mark { size_t n_chunks, used; };
+  Mark mark() const { return Mark{chunks.size(), used}; }
+  void rewind(const Mark& m);
   DeviceArena() {}
   DeviceArena(const DeviceArena&) = delete;
   DeviceArena& operator=(const DeviceArena&) = delete;
@@ -339,7 +344,6 @@ pba_status dense_cholesky_solve(Handle* h, double* A, double* b, int ld, int* fa
 int dense_ld(int n);
 int pcg_max_grid(int device);
 int schur_tile_l(int max_stride);
-void schur_set_smem(size_t bytes);
 int eval_grid(int64_t n);
 // host.cu
 pba_status allreduce_rcs(Handle* h);

@@ -898,14 +898,10 @@ pba_status launch_post_jacobian(Handle* h) {
   if (z.n_chunks > 0) {
     if (z.mode == PBA_MODE_PHOTOMETRIC) {
       constexpr size_t smem = (kGramStages * 9 * GramCfg<8, 15>::RS + 256) * sizeof(double);
-      static bool attr = false;
-      if (!attr) { PBA_CUDA_OK(cudaFuncSetAttribute(k_edge_gram_photo, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))); attr = true; }
       PBA_LAUNCH(h, K_EDGE_GRAM, k_edge_gram_photo, dim3(z.n_chunks), dim3(96), smem, z.ld, h->chunk_edge.p,
                  h->chunk_begin.p, h->chunk_end.p, h->edge_h.p, h->edge_t.p, h->d_slot.p, h->J.p, h->edge_M.p, h->part_dir.p);
     } else {
       constexpr size_t smem = (kGramStages * 9 * GramCfg<2, 13>::RS + 256) * sizeof(double);
-      static bool attr = false;
-      if (!attr) { PBA_CUDA_OK(cudaFuncSetAttribute(k_edge_gram_geom, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))); attr = true; }
       PBA_LAUNCH(h, K_EDGE_GRAM, k_edge_gram_geom, dim3(z.n_chunks), dim3(96), smem, z.ld, h->chunk_edge.p,
                  h->chunk_begin.p, h->chunk_end.p, h->edge_h.p, h->edge_t.p, h->d_slot.p, h->J.p, h->edge_M.p, h->part_dir.p);
     }
@@ -916,13 +912,6 @@ pba_status launch_post_jacobian(Handle* h) {
                h->lm_c.p, h->lm_g.p);
   }
   return PBA_OK;
-}
-
-void schur_set_smem(size_t bytes) {
-  if (bytes > 48 * 1024) {
-    cudaFuncSetAttribute(k_schur_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
-    cudaFuncSetAttribute(k_schur_syrk_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
-  }
 }
 
 int schur_tile_l(int max_stride) {

@@ -395,11 +395,6 @@ __global__ void __launch_bounds__(256) k_pcg(const PcgArgs a) {
 pba_status dense_cholesky_solve(Handle* h, double* A, double* b, int ld, int* fail_dev) {
   const int nt = ld / NB;
   constexpr size_t kSyrkSmem = 2 * NB * LDS * sizeof(double);  // 69,632 B: needs the opt-in limit
-  static bool attr_set = false;
-  if (!attr_set) {
-    PBA_CUDA_OK(cudaFuncSetAttribute(k_chol_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSyrkSmem)));
-    attr_set = true;
-  }
   for (int k = 0; k < nt; ++k) {
     PBA_LAUNCH(h, K_CHOL_PANEL, k_chol_diag, dim3(1), dim3(256), 0, ld, k, A, fail_dev);
     const int m = nt - k - 1;
@@ -838,11 +833,9 @@ pba_status launch_band_rcs(Handle* h) {
   const double* rhs = S + z.n_blocks * z.cd * z.cd;
   PBA_CUDA_OK(cudaMemsetAsync(h->chol_fail.p, 0, sizeof(int), h->stream));
   if (z.cd == 8) {
-    PBA_CUDA_OK(cudaFuncSetAttribute(k_band_cholesky<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     PBA_LAUNCH(h, K_BAND_CHOL, k_band_cholesky<8>, dim3(1), dim3(kBandThreads), smem, z.n_slots, bw, h->d_col_blk.p, S, rhs,
                h->band_L.p, h->y_cam.p, h->chol_fail.p);
   } else {
-    PBA_CUDA_OK(cudaFuncSetAttribute(k_band_cholesky<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     PBA_LAUNCH(h, K_BAND_CHOL, k_band_cholesky<6>, dim3(1), dim3(kBandThreads), smem, z.n_slots, bw, h->d_col_blk.p, S, rhs,
                h->band_L.p, h->y_cam.p, h->chol_fail.p);
   }
