@@ -61,7 +61,10 @@ def parse():
     ap.add_argument("--solver", type=int, default=0, help="0 auto, 1 cholesky, 2 pcg")
     ap.add_argument("--sample-kf", type=int, default=48, help="keyframes in the CPU-baseline sample")
     ap.add_argument("--cpu-iters", type=int, default=3, help="LM iterations of the cpu_baseline leg")
+    ap.add_argument("--ref-max-iters", type=int, default=3,
+                    help="--impl reference: LM iterations of the full-size CPU run (about a minute each at 2k x 2M)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
 
@@ -69,6 +72,28 @@ def parse():
 def workload_name(a, n_obs):
     kind = "photometric (8-px pattern, affine brightness, Huber 9)" if a.mode == 1 else "geometric reprojection (Huber 1)"
     return "%s BA, %d KF x %d pts (%d obs), %s 752x480, synthetic textured wall" % (kind, a.kf, a.pts, n_obs, a.model)
+
+
+def arm_independent_config(a, n_obs):
+    """`config` is the same dict in both arms (the driver compares them): it names the workload and what a
+    step is; everything arm-specific lives under `detail`."""
+    return {
+        "workload": workload_name(a, n_obs),
+        "step": "one Levenberg-Marquardt iteration: residual+Jacobian evaluation, Schur elimination to the reduced "
+                "camera system, RCS solve, back-substitution, candidate cost",
+        "l2": "inputs larger than L2 (Jacobian %.1f GB + images %.2f GB vs 126 MB)" %
+              (n_obs * (8 * 15 if a.mode == 1 else 2 * 13) * 8 / 1e9, (a.kf * 480 * 752 / 1e9) if a.mode == 1 else 0.0),
+    }
+
+
+def mem_available_gb():
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable:"):
+                return float(line.split()[1]) / 1e6
+    except OSError:
+        pass
+    return 0.0
 
 
 def measured_peaks():
@@ -136,17 +161,7 @@ class ClockSampler:
 def sample_problem(prob, n_kf_s):
     """Bounded sample of the same scene: the first n_kf_s keyframes and every
     landmark whose whole track lies inside them."""
-    import pba_b200 as pb
-    last_target = np.maximum.reduceat(prob.obs_target, prob.lm_obs_ptr[:-1].clip(max=prob.n_obs - 1))
-    inside = last_target < n_kf_s
-    L = int(np.argmin(inside)) if not inside.all() else prob.n_landmarks
-    o1 = int(prob.lm_obs_ptr[L])
-    return pb.Problem(prob.mode, prob.poses[:n_kf_s].copy(), prob.pose_fixed[:n_kf_s], prob.pose_calib[:n_kf_s],
-                      prob.calib_model, prob.intrinsics, prob.inv_depth[:L].copy(), prob.lm_host[:L],
-                      prob.lm_host_uv[:L], prob.lm_obs_ptr[:L + 1], prob.obs_target[:o1],
-                      None if prob.obs_uv is None else prob.obs_uv[:o1],
-                      None if prob.images is None else prob.images[:n_kf_s],
-                      None if prob.affine is None else prob.affine[:n_kf_s].copy())
+    return prob.prefix_keyframes(n_kf_s)
 
 
 def run_cpu_reference(prob, a, iters, n_obs_full):
@@ -169,16 +184,17 @@ def run_cpu_reference(prob, a, iters, n_obs_full):
     resjac = smp.n_obs * s.num_jacobian_evaluations / max(s.jacobian_evaluation_time_in_seconds, 1e-9)
     scale = smp.n_obs / float(n_obs_full)
     return {
-        "value": it_per_s * scale, "unit": "LM it/s", "cores": cores, "kind": kind,
+        "value": it_per_s * scale, "unit": "LM it/s", "cores": cores, "kind": kind, "extrapolated": True,
         "sample": ("first %d keyframes / %d points / %d observations of the same scene, %d LM iterations of the "
-                   "reference solver (Ceres 2.0.0 SPARSE_SCHUR, %d threads); LM it/s scaled by the observation "
-                   "ratio %.5f to the full workload (linear-cost assumption)" %
+                   "reference solver (Ceres 2.0.0 SPARSE_SCHUR, %d threads); EXTRAPOLATED: LM it/s scaled by the "
+                   "observation ratio %.5f to the full workload (linear-cost assumption) - the measured full-size "
+                   "number is the `--impl reference` arm" %
                    (smp.n_poses, smp.n_landmarks, smp.n_obs, lm_its, cores, scale)),
         "sample_lm_it_per_s": it_per_s, "sample_obs": int(smp.n_obs),
         "resjac_obs_per_s": resjac, "sample_wall_s": wall,
         "linear_solver_s_per_solve": s.linear_solver_time_in_seconds / max(s.num_linear_solves, 1),
         "final_cost": s.final_cost,
-    }
+    }, smp, s, opts
 
 
 def main():
@@ -190,28 +206,91 @@ def main():
     import pba_b200 as pb
 
     if a.impl == "reference":
-        # the reference's own CPU path; rank 0 alone runs it
+        # The reference's own CPU path (oracle/_ref: unmodified visnav functor + vendored Ceres 2.0.0,
+        # SPARSE_SCHUR, all host threads) on the FULL workload; rank 0 alone runs it.  Every number on the line
+        # is measured (Solver::Summary), nothing is extrapolated.  An LM iteration of the 2k x 2M scene costs the
+        # CPU about a minute, so the run does min(--steps, --ref-max-iters) iterations and reports that count
+        # as `steps` (`steps_requested` keeps the flag).
         if rank != 0:
             return
-        # same scene structure as the GPU arm; only the sample's keyframes are rendered (CPU renderer)
+        import oracle_ffi as of
+        kind = "reference" if of.have_ref() else "port"
+        lib = "ref" if kind == "reference" else "oracle"
+        cores = os.cpu_count() or 1
+        hub = 9.0 if a.mode == 1 else 1.0
+        t0 = time.time()
         prob, gt = pb.make_scene(a.mode, a.kf, a.pts, a.model, render=False)
+        full_obs = int(prob.n_obs)
+        # Ceres holds the Jacobian (960 B / photometric block) plus ~0.75 KB of bookkeeping per block
+        # (measured here: 31 GB resident at 18M blocks); if the host cannot hold that, the run uses the longest
+        # keyframe prefix that fits and says so (the config then differs from the GPU arm's).
+        need_gb = full_obs * ((8 * 15 * 8 + 800) if a.mode == 1 else (2 * 13 * 8 + 700)) / 1e9 + 2.0
+        avail_gb = mem_available_gb()
+        run_prob, note = prob, "full workload"
+        n_pref, pref = of.largest_reference_prefix(prob)
+        if pref is not prob:
+            # Ceres 2.0.0 counts Jacobian non-zeros in an int: 17,959,243 blocks x 120 entries = 2.155e9 > 2^31 - 1
+            # aborts in block_sparse_matrix.cc:80, so the reference can only run this prefix of the scene
+            run_prob = pref
+            note = ("vendored Ceres 2.0.0 holds at most 2^31-1 Jacobian entries (block_sparse_matrix.cc:80; the full "
+                    "scene has %.3fe9): longest keyframe prefix that fits = %d of %d keyframes, %.2f %% of the "
+                    "observations" % (full_obs * prob.res_per_obs * prob.cols_per_obs / 1e9, n_pref, prob.n_poses,
+                                      100.0 * pref.n_obs / full_obs))
+            need_gb *= pref.n_obs / float(full_obs)
+        if avail_gb and need_gb > 0.9 * avail_gb:
+            frac = 0.9 * avail_gb / need_gb
+            run_prob = sample_problem(prob, max(8, int(run_prob.n_poses * frac)))
+            note = ("host has %.0f GB available, the full problem needs ~%.0f GB in Ceres: first %d keyframes / %d "
+                    "observations" % (avail_gb, need_gb, run_prob.n_poses, run_prob.n_obs))
         if a.mode == 1:
             from pba_b200 import _ffi
-            n_img = min(a.kf, a.sample_kf)
-            _ffi.load_synth().pba_synth_render(C.byref(gt["params"]), 0, n_img, 752, _ffi.ptr(prob.images, C.c_uint8))
-        full_obs = int(prob.n_obs)
-        if a.warmup > 0:
+            _ffi.load_synth().pba_synth_render(C.byref(gt["params"]), 0, run_prob.n_poses, 752,
+                                               _ffi.ptr(prob.images, C.c_uint8))
+        t_scene = time.time() - t0
+        if a.warmup > 0:  # page the library in, spin the thread pool up
             run_cpu_reference(prob, argparse.Namespace(**{**vars(a), "sample_kf": 14}), 1, full_obs)
-        cb = run_cpu_reference(prob, a, max(a.steps, 1), full_obs)
+        iters = max(1, min(a.steps, a.ref_max_iters))
+        opts = of.default_options(huber_parameter=hub, max_num_iterations=iters)
+        t0 = time.time()
+        sm = of.solve(lib, run_prob, opts, threads=cores)
+        wall = time.time() - t0
+        its = sm.iterations
+        lm_its = max(len(its) - 1, 1)
+        # iteration 0 is the initial evaluation; the LM iterations are what lies after it
+        t_lm = its[-1]["cumulative_time_in_seconds"] - its[0]["cumulative_time_in_seconds"] if len(its) > 1 else \
+            sm.minimizer_time_in_seconds
+        value = lm_its / max(t_lm, 1e-9)
+        resjac = run_prob.n_obs * sm.num_jacobian_evaluations / max(sm.jacobian_evaluation_time_in_seconds, 1e-9)
+        cb = {"value": value, "unit": "LM it/s", "cores": cores, "kind": kind, "extrapolated": False,
+              "sample": "%s: %d keyframes / %d points / %d observations, %d LM iterations (Ceres 2.0.0 SPARSE_SCHUR, "
+                        "%d threads), times from Solver::Summary" %
+                        (note, run_prob.n_poses, run_prob.n_landmarks, run_prob.n_obs, lm_its, cores),
+              "resjac_obs_per_s": resjac, "wall_s": wall, "scene_s": t_scene,
+              "problem_build_and_preprocess_s": wall - sm.minimizer_time_in_seconds,
+              "minimizer_s": sm.minimizer_time_in_seconds,
+              "jacobian_s_per_eval": sm.jacobian_evaluation_time_in_seconds / max(sm.num_jacobian_evaluations, 1),
+              "residual_s_per_eval": sm.residual_evaluation_time_in_seconds / max(sm.num_residual_evaluations, 1),
+              "linear_solver_s_per_solve": sm.linear_solver_time_in_seconds / max(sm.num_linear_solves, 1),
+              "iteration_s": [it["iteration_time_in_seconds"] for it in its],
+              "iteration_cost": [it["cost"] for it in its],
+              "initial_cost": sm.initial_cost, "final_cost": sm.final_cost}
         line = {
-            "impl": "reference", "metric": "lm_iterations_per_s", "value": cb["value"], "unit": "LM it/s",
-            "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": 1e3 / max(cb["value"], 1e-30), "higher_is_better": True, "scaling": "strong",
+            "impl": "reference", "metric": "lm_iterations_per_s", "value": value, "unit": "LM it/s",
+            "n_gpus": a.gpus, "steps": lm_its, "steps_requested": a.steps, "warmup": a.warmup,
+            "ms_per_step": 1e3 / max(value, 1e-30), "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(a, full_obs), "sample": cb["sample"]},
-            "resjac_obs_per_s": cb["resjac_obs_per_s"],
+            # `config` names the benchmark workload (identical in both arms); what the reference could actually
+            # hold of it is in `reference_workload` (and in cpu_baseline.sample)
+            "config": arm_independent_config(a, full_obs),
+            "reference_workload": {"note": note, "keyframes": int(run_prob.n_poses), "points": int(run_prob.n_landmarks),
+                                   "observations": int(run_prob.n_obs),
+                                   "fraction_of_observations": run_prob.n_obs / float(full_obs)},
+            "resjac_obs_per_s": resjac,
             "cpu_baseline": cb,
-            "e2e": {"value": cb["value"], "unit": "LM it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "e2e": {"value": value, "unit": "LM it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                    "with_problem_build": lm_its / wall,
+                    "note": "value = the line's own; with_problem_build = LM iterations / wall clock of ceres::Problem "
+                            "build + Solve on host containers"},
             "gpu_launches": 0,
         }
         print(json.dumps(line))
@@ -322,6 +401,9 @@ def main():
             tj = json.load(open(tpath))
             key = "%d_%d_%d" % (a.mode, a.kf, a.pts)
             traffic = tj.get(key)
+            if traffic is not None and prob.n_obs > 0:
+                # the capture is one launch over ALL observations (N = 1); a shard's launch moves its share
+                traffic = traffic * n_obs_local / float(prob.n_obs)
         except Exception:
             traffic = None
     solver_used = ("bcr (block cyclic reduction)" if "bcr" in stats else "band_cholesky" if "band_cholesky" in stats
@@ -345,7 +427,7 @@ def main():
             e2 = pb.Engine(p2, o2, rank=rank, world_size=world)
             e2.comm_init(comm_id)
             s2 = e2.minimize()
-            e2.get_state()
+            p2.poses[:] = e2.get_state()[0]
             e2.close()
         torch.cuda.synchronize()
         t_e2e = torch.tensor([time.time() - t0], dtype=torch.float64, device="cuda")
@@ -362,27 +444,58 @@ def main():
         e2e = {"value": lm_its / float(t_e2e.item()), "unit": "LM it/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "call": ("pba_solve(max_num_iterations=20) on host buffers" if world == 1 else
                         "pba_create + pba_comm_init (cached communicator) + pba_minimize(20) + pba_get_state on host buffers, per rank"),
+               "bytes_are_per": "solve: one call = set-up + %d LM iterations; the copies happen once per call, "
+                                "not once per iteration" % lm_its,
+               "excludes": None if world == 1 else "ncclCommInitRank (the communicator of the resident engine is reused)",
                "lm_iterations": lm_its, "wall_s": float(t_e2e.item()), "setup_s": s2.setup_time_in_seconds,
                "minimizer_s": s2.minimizer_time_in_seconds, "solve_total_s": s2.total_time_in_seconds,
                "final_cost": s2.final_cost, "initial_cost": s2.initial_cost,
                "termination": {0: "CONVERGENCE", 1: "NO_CONVERGENCE", 2: "FAILURE"}.get(s2.termination_type)}
 
-    cpu_baseline = None
+    # ---- CPU baseline (bounded sample) and parity of the GPU path against it on the SAME sample ----
+    cpu_baseline, parity = None, {}
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        cpu_baseline = run_cpu_reference(prob, a, a.cpu_iters, prob.n_obs)
+        cpu_baseline, smp_cpu, s_cpu, _ = run_cpu_reference(prob, a, a.cpu_iters, prob.n_obs)
+        if not a.no_parity:
+            smp_gpu = sample_problem(prob, min(a.sample_kf, prob.n_poses))
+            s_gpu = pb.bundle_adjustment(smp_gpu, pb.BundleAdjustmentOptions(
+                verbosity_level=0, huber_parameter=hub, device=local_rank, solver=a.solver,
+                max_num_iterations=a.cpu_iters))
+            ci, gi = s_cpu.iterations, s_gpu.iterations
+            parity = {
+                "against": "%s on the cpu_baseline sample (%d observations, %d LM iterations, same image bytes)" %
+                           (cpu_baseline["kind"], smp_cpu.n_obs, a.cpu_iters),
+                "final_cost_rel": abs(s_gpu.final_cost - s_cpu.final_cost) / s_cpu.final_cost,
+                "iterations_equal": len(ci) == len(gi) and
+                                    [i["step_is_successful"] for i in ci] == [i["step_is_successful"] for i in gi],
+                "iteration_cost_rel_max": (max(abs(x["cost"] - y["cost"]) / y["cost"] for x, y in zip(gi, ci))
+                                           if len(ci) == len(gi) else None),
+                "poses_abs_max": float(np.abs(smp_gpu.poses - smp_cpu.poses).max()),
+                "inv_depth_abs_max": float(np.abs(smp_gpu.inv_depth - smp_cpu.inv_depth).max()),
+                "gpu_final_cost": s_gpu.final_cost, "cpu_final_cost": s_cpu.final_cost,
+            }
+    if world > 1 and e2e is not None and not a.no_parity:
+        # the sharded solve against ONE GPU solving the whole problem (rank 0; the others wait)
+        if rank == 0:
+            p1 = prob.copy()
+            s1 = pb.bundle_adjustment(p1, pb.BundleAdjustmentOptions(verbosity_level=0, huber_parameter=hub,
+                                                                     device=local_rank, solver=a.solver,
+                                                                     max_num_iterations=20))
+            parity = {"sharded_vs_single_rel": abs(e2e["final_cost"] - s1.final_cost) / s1.final_cost,
+                      "sharded_final_cost": e2e["final_cost"], "single_gpu_final_cost": s1.final_cost,
+                      "iterations_equal": s1.num_iterations - 1 == e2e["lm_iterations"],
+                      "poses_abs_max": float(np.abs(p1.poses - p2.poses).max())}
+        dist.barrier()
 
     if rank == 0:
         line = {
             "metric": "lm_iterations_per_s", "value": value, "unit": "LM it/s", "n_gpus": world, "steps": a.steps,
             "warmup": n_warm, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {
-                "workload": workload_name(a, prob.n_obs),
-                "step": "one full LM iteration (pba_lm_iterate): J+r eval, Schur/RCS build, solve, back-substitution, "
-                        "model cost, candidate cost; state not advanced",
-                "l2": "inputs larger than L2: stored Jacobian planes %.1f GB + images %.2f GB per GPU vs 126 MB L2" %
-                      (n_obs_local * 8 * 10 * 8 / 1e9 if a.mode == 1 else n_obs_local * 2 * 8 * 8 / 1e9,
-                       (prob.images.nbytes if prob.images is not None else 0) / 1e9),
+            "config": arm_independent_config(a, prob.n_obs),
+            "detail": {
+                "step": "pba_lm_iterate: J+r eval (K1), Schur/RCS build, solve, back-substitution, model cost, "
+                        "candidate cost (K2); state not advanced, so every step does identical work",
                 "rcs_solver": solver_used, "partition": "landmarks by observation count, %d shard(s)" % world,
                 "scene_s": t_scene, "create_s": t_create,
             },
@@ -390,7 +503,9 @@ def main():
             "clocks": clk, "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "k_eval_photo<true> (residual_jacobian)" if a.mode == 1 else "k_eval_geom<true>",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "bytes_per_obs": bpo,
+                         "traffic": traffic, "traffic_source": "ncu --set full capture at N=1 (profiles/k1_traffic.json) x "
+                                                                "this launch's share of the observations",
+                         "peak_source": peak_src, "bytes_per_obs": bpo,
                          "obs_per_launch": int(n_obs_local), "ms_per_launch": k1_ms,
                          "frac_without_schur_record": (n_obs_local * K1_BYTES_PER_OBS_JR_ONLY[a.mode] / (k1_ms * 1e-3) / 1e9 / peak
                                                        if k1_ms > 0 else 0.0),
@@ -409,6 +524,8 @@ def main():
             line["e2e"] = e2e
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
+        if parity:
+            line["parity"] = parity
         print(json.dumps(line))
     eng.close()
     if world > 1:

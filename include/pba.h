@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PBA_ABI_VERSION 1
+#define PBA_ABI_VERSION 2
 
 typedef enum pba_status {
   PBA_OK = 0,
@@ -128,6 +128,12 @@ typedef struct pba_options {
   int32_t jacobi_scaling;             /* 1 */
   int32_t device;                     /* CUDA device ordinal, default 0 */
   int32_t profile;                    /* 1 = bracket every kernel with CUDA events, 2 = only the residual/Jacobian kernel */
+  /* pba_solve only: GPUs of this node to shard the landmarks over, FROM ONE PROCESS (the reference's caller is a
+   * single thread, src/sfm.cpp:1883-1925): devices device .. device + num_gpus - 1, one host thread each, partial
+   * reduced camera systems summed with NCCL (ncclCommInitAll, communicators cached per process).  Default 1;
+   * 0 = all visible devices. */
+  int32_t num_gpus;
+  int32_t reserved0_;
 } pba_options;
 
 /* One row of Ceres' Solver::Summary::iterations (include/ceres/iteration_callback.h). */
@@ -144,6 +150,8 @@ typedef struct pba_iteration {
   double relative_decrease;
   double trust_region_radius;
   double model_cost_change;
+  double iteration_time_in_seconds;  /* IterationSummary::iteration_time_in_seconds */
+  double cumulative_time_in_seconds; /* since the minimizer started (iteration 0 = the initial evaluation) */
 } pba_iteration;
 
 /* Same wall-clock buckets as ceres::Solver::Summary (solver.h:822-851). */
@@ -232,6 +240,12 @@ pba_status pba_evaluate(pba_handle* h, int32_t with_jacobian, double* cost);
  * constness is applied when the reduced camera system is assembled. */
 pba_status pba_get_residuals(pba_handle* h, double* residuals);
 pba_status pba_get_jacobians(pba_handle* h, double* jacobians);
+/* The same outputs for a SELECTION of blocks only (parity checks on problems whose whole Jacobian
+ * is tens of GB): obs_index [n_sel] = caller-order local observation indices (any order, no
+ * duplicates); residuals [n_sel*R] and jacobians [n_sel*R*C] (either may be NULL) come back in the
+ * order of obs_index. */
+pba_status pba_get_blocks(pba_handle* h, int64_t n_sel, const int64_t* obs_index, double* residuals,
+                          double* jacobians);
 
 /* Replaces SchurEliminator::Eliminate (schur_eliminator_impl.h:177-306) on the
  * last evaluated Jacobian with Jacobi scaling and LM damping for `radius`

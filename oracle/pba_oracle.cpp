@@ -777,7 +777,16 @@ ORACLE_API int pba_oracle_solve(pba_problem* p, const pba_options* opt, int num_
   const int cap = sum ? sum->iterations_capacity : 0;
   if (sum) { memset(sum, 0, sizeof(*sum)); sum->iterations = its; sum->iterations_capacity = cap; }
   int n_it = 0;
-  auto push = [&](const pba_iteration& it) { if (its && n_it < cap) its[n_it] = it; ++n_it; };
+  double t_push0 = -1.0, t_push_prev = 0.0;
+  auto push = [&](pba_iteration& it) {
+    const double t = now();
+    if (t_push0 < 0.0) { t_push0 = t_push_prev = t; }
+    it.iteration_time_in_seconds = t - t_push_prev;
+    it.cumulative_time_in_seconds = t - t_push0;
+    t_push_prev = t;
+    if (its && n_it < cap) its[n_it] = it;
+    ++n_it;
+  };
 
   double t_jac = 0, t_res = 0, t_lin = 0;
   int n_jac = 0, n_res = 0, n_lin = 0;

@@ -287,6 +287,8 @@ void fill_summary(const ceres::Solver::Summary& s, pba_summary* out) {
     it[i].step_norm = a.step_norm;
     it[i].relative_decrease = a.relative_decrease;
     it[i].trust_region_radius = a.trust_region_radius;
+    it[i].iteration_time_in_seconds = a.iteration_time_in_seconds;
+    it[i].cumulative_time_in_seconds = a.cumulative_time_in_seconds;
     it[i].model_cost_change = 0.0;
   }
 }

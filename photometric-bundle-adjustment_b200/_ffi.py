@@ -54,7 +54,7 @@ class pba_options(C.Structure):
         ("function_tolerance", C.c_double), ("gradient_tolerance", C.c_double),
         ("parameter_tolerance", C.c_double),
         ("max_num_consecutive_invalid_steps", C.c_int32), ("jacobi_scaling", C.c_int32),
-        ("device", C.c_int32), ("profile", C.c_int32),
+        ("device", C.c_int32), ("profile", C.c_int32), ("num_gpus", C.c_int32), ("reserved0_", C.c_int32),
     ]
 
 
@@ -65,6 +65,7 @@ class pba_iteration(C.Structure):
         ("cost", C.c_double), ("cost_change", C.c_double), ("gradient_max_norm", C.c_double),
         ("gradient_norm", C.c_double), ("step_norm", C.c_double), ("relative_decrease", C.c_double),
         ("trust_region_radius", C.c_double), ("model_cost_change", C.c_double),
+        ("iteration_time_in_seconds", C.c_double), ("cumulative_time_in_seconds", C.c_double),
     ]
 
 
@@ -117,7 +118,7 @@ def ptr(a, ctype):
 PBA_SYMBOLS = [
     "pba_abi_version", "pba_status_string", "pba_device_count", "pba_options_init", "pba_solve",
     "pba_create", "pba_destroy", "pba_trim_device_cache", "pba_set_stream", "pba_synchronize", "pba_evaluate", "pba_get_residuals",
-    "pba_get_jacobians", "pba_build_rcs", "pba_get_rcs_dim", "pba_get_rcs", "pba_solve_rcs", "pba_minimize",
+    "pba_get_jacobians", "pba_get_blocks", "pba_build_rcs", "pba_get_rcs_dim", "pba_get_rcs", "pba_solve_rcs", "pba_minimize",
     "pba_lm_iterate",
     "pba_set_state", "pba_get_state", "pba_get_sizes", "pba_reset_kernel_stats", "pba_set_profile", "pba_get_kernel_stats",
     "pba_nccl_unique_id", "pba_comm_init", "pba_camera_project", "pba_camera_unproject", "pba_se3_plus",
@@ -162,6 +163,7 @@ def load_lib():
         "pba_evaluate": [H, C.c_int32, c_double_p],
         "pba_get_residuals": [H, c_double_p],
         "pba_get_jacobians": [H, c_double_p],
+        "pba_get_blocks": [H, C.c_int64, c_i64_p, c_double_p, c_double_p],
         "pba_build_rcs": [H, C.c_double],
         "pba_get_rcs_dim": [H, c_i32_p],
         "pba_get_rcs": [H, c_double_p, c_double_p],

@@ -9,6 +9,8 @@
 //
 // One thread per observation, observations in (host,target)-edge order, all
 // outputs in SoA planes: every warp store is 256 contiguous bytes.
+#include <stdlib.h>
+
 #include "launch.h"
 #include "pba_internal.h"
 
@@ -30,9 +32,10 @@ struct EvalArgs {
   const int* pose_calib;
   const int* calib_model;
   const double* intr;
-  const double* edge_T;  // [E][16]: A(9) t(3) ea b
+  const double* edge_T;  // [E][kEdgeStride] per-edge record (pba_internal.h)
   // landmark constants
   const double* lm_pat;
+  const double* lm_uv;   // [n_lm][2] host pixel (bearing recomputation, pinhole)
   const uint8_t* lm_ok;
   const double* obs_uv;  // geometric [2][n]
   // keyframes as quads: one uint32 (I00 | I10<<8 | I01<<16 | I11<<24) per pixel
@@ -61,7 +64,8 @@ struct EvalArgs {
 // Gram kernel derives the (h,t) and (t,t) blocks from the (h,h) block.
 __global__ void k_edge_prep(int n_edges, const int* __restrict__ edge_h, const int* __restrict__ edge_t,
                             const double* __restrict__ poses, const double* __restrict__ affine,
-                            double* __restrict__ edge_T, double* __restrict__ edge_M) {
+                            const int* __restrict__ pose_calib, const int* __restrict__ calib_model,
+                            const double* __restrict__ intr, double* __restrict__ edge_T, double* __restrict__ edge_M) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n_edges) return;
   const double* Th = poses + 7 * edge_h[e];
@@ -69,7 +73,15 @@ __global__ void k_edge_prep(int n_edges, const int* __restrict__ edge_h, const i
   double Rh[9], Rt[9];
   quat_to_rot(Th, Rh);
   quat_to_rot(Tt, Rt);
-  double* o = edge_T + 16 * e;
+  double* o = edge_T + kEdgeStride * int64_t(e);
+  {
+    const int tc = pose_calib[edge_t[e]], hc = pose_calib[edge_h[e]];
+    o[14] = double(tc);
+    o[15] = double(calib_model[hc]);
+    for (int q = 0; q < 8; ++q) o[16 + q] = intr[8 * tc + q];
+    o[24] = 1.0 / intr[8 * hc]; o[25] = 1.0 / intr[8 * hc + 1]; o[26] = intr[8 * hc + 2]; o[27] = intr[8 * hc + 3];
+    o[28] = o[29] = o[30] = o[31] = 0.0;
+  }
   for (int i = 0; i < 3; ++i)
     for (int j = 0; j < 3; ++j) o[3 * i + j] = Rt[0 + i] * Rh[0 + j] + Rt[3 + i] * Rh[3 + j] + Rt[6 + i] * Rh[6 + j];
   const double dx = Th[4] - Tt[4], dy = Th[5] - Tt[5], dz = Th[6] - Tt[6];
@@ -81,8 +93,6 @@ __global__ void k_edge_prep(int n_edges, const int* __restrict__ edge_h, const i
     o[12] = 1.0;
     o[13] = 0.0;
   }
-  o[14] = 0.0;
-  o[15] = 0.0;
   if (edge_M) {
     double* m = edge_M + 36 * e;
     const double tx = o[9], ty = o[10], tz = o[11];
@@ -214,6 +224,18 @@ __device__ __forceinline__ double huber(double s, int use_huber, double a, doubl
 constexpr int kPhotoThreads = 128;
 constexpr size_t kPhotoSmemBytes = 32 * kPhotoThreads * sizeof(double) + 16 * kPhotoThreads * 4;
 
+constexpr size_t kPhotoSmemBytesRC = (8 * kPhotoThreads + 4 * 32 * 17) * sizeof(double) + 16 * kPhotoThreads * 4;
+
+// Pinhole host point of pattern pixel k: X_h = b_k / rho with b_k = m_k / |m_k|,
+// m_k = (mx0 + o_x / fx, my0 + o_y / fy, 1)  (camera_models.h:93-107 + reprojection.h:106-107).
+__device__ __forceinline__ void pinhole_host_point(double mx0, double my0, double ifx, double ify, int k, double irho,
+                                                   double& xh, double& yh, double& zh) {
+  const double mx = fma(double(kPatternDev[k][0]), ifx, mx0);
+  const double my = fma(double(kPatternDev[k][1]), ify, my0);
+  const double sc = rsqrt(fma(mx, mx, fma(my, my, 1.0))) * irho;
+  xh = mx * sc; yh = my * sc; zh = sc;
+}
+
 struct PhotoCtx {
   double A[9], tr[3], ea, bb, in[8], irho;
   int model;
@@ -228,21 +250,37 @@ __device__ __forceinline__ double quad_sample(uint32_t q, double fx, double fy) 
 // MODEL >= 0: every camera of the problem uses that model (the usual case): the
 // projection is branch-free, so the compiler can batch the gathers.  MODEL = -1:
 // mixed models, runtime switch per observation.
-template <bool WITH_J, int MODEL>
-__global__ void __launch_bounds__(kPhotoThreads, WITH_J ? 3 : 4) k_eval_photo(const EvalArgs a) {
+//
+// RC (pinhole only): the host bearings of the 8 pattern pixels are RECOMPUTED from the host pixel
+// (b_k = m_k / |m_k|, m_k = ((u + o_x - cx) / fx, (v + o_y - cy) / fy, 1): two FMAs, a dot product and
+// one rsqrt per pixel) instead of being read from the 24 lm_pat planes.  That removes 192 B per
+// observation of L2 -> SM traffic, the 48 staging registers of phase 0 and the bearing part of the
+// pass-1 -> pass-2 hand-over (pass 2 recomputes them as well), which is what capped the kernel at 3
+// CTAs per SM (ncu, profiles/r01g_k1_*: 168 registers + 57 KB shared, 18.75 % occupancy, 65 % of the
+// cycles without an eligible warp).  The host intensities I_h stay a table (they need the image).
+// MINB = CTAs per SM the register allocation is bounded for, UNR = unroll factor of the pass-2 pixel loop.
+template <bool WITH_J, int MODEL, bool RC, int MINB = (WITH_J ? 3 : 4), int UNR = 2>
+__global__ void __launch_bounds__(kPhotoThreads, MINB) k_eval_photo(const EvalArgs a) {
+  static_assert(!RC || MODEL == PBA_CAM_PINHOLE, "bearing recomputation is implemented for the pinhole model");
   __shared__ double s_red[kPhotoThreads / 32];
-  // Dynamic shared memory (K1 only, kPhotoSmemBytes = 57 KB > the 48 KB static limit):
-  //   s_pat  [4 warps][32 values][32 lanes] doubles  pass-1 -> pass-2 hand-over: bx by bz Ih per pixel
-  //   s_rec  [4 warps][32][17] doubles  Schur-record transposition, ALIASED on the warp's own s_pat
-  //          block (dead once the warp has left the pixel loop)
-  //   s_quad [8][128] u32, s_off [8][128] int
+  // Dynamic shared memory (K1 only):
+  //   table path (kPhotoSmemBytes = 40 KB):
+  //     s_pat  [4 warps][32 values][32 lanes] doubles  pass-1 -> pass-2 hand-over: bx by bz Ih per pixel
+  //     s_rec  [4 warps][32][17] doubles  Schur-record transposition, ALIASED on the warp's own s_pat
+  //            block (dead once the warp has left the pixel loop)
+  //   RC path (kPhotoSmemBytesRC = 33 KB): s_pat holds only I_h: [4 warps][8 values][32 lanes]; s_rec
+  //            [4 warps][32][17] has its own region behind it
+  //   both: s_quad [8][128] u32, s_off [8][128] int
   // [value][thread] layouts are conflict-free.  Keeping the hand-over in SHARED memory
   // matters: as a per-thread local array it spills through L2 to HBM (ncu,
   // profiles/r01b_*: 26.4 GB written per launch against 20.7 GB of outputs).
   extern __shared__ __align__(16) unsigned char k1_sm[];
-  double* s_pat = reinterpret_cast<double*>(k1_sm) + (threadIdx.x >> 5) * 1024 + (threadIdx.x & 31);  // + 32 * value
-  double* s_rec = reinterpret_cast<double*>(k1_sm) + (threadIdx.x >> 5) * 1024;
-  uint32_t* s_quad = reinterpret_cast<uint32_t*>(reinterpret_cast<double*>(k1_sm) + 32 * kPhotoThreads);
+  constexpr int kPatVals = RC ? 8 : 32;           // hand-over values per thread
+  constexpr int kRecBase = RC ? 8 * kPhotoThreads : 0;  // doubles
+  constexpr int kWordBase = RC ? 8 * kPhotoThreads + 4 * 32 * 17 : 32 * kPhotoThreads;  // doubles
+  double* s_pat = reinterpret_cast<double*>(k1_sm) + (threadIdx.x >> 5) * (32 * kPatVals) + (threadIdx.x & 31);  // + 32 * value
+  double* s_rec = reinterpret_cast<double*>(k1_sm) + kRecBase + (threadIdx.x >> 5) * (RC ? 32 * 17 : 1024);
+  uint32_t* s_quad = reinterpret_cast<uint32_t*>(reinterpret_cast<double*>(k1_sm) + kWordBase);
   int* s_off = reinterpret_cast<int*>(s_quad + 8 * kPhotoThreads);
   const int tid = threadIdx.x;
   const int64_t i = int64_t(blockIdx.x) * kPhotoThreads + tid;
@@ -255,28 +293,36 @@ __global__ void __launch_bounds__(kPhotoThreads, WITH_J ? 3 : 4) k_eval_photo(co
     const int e = a.obs_edge[i];
     const int l = a.obs_lm[i];
     const int t = a.edge_t[e];
-    const int tc = a.pose_calib[t];
+    const double2* T2 = reinterpret_cast<const double2*>(a.edge_T + kEdgeStride * int64_t(e));
     PhotoCtx c;
-    c.model = MODEL >= 0 ? MODEL : a.calib_model[tc];
+    c.model = MODEL >= 0 ? MODEL : a.calib_model[int(T2[7].x)];
     // ---- phase 0: all independent loads first (pattern constants, edge, intrinsics) ----
-    double bx[8], by[8], bz[8], Ih[8];
+    double bx[RC ? 1 : 8], by[RC ? 1 : 8], bz[RC ? 1 : 8], Ih[8];
+    double mx0 = 0.0, my0 = 0.0, ifx = 0.0, ify = 0.0;  // RC: normalised host pixel and 1 / f of the HOST camera
     {
       const double* pk = a.lm_pat + l;
       const int64_t nl = a.n_lm;
+      if (RC) {
+        const double2 huv = reinterpret_cast<const double2*>(a.lm_uv)[l];
+        const double2 hif = T2[12], hcxy = T2[13];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        bx[k] = __ldg(pk + int64_t(4 * k) * nl);
-        by[k] = __ldg(pk + int64_t(4 * k + 1) * nl);
-        bz[k] = __ldg(pk + int64_t(4 * k + 2) * nl);
-        Ih[k] = __ldg(pk + int64_t(4 * k + 3) * nl);
+        for (int k = 0; k < 8; ++k) Ih[k] = __ldg(pk + int64_t(4 * k + 3) * nl);
+        ifx = hif.x; ify = hif.y;
+        mx0 = (huv.x - hcxy.x) * ifx; my0 = (huv.y - hcxy.y) * ify;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          bx[RC ? 0 : k] = __ldg(pk + int64_t(4 * k) * nl);
+          by[RC ? 0 : k] = __ldg(pk + int64_t(4 * k + 1) * nl);
+          bz[RC ? 0 : k] = __ldg(pk + int64_t(4 * k + 2) * nl);
+          Ih[k] = __ldg(pk + int64_t(4 * k + 3) * nl);
+        }
       }
-      const double2* T2 = reinterpret_cast<const double2*>(a.edge_T + 16 * int64_t(e));
       const double2 t0 = T2[0], t1 = T2[1], t2 = T2[2], t3 = T2[3], t4 = T2[4], t5 = T2[5], t6 = T2[6];
       c.A[0] = t0.x; c.A[1] = t0.y; c.A[2] = t1.x; c.A[3] = t1.y; c.A[4] = t2.x; c.A[5] = t2.y; c.A[6] = t3.x;
       c.A[7] = t3.y; c.A[8] = t4.x; c.tr[0] = t4.y; c.tr[1] = t5.x; c.tr[2] = t5.y; c.ea = t6.x; c.bb = t6.y;
-      const double2* I2 = reinterpret_cast<const double2*>(a.intr + 8 * tc);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) { const double2 v = I2[q]; c.in[2 * q] = v.x; c.in[2 * q + 1] = v.y; }
+      for (int q = 0; q < (MODEL == PBA_CAM_PINHOLE ? 2 : 4); ++q) { const double2 v = T2[8 + q]; c.in[2 * q] = v.x; c.in[2 * q + 1] = v.y; }
     }
     c.irho = 1.0 / a.rho[l];
     const uint32_t* img = a.quads + int64_t(t) * a.image_stride;
@@ -288,7 +334,12 @@ __global__ void __launch_bounds__(kPhotoThreads, WITH_J ? 3 : 4) k_eval_photo(co
     const double umax = double(a.width - 1), vmax = double(a.height - 1);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const double xh = bx[k] * c.irho, yh = by[k] * c.irho, zh = bz[k] * c.irho;
+      double xh, yh, zh;
+      if (RC) {
+        pinhole_host_point(mx0, my0, ifx, ify, k, c.irho, xh, yh, zh);
+      } else {
+        xh = bx[RC ? 0 : k] * c.irho; yh = by[RC ? 0 : k] * c.irho; zh = bz[RC ? 0 : k] * c.irho;
+      }
       const double xt = c.A[0] * xh + c.A[1] * yh + c.A[2] * zh + c.tr[0];
       const double yt = c.A[3] * xh + c.A[4] * yh + c.A[5] * zh + c.tr[1];
       const double zt = c.A[6] * xh + c.A[7] * yh + c.A[8] * zh + c.tr[2];
@@ -322,23 +373,33 @@ __global__ void __launch_bounds__(kPhotoThreads, WITH_J ? 3 : 4) k_eval_photo(co
       if (!ok) c.irho = 0.0;
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        s_pat[(4 * k + 0) * 32] = bx[k];
-        s_pat[(4 * k + 1) * 32] = by[k];
-        s_pat[(4 * k + 2) * 32] = bz[k];
-        s_pat[(4 * k + 3) * 32] = Ih[k];
+        if (RC) {
+          s_pat[k * 32] = Ih[k];
+        } else {
+          s_pat[(4 * k + 0) * 32] = bx[RC ? 0 : k];
+          s_pat[(4 * k + 1) * 32] = by[RC ? 0 : k];
+          s_pat[(4 * k + 2) * 32] = bz[RC ? 0 : k];
+          s_pat[(4 * k + 3) * 32] = Ih[k];
+        }
         s_quad[k * kPhotoThreads + tid] = quad[k];
         s_off[k * kPhotoThreads + tid] = off[k];
       }
       // ---- phase 2: one pixel at a time: recompute the warp with its projection Jacobian
       //      (no global loads), weight, stream the row out ----
       const int64_t n = a.ld;
-#pragma unroll 2
+#pragma unroll UNR
       for (int k = 0; k < 8; ++k) {
-        const double bxk = s_pat[(4 * k + 0) * 32], byk = s_pat[(4 * k + 1) * 32];
-        const double bzk = s_pat[(4 * k + 2) * 32], Ihk = s_pat[(4 * k + 3) * 32];
+        double xh, yh, zh, Ihk;
+        if (RC) {
+          Ihk = s_pat[k * 32];
+          pinhole_host_point(mx0, my0, ifx, ify, k, c.irho, xh, yh, zh);
+        } else {
+          const double bxk = s_pat[(4 * k + 0) * 32], byk = s_pat[(4 * k + 1) * 32], bzk = s_pat[(4 * k + 2) * 32];
+          Ihk = s_pat[(4 * k + 3) * 32];
+          xh = bxk * c.irho; yh = byk * c.irho; zh = bzk * c.irho;
+        }
         const uint32_t q = s_quad[k * kPhotoThreads + tid];
         const int ofk = s_off[k * kPhotoThreads + tid];
-        const double xh = bxk * c.irho, yh = byk * c.irho, zh = bzk * c.irho;
         const double xt = c.A[0] * xh + c.A[1] * yh + c.A[2] * zh + c.tr[0];
         const double yt = c.A[3] * xh + c.A[4] * yh + c.A[5] * zh + c.tr[1];
         const double zt = c.A[6] * xh + c.A[7] * yh + c.A[8] * zh + c.tr[2];
@@ -406,7 +467,7 @@ __global__ void __launch_bounds__(kPhotoThreads, WITH_J ? 3 : 4) k_eval_photo(co
   if (WITH_J) {
     // Schur record [obs][16]: transpose the warp's 32 x 16 values through shared
     // memory (row stride 17) and store them as 16 coalesced 256 B runs.
-    __syncwarp();  // the warp is done with its s_pat block, which s_rec aliases
+    __syncwarp();  // table path: the warp is done with its s_pat block, which s_rec aliases
     double* rec = s_rec;
 #pragma unroll
     for (int q = 0; q < 16; ++q) rec[lane * 17 + q] = acc[q];
@@ -422,15 +483,34 @@ __global__ void __launch_bounds__(kPhotoThreads, WITH_J ? 3 : 4) k_eval_photo(co
   if (threadIdx.x == 0) a.block_cost[blockIdx.x] = bs;
 }
 
+// rc: recompute the pattern bearings (all cameras pinhole); see the kernel's comment.
+// PBA_K1_VARIANT / PBA_K2_VARIANT pick the occupancy / unroll variants kept for A/B measurements.
 template <bool WITH_J>
-void (*photo_kernel(int model))(const EvalArgs) {
-  switch (model) {
-    case PBA_CAM_PINHOLE: return k_eval_photo<WITH_J, PBA_CAM_PINHOLE>;
-    case PBA_CAM_DS: return k_eval_photo<WITH_J, PBA_CAM_DS>;
-    case PBA_CAM_KB4: return k_eval_photo<WITH_J, PBA_CAM_KB4>;
-    case PBA_CAM_EUCM: return k_eval_photo<WITH_J, PBA_CAM_EUCM>;
+void (*photo_kernel(int model, bool rc))(const EvalArgs) {
+  static const int var = [] { const char* e = getenv(WITH_J ? "PBA_K1_VARIANT" : "PBA_K2_VARIANT"); return e ? atoi(e) : 0; }();
+  if (model == PBA_CAM_PINHOLE && rc) {
+    if (WITH_J) {
+      switch (var) {
+        case 1: return k_eval_photo<WITH_J, PBA_CAM_PINHOLE, true, 4, 1>;
+        case 2: return k_eval_photo<WITH_J, PBA_CAM_PINHOLE, true, 5, 1>;
+        case 3: return k_eval_photo<WITH_J, PBA_CAM_PINHOLE, true, 3, 2>;
+        default: return k_eval_photo<WITH_J, PBA_CAM_PINHOLE, true, 4, 2>;
+      }
+    } else {
+      switch (var) {
+        case 1: return k_eval_photo<WITH_J, PBA_CAM_PINHOLE, true, 4, 2>;
+        case 2: return k_eval_photo<WITH_J, PBA_CAM_PINHOLE, true, 6, 2>;
+        default: return k_eval_photo<WITH_J, PBA_CAM_PINHOLE, true, 5, 2>;
+      }
+    }
   }
-  return k_eval_photo<WITH_J, -1>;
+  switch (model) {
+    case PBA_CAM_PINHOLE: return k_eval_photo<WITH_J, PBA_CAM_PINHOLE, false>;
+    case PBA_CAM_DS: return k_eval_photo<WITH_J, PBA_CAM_DS, false>;
+    case PBA_CAM_KB4: return k_eval_photo<WITH_J, PBA_CAM_KB4, false>;
+    case PBA_CAM_EUCM: return k_eval_photo<WITH_J, PBA_CAM_EUCM, false>;
+  }
+  return k_eval_photo<WITH_J, -1, false>;
 }
 
 // -------------------------------------------------------------- geometric --
@@ -445,15 +525,13 @@ __global__ void __launch_bounds__(kEvalThreads) k_eval_geom(const EvalArgs a) {
   if (i < a.n) {
     const int e = a.obs_edge[i];
     const int l = a.obs_lm[i];
-    const int t = a.edge_t[e];
-    const int tc = a.pose_calib[t];
-    const int model = a.calib_model[a.pose_calib[a.edge_h[e]]];
-    const double* T = a.edge_T + 16 * int64_t(e);
+    const double* T = a.edge_T + kEdgeStride * int64_t(e);
+    const int model = int(T[15]);  // both cameras use the HOST's model (map_utils.h:363-364)
     double A[9], in[8];
 #pragma unroll
     for (int k = 0; k < 9; ++k) A[k] = T[k];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) in[k] = a.intr[8 * tc + k];
+    for (int k = 0; k < 8; ++k) in[k] = T[16 + k];
     const double rho = a.rho[l];
     const double irho = 1.0 / rho;
     const double4 bk = reinterpret_cast<const double4*>(a.lm_pat)[l];
@@ -584,6 +662,31 @@ __global__ void k_unpermute(int64_t n, int64_t ld, int R, int C, int which, cons
   }
 }
 
+// Selected blocks only: sel_pos[j] = edge-order position of the j-th requested block.
+__global__ void k_gather_blocks(int64_t n_sel, int64_t ld, int R, int C, const int64_t* __restrict__ sel_pos,
+                                const double* __restrict__ src, const int* __restrict__ obs_edge,
+                                const double* __restrict__ edge_M, double* __restrict__ res, double* __restrict__ jac) {
+  const int64_t j = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (j >= n_sel) return;
+  const int64_t i = sel_pos[j];
+  const int P = C + 1 - 6;  // stored planes per row
+  const double* m = edge_M + 36 * int64_t(obs_edge[i]);
+  for (int k = 0; k < R; ++k) {
+    const double* row = src + int64_t(k) * P * ld + i;
+    if (res) res[j * R + k] = row[int64_t(stored_plane(C)) * ld];
+    if (!jac) continue;
+    double hcol[6];
+    for (int q = 0; q < 6; ++q) hcol[q] = row[int64_t(q) * ld];
+    for (int c = 0; c < C; ++c) {
+      double v;
+      if (c < 6) v = hcol[c];
+      else if (c < 12) { v = 0.0; for (int q = 0; q < 6; ++q) v += hcol[q] * m[6 * q + (c - 6)]; }
+      else v = row[int64_t(stored_plane(c)) * ld];
+      jac[(j * R + k) * C + c] = v;
+    }
+  }
+}
+
 // Set-up: obs_edge[i] = e and obs_col[i] = edge_col[e] for the observations [edge_ptr[e], edge_ptr[e+1]) of edge e.
 __global__ void k_expand_edges(int n_edges, const int64_t* __restrict__ edge_ptr, const int* __restrict__ edge_col,
                                int* __restrict__ obs_edge, int* __restrict__ obs_col) {
@@ -635,25 +738,30 @@ pba_status launch_evaluate(Handle* h, bool with_jacobian, const double* poses, c
   const bool photo = z.mode == PBA_MODE_PHOTOMETRIC;
   if (z.n_edges > 0) {
     PBA_LAUNCH(h, K_EDGE_PREP, k_edge_prep, dim3((z.n_edges + 127) / 128), dim3(128), 0, z.n_edges, h->edge_h.p,
-               h->edge_t.p, poses, photo ? affine : nullptr, h->edge_T.p,
+               h->edge_t.p, poses, photo ? affine : nullptr, h->pose_calib.p, h->calib_model.p, h->intr.p, h->edge_T.p,
                with_jacobian ? h->edge_M.p : nullptr);
   }
   EvalArgs a;
   a.n = z.n_obs; a.ld = z.ld; a.n_lm = z.n_lm;
   a.obs_lm = h->obs_lm.p; a.obs_edge = h->obs_edge.p; a.edge_h = h->edge_h.p; a.edge_t = h->edge_t.p;
   a.pose_calib = h->pose_calib.p; a.calib_model = h->calib_model.p; a.intr = h->intr.p; a.edge_T = h->edge_T.p;
-  a.lm_pat = h->lm_pat.p; a.lm_ok = h->lm_ok.p; a.obs_uv = h->obs_uv.p;
+  a.lm_pat = h->lm_pat.p; a.lm_uv = h->lm_uv.p; a.lm_ok = h->lm_ok.p; a.obs_uv = h->obs_uv.p;
   a.quads = h->quads.p; a.image_stride = z.image_stride; a.width = z.width; a.height = z.height; a.pitch = z.width;  // quad rows are packed
   a.rho = rho; a.use_huber = h->opt.use_huber; a.huber = h->opt.huber_parameter;
   a.J = h->J.p; a.orec = h->orec.p; a.block_cost = h->red_ws.p;
   static_assert(kPhotoThreads == kEvalThreads, "block-cost workspace is sized for one CTA width");
   const int grid = eval_grid(z.n_obs);
+  // pinhole everywhere: the pattern bearings are recomputed instead of read (PBA_K1_TABLE=1 keeps the table path,
+  // for A/B measurements)
+  static const bool force_table = getenv("PBA_K1_TABLE") != nullptr;
+  const bool rc = h->uniform_model == PBA_CAM_PINHOLE && !force_table;
   if (grid > 0) {
     if (photo) {
       if (with_jacobian) {
-        PBA_LAUNCH(h, K_RESJAC, photo_kernel<true>(h->uniform_model), dim3(grid), dim3(kPhotoThreads), kPhotoSmemBytes, a);
+        PBA_LAUNCH(h, K_RESJAC, photo_kernel<true>(h->uniform_model, rc), dim3(grid), dim3(kPhotoThreads),
+                   rc ? kPhotoSmemBytesRC : kPhotoSmemBytes, a);
       }
-      else { PBA_LAUNCH(h, K_COST, photo_kernel<false>(h->uniform_model), dim3(grid), dim3(kPhotoThreads), 0, a); }
+      else { PBA_LAUNCH(h, K_COST, photo_kernel<false>(h->uniform_model, rc), dim3(grid), dim3(kPhotoThreads), 0, a); }
     } else {
       if (with_jacobian) { PBA_LAUNCH(h, K_RESJAC, k_eval_geom<true>, dim3(grid), dim3(kEvalThreads), 0, a); }
       else { PBA_LAUNCH(h, K_COST, k_eval_geom<false>, dim3(grid), dim3(kEvalThreads), 0, a); }
@@ -671,6 +779,14 @@ pba_status launch_unpermute(Handle* h, int which, double* dst) {
   PBA_LAUNCH(h, K_UNPERMUTE, k_unpermute, dim3(int((z.n_obs + 127) / 128)), dim3(128), 0, z.n_obs, z.ld, z.R, z.C, which, order.p,
              h->J.p, h->obs_edge.p, h->edge_M.p, dst);
   PBA_CUDA_OK(cudaStreamSynchronize(h->stream));
+  return PBA_OK;
+}
+
+pba_status launch_gather_blocks(Handle* h, int64_t n_sel, const int64_t* sel_pos_dev, double* res_dev, double* jac_dev) {
+  const Sizes& z = h->sz;
+  if (n_sel == 0) return PBA_OK;
+  PBA_LAUNCH(h, K_UNPERMUTE, k_gather_blocks, dim3(unsigned((n_sel + 127) / 128)), dim3(128), 0, n_sel, z.ld, z.R, z.C,
+             sel_pos_dev, h->J.p, h->obs_edge.p, h->edge_M.p, res_dev, jac_dev);
   return PBA_OK;
 }
 

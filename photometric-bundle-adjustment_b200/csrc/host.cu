@@ -740,7 +740,7 @@ pba_status create_impl(const pba_problem* p, const pba_options* o, int rank, int
   PBA_CUDA_OK(h->affine_c.alloc(size_t(2) * p->n_poses)); PBA_CUDA_OK(h->affine_best.alloc(size_t(2) * p->n_poses));
   PBA_CUDA_OK(h->rho_c.alloc(n_lm)); PBA_CUDA_OK(h->rho_best.alloc(n_lm));
   PBA_CUDA_OK(h->lm_pat.alloc(size_t(n_lm) * (photo ? 32 : 4))); PBA_CUDA_OK(h->lm_ok.alloc(n_lm));
-  PBA_CUDA_OK(h->edge_T.alloc(size_t(16) * z.n_edges));
+  PBA_CUDA_OK(h->edge_T.alloc(size_t(kEdgeStride) * z.n_edges));
   PBA_CUDA_OK(h->edge_M.alloc(size_t(36) * z.n_edges));
   PBA_CUDA_OK(h->J.alloc(size_t(z.ld) * z.R * (z.C + 1 - 6))); PBA_CUDA_OK(h->orec.alloc(nn * 16));  // stored planes: pba_internal.h
   PBA_CUDA_OK(h->W.alloc(size_t(w_total)));
@@ -841,7 +841,16 @@ pba_status minimize_impl(Handle* h, pba_summary* sum) {
   const int cap = sum ? sum->iterations_capacity : 0;
   if (sum) { memset(sum, 0, sizeof(*sum)); sum->iterations = its; sum->iterations_capacity = cap; }
   int n_it = 0;
-  auto push = [&](const pba_iteration& it) { if (its && n_it < cap) its[n_it] = it; ++n_it; };
+  double t_prev_it = t_start;
+  auto push = [&](pba_iteration& it) {
+    // host clock after the iteration's last device read-back (every iteration ends in read_scalars)
+    const double now = wall();
+    it.iteration_time_in_seconds = now - t_prev_it;
+    it.cumulative_time_in_seconds = now - t_start;
+    t_prev_it = now;
+    if (its && n_it < cap) its[n_it] = it;
+    ++n_it;
+  };
   KernelStats& ks = h->stats;
   const int64_t launches0 = std::accumulate(ks.launches, ks.launches + K_NUM, int64_t(0));
 
@@ -1106,7 +1115,7 @@ PBA_API void pba_options_init(pba_options* o) {
   o->initial_trust_region_radius = 1e4; o->max_trust_region_radius = 1e16; o->min_trust_region_radius = 1e-32;
   o->min_relative_decrease = 1e-3; o->min_lm_diagonal = 1e-6; o->max_lm_diagonal = 1e32;
   o->function_tolerance = 1e-6; o->gradient_tolerance = 1e-10; o->parameter_tolerance = 1e-8;
-  o->max_num_consecutive_invalid_steps = 5; o->jacobi_scaling = 1; o->device = 0; o->profile = 0;
+  o->max_num_consecutive_invalid_steps = 5; o->jacobi_scaling = 1; o->device = 0; o->profile = 0; o->num_gpus = 1;
 }
 
 PBA_API pba_status pba_create(const pba_problem* problem, const pba_options* options, int32_t rank, int32_t world_size,
@@ -1189,6 +1198,38 @@ PBA_API pba_status pba_get_jacobians(pba_handle* hh, double* jacobians) {
   pba_status st = launch_unpermute(h, 1, tmp.p);
   if (st != PBA_OK) return st;
   PBA_CUDA_OK(cudaMemcpy(jacobians, tmp.p, sizeof(double) * z.n_obs * z.R * z.C, cudaMemcpyDeviceToHost));
+  return PBA_OK;
+}
+
+PBA_API pba_status pba_get_blocks(pba_handle* hh, int64_t n_sel, const int64_t* obs_index, double* residuals,
+                                  double* jacobians) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h || n_sel < 0 || (n_sel > 0 && !obs_index) || !h->have_jac) return PBA_ERR_INVALID_ARGUMENT;
+  const Sizes& z = h->sz;
+  if (n_sel == 0 || (!residuals && !jacobians)) return PBA_OK;
+  PBA_CUDA_OK(cudaSetDevice(h->device));
+  // caller index -> edge-order position, for the selection only: one parallel scan of the permutation
+  std::vector<int64_t> where(size_t(z.n_obs), -1);
+  for (int64_t j = 0; j < n_sel; ++j) {
+    if (obs_index[j] < 0 || obs_index[j] >= z.n_obs || where[size_t(obs_index[j])] >= 0) return PBA_ERR_INVALID_ARGUMENT;
+    where[size_t(obs_index[j])] = j;
+  }
+  std::vector<int64_t> pos(size_t(n_sel), -1);
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < z.n_obs; ++i) {
+    const int64_t j = where[size_t(h->obs_order[size_t(i)])];
+    if (j >= 0) pos[size_t(j)] = i;
+  }
+  DevBuf<int64_t> d_pos;
+  DevBuf<double> d_res, d_jac;
+  PBA_CUDA_OK(d_pos.upload(pos, h->stream));
+  if (residuals) PBA_CUDA_OK(d_res.alloc(size_t(n_sel) * z.R));
+  if (jacobians) PBA_CUDA_OK(d_jac.alloc(size_t(n_sel) * z.R * z.C));
+  pba_status st = launch_gather_blocks(h, n_sel, d_pos.p, d_res.p, d_jac.p);
+  if (st != PBA_OK) return st;
+  if (residuals) PBA_CUDA_OK(cudaMemcpyAsync(residuals, d_res.p, sizeof(double) * n_sel * z.R, cudaMemcpyDeviceToHost, h->stream));
+  if (jacobians) PBA_CUDA_OK(cudaMemcpyAsync(jacobians, d_jac.p, sizeof(double) * n_sel * z.R * z.C, cudaMemcpyDeviceToHost, h->stream));
+  PBA_CUDA_OK(cudaStreamSynchronize(h->stream));
   return PBA_OK;
 }
 

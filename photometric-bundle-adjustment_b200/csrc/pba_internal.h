@@ -163,6 +163,14 @@ struct KernelStats {
 // the host-pose columns x a per-edge adjoint), so a row of C columns + residual has C + 1 - 6 planes:
 // columns 0..5 (host pose) -> planes 0..5, every later column c (affine, inverse distance) and the
 // residual (c = C) -> plane c - 6.  Photometric: 10 planes per row, geometric: 8.
+// Per-edge record written by k_edge_prep before every evaluation: everything an observation needs
+// that is constant along its (host, target) edge sits in ONE 256-byte record, so the dependent load
+// chain of the evaluation kernels is obs_edge -> record (it used to be obs_edge -> edge_t -> pose_calib
+// -> intrinsics: four dependent global loads before the first useful flop).
+//   [0..8] A = R_t^T R_h   [9..11] t = R_t^T (t_h - t_t)   [12] exp(a_t)   [13] b_t
+//   [14] target calibration index   [15] host camera model id
+//   [16..23] target intrinsics   [24] 1 / fx_host  [25] 1 / fy_host  [26] cx_host  [27] cy_host
+constexpr int kEdgeStride = 32;
 constexpr int kReduceMid = 64;  // CTAs of the first stage of a long scalar reduction
 constexpr int kPhotoPlanes = 10;
 constexpr int kGeomPlanes = 8;
@@ -250,7 +258,7 @@ struct Handle {
   DevBuf<double> poses_best, affine_best, rho_best;
 
   // ---- per-evaluation data ----
-  DevBuf<double> edge_T;       // [E][16]
+  DevBuf<double> edge_T;       // [E][kEdgeStride] per-edge record (eval.cu: k_edge_prep)
   DevBuf<double> edge_M;       // [E][36] photometric: target-pose Jacobian columns = host-pose columns x M (adjoint)
   DevBuf<double> J;            // interleaved planes [R][C+1][ld]: Jacobian row columns + residual
   DevBuf<double> orec;         // [n][16]
@@ -325,6 +333,7 @@ pba_status launch_build_quads(Handle* h, const uint8_t* images_u8, int first, in
 pba_status launch_evaluate(Handle* h, bool with_jacobian, const double* poses, const double* affine,
                            const double* rho, int cost_slot);
 pba_status launch_unpermute(Handle* h, int which, double* dst_host_order_dev);
+pba_status launch_gather_blocks(Handle* h, int64_t n_sel, const int64_t* sel_pos_dev, double* res_dev, double* jac_dev);
 pba_status launch_expand_edges(Handle* h, const int* edge_col_dev);  // fills obs_edge / obs_col from edge_ptr
 // schur.cu
 pba_status launch_post_jacobian(Handle* h);              // edge Gram + landmark gather (+ scales on first call)

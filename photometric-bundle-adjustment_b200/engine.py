@@ -34,6 +34,7 @@ class BundleAdjustmentOptions:
     parameter_tolerance: float = None
     initial_trust_region_radius: float = None
     device: int = 0
+    num_gpus: int = None  # pba_solve from one process over this many GPUs (None = 1, 0 = all visible)
     profile: int = 0  # 0 none, 1 CUDA events around every kernel, 2 only around the residual/Jacobian kernel
 
     def to_c(self):
@@ -135,6 +136,15 @@ class Engine:
         J = np.zeros((self.n_obs_local, self.problem.res_per_obs, self.problem.cols_per_obs))
         _ffi.check(self.lib.pba_get_jacobians(self._h, _ffi.ptr(J, C.c_double)))
         return J
+
+    def blocks(self, obs_index, want_jacobians=True):
+        """Residuals [n,R] and local Jacobians [n,R,C] of the selected blocks (caller-order local indices)."""
+        idx = np.ascontiguousarray(obs_index, np.int64)
+        r = np.zeros((idx.shape[0], self.problem.res_per_obs))
+        J = np.zeros((idx.shape[0], self.problem.res_per_obs, self.problem.cols_per_obs)) if want_jacobians else None
+        _ffi.check(self.lib.pba_get_blocks(self._h, idx.shape[0], _ffi.ptr(idx, C.c_int64), _ffi.ptr(r, C.c_double),
+                                           _ffi.ptr(J, C.c_double)), "pba_get_blocks")
+        return r, J
 
     def build_rcs(self, radius=1e4):
         _ffi.check(self.lib.pba_build_rcs(self._h, float(radius)), "pba_build_rcs")

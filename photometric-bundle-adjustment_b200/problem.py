@@ -87,6 +87,38 @@ class Problem:
                        None if self.affine is None else self.affine.copy())
 
 
+    def prefix_keyframes(self, n_kf):
+        """The first n_kf keyframes and every landmark whose whole track lies inside them (landmarks must be
+        ordered by host, as the synthetic scenes are); state copied."""
+        if n_kf >= self.n_poses:
+            return self.copy()
+        last_target = np.maximum.reduceat(self.obs_target, self.lm_obs_ptr[:-1].clip(max=max(self.n_obs - 1, 0)))
+        inside = (last_target < n_kf) & (self.lm_host < n_kf)
+        L = int(np.argmin(inside)) if not inside.all() else self.n_landmarks
+        o1 = int(self.lm_obs_ptr[L])
+        return Problem(self.mode, self.poses[:n_kf].copy(), self.pose_fixed[:n_kf], self.pose_calib[:n_kf],
+                       self.calib_model, self.intrinsics, self.inv_depth[:L].copy(), self.lm_host[:L],
+                       self.lm_host_uv[:L], self.lm_obs_ptr[:L + 1], self.obs_target[:o1],
+                       None if self.obs_uv is None else self.obs_uv[:o1],
+                       None if self.images is None else self.images[:n_kf],
+                       None if self.affine is None else self.affine[:n_kf].copy())
+
+    def select_landmarks(self, lm_index):
+        """Problem made of the given landmarks only (all poses kept, state shared by value) plus the
+        caller-order observation indices of their blocks in this problem."""
+        lm_index = np.asarray(lm_index, np.int64)
+        lo, hi = self.lm_obs_ptr[lm_index], self.lm_obs_ptr[lm_index + 1]
+        cnt = hi - lo
+        ptr = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
+        obs = np.repeat(lo - ptr[:-1], cnt) + np.arange(int(ptr[-1]), dtype=np.int64)
+        sub = Problem(self.mode, self.poses.copy(), self.pose_fixed, self.pose_calib, self.calib_model,
+                      self.intrinsics, self.inv_depth[lm_index].copy(), self.lm_host[lm_index],
+                      self.lm_host_uv[lm_index], ptr, self.obs_target[obs],
+                      None if self.obs_uv is None else self.obs_uv[obs], self.images,
+                      None if self.affine is None else self.affine.copy())
+        return sub, obs
+
+
 def partition_landmarks(lm_obs_ptr, world_size):
     """Contiguous landmark ranges balanced by observation count.
 

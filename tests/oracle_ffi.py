@@ -91,10 +91,33 @@ def default_options(**kw):
     o.initial_trust_region_radius, o.max_trust_region_radius, o.min_trust_region_radius = 1e4, 1e16, 1e-32
     o.min_relative_decrease, o.min_lm_diagonal, o.max_lm_diagonal = 1e-3, 1e-6, 1e32
     o.function_tolerance, o.gradient_tolerance, o.parameter_tolerance = 1e-6, 1e-10, 1e-8
-    o.max_num_consecutive_invalid_steps, o.jacobi_scaling, o.device, o.profile = 5, 1, 0, 0
+    o.max_num_consecutive_invalid_steps, o.jacobi_scaling, o.device, o.profile, o.num_gpus = 5, 1, 0, 0, 1
     for k, v in kw.items():
         setattr(o, k, v)
     return o
+
+
+# The vendored Ceres 2.0.0 counts Jacobian non-zeros in an `int` (internal/ceres/block_sparse_matrix.cc:80,
+# "Check failed: num_nonzeros_ >= 0"): a problem with more than 2^31 - 1 Jacobian entries aborts.  BASELINE
+# config 4 (17,959,243 photometric blocks x 8 x 15 = 2.155e9 entries) is 0.36 % over that limit, so the
+# reference itself can only run a prefix of it.
+CERES_MAX_NONZEROS = 2 ** 31 - 1
+
+
+def largest_reference_prefix(prob):
+    """(n_kf, problem): the longest keyframe prefix of `prob` whose Jacobian the reference's Ceres can hold."""
+    per_block = prob.res_per_obs * prob.cols_per_obs
+    if prob.n_obs * per_block <= CERES_MAX_NONZEROS:
+        return prob.n_poses, prob
+    lo, hi = 2, prob.n_poses
+    while hi - lo > 1:  # observations grow monotonically with the prefix length
+        mid = (lo + hi) // 2
+        last = np.searchsorted(prob.lm_host, mid, side="left")  # landmarks hosted before `mid` (upper bound)
+        if int(prob.lm_obs_ptr[last]) * per_block <= CERES_MAX_NONZEROS:
+            lo = mid
+        else:
+            hi = mid
+    return lo, prob.prefix_keyframes(lo)
 
 
 def evaluate(lib_kind, prob, use_huber=True, huber=1.0, threads=0, jac=True):

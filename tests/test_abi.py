@@ -28,13 +28,13 @@ def test_library_exports_every_declared_symbol():
     lib = C.CDLL(_ffi.lib_path())
     for name in declared_symbols():
         assert hasattr(lib, name), "libpba_b200.so does not export %s" % name
-    assert lib.pba_abi_version() == 1
+    assert lib.pba_abi_version() == 2
 
 
 def test_struct_layouts_match_header():
     # sizes the C side computes for the same structs (compiled into the synth lib's translation unit)
     assert C.sizeof(_ffi.pba_problem) == 4 * 4 + 8 + 5 * 8 + 6 * 8 + 2 * 8 + 8 + 3 * 4 + 4 + 8
-    assert C.sizeof(_ffi.pba_iteration) == 4 * 4 + 8 * 8
+    assert C.sizeof(_ffi.pba_iteration) == 4 * 4 + 10 * 8
     assert C.sizeof(_ffi.pba_kernel_stat) == 48 + 8 + 8
 
 
