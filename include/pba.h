@@ -206,6 +206,12 @@ void pba_options_init(pba_options* o); /* BundleAdjustmentOptions + Ceres defaul
 pba_status pba_solve(pba_problem* problem, const pba_options* options,
                      pba_summary* summary);
 
+/* Optional: create (and cache for the life of the process) the NCCL communicators that
+ * pba_solve(options.num_gpus > 1) uses on devices device .. device + num_gpus - 1 (num_gpus 0 = all from
+ * `device` on).  pba_solve does this on demand; calling it up front keeps the seconds ncclCommInitAll
+ * takes out of the first solve. */
+pba_status pba_multi_gpu_init(int32_t device, int32_t num_gpus);
+
 /* ---- split entry points (tests / bench): device-resident problem ---- */
 /* Replaces Problem construction + Ceres preprocessing (map_utils.h:327-375,
  * trust_region_preprocessor.cc:373): validates, orders observations by

@@ -506,7 +506,7 @@ pba_status bcr_setup(Handle* h) {
   // level 0 is rebuilt from the RCS blocks by k_bcr_build before every solve; the block pattern is
   // static, so the entries it never writes are zeroed here once (A and B of level 0 are contiguous)
   PBA_CUDA_OK(cudaMemsetAsync(h->bcr_ws.p + offA[0], 0, sizeof(double) * (size_t(S) * M * M + size_t(S > 1 ? S - 1 : 0) * M * M), h->stream));
-  return PBA_OK;
+  return bcr2_setup(h);
 }
 
 pba_status launch_bcr_rcs(Handle* h) {

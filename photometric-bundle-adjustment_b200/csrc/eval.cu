@@ -733,7 +733,7 @@ pba_status launch_init_landmarks(Handle* h) {
 int eval_grid(int64_t n) { return int((n + kEvalThreads - 1) / kEvalThreads); }
 
 pba_status launch_evaluate(Handle* h, bool with_jacobian, const double* poses, const double* affine,
-                           const double* rho, int cost_slot) {
+                           const double* rho, double* cost_out) {
   const Sizes& z = h->sz;
   const bool photo = z.mode == PBA_MODE_PHOTOMETRIC;
   if (z.n_edges > 0) {
@@ -767,7 +767,7 @@ pba_status launch_evaluate(Handle* h, bool with_jacobian, const double* poses, c
       else { PBA_LAUNCH(h, K_COST, k_eval_geom<false>, dim3(grid), dim3(kEvalThreads), 0, a); }
     }
   }
-  launch_reduce_sum(h, h->red_ws.p, int64_t(grid), h->scalars.p + cost_slot);
+  launch_reduce_sum(h, h->red_ws.p, int64_t(grid), cost_out);
   return PBA_OK;
 }
 

@@ -23,8 +23,10 @@
 #include <limits>
 #include <array>
 #include <memory>
+#include <condition_variable>
 #include <mutex>
 #include <numeric>
+#include <thread>
 #include <string>
 #include <unordered_set>
 
@@ -104,6 +106,7 @@ struct NcclApi {
   void* lib = nullptr;
   int (*GetUniqueId)(NcclId*) = nullptr;
   int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+  int (*CommInitAll)(void**, int, const int*) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
   int (*CommDestroy)(void*) = nullptr;
   bool load() {
@@ -120,7 +123,8 @@ struct NcclApi {
     CommInitRank = (int (*)(void**, int, NcclId, int))dlsym(lib, "ncclCommInitRank");
     AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(lib, "ncclAllReduce");
     CommDestroy = (int (*)(void*))dlsym(lib, "ncclCommDestroy");
-    return GetUniqueId && CommInitRank && AllReduce && CommDestroy;
+    CommInitAll = (int (*)(void**, int, const int*))dlsym(lib, "ncclCommInitAll");
+    return GetUniqueId && CommInitRank && AllReduce && CommDestroy && CommInitAll;
   }
 };
 NcclApi g_nccl;
@@ -233,11 +237,11 @@ cudaError_t ensure_dynamic_smem(const void* kernel, size_t bytes, int device) {
   return err;
 }
 
-pba_status allreduce_rcs(Handle* h) {
+pba_status allreduce_rcs(Handle* h, bool with_scalars) {
   if (h->world <= 1) return PBA_OK;
   if (!h->nccl_comm) return PBA_ERR_NCCL;
   const Sizes& z = h->sz;
-  const size_t count = size_t(z.n_blocks) * z.cd * z.cd + 3 * size_t(z.dim);
+  const size_t count = size_t(z.n_blocks) * z.cd * z.cd + 3 * size_t(z.dim) + (with_scalars ? size_t(2 + h->world) : 0);
   h->stats.begin(K_COPY, h->stream);
   const int rc = g_nccl.AllReduce(h->rcs.p, h->rcs.p, count, kNcclDouble, kNcclSum, h->nccl_comm, h->stream);
   h->stats.end(h->stream);
@@ -748,7 +752,7 @@ pba_status create_impl(const pba_problem* p, const pba_options* o, int rank, int
   PBA_CUDA_OK(h->lm_c.alloc(n_lm)); PBA_CUDA_OK(h->lm_g.alloc(n_lm)); PBA_CUDA_OK(h->lm_scale.alloc(n_lm));
   PBA_CUDA_OK(h->lm_diag.alloc(n_lm)); PBA_CUDA_OK(h->lm_s2.alloc(n_lm)); PBA_CUDA_OK(h->lm_iete.alloc(n_lm));
   PBA_CUDA_OK(h->part_dir.alloc(size_t(z.n_chunks) * dir_stride)); PBA_CUDA_OK(h->part_sch.alloc(size_t(part_total)));
-  PBA_CUDA_OK(h->rcs.alloc(size_t(z.n_blocks) * cd * cd + 3 * size_t(z.dim)));
+  PBA_CUDA_OK(h->rcs.alloc(size_t(z.n_blocks) * cd * cd + 3 * size_t(z.dim) + 2 + size_t(world)));  // + rcs_tail()
   PBA_CUDA_OK(h->rcs_B.alloc(size_t(z.n_blocks) * cd * cd + size_t(z.dim)));
   PBA_CUDA_OK(h->cam_scale.alloc(z.dim)); PBA_CUDA_OK(h->cam_diag.alloc(z.dim)); PBA_CUDA_OK(h->cam_D2.alloc(z.dim));
   PBA_CUDA_OK(h->y_cam.alloc(z.dim)); PBA_CUDA_OK(h->d_cam.alloc(z.dim)); PBA_CUDA_OK(h->d_rho.alloc(n_lm));
@@ -799,7 +803,11 @@ int pick_solver(const Handle* h, int requested) {
 
 pba_status solve_rcs(Handle* h, int solver) {
   h->last_solver = pick_solver(h, solver);
-  if (h->last_solver == PBA_SOLVER_BCR) return launch_bcr_rcs(h);
+  if (h->last_solver == PBA_SOLVER_BCR) {
+    // second generation (bcr2.cu) whenever its padded super blocks fit; PBA_BCR_V1=1 keeps the first for A/B runs
+    static const bool force_v1 = getenv("PBA_BCR_V1") != nullptr;
+    return (h->b2_nbk > 0 && !force_v1) ? launch_bcr2_rcs(h) : launch_bcr_rcs(h);
+  }
   if (h->last_solver == PBA_SOLVER_BAND) return launch_band_rcs(h);
   return h->last_solver == PBA_SOLVER_CHOLESKY ? launch_cholesky_rcs(h) : launch_pcg_rcs(h);
 }
@@ -808,18 +816,17 @@ pba_status solve_rcs(Handle* h, int solver) {
 // that only depends on the new Jacobian: direct partials, landmark rows, the
 // RCS for `radius`, gradient norms.
 pba_status eval_jacobian_and_build(Handle* h, double radius) {
-  pba_status st = launch_evaluate(h, true, h->poses.p, h->affine.p, h->rho.p, S_COST);
+  // Multi-rank: this rank's cost and landmark gradient norms ride in the tail of the RCS all-reduce
+  // (rcs_tail()); launch_gradient_norms then finishes S_COST / S_GMAX / S_GNORM2 from the reduced buffer.
+  // One collective per evaluation (it used to be four).
+  const bool multi = h->world > 1;
+  pba_status st = launch_evaluate(h, true, h->poses.p, h->affine.p, h->rho.p, multi ? h->rcs_tail() : h->scalars.p + S_COST);
   if (st != PBA_OK) return st;
   h->have_jac = true;
   if ((st = launch_post_jacobian(h)) != PBA_OK) return st;
-  if ((st = launch_build_rcs(h, radius, true)) != PBA_OK) return st;
-  if ((st = launch_gradient_norms(h)) != PBA_OK) return st;
-  if (h->world > 1) {
-    if ((st = allreduce_scalars(h, h->scalars.p + S_COST, 1, false)) != PBA_OK) return st;
-    if ((st = allreduce_scalars(h, h->scalars.p + S_GNORM2, 1, false)) != PBA_OK) return st;
-    if ((st = allreduce_scalars(h, h->scalars.p + S_GMAX, 1, true)) != PBA_OK) return st;
-  }
-  return PBA_OK;
+  if (multi && (st = launch_landmark_gradient_norms(h)) != PBA_OK) return st;
+  if ((st = launch_build_rcs(h, radius, true, multi)) != PBA_OK) return st;
+  return launch_gradient_norms(h);
 }
 
 pba_status copy_state(Handle* h, DevBuf<double>& dp, DevBuf<double>& da, DevBuf<double>& dr, const DevBuf<double>& sp,
@@ -919,7 +926,7 @@ pba_status minimize_impl(Handle* h, pba_summary* sum) {
     if ((st = launch_backsub(h)) != PBA_OK) return st;
     // speculative: candidate point and its cost (needed unless the step is invalid)
     if ((st = launch_retract(h)) != PBA_OK) return st;
-    if ((st = launch_evaluate(h, false, h->poses_c.p, h->affine_c.p, h->rho_c.p, S_COST_C)) != PBA_OK) return st;
+    if ((st = launch_evaluate(h, false, h->poses_c.p, h->affine_c.p, h->rho_c.p, h->scalars.p + S_COST_C)) != PBA_OK) return st;
     if (h->world > 1) {
       // S_COST_C, S_MODEL, S_STEP2, S_XNORM2 are contiguous
       if ((st = allreduce_scalars(h, h->scalars.p + S_COST_C, 4, false)) != PBA_OK) return st;
@@ -1164,7 +1171,7 @@ PBA_API pba_status pba_evaluate(pba_handle* hh, int32_t with_jacobian, double* c
   Handle* h = reinterpret_cast<Handle*>(hh);
   if (!h) return PBA_ERR_INVALID_ARGUMENT;
   PBA_CUDA_OK(cudaSetDevice(h->device));
-  pba_status st = launch_evaluate(h, with_jacobian != 0, h->poses.p, h->affine.p, h->rho.p, S_COST);
+  pba_status st = launch_evaluate(h, with_jacobian != 0, h->poses.p, h->affine.p, h->rho.p, h->scalars.p + S_COST);
   if (st != PBA_OK) return st;
   if (with_jacobian) { h->have_jac = true; h->have_rcs = false; }
   if (cost) {
@@ -1239,7 +1246,7 @@ PBA_API pba_status pba_build_rcs(pba_handle* hh, double radius) {
   PBA_CUDA_OK(cudaSetDevice(h->device));
   pba_status st;
   if (!h->have_jac) {
-    if ((st = launch_evaluate(h, true, h->poses.p, h->affine.p, h->rho.p, S_COST)) != PBA_OK) return st;
+    if ((st = launch_evaluate(h, true, h->poses.p, h->affine.p, h->rho.p, h->scalars.p + S_COST)) != PBA_OK) return st;
     h->have_jac = true;
   }
   // stand-alone use = iteration 0 semantics: scales and LM diagonal from this Jacobian
@@ -1307,7 +1314,7 @@ PBA_API pba_status pba_lm_iterate(pba_handle* hh, double radius, int32_t apply, 
   if ((st = solve_rcs(h, PBA_SOLVER_AUTO)) != PBA_OK) return st;
   if ((st = launch_backsub(h)) != PBA_OK) return st;
   if ((st = launch_retract(h)) != PBA_OK) return st;
-  if ((st = launch_evaluate(h, false, h->poses_c.p, h->affine_c.p, h->rho_c.p, S_COST_C)) != PBA_OK) return st;
+  if ((st = launch_evaluate(h, false, h->poses_c.p, h->affine_c.p, h->rho_c.p, h->scalars.p + S_COST_C)) != PBA_OK) return st;
   if (h->world > 1 && (st = allreduce_scalars(h, h->scalars.p + S_COST_C, 4, false)) != PBA_OK) return st;
   if ((st = read_scalars(h)) != PBA_OK) return st;
   const double* hs = h->h_scalars;
@@ -1432,9 +1439,128 @@ PBA_API pba_status pba_comm_init(pba_handle* hh, const uint8_t id[PBA_NCCL_ID_BY
   return PBA_OK;
 }
 
+// ---- single-process multi-GPU (pba_options.num_gpus) ----
+// The reference's caller is one thread of one process (src/sfm.cpp:1883-1925), so the drop-in call drives
+// all GPUs itself: one host thread per device, each with its landmark shard (create_impl(rank, world)), the
+// partial reduced camera systems summed by NCCL.  Communicators come from ncclCommInitAll and are cached per
+// process and device list (creating them costs seconds; the SfM loop calls optimize() again and again).
+namespace pba {
+namespace {
+
+std::mutex g_multi_mu;
+struct MultiComms { int device0, n; std::vector<void*> comms; };
+std::vector<MultiComms> g_multi;
+
+pba_status multi_comms(int device0, int n, std::vector<void*>* out) {
+  if (!g_nccl.load()) return PBA_ERR_NCCL;
+  std::lock_guard<std::mutex> lock(g_multi_mu);
+  for (const MultiComms& m : g_multi)
+    if (m.device0 == device0 && m.n == n) { *out = m.comms; return PBA_OK; }
+  std::vector<int> devs(n);
+  for (int i = 0; i < n; ++i) devs[i] = device0 + i;
+  std::vector<void*> comms(n, nullptr);
+  if (g_nccl.CommInitAll(comms.data(), n, devs.data()) != 0) return PBA_ERR_NCCL;
+  g_multi.push_back(MultiComms{device0, n, comms});
+  *out = comms;
+  return PBA_OK;
+}
+
+// all threads arrive, then everyone learns whether anyone failed (no rank may enter a collective alone)
+struct StatusBarrier {
+  std::mutex mu;
+  std::condition_variable cv;
+  int n, arrived = 0, generation = 0;
+  pba_status worst = PBA_OK;
+  explicit StatusBarrier(int n_) : n(n_) {}
+  pba_status wait(pba_status mine) {
+    std::unique_lock<std::mutex> lock(mu);
+    if (mine != PBA_OK && worst == PBA_OK) worst = mine;
+    const int gen = generation;
+    if (++arrived == n) { arrived = 0; ++generation; cv.notify_all(); }
+    else cv.wait(lock, [&] { return generation != gen; });
+    return worst;
+  }
+};
+
+pba_status solve_multi_gpu(pba_problem* problem, const pba_options* options, int n_gpus, pba_summary* summary) {
+  const double t0 = wall();
+  std::vector<void*> comms;
+  pba_status st = multi_comms(options->device, n_gpus, &comms);
+  if (st != PBA_OK) return st;
+  StatusBarrier barrier(n_gpus);
+  std::vector<pba_status> status(n_gpus, PBA_OK);
+  std::vector<double> t_setup(n_gpus, 0.0);
+  pba_iteration* its = summary ? summary->iterations : nullptr;
+  const int cap = summary ? summary->iterations_capacity : 0;
+  auto worker = [&](int r) {
+    pba_options o = *options;
+    o.device = options->device + r;
+    o.num_gpus = 1;
+    Handle* h = nullptr;
+    pba_status s = create_impl(problem, &o, r, n_gpus, &h);
+    std::unique_ptr<Handle> guard(h);
+    t_setup[r] = wall() - t0;
+    if (barrier.wait(s) != PBA_OK) { status[r] = s; return; }
+    h->nccl_comm = comms[r];
+    pba_summary local;
+    memset(&local, 0, sizeof(local));
+    if (r == 0) { local.iterations = its; local.iterations_capacity = cap; }
+    s = minimize_impl(h, &local);
+    // every rank takes the same decisions (all of them see the all-reduced scalars), so termination agrees
+    if (s == PBA_OK && local.termination_type != PBA_FAILURE)
+      s = get_state_impl(h, r == 0 ? problem->poses : nullptr, problem->inv_depth + h->first_landmark,
+                         (r == 0 && problem->mode == PBA_MODE_PHOTOMETRIC) ? problem->affine : nullptr);
+    if (r == 0 && summary) *summary = local;
+    status[r] = s;
+  };
+  std::vector<std::thread> threads;
+  for (int r = 1; r < n_gpus; ++r) threads.emplace_back(worker, r);
+  worker(0);
+  for (std::thread& t : threads) t.join();
+  for (int r = 0; r < n_gpus; ++r)
+    if (status[r] != PBA_OK) return status[r];
+  if (summary) {
+    summary->setup_time_in_seconds = *std::max_element(t_setup.begin(), t_setup.end());
+    summary->total_time_in_seconds = wall() - t0;
+    print_report(*summary, options->verbosity_level);
+  }
+  cudaSetDevice(options->device);
+  return PBA_OK;
+}
+
+}  // namespace
+}  // namespace pba
+
+// Creates (and caches) the NCCL communicators pba_solve(num_gpus > 1) uses, so that the first solve does not
+// pay for them.  Optional: pba_solve does it on demand.
+PBA_API pba_status pba_multi_gpu_init(int32_t device, int32_t num_gpus) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return PBA_ERR_NO_DEVICE; }
+  if (num_gpus == 0) num_gpus = ndev - device;
+  if (device < 0 || num_gpus < 1 || device + num_gpus > ndev) return PBA_ERR_INVALID_ARGUMENT;
+  if (num_gpus == 1) return PBA_OK;
+  std::vector<void*> comms;
+  return multi_comms(device, num_gpus, &comms);
+}
+
 // The drop-in call (map_utils.h:322): host buffers in, updated in place.
 PBA_API pba_status pba_solve(pba_problem* problem, const pba_options* options, pba_summary* summary) {
   const double t0 = wall();
+  if (!problem || !options) return PBA_ERR_INVALID_ARGUMENT;
+  int n_gpus = options->num_gpus;
+  if (n_gpus != 1) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return PBA_ERR_NO_DEVICE; }
+    if (n_gpus == 0) n_gpus = ndev - options->device;
+    if (n_gpus < 1 || options->device < 0 || options->device + n_gpus > ndev) return PBA_ERR_INVALID_ARGUMENT;
+    // a shard needs landmarks to work on
+    n_gpus = int(std::max<int64_t>(1, std::min<int64_t>(n_gpus, problem->n_landmarks)));
+  }
+  if (n_gpus > 1) {
+    pba_status vst = validate(problem, options);
+    if (vst != PBA_OK) return vst;
+    return solve_multi_gpu(problem, options, n_gpus, summary);
+  }
   Handle* h = nullptr;
   pba_status st = create_impl(problem, options, 0, 1, &h);
   if (st != PBA_OK) return st;

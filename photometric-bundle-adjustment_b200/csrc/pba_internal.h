@@ -307,10 +307,20 @@ struct Handle {
   std::vector<size_t> bcr_off; // 7 offsets per level into bcr_ws (A B b L U V y)
   size_t bcr_x_off = 0;
   DevBuf<double> bcr_ws;
+  // second-generation BCR (bcr2.cu): padded super blocks Mp = 8 b2_nbk; 0 = not applicable (first generation runs)
+  int b2_nbk = 0;
+  std::vector<int> b2_n;       // super blocks per level
+  std::vector<size_t> b2_off;  // 6 offsets per level into b2_ws (A B b Uh Vh yh)
+  size_t b2_x_off = 0;
+  DevBuf<double> b2_ws;
   int uniform_model = -1;      // PBA_CAM_* when every calibration uses the same model, else -1
 
   // NCCL
   void* nccl_comm = nullptr;
+  // Tail of the all-reduce buffer `rcs` (world > 1): [0] cost, [1] sum of squared landmark gradients,
+  // [2 + r] max |landmark gradient| of rank r (every rank writes its own slot, the others stay 0, so the SUM
+  // all-reduce gathers them): one collective per Jacobian evaluation carries the RCS and every scalar.
+  double* rcs_tail() { return rcs.p + size_t(sz.n_blocks) * sz.cd * sz.cd + 3 * size_t(sz.dim); }
 
   ~Handle();
 };
@@ -331,13 +341,16 @@ pba_status map_cuda(cudaError_t e);
 pba_status launch_init_landmarks(Handle* h);
 pba_status launch_build_quads(Handle* h, const uint8_t* images_u8, int first, int n_img);
 pba_status launch_evaluate(Handle* h, bool with_jacobian, const double* poses, const double* affine,
-                           const double* rho, int cost_slot);
+                           const double* rho, double* cost_out);
 pba_status launch_unpermute(Handle* h, int which, double* dst_host_order_dev);
 pba_status launch_gather_blocks(Handle* h, int64_t n_sel, const int64_t* sel_pos_dev, double* res_dev, double* jac_dev);
 pba_status launch_expand_edges(Handle* h, const int* edge_col_dev);  // fills obs_edge / obs_col from edge_ptr
 // schur.cu
 pba_status launch_post_jacobian(Handle* h);              // edge Gram + landmark gather (+ scales on first call)
-pba_status launch_build_rcs(Handle* h, double radius, bool refresh_diag);
+// with_scalars (multi-rank Jacobian evaluations): the all-reduce also carries rcs_tail() — this rank's cost and
+// landmark gradient norms — so an evaluation needs ONE collective
+pba_status launch_build_rcs(Handle* h, double radius, bool refresh_diag, bool with_scalars = false);
+pba_status launch_landmark_gradient_norms(Handle* h);  // world > 1: fills rcs_tail()[1], [2 + rank] before the all-reduce
 pba_status launch_backsub(Handle* h);  // also leaves the model cost change in S_MODEL
 void launch_reduce_sum(Handle* h, const double* part, int64_t n, double* out);
 pba_status launch_retract(Handle* h);
@@ -348,6 +361,8 @@ pba_status launch_pcg_rcs(Handle* h);
 pba_status launch_band_rcs(Handle* h);
 pba_status launch_bcr_rcs(Handle* h);
 pba_status bcr_setup(Handle* h);
+pba_status bcr2_setup(Handle* h);
+pba_status launch_bcr2_rcs(Handle* h);
 int band_max_bw(int cd);
 pba_status dense_cholesky_solve(Handle* h, double* A, double* b, int ld, int* fail_dev);
 int dense_ld(int n);
@@ -355,7 +370,7 @@ int pcg_max_grid(int device);
 int schur_tile_l(int max_stride);
 int eval_grid(int64_t n);
 // host.cu
-pba_status allreduce_rcs(Handle* h);
+pba_status allreduce_rcs(Handle* h, bool with_scalars);
 pba_status allreduce_scalars(Handle* h, double* dev, int n, bool max_op);
 
 }  // namespace pba

@@ -887,6 +887,30 @@ __global__ void __launch_bounds__(1024) k_reduce2(const double* __restrict__ pa,
   }
 }
 
+// world > 1: S_GMAX / S_GNORM2 / S_COST from the pose partials (every rank computes them from the all-reduced
+// camera gradient) and the all-reduced tail [cost | sum g_l^2 | max |g_l| per rank].
+__global__ void __launch_bounds__(1024) k_finish_norms(const double* __restrict__ pmax, const double* __restrict__ psq, int64_t n,
+                                                        const double* __restrict__ tail, int world,
+                                                        double* __restrict__ scalars) {
+  __shared__ double s[32], t[32];
+  double va = 0.0, vb = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += 1024) { va = fmax(va, pmax[i]); vb += psq[i]; }
+  for (int i = threadIdx.x; i < world; i += 1024) va = fmax(va, tail[2 + i]);
+  for (int o = 16; o > 0; o >>= 1) {
+    va = fmax(va, __shfl_down_sync(0xffffffffu, va, o));
+    vb += __shfl_down_sync(0xffffffffu, vb, o);
+  }
+  if ((threadIdx.x & 31) == 0) { s[threadIdx.x >> 5] = va; t[threadIdx.x >> 5] = vb; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double x = 0.0, y = 0.0;
+    for (int i = 0; i < 32; ++i) { x = fmax(x, s[i]); y += t[i]; }
+    scalars[S_GMAX] = x;
+    scalars[S_GNORM2] = y + tail[1];
+    scalars[S_COST] = tail[0];
+  }
+}
+
 constexpr auto k_edge_gram_photo = k_edge_gram<8, 15>;
 constexpr auto k_edge_gram_geom = k_edge_gram<2, 13>;
 
@@ -922,7 +946,7 @@ int schur_tile_l(int max_stride) {
 
 // Build the damped, Jacobi-scaled RCS for `radius` from the partials of the
 // last Jacobian evaluation (SchurEliminator::Eliminate).
-pba_status launch_build_rcs(Handle* h, double radius, bool refresh_diag) {
+pba_status launch_build_rcs(Handle* h, double radius, bool refresh_diag, bool with_scalars) {
   const Sizes& z = h->sz;
   const int init_scale = h->scale_ready ? 0 : 1;
   const int jacobi = h->opt.jacobi_scaling;
@@ -954,7 +978,7 @@ pba_status launch_build_rcs(Handle* h, double radius, bool refresh_diag) {
                h->part_sch.p, S, rhs, diagB, gcam, h->rcs_B.p, h->rcs_B.p + z.n_blocks * z.cd * z.cd);
   }
   if (h->world > 1) {
-    pba_status st = allreduce_rcs(h);
+    pba_status st = allreduce_rcs(h, with_scalars);
     if (st != PBA_OK) return st;
   }
   if (z.dim > 0) {
@@ -1010,8 +1034,37 @@ pba_status launch_retract(Handle* h) {
   return PBA_OK;
 }
 
+// world > 1, before the RCS all-reduce: this rank's landmark gradient norms into rcs_tail()
+pba_status launch_landmark_gradient_norms(Handle* h) {
+  const Sizes& z = h->sz;
+  double* tail = h->rcs_tail();
+  PBA_CUDA_OK(cudaMemsetAsync(tail + 1, 0, sizeof(double) * size_t(1 + h->world), h->stream));
+  const int grid = (z.n_lm + 255) / 256;
+  if (grid == 0) return PBA_OK;
+  double* pa = h->red_ws.p;
+  double* pb = pa + grid;
+  PBA_LAUNCH(h, K_REDUCE_SUM, k_grad_norms, dim3(grid), dim3(256), 0, 0, z.n_lm, z.cd, 0, h->d_slot.p, h->d_affine_active.p,
+             h->lm_ptr.p, h->poses.p, (const double*)nullptr, h->lm_g.p, pa, pb);
+  PBA_LAUNCH(h, K_REDUCE_SUM, k_reduce2, dim3(1), dim3(1024), 0, pa, pb, int64_t(grid), 1, tail + 2 + h->rank, tail + 1);
+  return PBA_OK;
+}
+
 pba_status launch_gradient_norms(Handle* h) {
   const Sizes& z = h->sz;
+  if (h->world > 1) {
+    // poses only (identical on every rank: the camera gradient is all-reduced), then the finishing kernel
+    const int grid = (z.n_poses + 255) / 256;
+    double* pa = h->red_ws.p;
+    double* pb = pa + grid;
+    const double* gcam = h->rcs.p + z.n_blocks * z.cd * z.cd + 2 * z.dim;
+    if (grid > 0) {
+      PBA_LAUNCH(h, K_REDUCE_SUM, k_grad_norms, dim3(grid), dim3(256), 0, z.n_poses, 0, z.cd, 1, h->d_slot.p,
+                 h->d_affine_active.p, h->lm_ptr.p, h->poses.p, gcam, h->lm_g.p, pa, pb);
+    }
+    PBA_LAUNCH(h, K_REDUCE_SUM, k_finish_norms, dim3(1), dim3(1024), 0, pa, pb, int64_t(grid), h->rcs_tail(), h->world,
+               h->scalars.p);
+    return PBA_OK;
+  }
   const int items = z.n_poses + z.n_lm;
   const int grid = (items + 255) / 256;
   double* pa = h->red_ws.p;

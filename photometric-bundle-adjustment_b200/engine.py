@@ -81,6 +81,11 @@ def device_count():
     return int(_ffi.load_lib().pba_device_count())
 
 
+def multi_gpu_init(device=0, num_gpus=0):
+    """Create the NCCL communicators of bundle_adjustment(..., num_gpus > 1) ahead of the first solve."""
+    _ffi.check(_ffi.load_lib().pba_multi_gpu_init(int(device), int(num_gpus)), "pba_multi_gpu_init")
+
+
 def bundle_adjustment(problem: Problem, options: BundleAdjustmentOptions = None) -> Summary:
     """Drop-in for visnav::bundle_adjustment (map_utils.h:322-399) on flat containers."""
     options = options or BundleAdjustmentOptions()

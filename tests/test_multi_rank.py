@@ -79,3 +79,42 @@ def test_two_gpu_sharded_lm_matches_single_gpu(tmp_path, mode):
     rho = np.r_[r0["rho"], r1["rho"]]
     assert int(r0["first"]) == 0 and int(r1["first"]) == len(r0["rho"])
     assert np.abs(rho - ref.inv_depth).max() < 1e-8
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", [pb.MODE_GEOMETRIC, pb.MODE_PHOTOMETRIC])
+def test_single_process_two_gpus_matches_single_gpu(mode):
+    """The drop-in call from ONE process over two GPUs (pba_options.num_gpus; the reference's caller is a single
+    thread, src/sfm.cpp:1903-1913): same iteration trace and state as the one-GPU solve."""
+    if pb.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    hub = 9.0 if mode == pb.MODE_PHOTOMETRIC else 1.0
+    prob, _ = pb.make_scene(mode, 14, 900, "pinhole")
+    one, two = prob.copy(), prob.copy()
+    s1 = pb.bundle_adjustment(one, pb.BundleAdjustmentOptions(verbosity_level=0, huber_parameter=hub))
+    pb.multi_gpu_init(0, 2)
+    s2 = pb.bundle_adjustment(two, pb.BundleAdjustmentOptions(verbosity_level=0, huber_parameter=hub, num_gpus=2))
+    assert s2.num_iterations == s1.num_iterations and s2.termination_type == s1.termination_type
+    np.testing.assert_allclose([i["cost"] for i in s2.iterations], [i["cost"] for i in s1.iterations], rtol=1e-9)
+    assert abs(s2.final_cost - s1.final_cost) <= 1e-9 * s1.final_cost
+    assert np.abs(two.poses - one.poses).max() < 1e-8
+    assert np.abs(two.inv_depth - one.inv_depth).max() < 1e-8
+    if mode == pb.MODE_PHOTOMETRIC:
+        assert np.abs(two.affine - one.affine).max() < 1e-8
+    # a second call reuses the cached communicators and the device arena
+    again = prob.copy()
+    s3 = pb.bundle_adjustment(again, pb.BundleAdjustmentOptions(verbosity_level=0, huber_parameter=hub, num_gpus=2))
+    assert s3.final_cost == s2.final_cost and np.array_equal(again.poses, two.poses)
+
+
+@pytest.mark.gpu
+def test_second_device_after_first():
+    """Handles on two devices in one process (the shared-memory opt-in is per device)."""
+    if pb.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    prob, _ = pb.make_scene(pb.MODE_PHOTOMETRIC, 14, 900, "pinhole")
+    out = []
+    for dev in (0, 1, 0):
+        p = prob.copy()
+        out.append(pb.bundle_adjustment(p, pb.BundleAdjustmentOptions(verbosity_level=0, huber_parameter=9.0, device=dev)))
+    assert out[0].final_cost == out[1].final_cost == out[2].final_cost
