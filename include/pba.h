@@ -212,6 +212,16 @@ pba_status pba_solve(pba_problem* problem, const pba_options* options,
  * takes out of the first solve. */
 pba_status pba_multi_gpu_init(int32_t device, int32_t num_gpus);
 
+/* Host-only (needs no GPU): the camera layout pba_create derives — which poses become RCS slots and in what
+ * ORDER (the keyframes' own order, or reverse Cuthill-McKee on the covisibility graph when that order is too
+ * wide for the banded solvers: loop closures, unordered maps), the half-bandwidth in blocks before / after,
+ * and the number of stored upper-triangular RCS blocks.  slot [n_poses] receives the slot or -1; every output
+ * may be NULL.  Replaces Ceres' ordering + block-structure detection (trust_region_preprocessor.cc:373,
+ * schur_complement_solver.cc:250-297). */
+pba_status pba_analyze_structure(const pba_problem* problem, const pba_options* options, int32_t* slot,
+                                 int32_t* n_slots, int32_t* bandwidth_natural, int32_t* bandwidth,
+                                 int64_t* n_blocks);
+
 /* ---- split entry points (tests / bench): device-resident problem ---- */
 /* Replaces Problem construction + Ceres preprocessing (map_utils.h:327-375,
  * trust_region_preprocessor.cc:373): validates, orders observations by

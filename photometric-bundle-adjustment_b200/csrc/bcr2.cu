@@ -25,8 +25,12 @@
 
 #include <algorithm>
 
+#include <cooperative_groups.h>
+
 #include "launch.h"
 #include "pba_internal.h"
+
+namespace cg = cooperative_groups;
 
 namespace pba {
 
@@ -118,62 +122,46 @@ __global__ void k_b2_unpad(int M, int Mp, int dim, const double* __restrict__ x,
   if (i < dim) y[i] = x[size_t(i / M) * Mp + i % M];
 }
 
-// ---- 8x8 diagonal block: lower Cholesky in place + W = inverse of the factor (row-major 8x8, zeros above
-// the diagonal).  One warp: lane 0 factors in registers (the pivot chain rsqrt -> scale -> update is
-// sequential anyway), lanes 0..7 then each solve one column of the inverse. ----
-__device__ __forceinline__ void b2_diag_factor(double* D, int ld, double* W, int* fail) {
+// ---- 8x8 diagonal block, factored IN REGISTERS by the warp that owns the tile.  The tile sits in the DMMA
+// accumulator layout (lane (g, t) holds A[g][2t], A[g][2t+1]); the warp runs the square-root form of
+// Gaussian elimination on [A | I] with row operations: step j scales row j by 1 / sqrt(a_jj) and subtracts
+// multiples of it from the rows below, so that A becomes L^T and the identity becomes W = L^-1 — the only
+// thing the panel and the triangular solves need.  Per pivot the dependent chain is shuffle -> rsqrt ->
+// multiply -> FMA (~110 cycles), every lane issues ~20 instructions; the single-thread version of the first
+// generation (factor, then invert) took ~2,100 cycles per block and was the longest item of a level.
+// Returns W in (w0, w1) = W[g][2t], W[g][2t+1]. ----
+__device__ __forceinline__ void b2_diag_factor(double a0, double a1, double& w0, double& w1, int* fail) {
   const int lane = threadIdx.x & 31;
-  double idg[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-  if (lane == 0) {
-    double L[8][8];
+  const int g = lane >> 2, t = lane & 3;
+  w0 = g == 2 * t ? 1.0 : 0.0;
+  w1 = g == 2 * t + 1 ? 1.0 : 0.0;
+  bool bad = false;
 #pragma unroll
-    for (int r = 0; r < 8; ++r)
-#pragma unroll
-      for (int c = 0; c <= r; ++c) L[r][c] = D[r * ld + c];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      double d = L[j][j];
-      if (!(d > 0.0)) { *fail = 1; d = 1.0; }
-      const double inv = rsqrt(d);
-      L[j][j] = d * inv;
-      idg[j] = inv;
-#pragma unroll
-      for (int r = j + 1; r < 8; ++r) L[r][j] *= inv;
-#pragma unroll
-      for (int c = j + 1; c < 8; ++c)
-#pragma unroll
-        for (int r = c; r < 8; ++r) L[r][c] -= L[r][j] * L[c][j];
-    }
-#pragma unroll
-    for (int r = 0; r < 8; ++r)
-#pragma unroll
-      for (int c = 0; c <= r; ++c) D[r * ld + c] = L[r][c];
+  for (int j = 0; j < 8; ++j) {
+    const int jt = j >> 1;
+    const double colj = (j & 1) ? a1 : a0;                      // column j of a lane whose t == jt
+    double ajj = __shfl_sync(0xffffffffu, colj, 4 * j + jt);     // pivot
+    const double arj = __shfl_sync(0xffffffffu, colj, 4 * g + jt);  // this row's entry in column j
+    const double p0 = __shfl_sync(0xffffffffu, a0, 4 * j + t), p1 = __shfl_sync(0xffffffffu, a1, 4 * j + t);  // pivot row,
+    const double q0 = __shfl_sync(0xffffffffu, w0, 4 * j + t), q1 = __shfl_sync(0xffffffffu, w1, 4 * j + t);  // my columns
+    if (!(ajj > 0.0)) { bad = true; ajj = 1.0; }
+    const double inv = rsqrt(ajj);
+    const double m = arj * inv;
+    const double u0 = p0 * inv, u1 = p1 * inv, v0 = q0 * inv, v1 = q1 * inv;
+    if (g > j) { a0 -= m * u0; a1 -= m * u1; w0 -= m * v0; w1 -= m * v1; }
+    else if (g == j) { a0 = u0; a1 = u1; w0 = v0; w1 = v1; }
   }
-#pragma unroll
-  for (int j = 0; j < 8; ++j) idg[j] = __shfl_sync(0xffffffffu, idg[j], 0);
-  __syncwarp();
-  if (lane < 8) {
-    const int c = lane;  // column c of the inverse: forward substitution on e_c
-    double mcol[8];
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      double s = r == c ? 1.0 : 0.0;
-#pragma unroll
-      for (int q = 0; q < r; ++q) s -= (q >= c ? D[r * ld + q] * mcol[q] : 0.0);
-      mcol[r] = r >= c ? s * idg[r] : 0.0;
-    }
-#pragma unroll
-    for (int r = 0; r < 8; ++r) W[r * 8 + c] = mcol[r];
-  }
-  __syncwarp();
+  if (bad && lane == 0) *fail = 1;
 }
 
-// ---- A (Mp x Mp, shared, lower 8x8 tiles valid) <- its lower Cholesky factor; Dinv[J] = inverse of the
-// J-th diagonal block of the factor.  Right-looking, block size 8.  The trailing matrix lives in
-// registers as DMMA accumulator fragments (tile u = I (I + 1) / 2 + K is owned by warp u % 16 for the
-// whole factorisation); per block column: owners write the column's tiles to shared memory, warp 0
-// factors the diagonal block, the warps scale the panel (one DMMA pair per tile), then every owned
-// trailing tile takes  C -= P_I P_K^T  (one DMMA pair, A and B fragments straight from the panel). ----
+// ---- A (Mp x Mp, shared, lower 8x8 tiles valid) <- the panels of its lower Cholesky factor (tiles (I, J),
+// I > J); Dinv[J] = inverse of the J-th diagonal block of the factor (the diagonal tiles themselves are
+// not stored: nothing reads them).  Right-looking, block size 8.  The whole matrix lives in registers as
+// DMMA accumulator fragments (tile u = I (I + 1) / 2 + K is owned by warp u % 8 for the whole
+// factorisation); per block column J: the owners write the column's sub-diagonal tiles to shared memory
+// while the owner of (J, J) factors it in registers and publishes W_J; barrier; the warps scale the panel
+// P_I = A_IJ W_J^T (one DMMA pair per tile); barrier; every owned trailing tile takes C -= P_I P_K^T (one
+// DMMA pair, A and B fragments straight from the panel). ----
 template <int NBK>
 __device__ void b2_cholesky(double* As, double* Dinv, int* fail) {
   constexpr int LD = 8 * NBK + 4;
@@ -195,21 +183,24 @@ __device__ void b2_cholesky(double* As, double* Dinv, int* fail) {
     }
     ti[s] = I; tk[s] = K;
     c[s][0] = 0.0; c[s][1] = 0.0;
-    if (I >= 0 && K >= 1) {  // block column 0 is the first panel: it stays in shared memory
+    if (I >= 0 && (K >= 1 || I == 0)) {  // the sub-diagonal tiles of block column 0 are the first panel: they stay in shared memory
       const double2 v = *reinterpret_cast<const double2*>(As + (8 * I + g) * LD + 8 * K + 2 * t);
       c[s][0] = v.x; c[s][1] = v.y;
     }
   }
 #pragma unroll 1
   for (int J = 0; J < NBK; ++J) {
-    if (J > 0) {
 #pragma unroll
-      for (int s = 0; s < TPW; ++s)
-        if (ti[s] >= 0 && tk[s] == J)
-          *reinterpret_cast<double2*>(As + (8 * ti[s] + g) * LD + 8 * J + 2 * t) = make_double2(c[s][0], c[s][1]);
+    for (int s = 0; s < TPW; ++s) {
+      if (ti[s] < 0 || tk[s] != J) continue;
+      if (ti[s] == J) {  // warp-uniform: this warp owns the diagonal tile
+        double w0, w1;
+        b2_diag_factor(c[s][0], c[s][1], w0, w1, fail);
+        *reinterpret_cast<double2*>(Dinv + 64 * J + g * 8 + 2 * t) = make_double2(w0, w1);
+      } else if (J > 0) {
+        *reinterpret_cast<double2*>(As + (8 * ti[s] + g) * LD + 8 * J + 2 * t) = make_double2(c[s][0], c[s][1]);
+      }
     }
-    __syncthreads();
-    if (warp == 0) b2_diag_factor(As + (8 * J) * LD + 8 * J, LD, Dinv + 64 * J, fail);
     __syncthreads();
     // panel: P_I = A_IJ W^T  (W = inverse of the diagonal factor)
     {
@@ -457,7 +448,7 @@ __global__ void __launch_bounds__(kB2Threads, 1) k_b2_top(B2Level lv, double* __
 // Operands are staged in shared memory two matrices at a time; a warp runs up to TW tiles in lockstep
 // (independent accumulator chains), 2 NBK DMMAs per tile and operand pair. ----
 template <int NBK>
-__global__ void __launch_bounds__(kB2RedThreads, 1) k_b2_reduce(B2Level lv, B2Level nx) {
+__global__ void __launch_bounds__(kB2RedThreads, 1) k_b2_reduce(B2Level lv, B2Level nx, int PA, int PB) {
   constexpr int Mp = 8 * NBK, LD = Mp + 4;
   constexpr int NTL = NBK * (NBK + 1) / 2, NTF = NBK * NBK;
   constexpr int TWL = (NTL + kB2RedWarps - 1) / kB2RedWarps, TWF = (NTF + kB2RedWarps - 1) / kB2RedWarps;
@@ -465,7 +456,11 @@ __global__ void __launch_bounds__(kB2RedThreads, 1) k_b2_reduce(B2Level lv, B2Le
   double* Xs = b2_sm;            // [Mp][LD]
   double* Ys = Xs + Mp * LD;     // [Mp][LD]
   const int pe = blockIdx.x, e = 2 * pe;
-  const int role = blockIdx.y;
+  // blockIdx.y: [0, PA) = parts of A' (its lower tiles split into PA contiguous ranges), [PA, PA + PB) = parts of
+  // B', PA + PB = b'.  At the sparse upper levels the products are FP64-bound on one SM (a million FMAs at 64 per
+  // clock), so they are spread over many CTAs; every part stages the full operand matrices from L2.
+  const int role = int(blockIdx.y) < PA ? 0 : (int(blockIdx.y) < PA + PB ? 1 : 2);
+  const int part = role == 0 ? blockIdx.y : int(blockIdx.y) - PA;
   const bool has_l = e - 1 >= 0, has_r = e + 1 < lv.n;
   const size_t MM = size_t(Mp) * Mp;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -501,11 +496,12 @@ __global__ void __launch_bounds__(kB2RedThreads, 1) k_b2_reduce(B2Level lv, B2Le
     __syncthreads();
     double c[TWF][2];
     int tI[TWF], tK[TWF];
+    const int per = (NTF + PB - 1) / PB, u_lo = part * per, u_hi = min(NTF, u_lo + per);
 #pragma unroll
     for (int s = 0; s < TWF; ++s) {
-      const int u = warp + s * kB2RedWarps;
-      tI[s] = u < NTF ? u / NBK : -1;
-      tK[s] = u < NTF ? u % NBK : 0;
+      const int u = u_lo + warp + s * kB2RedWarps;
+      tI[s] = u < u_hi ? u / NBK : -1;
+      tK[s] = u < u_hi ? u % NBK : 0;
       c[s][0] = c[s][1] = 0.0;
     }
 #pragma unroll 2
@@ -529,11 +525,12 @@ __global__ void __launch_bounds__(kB2RedThreads, 1) k_b2_reduce(B2Level lv, B2Le
   double c[TWL][2];
   int tI[TWL], tK[TWL];
   const double* Ae = lv.A + size_t(e) * MM;
+  const int per = (NTL + PA - 1) / PA, u_lo = part * per, u_hi = min(NTL, u_lo + per);
 #pragma unroll
   for (int s = 0; s < TWL; ++s) {
-    const int u = warp + s * kB2RedWarps;
+    const int u = u_lo + warp + s * kB2RedWarps;
     int I = -1, K = 0;
-    if (u < NTL) {
+    if (u < u_hi) {
       I = int((sqrtf(8.0f * float(u) + 1.0f) - 1.0f) * 0.5f);
       while (I * (I + 1) / 2 > u) --I;
       while ((I + 1) * (I + 2) / 2 <= u) ++I;
@@ -588,47 +585,49 @@ __global__ void __launch_bounds__(kB2RedThreads, 1) k_b2_reduce(B2Level lv, B2Le
       *reinterpret_cast<double2*>(An + size_t(8 * tI[s] + g) * Mp + 8 * tK[s] + 2 * t) = make_double2(c[s][0], c[s][1]);
 }
 
-// ---- back-substitution: x_p = yh_p - Uh_p x_{p-1} - Vh_p x_{p+1} for the odd blocks of a level; x is
-// indexed by ORIGINAL super block (p << shift).  A warp per row, lanes along the row (coalesced). ----
-__device__ __forceinline__ void b2_back_block(int Mp, const B2Level& lv, int q, int shift, double* __restrict__ x,
-                                              double* xs /* shared [2 Mp] */) {
-  const int p = 2 * q + 1;
-  const bool has_r = p + 1 < lv.n;
-  const size_t MM = size_t(Mp) * Mp;
-  for (int i = threadIdx.x; i < Mp; i += blockDim.x) {
-    xs[i] = x[(size_t(p - 1) << shift) * Mp + i];
-    xs[Mp + i] = has_r ? x[(size_t(p + 1) << shift) * Mp + i] : 0.0;
-  }
-  __syncthreads();
-  const double* U = lv.Uh + size_t(q) * MM;
-  const double* V = lv.Vh + size_t(q) * MM;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int r = warp; r < Mp; r += nw) {
-    double s = 0.0;
-    for (int cc = lane; cc < Mp; cc += 32) {
-      s += U[size_t(r) * Mp + cc] * xs[cc];
-      if (has_r) s += V[size_t(r) * Mp + cc] * xs[Mp + cc];
-    }
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) x[(size_t(p) << shift) * Mp + r] = lv.yh[size_t(q) * Mp + r] - s;
-  }
-  __syncthreads();
-}
-
-__global__ void __launch_bounds__(256) k_b2_back(int Mp, B2Level lv, int shift, double* __restrict__ x) {
-  extern __shared__ double b2_xs[];
-  b2_back_block(Mp, lv, blockIdx.x, shift, x, b2_xs);
-}
-
+// ---- back-substitution: x_p = yh_p - Uh_p x_{p-1} - Vh_p x_{p+1} for the odd blocks of every level, top down,
+// in ONE cooperative kernel (a grid-wide barrier between levels instead of a launch per level; the first
+// version's single-CTA kernel for the upper levels took 185 us, a launch per level 21 us each).  x is indexed
+// by ORIGINAL super block (p << level).  A warp per row of a block, lanes along the row (coalesced), up to
+// four rows of a warp in flight. ----
 struct B2LevelPack { B2Level lv[24]; };
 
-// the sparse upper levels [l_lo, l_hi] (few odd blocks each) in ONE CTA, top down
-__global__ void __launch_bounds__(256) k_b2_back_upper(int Mp, B2LevelPack pk, int l_hi, int l_lo, double* __restrict__ x) {
-  extern __shared__ double b2_xs[];
-  for (int l = l_hi; l >= l_lo; --l) {
-    const int n_odd = pk.lv[l].n / 2;
-    for (int q = 0; q < n_odd; ++q) b2_back_block(Mp, pk.lv[l], q, l, x, b2_xs);
-    __threadfence_block();
+__global__ void __launch_bounds__(256) k_b2_back_all(int Mp, B2LevelPack pk, int n_levels, double* __restrict__ x) {
+  cg::grid_group grid = cg::this_grid();
+  const int lane = threadIdx.x & 31;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  const size_t MM = size_t(Mp) * Mp;
+  for (int l = n_levels - 2; l >= 0; --l) {
+    const B2Level& lv = pk.lv[l];
+    const int rows = (lv.n / 2) * Mp;
+    for (int r0 = gw; r0 < rows; r0 += 4 * nw) {
+      double s[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int row = r0 + j * nw;
+        if (row >= rows) continue;
+        const int q = row / Mp, r = row - q * Mp, p = 2 * q + 1;
+        const bool has_r = p + 1 < lv.n;
+        const double* U = lv.Uh + q * MM + size_t(r) * Mp;
+        const double* V = lv.Vh + q * MM + size_t(r) * Mp;
+        const double* xl = x + (size_t(p - 1) << l) * Mp;
+        const double* xr = x + (size_t(p + 1) << l) * Mp;
+        for (int cc = lane; cc < Mp; cc += 32) {
+          s[j] += U[cc] * xl[cc];
+          if (has_r) s[j] += V[cc] * xr[cc];
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        for (int o = 16; o > 0; o >>= 1) s[j] += __shfl_xor_sync(0xffffffffu, s[j], o);
+        const int row = r0 + j * nw;
+        if (lane == 0 && row < rows) {
+          const int q = row / Mp, r = row - q * Mp, p = 2 * q + 1;
+          x[(size_t(p) << l) * Mp + r] = lv.yh[size_t(q) * Mp + r] - s[j];
+        }
+      }
+    }
+    if (l > 0) grid.sync();
   }
 }
 
@@ -640,11 +639,23 @@ size_t b2_fs_smem(int nbk, int nct_cta) {
 constexpr size_t kB2SmemCap = 225 * 1024;
 
 template <int NBK>
-pba_status b2_launch_level(Handle* h, const B2Level& lv, const B2Level& nx, int nct_cta, int R) {
-  PBA_LAUNCH(h, K_BCR, k_b2_fs<NBK>, dim3(lv.n / 2, R), dim3(kB2Threads), b2_fs_smem(NBK, nct_cta), lv, nct_cta,
+pba_status b2_launch_level(Handle* h, const B2Level& lv, const B2Level& nx, int R_min, int n_sm) {
+  // Column tiles of the triangular solves over R CTAs per odd block (each factors A_p itself): the solves are
+  // FP64-bound on one SM (1.4 M FMAs at 64 per clock = 11 us for 88 x 88), so the SMs a sparse level leaves idle
+  // take a share; R grows until the level fills the GPU once.
+  const int NCT = 2 * NBK + 1, n_odd = lv.n / 2;
+  int R = std::max(R_min, std::min(8, n_sm / std::max(1, n_odd)));
+  R = std::min(R, NCT);
+  const int nct_cta = (NCT + R - 1) / R;
+  R = (NCT + nct_cta - 1) / nct_cta;
+  PBA_LAUNCH(h, K_BCR, k_b2_fs<NBK>, dim3(n_odd, R), dim3(kB2Threads), b2_fs_smem(NBK, nct_cta), lv, nct_cta,
              h->chol_fail.p);
+  // products: parts per next-level block chosen so that a level is about one wave of CTAs
+  int PA = 1, PB = 1;
+  if (nx.n * 11 <= n_sm) { PA = 4; PB = 6; }
+  else if (nx.n * 6 <= n_sm) { PA = 2; PB = 3; }
   const size_t smem_r = size_t(2) * (8 * NBK) * b2_ld(8 * NBK) * sizeof(double);
-  PBA_LAUNCH(h, K_BCR, k_b2_reduce<NBK>, dim3(nx.n, 3), dim3(kB2RedThreads), smem_r, lv, nx);
+  PBA_LAUNCH(h, K_BCR, k_b2_reduce<NBK>, dim3(nx.n, PA + PB + 1), dim3(kB2RedThreads), smem_r, lv, nx, PA, PB);
   return PBA_OK;
 }
 template <int NBK>
@@ -703,14 +714,15 @@ pba_status launch_bcr2_rcs(Handle* h) {
   PBA_CUDA_OK(cudaMemsetAsync(h->chol_fail.p, 0, sizeof(int), h->stream));
   PBA_LAUNCH(h, K_BCR, k_b2_build, dim3((unsigned)(z.n_blocks + S)), dim3(64), 0, z.cd, m, M, Mp, z.n_blocks, z.dim,
              h->d_blk_row.p, h->d_blk_col.p, Sblk, rhs, S, pk.lv[0].A, pk.lv[0].B, pk.lv[0].b);
-  // column tiles per CTA of the factor + solve kernel: everything in one CTA when it fits shared memory
+  // fewest CTAs per odd block of the factor + solve kernel whose share of the right-hand sides fits shared memory
   const int NCT = 2 * nbk + 1;
   int R = 1;
   while (b2_fs_smem(nbk, (NCT + R - 1) / R) > kB2SmemCap) ++R;
-  const int nct_cta = (NCT + R - 1) / R;
+  int n_sm = 148;
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, h->device);
   pba_status st = PBA_OK;
   for (int l = 0; l + 1 < nl; ++l) {
-#define B2_LEVEL_CALL(N) b2_launch_level<N>(h, pk.lv[l], pk.lv[l + 1], nct_cta, R)
+#define B2_LEVEL_CALL(N) b2_launch_level<N>(h, pk.lv[l], pk.lv[l + 1], R, n_sm)
     switch (nbk) {
       case 1: st = B2_LEVEL_CALL(1); break;   case 2: st = B2_LEVEL_CALL(2); break;
       case 3: st = B2_LEVEL_CALL(3); break;   case 4: st = B2_LEVEL_CALL(4); break;
@@ -739,15 +751,14 @@ pba_status launch_bcr2_rcs(Handle* h) {
   }
 #undef B2_TOP_CALL
   if (st != PBA_OK) return st;
-  // back-substitution: the sparse upper levels (<= 8 odd blocks each) in one CTA, the wide ones one launch each
-  int l_split = nl - 1;  // levels >= l_split go to the single-CTA kernel
-  while (l_split > 0 && h->b2_n[l_split - 1] / 2 <= 8) --l_split;
-  const size_t smem_x = size_t(2) * Mp * sizeof(double);
-  if (l_split <= nl - 2) {
-    PBA_LAUNCH(h, K_BCR, k_b2_back_upper, dim3(1), dim3(256), smem_x, Mp, pk, nl - 2, l_split, x);
-  }
-  for (int l = std::min(l_split - 1, nl - 2); l >= 0; --l) {
-    PBA_LAUNCH(h, K_BCR, k_b2_back, dim3(h->b2_n[l] / 2), dim3(256), smem_x, Mp, pk.lv[l], l, x);
+  // back-substitution: every level in one cooperative launch (one CTA per SM)
+  if (nl >= 2) {
+    int n_lev = nl;
+    void* args[] = {(void*)&Mp, (void*)&pk, (void*)&n_lev, (void*)&x};
+    h->stats.begin(K_BCR, h->stream);
+    const cudaError_t e = cudaLaunchCooperativeKernel((void*)k_b2_back_all, dim3(n_sm), dim3(256), args, 0, h->stream);
+    h->stats.end(h->stream);
+    if (e != cudaSuccess) return map_cuda(e);
   }
   PBA_LAUNCH(h, K_BCR, k_b2_unpad, dim3((z.dim + 255) / 256), dim3(256), 0, M, Mp, z.dim, x, h->y_cam.p);
   return PBA_OK;

@@ -490,17 +490,18 @@ void (*photo_kernel(int model, bool rc))(const EvalArgs) {
   static const int var = [] { const char* e = getenv(WITH_J ? "PBA_K1_VARIANT" : "PBA_K2_VARIANT"); return e ? atoi(e) : 0; }();
   if (model == PBA_CAM_PINHOLE && rc) {
     if (WITH_J) {
-      switch (var) {
+      switch (var) {  // measured (profiles/r02a_variants.txt): 4 CTAs/SM unroll 2: 3.40 ms, unroll 1: 3.45, 5 CTAs (spills): 4.77,
+                      // 3 CTAs (166 registers, no spill): 3.43; table path: 3.84
         case 1: return k_eval_photo<WITH_J, PBA_CAM_PINHOLE, true, 4, 1>;
         case 2: return k_eval_photo<WITH_J, PBA_CAM_PINHOLE, true, 5, 1>;
         case 3: return k_eval_photo<WITH_J, PBA_CAM_PINHOLE, true, 3, 2>;
         default: return k_eval_photo<WITH_J, PBA_CAM_PINHOLE, true, 4, 2>;
       }
     } else {
-      switch (var) {
-        case 1: return k_eval_photo<WITH_J, PBA_CAM_PINHOLE, true, 4, 2>;
+      switch (var) {  // measured (profiles/r02a_variants.txt): 4 CTAs/SM 1.055 ms, 5 (spills) 1.080, 6 1.131; table path 1.041
+        case 1: return k_eval_photo<WITH_J, PBA_CAM_PINHOLE, true, 5, 2>;
         case 2: return k_eval_photo<WITH_J, PBA_CAM_PINHOLE, true, 6, 2>;
-        default: return k_eval_photo<WITH_J, PBA_CAM_PINHOLE, true, 5, 2>;
+        default: return k_eval_photo<WITH_J, PBA_CAM_PINHOLE, true, 4, 2>;
       }
     }
   }
@@ -711,13 +712,15 @@ pba_status launch_expand_edges(Handle* h, const int* edge_col_dev) {
 
 // Upload-time conversion of the 8-bit keyframes (staged in `images_u8`, n_img
 // keyframes of pitch*height bytes) into the quad layout at keyframe `first`.
-pba_status launch_build_quads(Handle* h, const uint8_t* images_u8, int first, int n_img) {
+// `stream` is the set-up thread's own stream (pba_create uploads the keyframes from a helper thread while
+// the main thread orders the observations), so the launch is not routed through the handle's statistics.
+pba_status launch_build_quads(Handle* h, cudaStream_t stream, const uint8_t* images_u8, int first, int n_img) {
   const Sizes& z = h->sz;
   const int64_t tot = int64_t(z.width) * z.height * n_img;
   if (tot == 0) return PBA_OK;
-  PBA_LAUNCH(h, K_INIT_LM, k_build_quads, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, z.width, z.height, z.pitch,
-             int64_t(n_img), images_u8, h->quads.p + int64_t(first) * z.image_stride);
-  return PBA_OK;
+  k_build_quads<<<dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, stream>>>(z.width, z.height, z.pitch, int64_t(n_img), images_u8,
+                                                                         h->quads.p + int64_t(first) * z.image_stride);
+  return map_cuda(cudaGetLastError());
 }
 
 pba_status launch_init_landmarks(Handle* h) {

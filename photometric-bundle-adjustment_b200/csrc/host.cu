@@ -310,6 +310,240 @@ pba_status validate(const pba_problem* p, const pba_options* o) {
   return PBA_OK;
 }
 
+
+// ---- pinned host staging (set-up uploads) ----
+// The observation-sized index arrays pba_create builds go to the device from PINNED host memory: the
+// copies run at PCIe speed and asynchronously, under the host work that follows.  Pinning hundreds of
+// MB costs more than a solve, so released buffers stay in a per-process pool (like the device arena).
+struct PinnedPool {
+  std::mutex mu;
+  struct Buf { void* p; size_t bytes; };
+  std::vector<Buf> free_list;
+  void* acquire(size_t bytes, size_t* got) {
+    {
+      std::lock_guard<std::mutex> lock(mu);
+      int best = -1;
+      for (int i = 0; i < int(free_list.size()); ++i)
+        if (free_list[i].bytes >= bytes && (best < 0 || free_list[i].bytes < free_list[best].bytes)) best = i;
+      if (best >= 0) {
+        Buf b = free_list[best];
+        free_list.erase(free_list.begin() + best);
+        *got = b.bytes;
+        return b.p;
+      }
+    }
+    void* q = nullptr;
+    const size_t want = (bytes + (size_t(1) << 20) - 1) & ~((size_t(1) << 20) - 1);
+    if (cudaHostAlloc(&q, want, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); *got = 0; return nullptr; }
+    *got = want;
+    return q;
+  }
+  void release(void* p, size_t bytes) {
+    std::lock_guard<std::mutex> lock(mu);
+    free_list.push_back({p, bytes});
+  }
+  void trim() {
+    std::lock_guard<std::mutex> lock(mu);
+    for (Buf& b : free_list) cudaFreeHost(b.p);
+    free_list.clear();
+  }
+};
+PinnedPool g_pinned;
+
+// Array in pinned staging memory (pageable `new[]` if pinning fails).  Not value-initialised.
+template <class T>
+struct StageVec {
+  T* p = nullptr;
+  size_t n = 0, cap_bytes = 0;
+  bool pinned = false;
+  StageVec() {}
+  explicit StageVec(size_t count) { resize(count); }
+  StageVec(const StageVec&) = delete;
+  StageVec& operator=(const StageVec&) = delete;
+  ~StageVec() { reset(); }
+  void reset() {
+    if (p) { if (pinned) g_pinned.release(p, cap_bytes); else delete[] p; }
+    p = nullptr; n = 0;
+  }
+  void resize(size_t count) {
+    reset();
+    n = count;
+    if (!count) return;
+    p = static_cast<T*>(g_pinned.acquire(count * sizeof(T), &cap_bytes));
+    pinned = p != nullptr;
+    if (!p) p = new T[count];
+  }
+  void fill(const T& v) { for (size_t i = 0; i < n; ++i) p[i] = v; }
+  T& operator[](size_t i) { return p[i]; }
+  const T& operator[](size_t i) const { return p[i]; }
+  const T* data() const { return p; }
+  T* data() { return p; }
+  size_t size() const { return n; }
+  bool empty() const { return n == 0; }
+};
+
+// ---- camera layout: which poses are optimised, in which ORDER, and the RCS block pattern ----
+// Replaces the parameter-block ordering + block-structure detection of Ceres' preprocessor
+// (trust_region_preprocessor.cc:373, schur_complement_solver.cc:250-297; Ceres orders the reduced
+// camera system with AMD inside its sparse Cholesky).  Here the exact solvers want a small BANDWIDTH:
+// when the keyframes' natural order does not give one (loop closures, maps whose keyframes are not in
+// temporal order) the free cameras are renumbered by reverse Cuthill-McKee on the covisibility graph.
+// The block pattern is the union over host keyframes h of all pairs within {h} + targets(h) — a
+// superset of the per-landmark pairs Ceres uses, exactly the blocks the per-host-group Schur products write.
+struct CameraLayout {
+  std::vector<int> slot;               // pose -> RCS slot or -1 (constant / unused)
+  std::vector<uint8_t> affine_active;
+  int n_slots = 0;
+  int64_t n_active_lm = 0;
+  std::vector<std::vector<int>> adj;   // per slot a: ascending slots b >= a with an RCS block (a, b), diagonal included
+  int bandwidth = 0;                   // max (b - a) in blocks, final order
+  int bandwidth_natural = 0;           // the same in the keyframes' own order
+  bool reordered = false;
+};
+
+// new position -> node, reverse Cuthill-McKee; nb = symmetric neighbour lists without self loops
+std::vector<int> rcm_order(const std::vector<std::vector<int>>& nb) {
+  const int n = int(nb.size());
+  std::vector<int> order;
+  order.reserve(n);
+  std::vector<int> level(n, -1);
+  std::vector<char> done(n, 0);
+  auto bfs_levels = [&](int start, std::vector<int>& visited) {  // fills level[] for the component, returns the depth
+    visited.clear();
+    visited.push_back(start);
+    level[start] = 0;
+    for (size_t q = 0; q < visited.size(); ++q)
+      for (int v : nb[visited[q]])
+        if (level[v] < 0) { level[v] = level[visited[q]] + 1; visited.push_back(v); }
+    return level[visited.back()];
+  };
+  std::vector<int> comp, scratch;
+  for (int seed = 0; seed < n; ++seed) {
+    if (done[seed]) continue;
+    // component of `seed`; start from a pseudo-peripheral node (George-Liu: repeat BFS from a
+    // minimum-degree node of the last level while the depth grows)
+    int start = seed;
+    int depth = bfs_levels(start, comp);
+    for (int v : comp) if (nb[v].size() < nb[start].size()) start = v;  // first guess: minimum degree
+    for (int v : comp) level[v] = -1;
+    depth = bfs_levels(start, comp);
+    for (int iter = 0; iter < 8; ++iter) {
+      int cand = -1;
+      for (int v : comp)
+        if (level[v] == depth && (cand < 0 || nb[v].size() < nb[cand].size())) cand = v;
+      for (int v : comp) level[v] = -1;
+      const int d2 = bfs_levels(cand, scratch);
+      if (d2 > depth) { start = cand; depth = d2; comp = scratch; }
+      else { for (int v : scratch) level[v] = -1; bfs_levels(start, comp); break; }
+    }
+    for (int v : comp) level[v] = -1;
+    // Cuthill-McKee from `start`: neighbours in order of increasing degree
+    const size_t first = order.size();
+    order.push_back(start);
+    done[start] = 1;
+    for (size_t q = first; q < order.size(); ++q) {
+      scratch.clear();
+      for (int v : nb[order[q]]) if (!done[v]) { done[v] = 1; scratch.push_back(v); }
+      std::sort(scratch.begin(), scratch.end(), [&](int a, int b) {
+        return nb[a].size() != nb[b].size() ? nb[a].size() < nb[b].size() : a < b;
+      });
+      order.insert(order.end(), scratch.begin(), scratch.end());
+    }
+  }
+  std::reverse(order.begin(), order.end());
+  return order;
+}
+
+void analyze_cameras(const pba_problem* p, int nthr, int max_band_blocks, CameraLayout* L) {
+  const bool photo = p->mode == PBA_MODE_PHOTOMETRIC;
+  const int np = p->n_poses;
+  std::vector<uint8_t> used(np, 0), is_target(np, 0);
+  std::vector<std::vector<int>> host_targets(np);  // distinct targets of the landmarks hosted by a keyframe
+  int64_t n_active = 0;
+#pragma omp parallel num_threads(nthr) reduction(+ : n_active)
+  {
+    std::vector<uint8_t> u(np, 0), t(np, 0);
+    std::vector<int> stamp(np, -1);  // stamp[target] = host while consecutive landmarks share the host
+    std::vector<std::vector<int>> mine(np);
+#pragma omp for schedule(static)
+    for (int l = 0; l < p->n_landmarks; ++l) {
+      const int64_t k0 = p->lm_obs_ptr[l], k1 = p->lm_obs_ptr[l + 1];
+      if (k1 == k0) continue;
+      const int hst = p->lm_host[l];
+      u[hst] = 1;
+      ++n_active;
+      for (int64_t k = k0; k < k1; ++k) {
+        const int tg = p->obs_target[k];
+        u[tg] = 1; t[tg] = 1;
+        if (stamp[tg] != hst) { stamp[tg] = hst; mine[hst].push_back(tg); }
+      }
+    }
+#pragma omp critical
+    for (int i = 0; i < np; ++i) {
+      used[i] |= u[i]; is_target[i] |= t[i];
+      host_targets[i].insert(host_targets[i].end(), mine[i].begin(), mine[i].end());
+    }
+  }
+  for (auto& v : host_targets) { std::sort(v.begin(), v.end()); v.erase(std::unique(v.begin(), v.end()), v.end()); }
+  L->n_active_lm = n_active;
+  L->slot.assign(np, -1);
+  L->affine_active.assign(np, 0);
+  L->n_slots = 0;
+  for (int i = 0; i < np; ++i) {
+    const bool fixed = p->pose_fixed && p->pose_fixed[i];
+    if (!fixed && used[i]) L->slot[i] = L->n_slots++;
+    L->affine_active[i] = photo && !fixed && is_target[i];
+  }
+  const int ns = L->n_slots;
+  // covisibility graph on the provisional (natural) slots
+  std::vector<std::vector<int>> nb(ns);
+  std::vector<int> cams;
+  for (int hst = 0; hst < np; ++hst) {
+    if (host_targets[hst].empty()) continue;
+    cams.clear();
+    if (L->slot[hst] >= 0) cams.push_back(L->slot[hst]);
+    for (int tg : host_targets[hst]) if (L->slot[tg] >= 0) cams.push_back(L->slot[tg]);
+    for (size_t i = 0; i < cams.size(); ++i)
+      for (size_t j = i + 1; j < cams.size(); ++j) { nb[cams[i]].push_back(cams[j]); nb[cams[j]].push_back(cams[i]); }
+  }
+  int bw_nat = 0;
+  for (int a = 0; a < ns; ++a) {
+    std::sort(nb[a].begin(), nb[a].end());
+    nb[a].erase(std::unique(nb[a].begin(), nb[a].end()), nb[a].end());
+    for (int b : nb[a]) bw_nat = std::max(bw_nat, std::abs(a - b));
+  }
+  L->bandwidth_natural = bw_nat;
+  L->bandwidth = bw_nat;
+  L->reordered = false;
+  std::vector<int> newpos(ns);
+  std::iota(newpos.begin(), newpos.end(), 0);
+  if (bw_nat > max_band_blocks && ns > 2) {
+    // the natural order is too wide for the banded solvers: try reverse Cuthill-McKee
+    const std::vector<int> order = rcm_order(nb);
+    std::vector<int> pos(ns);
+    for (int i = 0; i < ns; ++i) pos[order[i]] = i;
+    int bw = 0;
+    for (int a = 0; a < ns; ++a)
+      for (int b : nb[a]) bw = std::max(bw, std::abs(pos[a] - pos[b]));
+    if (bw < bw_nat) {
+      newpos = pos;
+      L->bandwidth = bw;
+      L->reordered = true;
+      for (int i = 0; i < np; ++i) if (L->slot[i] >= 0) L->slot[i] = newpos[L->slot[i]];
+    }
+  }
+  L->adj.assign(ns, std::vector<int>());
+  for (int a = 0; a < ns; ++a) {
+    const int pa = newpos[a];
+    L->adj[pa].push_back(pa);
+    for (int b : nb[a]) {
+      const int pb = newpos[b];
+      if (pb > pa) L->adj[pa].push_back(pb);
+    }
+  }
+  for (auto& v : L->adj) std::sort(v.begin(), v.end());
+}
+
 constexpr int kChunkObs = 1024;
 
 pba_status create_impl(const pba_problem* p, const pba_options* o, int rank, int world, Handle** out) {
@@ -351,77 +585,81 @@ pba_status create_impl(const pba_problem* p, const pba_options* o, int rank, int
   mark("validate + device init");
   // One process per GPU shares the host cores: each rank takes its share of the OpenMP threads.
   const int nthr = std::max(1, omp_get_num_procs() / std::max(1, world));
-  // ---- global layout: which parameter blocks survive Ceres' reduced program ----
-  std::vector<uint8_t> used(p->n_poses, 0), is_target(p->n_poses, 0);
-  {
-    int64_t n_active = 0;
-#pragma omp parallel num_threads(nthr) reduction(+ : n_active)
-    {
-      std::vector<uint8_t> u(p->n_poses, 0), t(p->n_poses, 0);
-#pragma omp for schedule(static)
-      for (int l = 0; l < p->n_landmarks; ++l) {
-        if (p->lm_obs_ptr[l + 1] > p->lm_obs_ptr[l]) { u[p->lm_host[l]] = 1; ++n_active; }
-        for (int64_t k = p->lm_obs_ptr[l]; k < p->lm_obs_ptr[l + 1]; ++k) { u[p->obs_target[k]] = 1; t[p->obs_target[k]] = 1; }
-      }
-#pragma omp critical
-      for (int i = 0; i < p->n_poses; ++i) { used[i] |= u[i]; is_target[i] |= t[i]; }
+  // ---- this rank's landmark range (contiguous, balanced by observation count) ----
+  std::vector<int> bounds;
+  partition_landmarks(p->lm_obs_ptr, p->n_landmarks, world, bounds);
+  const int lm_lo = bounds[rank], lm_hi = bounds[rank + 1];
+  h->first_landmark = lm_lo;
+  z.n_lm = lm_hi - lm_lo;
+  const int64_t obs_lo = p->lm_obs_ptr[lm_lo];
+  z.n_obs = p->lm_obs_ptr[lm_hi] - obs_lo;
+  z.ld = (z.n_obs + 31) / 32 * 32;
+  const int n_lm = z.n_lm;
+  const int64_t n = z.n_obs;
+
+  // ---- keyframe upload, started first and run by a helper thread on its own stream: 8-bit rows go to the
+  //      device in batches and are expanded there into the quad layout the evaluation kernels gather from.
+  //      It overlaps all the host-side ordering below.  The staging area is the head of the Jacobian buffer
+  //      (not needed before the first evaluation). ----
+  PBA_CUDA_OK(h->J.alloc(size_t(z.ld) * z.R * (z.C + 1 - 6)));  // stored planes: pba_internal.h
+  std::thread image_thread;
+  pba_status image_status = PBA_OK;
+  DevBuf<uint8_t> own_stage;
+  struct JoinGuard { std::thread& t; ~JoinGuard() { if (t.joinable()) t.join(); } } join_guard{image_thread};
+  if (photo) {
+    z.image_stride = int64_t(p->width) * p->height;  // pixels
+    const size_t img_bytes = size_t(p->pitch) * p->height;
+    PBA_CUDA_OK(h->quads.alloc(size_t(z.image_stride) * p->n_poses));
+    const int batch = std::max(1, std::min(p->n_poses, 256));
+    uint8_t* stage = reinterpret_cast<uint8_t*>(h->J.p);
+    if (h->J.n * sizeof(double) < img_bytes * batch) {
+      PBA_CUDA_OK(own_stage.alloc(img_bytes * batch));
+      stage = own_stage.p;
     }
-    h->n_active_lm += n_active;
+    const int dev = o->device;
+    image_thread = std::thread([=, &image_status]() {
+      auto fail = [&](cudaError_t e) { image_status = map_cuda(e); };
+      cudaError_t e = cudaSetDevice(dev);
+      if (e != cudaSuccess) return fail(e);
+      cudaStream_t is = nullptr;
+      if ((e = cudaStreamCreateWithFlags(&is, cudaStreamNonBlocking)) != cudaSuccess) return fail(e);
+      for (int f0 = 0; f0 < p->n_poses && image_status == PBA_OK; f0 += batch) {
+        const int cnt = std::min(batch, p->n_poses - f0);
+        if (!p->image_ptrs && p->image_stride == int64_t(img_bytes)) {
+          e = cudaMemcpyAsync(stage, p->images + size_t(f0) * img_bytes, img_bytes * cnt, cudaMemcpyHostToDevice, is);
+        } else {
+          for (int i = 0; i < cnt && e == cudaSuccess; ++i) {
+            const uint8_t* src = p->image_ptrs ? p->image_ptrs[f0 + i] : p->images + size_t(f0 + i) * p->image_stride;
+            e = cudaMemcpyAsync(stage + size_t(i) * img_bytes, src, img_bytes, cudaMemcpyHostToDevice, is);
+          }
+        }
+        if (e != cudaSuccess) { fail(e); break; }
+        const pba_status ls = launch_build_quads(h, is, stage, f0, cnt);
+        if (ls != PBA_OK) image_status = ls;
+      }
+      e = cudaStreamSynchronize(is);
+      if (e != cudaSuccess && image_status == PBA_OK) fail(e);
+      cudaStreamDestroy(is);
+    });
+    h->stats.launches[K_INIT_LM] += (p->n_poses + batch - 1) / batch;
   }
+  mark("sizes + start of the keyframe upload");
+
+  // ---- global layout (identical on every rank): which parameter blocks survive Ceres' reduced program,
+  //      the order of the free cameras, the RCS block pattern ----
+  CameraLayout layout;
+  analyze_cameras(p, nthr, 128 / cd, &layout);
+  h->n_active_lm += layout.n_active_lm;
   h->n_obs_global = p->n_obs;
-  h->slot.assign(p->n_poses, -1);
-  h->affine_active.assign(p->n_poses, 0);
-  for (int i = 0; i < p->n_poses; ++i) {
-    const bool fixed = p->pose_fixed && p->pose_fixed[i];
-    if (!fixed && used[i]) h->slot[i] = z.n_slots++;
-    h->affine_active[i] = photo && !fixed && is_target[i];
-  }
+  h->slot = layout.slot;
+  h->affine_active = layout.affine_active;
+  z.n_slots = layout.n_slots;
   z.dim = z.n_slots * cd;
   const std::vector<int>& slot = h->slot;
-
-  mark("active layout");
-  // ---- global RCS block pattern: all camera pairs co-observing a landmark
-  //      (schur_complement_solver.cc:261-297); identical on every rank ----
-  std::vector<std::vector<int>> adj(z.n_slots);
-  {
-    // many landmarks share a camera set: find the distinct sets (parallel scan, per-thread
-    // hash sets merged serially), then insert the pairs of each set once
-    std::unordered_set<std::string> seen;
-#pragma omp parallel num_threads(nthr)
-    {
-      std::unordered_set<std::string> mine;
-      std::vector<int> cams;
-      std::string last;
-#pragma omp for schedule(static)
-      for (int l = 0; l < p->n_landmarks; ++l) {
-        if (p->lm_obs_ptr[l + 1] == p->lm_obs_ptr[l]) continue;
-        cams.clear();
-        if (slot[p->lm_host[l]] >= 0) cams.push_back(slot[p->lm_host[l]]);
-        for (int64_t k = p->lm_obs_ptr[l]; k < p->lm_obs_ptr[l + 1]; ++k)
-          if (slot[p->obs_target[k]] >= 0) cams.push_back(slot[p->obs_target[k]]);
-        if (cams.empty()) continue;
-        std::sort(cams.begin(), cams.end());
-        const size_t bytes = cams.size() * sizeof(int);
-        if (last.size() == bytes && memcmp(last.data(), cams.data(), bytes) == 0) continue;  // same set as the previous landmark
-        last.assign(reinterpret_cast<const char*>(cams.data()), bytes);
-        mine.insert(last);
-      }
-#pragma omp critical
-      seen.insert(mine.begin(), mine.end());
-    }
-    for (const std::string& key : seen) {
-      const int* cams = reinterpret_cast<const int*>(key.data());
-      const size_t nc = key.size() / sizeof(int);
-      for (size_t i = 0; i < nc; ++i)
-        for (size_t j = i; j < nc; ++j) adj[cams[i]].push_back(cams[j]);
-    }
-    for (auto& v : adj) { std::sort(v.begin(), v.end()); v.erase(std::unique(v.begin(), v.end()), v.end()); }
-  }
+  std::vector<std::vector<int>>& adj = layout.adj;
+  mark("camera layout + RCS pattern");
   std::vector<int64_t> adj_ptr(z.n_slots + 1, 0);
-  for (int a = 0; a < z.n_slots; ++a) {
-    if (adj[a].empty() || adj[a][0] != a) adj[a].insert(adj[a].begin(), a);  // always keep the diagonal block
-    adj_ptr[a + 1] = adj_ptr[a] + int64_t(adj[a].size());
-  }
+  for (int a = 0; a < z.n_slots; ++a) adj_ptr[a + 1] = adj_ptr[a] + int64_t(adj[a].size());  // adj[a][0] == a
   z.n_blocks = adj_ptr[z.n_slots];
   h->blk_row.resize(z.n_blocks); h->blk_col.resize(z.n_blocks); h->diag_blk.assign(z.n_slots, 0);
   for (int a = 0; a < z.n_slots; ++a)
@@ -436,18 +674,7 @@ pba_status create_impl(const pba_problem* p, const pba_options* o, int rank, int
     return adj_ptr[a] + (it - adj[a].begin());
   };
 
-  mark("RCS block pattern");
   // ---- local shard: landmarks ordered by host, observations by (host,target) edge ----
-  std::vector<int> bounds;
-  partition_landmarks(p->lm_obs_ptr, p->n_landmarks, world, bounds);
-  const int lm_lo = bounds[rank], lm_hi = bounds[rank + 1];
-  h->first_landmark = lm_lo;
-  z.n_lm = lm_hi - lm_lo;
-  const int64_t obs_lo = p->lm_obs_ptr[lm_lo];
-  z.n_obs = p->lm_obs_ptr[lm_hi] - obs_lo;
-  z.ld = (z.n_obs + 31) / 32 * 32;
-  const int n_lm = z.n_lm;
-  const int64_t n = z.n_obs;
 
   h->lm_order.resize(n_lm);
   std::iota(h->lm_order.begin(), h->lm_order.end(), 0);
@@ -460,7 +687,10 @@ pba_status create_impl(const pba_problem* p, const pba_options* o, int rank, int
   }
   // lm-major observation index space k (internal landmark order); a host group's
   // observations are contiguous in k, and the edge order only permutes inside a group
-  std::vector<int64_t> lm_ptr(n_lm + 1, 0);
+  // observation-/landmark-sized tables are built in pinned staging memory (StageVec) and uploaded asynchronously;
+  // they live until the final synchronisation of this function
+  StageVec<int64_t> lm_ptr(size_t(n_lm) + 1);
+  lm_ptr[0] = 0;
   for (int li = 0; li < n_lm; ++li) {
     const int l = lm_lo + h->lm_order[li];
     lm_ptr[li + 1] = lm_ptr[li] + (p->lm_obs_ptr[l + 1] - p->lm_obs_ptr[l]);
@@ -532,11 +762,11 @@ pba_status create_impl(const pba_problem* p, const pba_options* o, int rank, int
   h->schur_tile_l = schur_tile_l(h->max_w_stride);
 
   // pass B (parallel over groups): place every observation at its edge-order position
-  RawVec<int> obs_lm(n);  // every entry is written in pass B
+  StageVec<int> obs_lm(n);  // every entry is written in pass B
   std::vector<int> edge_col(z.n_edges, -1);  // W column of an edge's target; obs_edge / obs_col are expanded on the device
-  RawVec<int64_t> lm_pos(n);
-  std::vector<int> lm_group(n_lm), lm_hostcol(n_lm, -1), lm_w_stride(n_lm);
-  std::vector<int64_t> lm_w_off(n_lm);
+  StageVec<int64_t> lm_pos(n);
+  StageVec<int> lm_group(n_lm), lm_hostcol(n_lm), lm_w_stride(n_lm);
+  StageVec<int64_t> lm_w_off(n_lm);
   h->obs_order.resize(n);
 #pragma omp parallel num_threads(nthr)
   {
@@ -655,8 +885,7 @@ pba_status create_impl(const pba_problem* p, const pba_options* o, int rank, int
     DevBuf<int> d_edge_col;
     PBA_CUDA_OK(up(d_edge_col, edge_col));
     if ((st = launch_expand_edges(h, d_edge_col.p)) != PBA_OK) return st;
-    PBA_CUDA_OK(cudaStreamSynchronize(s));
-    d_edge_col.release();
+    d_edge_col.release();  // whatever takes this memory next is ordered behind the kernel on the same stream
     h->arena.rewind(tmp_mark);
   }
   PBA_CUDA_OK(up(h->chunk_edge, chunk_edge)); PBA_CUDA_OK(up(h->chunk_begin, chunk_begin)); PBA_CUDA_OK(up(h->chunk_end, chunk_end));
@@ -675,14 +904,13 @@ pba_status create_impl(const pba_problem* p, const pba_options* o, int rank, int
     std::vector<int> col_blk(size_t(z.n_slots) * B, -1);
     for (int64_t b = 0; b < z.n_blocks; ++b) col_blk[size_t(h->blk_row[b]) * B + (h->blk_col[b] - h->blk_row[b])] = int(b);
     PBA_CUDA_OK(up(h->d_col_blk, col_blk));
-    PBA_CUDA_OK(cudaStreamSynchronize(s));
     PBA_CUDA_OK(h->band_L.alloc(size_t(z.n_slots) * B * cd * cd));
   }
   if ((st = bcr_setup(h)) != PBA_OK) return st;
+  StageVec<int> lm_host(n_lm);
+  StageVec<double> lm_uv(size_t(2) * n_lm), rho(n_lm), uv;
   {
-    std::vector<int> lm_host(n_lm);
-    std::vector<double> lm_uv(size_t(2) * n_lm), rho(n_lm);
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for num_threads(nthr) schedule(static)
     for (int li = 0; li < n_lm; ++li) {
       const int l = lm_lo + h->lm_order[li];
       lm_host[li] = p->lm_host[l];
@@ -691,53 +919,23 @@ pba_status create_impl(const pba_problem* p, const pba_options* o, int rank, int
     }
     PBA_CUDA_OK(up(h->lm_host, lm_host)); PBA_CUDA_OK(up(h->lm_uv, lm_uv)); PBA_CUDA_OK(up(h->rho, rho));
     if (!photo) {
-      std::vector<double> uv(size_t(2) * n);
-#pragma omp parallel for schedule(static)
+      uv.resize(size_t(2) * n);
+#pragma omp parallel for num_threads(nthr) schedule(static)
       for (int64_t i = 0; i < n; ++i) {
         const int64_t q = obs_lo + h->obs_order[i];
         uv[i] = p->obs_uv[2 * q]; uv[n + i] = p->obs_uv[2 * q + 1];
       }
       PBA_CUDA_OK(up(h->obs_uv, uv));
     }
-    PBA_CUDA_OK(cudaStreamSynchronize(s));  // the temporaries above go out of scope
   }
   {
     std::vector<double> poses(p->poses, p->poses + size_t(7) * p->n_poses);
     PBA_CUDA_OK(up(h->poses, poses));
     std::vector<double> aff(size_t(2) * p->n_poses, 0.0);
     if (photo && p->affine) aff.assign(p->affine, p->affine + size_t(2) * p->n_poses);
-    PBA_CUDA_OK(up(h->affine, aff));
-    PBA_CUDA_OK(cudaStreamSynchronize(s));
+    PBA_CUDA_OK(up(h->affine, aff));  // pageable sources are staged by the driver before the call returns
   }
   mark("upload structure");
-  if (photo) {
-    // keyframes go to the device as 8-bit rows (staged in batches) and are expanded
-    // there into the quad layout the evaluation kernels gather from
-    z.image_stride = int64_t(p->width) * p->height;  // pixels
-    const size_t img_bytes = size_t(p->pitch) * p->height;
-    PBA_CUDA_OK(h->quads.alloc(size_t(z.image_stride) * p->n_poses));
-    const int batch = std::max(1, std::min(p->n_poses, 256));
-    const DeviceArena::Mark tmp_mark = h->arena.mark();  // the staging buffer is handed back below
-    DevBuf<uint8_t> stage;
-    PBA_CUDA_OK(stage.alloc(img_bytes * batch));
-    for (int f0 = 0; f0 < p->n_poses; f0 += batch) {
-      const int cnt = std::min(batch, p->n_poses - f0);
-      if (!p->image_ptrs && p->image_stride == int64_t(img_bytes)) {
-        PBA_CUDA_OK(cudaMemcpyAsync(stage.p, p->images + size_t(f0) * img_bytes, img_bytes * cnt, cudaMemcpyHostToDevice, s));
-      } else {
-        for (int i = 0; i < cnt; ++i) {
-          const uint8_t* src = p->image_ptrs ? p->image_ptrs[f0 + i] : p->images + size_t(f0 + i) * p->image_stride;
-          PBA_CUDA_OK(cudaMemcpyAsync(stage.p + size_t(i) * img_bytes, src, img_bytes, cudaMemcpyHostToDevice, s));
-        }
-      }
-      if ((st = launch_build_quads(h, stage.p, f0, cnt)) != PBA_OK) return st;
-    }
-    PBA_CUDA_OK(cudaStreamSynchronize(s));
-    stage.release();
-    h->arena.rewind(tmp_mark);
-  }
-
-  mark("upload images + quads");
   // ---- work buffers ----
   const size_t nn = size_t(n);
   PBA_CUDA_OK(h->poses_c.alloc(size_t(7) * p->n_poses)); PBA_CUDA_OK(h->poses_best.alloc(size_t(7) * p->n_poses));
@@ -746,7 +944,7 @@ pba_status create_impl(const pba_problem* p, const pba_options* o, int rank, int
   PBA_CUDA_OK(h->lm_pat.alloc(size_t(n_lm) * (photo ? 32 : 4))); PBA_CUDA_OK(h->lm_ok.alloc(n_lm));
   PBA_CUDA_OK(h->edge_T.alloc(size_t(kEdgeStride) * z.n_edges));
   PBA_CUDA_OK(h->edge_M.alloc(size_t(36) * z.n_edges));
-  PBA_CUDA_OK(h->J.alloc(size_t(z.ld) * z.R * (z.C + 1 - 6))); PBA_CUDA_OK(h->orec.alloc(nn * 16));  // stored planes: pba_internal.h
+  PBA_CUDA_OK(h->orec.alloc(nn * 16));
   PBA_CUDA_OK(h->W.alloc(size_t(w_total)));
   if (w_total) PBA_CUDA_OK(cudaMemsetAsync(h->W.p, 0, sizeof(double) * size_t(w_total), s));  // unseen camera slots stay 0
   PBA_CUDA_OK(h->lm_c.alloc(n_lm)); PBA_CUDA_OK(h->lm_g.alloc(n_lm)); PBA_CUDA_OK(h->lm_scale.alloc(n_lm));
@@ -768,6 +966,10 @@ pba_status create_impl(const pba_problem* p, const pba_options* o, int rank, int
   PBA_CUDA_OK(cudaMemsetAsync(h->chol_fail.p, 0, sizeof(int), s));
   PBA_CUDA_OK(cudaMallocHost(&h->h_scalars, sizeof(double) * (S_NUM + 2)));
   mark("allocate work buffers");
+  if (image_thread.joinable()) image_thread.join();  // quads are complete (the helper synchronised its stream)
+  if (image_status != PBA_OK) return image_status;
+  own_stage.release();
+  mark("wait for the keyframe upload");
   st = launch_init_landmarks(h);
   if (st != PBA_OK) return st;
   PBA_CUDA_OK(cudaStreamSynchronize(s));
@@ -1143,7 +1345,31 @@ PBA_API void pba_destroy(pba_handle* hh) {
   delete h;
 }
 
-PBA_API void pba_trim_device_cache(void) { trim_device_cache(); }
+PBA_API void pba_trim_device_cache(void) {
+  trim_device_cache();
+  g_pinned.trim();
+}
+
+// Host-only: the camera layout pba_create would use (no device needed; CPU tests of the ordering logic).
+PBA_API pba_status pba_analyze_structure(const pba_problem* problem, const pba_options* options, int32_t* slot,
+                                         int32_t* n_slots, int32_t* bandwidth_natural, int32_t* bandwidth,
+                                         int64_t* n_blocks) {
+  pba_status st = validate(problem, options);
+  if (st != PBA_OK) return st;
+  const int cd = problem->mode == PBA_MODE_PHOTOMETRIC ? 8 : 6;
+  CameraLayout L;
+  analyze_cameras(problem, std::max(1, omp_get_num_procs()), 128 / cd, &L);
+  if (slot) for (int i = 0; i < problem->n_poses; ++i) slot[i] = L.slot[i];
+  if (n_slots) *n_slots = L.n_slots;
+  if (bandwidth_natural) *bandwidth_natural = L.bandwidth_natural;
+  if (bandwidth) *bandwidth = L.bandwidth;
+  if (n_blocks) {
+    int64_t nb = 0;
+    for (const auto& v : L.adj) nb += int64_t(v.size());
+    *n_blocks = nb;
+  }
+  return PBA_OK;
+}
 
 PBA_API pba_status pba_set_stream(pba_handle* hh, void* cuda_stream) {
   Handle* h = reinterpret_cast<Handle*>(hh);

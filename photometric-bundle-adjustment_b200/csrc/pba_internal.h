@@ -339,7 +339,7 @@ pba_status map_cuda(cudaError_t e);
 // -------------------------------------------------------------- launchers --
 // eval.cu
 pba_status launch_init_landmarks(Handle* h);
-pba_status launch_build_quads(Handle* h, const uint8_t* images_u8, int first, int n_img);
+pba_status launch_build_quads(Handle* h, cudaStream_t stream, const uint8_t* images_u8, int first, int n_img);
 pba_status launch_evaluate(Handle* h, bool with_jacobian, const double* poses, const double* affine,
                            const double* rho, double* cost_out);
 pba_status launch_unpermute(Handle* h, int which, double* dst_host_order_dev);

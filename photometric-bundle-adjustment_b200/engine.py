@@ -81,6 +81,17 @@ def device_count():
     return int(_ffi.load_lib().pba_device_count())
 
 
+def analyze_structure(problem: Problem, options: BundleAdjustmentOptions = None):
+    """Host-only: (slot per pose, n_slots, natural half-bandwidth, final half-bandwidth, stored RCS blocks)."""
+    o = (options or BundleAdjustmentOptions()).to_c()
+    slot = np.zeros(problem.n_poses, np.int32)
+    ns, bw0, bw1, nb = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int64()
+    pc = problem.c
+    _ffi.check(_ffi.load_lib().pba_analyze_structure(C.byref(pc), C.byref(o), _ffi.ptr(slot, C.c_int32), C.byref(ns),
+                                                     C.byref(bw0), C.byref(bw1), C.byref(nb)), "pba_analyze_structure")
+    return slot, ns.value, bw0.value, bw1.value, nb.value
+
+
 def multi_gpu_init(device=0, num_gpus=0):
     """Create the NCCL communicators of bundle_adjustment(..., num_gpus > 1) ahead of the first solve."""
     _ffi.check(_ffi.load_lib().pba_multi_gpu_init(int(device), int(num_gpus)), "pba_multi_gpu_init")
