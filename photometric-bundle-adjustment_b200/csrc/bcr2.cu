@@ -130,11 +130,16 @@ __global__ void k_b2_unpad(int M, int Mp, int dim, const double* __restrict__ x,
 // multiply -> FMA (~110 cycles), every lane issues ~20 instructions; the single-thread version of the first
 // generation (factor, then invert) took ~2,100 cycles per block and was the longest item of a level.
 // Returns W in (w0, w1) = W[g][2t], W[g][2t+1]. ----
-__device__ __forceinline__ void b2_diag_factor(double a0, double a1, double& w0, double& w1, int* fail) {
+//
+// NOT inlined: the factorisation calls it from every slot of its unrolled tile loop, and these kernels run
+// through their code once per launch — the first version (everything unrolled: 13,700 instructions = 219 KB
+// for k_b2_fs<11>, more than the instruction cache) was bound by instruction fetch, 45 us a level whatever
+// the amount of arithmetic.
+__device__ __noinline__ double2 b2_diag_factor(double a0, double a1, int* fail) {
   const int lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
-  w0 = g == 2 * t ? 1.0 : 0.0;
-  w1 = g == 2 * t + 1 ? 1.0 : 0.0;
+  double w0 = g == 2 * t ? 1.0 : 0.0;
+  double w1 = g == 2 * t + 1 ? 1.0 : 0.0;
   bool bad = false;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -152,6 +157,7 @@ __device__ __forceinline__ void b2_diag_factor(double a0, double a1, double& w0,
     else if (g == j) { a0 = u0; a1 = u1; w0 = v0; w1 = v1; }
   }
   if (bad && lane == 0) *fail = 1;
+  return make_double2(w0, w1);
 }
 
 // ---- A (Mp x Mp, shared, lower 8x8 tiles valid) <- the panels of its lower Cholesky factor (tiles (I, J),
@@ -194,9 +200,7 @@ __device__ void b2_cholesky(double* As, double* Dinv, int* fail) {
     for (int s = 0; s < TPW; ++s) {
       if (ti[s] < 0 || tk[s] != J) continue;
       if (ti[s] == J) {  // warp-uniform: this warp owns the diagonal tile
-        double w0, w1;
-        b2_diag_factor(c[s][0], c[s][1], w0, w1, fail);
-        *reinterpret_cast<double2*>(Dinv + 64 * J + g * 8 + 2 * t) = make_double2(w0, w1);
+        *reinterpret_cast<double2*>(Dinv + 64 * J + g * 8 + 2 * t) = b2_diag_factor(c[s][0], c[s][1], fail);
       } else if (J > 0) {
         *reinterpret_cast<double2*>(As + (8 * ti[s] + g) * LD + 8 * J + 2 * t) = make_double2(c[s][0], c[s][1]);
       }
@@ -229,119 +233,75 @@ __device__ void b2_cholesky(double* As, double* Dinv, int* fail) {
   __syncthreads();
 }
 
-// ---- W (Mp x 8 nct, shared, leading dimension ldw) <- A^-1 W = L^-T L^-1 W.  A warp owns CT column
-// tiles (8 columns each) at a time and keeps all their NBK row tiles in registers as accumulator
-// fragments; the only shared-memory traffic is the current row tile's C-layout -> B-layout conversion
-// (through its own place in W) and the factor's fragments.  No block-wide barrier.  The result is left
-// in registers and handed to `store(ct, I, c0, c1)`. ----
-template <int NBK, int CT, class Store>
-__device__ __forceinline__ void b2_solve_tiles(const double* As, const double* Dinv, double* Ws, int ldw, int nct, Store store) {
+// ---- W (Mp x 8 nct, shared, leading dimension ldw) <- A^-1 W = L^-T L^-1 W, in place.  A warp owns CT column
+// tiles (8 columns each) at a time and sweeps them forward and backward on its own: the only
+// synchronisation is __syncwarp (no block-wide barrier).  Tiles stay in shared memory in the accumulator
+// layout (one 16-byte load / store per lane and update) and the loops are NOT unrolled over the block rows:
+// the straight-line version with the strip in registers was 2.4 k instructions per sweep and column-tile
+// count, executed once — instruction fetch, not arithmetic, set its time. ----
+template <int NBK, int CT>
+__device__ __forceinline__ void b2_solve_tiles(const double* As, const double* Dinv, double* Ws, int ldw, int nct) {
   constexpr int LD = 8 * NBK + 4;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
   for (int ct0 = warp * CT; ct0 < nct; ct0 += kB2Warps * CT) {
-    double c[CT][NBK][2];
-    // a slot beyond the last tile repeats the last tile (same warp, same data, same result: harmless) so that
-    // the code below is branch-free; only the final store is guarded
+    // a slot beyond the last tile repeats the last tile (same warp, same data, same result: harmless)
     double* col[CT];
 #pragma unroll
-    for (int q = 0; q < CT; ++q) {
-      col[q] = Ws + 8 * min(ct0 + q, nct - 1);
-#pragma unroll
-      for (int I = 0; I < NBK; ++I) {
-        const double2 v = *reinterpret_cast<const double2*>(col[q] + (8 * I + g) * ldw + 2 * t);
-        c[q][I][0] = v.x; c[q][I][1] = v.y;
-      }
-    }
-    // forward: L y = w
-#pragma unroll
-    for (int J = 0; J < NBK; ++J) {
-      double xb0[CT], xb1[CT];
-      const double d0 = Dinv[64 * J + g * 8 + t], d1 = Dinv[64 * J + g * 8 + 4 + t];
-      if (J > 0) {  // J == 0: W still holds the staged values
-#pragma unroll
-        for (int q = 0; q < CT; ++q)
-          *reinterpret_cast<double2*>(col[q] + (8 * J + g) * ldw + 2 * t) = make_double2(c[q][J][0], c[q][J][1]);
-        __syncwarp();
-      }
-#pragma unroll
-      for (int q = 0; q < CT; ++q) {
-        const double* tile = col[q] + 8 * J * ldw;
-        const double b0 = tile[t * ldw + g], b1 = tile[(4 + t) * ldw + g];
-        double x[2] = {0.0, 0.0};
-        dmma(x, d0, b0);
-        dmma(x, d1, b1);
-        c[q][J][0] = x[0]; c[q][J][1] = x[1];
-      }
-      __syncwarp();
-#pragma unroll
-      for (int q = 0; q < CT; ++q)
-        *reinterpret_cast<double2*>(col[q] + (8 * J + g) * ldw + 2 * t) = make_double2(c[q][J][0], c[q][J][1]);
-      __syncwarp();
-#pragma unroll
-      for (int q = 0; q < CT; ++q) {
-        const double* tile = col[q] + 8 * J * ldw;
-        xb0[q] = tile[t * ldw + g]; xb1[q] = tile[(4 + t) * ldw + g];
-      }
-#pragma unroll
-      for (int I = J + 1; I < NBK; ++I) {
-        const double* la = As + (8 * I + g) * LD + 8 * J;
-        const double a0 = -la[t], a1 = -la[4 + t];
+    for (int q = 0; q < CT; ++q) col[q] = Ws + 8 * min(ct0 + q, nct - 1);
+#pragma unroll 1
+    for (int dir = 0; dir < 2; ++dir) {
+      // dir 0: forward, L y = w (J ascending, rows below J updated); dir 1: backward, L^T x = y
+#pragma unroll 1
+      for (int jj = 0; jj < NBK; ++jj) {
+        const int J = dir == 0 ? jj : NBK - 1 - jj;
+        // diagonal block: X_J = W_J tile (forward) or W_J^T tile (backward)
+        const double d0 = dir == 0 ? Dinv[64 * J + g * 8 + t] : Dinv[64 * J + t * 8 + g];
+        const double d1 = dir == 0 ? Dinv[64 * J + g * 8 + 4 + t] : Dinv[64 * J + (4 + t) * 8 + g];
+        double xb0[CT], xb1[CT];
+        double x[CT][2];
 #pragma unroll
         for (int q = 0; q < CT; ++q) {
-          dmma(c[q][I], a0, xb0[q]);
-          dmma(c[q][I], a1, xb1[q]);
+          const double* tile = col[q] + 8 * J * ldw;
+          const double b0 = tile[t * ldw + g], b1 = tile[(4 + t) * ldw + g];
+          x[q][0] = 0.0; x[q][1] = 0.0;
+          dmma(x[q], d0, b0);
+          dmma(x[q], d1, b1);
         }
-      }
-    }
-    // backward: L^T x = y
-#pragma unroll
-    for (int J = NBK - 1; J >= 0; --J) {
-      double xb0[CT], xb1[CT];
-      const double d0 = Dinv[64 * J + t * 8 + g], d1 = Dinv[64 * J + (4 + t) * 8 + g];  // (W^T)[g][k] = W[k][g]
-      if (J < NBK - 1) {  // J == NBK - 1: the forward sweep just left this tile in W
         __syncwarp();
 #pragma unroll
         for (int q = 0; q < CT; ++q)
-          *reinterpret_cast<double2*>(col[q] + (8 * J + g) * ldw + 2 * t) = make_double2(c[q][J][0], c[q][J][1]);
+          *reinterpret_cast<double2*>(col[q] + (8 * J + g) * ldw + 2 * t) = make_double2(x[q][0], x[q][1]);
         __syncwarp();
-      }
-#pragma unroll
-      for (int q = 0; q < CT; ++q) {
-        const double* tile = col[q] + 8 * J * ldw;
-        const double b0 = tile[t * ldw + g], b1 = tile[(4 + t) * ldw + g];
-        double x[2] = {0.0, 0.0};
-        dmma(x, d0, b0);
-        dmma(x, d1, b1);
-        c[q][J][0] = x[0]; c[q][J][1] = x[1];
-      }
-      __syncwarp();
-#pragma unroll
-      for (int q = 0; q < CT; ++q)
-        *reinterpret_cast<double2*>(col[q] + (8 * J + g) * ldw + 2 * t) = make_double2(c[q][J][0], c[q][J][1]);
-      __syncwarp();
-#pragma unroll
-      for (int q = 0; q < CT; ++q) {
-        const double* tile = col[q] + 8 * J * ldw;
-        xb0[q] = tile[t * ldw + g]; xb1[q] = tile[(4 + t) * ldw + g];
-      }
-#pragma unroll
-      for (int I = 0; I < J; ++I) {
-        // (L_JI)^T as the A operand: element (g, k) = L[8 J + k][8 I + g]
-        const double* la = As + (8 * J) * LD + 8 * I + g;
-        const double a0 = -la[t * LD], a1 = -la[(4 + t) * LD];
 #pragma unroll
         for (int q = 0; q < CT; ++q) {
-          dmma(c[q][I], a0, xb0[q]);
-          dmma(c[q][I], a1, xb1[q]);
+          const double* tile = col[q] + 8 * J * ldw;
+          xb0[q] = tile[t * ldw + g]; xb1[q] = tile[(4 + t) * ldw + g];
         }
+        // other block rows: tile_I -= L_IJ X_J (forward, I > J) or (L_JI)^T X_J (backward, I < J)
+        const int i_lo = dir == 0 ? J + 1 : 0, i_hi = dir == 0 ? NBK : J;
+#pragma unroll 2
+        for (int I = i_lo; I < i_hi; ++I) {
+          double a0, a1;
+          if (dir == 0) {
+            const double* la = As + (8 * I + g) * LD + 8 * J;
+            a0 = -la[t]; a1 = -la[4 + t];
+          } else {
+            const double* la = As + (8 * J) * LD + 8 * I + g;  // element (g, k) = L[8 J + k][8 I + g]
+            a0 = -la[t * LD]; a1 = -la[(4 + t) * LD];
+          }
+#pragma unroll
+          for (int q = 0; q < CT; ++q) {
+            double2* cp = reinterpret_cast<double2*>(col[q] + (8 * I + g) * ldw + 2 * t);
+            const double2 v = *cp;
+            double c[2] = {v.x, v.y};
+            dmma(c, a0, xb0[q]);
+            dmma(c, a1, xb1[q]);
+            *cp = make_double2(c[0], c[1]);
+          }
+        }
+        __syncwarp();
       }
-    }
-#pragma unroll
-    for (int q = 0; q < CT; ++q) {
-      if (ct0 + q >= nct) continue;
-#pragma unroll
-      for (int I = 0; I < NBK; ++I) store(ct0 + q, I, c[q][I][0], c[q][I][1]);
     }
   }
 }
@@ -351,7 +311,7 @@ struct B2Cfg {
   static constexpr int Mp = 8 * NBK;
   static constexpr int LD = Mp + 4;
   static constexpr int NCT = 2 * NBK + 1;             // column tiles of [B_{p-1} | B_p^T | b_p 0..]
-  static constexpr int CT = NBK <= 11 ? 3 : 2;        // column tiles a warp keeps in registers at a time
+  static constexpr int CT = 3;        // column tiles a warp sweeps in lockstep (independent DMMA chains)
 };
 
 // ---- one level: eliminate the odd super blocks.  grid (n / 2, R): CTA (q, y) factors A_p (p = 2q + 1;
@@ -407,16 +367,23 @@ __global__ void __launch_bounds__(kB2Threads, 1) k_b2_fs(B2Level lv, int nct_cta
   b2_cholesky<NBK>(As, Dinv, fail);
   cp_wait<0>();
   __syncthreads();
+  b2_solve_tiles<NBK, Cfg::CT>(As, Dinv, Ws, ldw, nct);
+  __syncthreads();
+  // solution columns -> Uh | Vh | yh (16-byte stores, rows contiguous)
   double* Uq = lv.Uh + size_t(q) * MM;
   double* Vq = lv.Vh + size_t(q) * MM;
   double* yq = lv.yh + size_t(q) * Mp;
-  const int g = (threadIdx.x & 31) >> 2, t = threadIdx.x & 3;
-  b2_solve_tiles<NBK, Cfg::CT>(As, Dinv, Ws, ldw, nct, [&](int ct, int I, double c0, double c1) {
-    const int gc = 8 * (ct_first + ct) + 2 * t, r = 8 * I + g;
-    if (gc < Mp) *reinterpret_cast<double2*>(Uq + size_t(r) * Mp + gc) = make_double2(c0, c1);
-    else if (gc < 2 * Mp) { if (has_v) *reinterpret_cast<double2*>(Vq + size_t(r) * Mp + (gc - Mp)) = make_double2(c0, c1); }
-    else if (t == 0) yq[r] = c0;
-  });
+  {
+    const int ncol = 8 * nct, half = ncol >> 1;
+    for (int i = threadIdx.x; i < Mp * half; i += kB2Threads) {
+      const int r = i / half, lc = 2 * (i - r * half);
+      const int gc = 8 * ct_first + lc;
+      const double2 v = *reinterpret_cast<const double2*>(Ws + r * ldw + lc);
+      if (gc < Mp) *reinterpret_cast<double2*>(Uq + size_t(r) * Mp + gc) = v;
+      else if (gc < 2 * Mp) { if (has_v) *reinterpret_cast<double2*>(Vq + size_t(r) * Mp + (gc - Mp)) = v; }
+      else if (gc == 2 * Mp) yq[r] = v.x;
+    }
+  }
 }
 
 // ---- the last block: x_0 = A^-1 b ----
@@ -435,10 +402,9 @@ __global__ void __launch_bounds__(kB2Threads, 1) k_b2_top(B2Level lv, double* __
   cp_wait<0>();
   __syncthreads();
   b2_cholesky<NBK>(As, Dinv, fail);
-  const int g = (threadIdx.x & 31) >> 2, t = threadIdx.x & 3;
-  b2_solve_tiles<NBK, 1>(As, Dinv, Ws, ldw, 1, [&](int, int I, double c0, double) {
-    if (t == 0) x[8 * I + g] = c0;
-  });
+  b2_solve_tiles<NBK, 1>(As, Dinv, Ws, ldw, 1);
+  __syncthreads();
+  for (int i = threadIdx.x; i < Mp; i += kB2Threads) x[i] = Ws[i * ldw];
 }
 
 // ---- even super blocks of a level -> next level.  grid (n_next, 3):
