@@ -44,6 +44,16 @@ constexpr int kB2RedThreads = 512;
 constexpr int kB2RedWarps = kB2RedThreads / 32;
 constexpr int kB2MaxNbk = 14;  // Mp <= 112: two Mp x (Mp + 4) operand matrices of the reduce kernel must fit shared memory
 
+// Debug only (make EXTRA=-DPBA_B2_TIMING): clock64 deltas of thread 0 of CTA (0, 0), accumulated per phase.
+#ifdef PBA_B2_TIMING
+__device__ long long g_b2_t[32];
+#define B2_T0() long long _bt = clock64()
+#define B2_T(i) do { if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) { const long long _n = clock64(); g_b2_t[i] += _n - _bt; _bt = _n; } } while (0)
+#else
+#define B2_T0()
+#define B2_T(i)
+#endif
+
 struct B2Level {
   int n;          // super blocks at this level
   double* A;      // [n][Mp*Mp]     symmetric; consumers read the lower 8x8 tiles only
@@ -194,6 +204,7 @@ __device__ void b2_cholesky(double* As, double* Dinv, int* fail) {
       c[s][0] = v.x; c[s][1] = v.y;
     }
   }
+  B2_T0();
 #pragma unroll 1
   for (int J = 0; J < NBK; ++J) {
 #pragma unroll
@@ -205,7 +216,9 @@ __device__ void b2_cholesky(double* As, double* Dinv, int* fail) {
         *reinterpret_cast<double2*>(As + (8 * ti[s] + g) * LD + 8 * J + 2 * t) = make_double2(c[s][0], c[s][1]);
       }
     }
+    B2_T(0);
     __syncthreads();
+    B2_T(1);
     // panel: P_I = A_IJ W^T  (W = inverse of the diagonal factor)
     {
       const double w0 = Dinv[64 * J + g * 8 + t], w1 = Dinv[64 * J + g * 8 + 4 + t];
@@ -219,7 +232,9 @@ __device__ void b2_cholesky(double* As, double* Dinv, int* fail) {
         *reinterpret_cast<double2*>(tile + 2 * t) = make_double2(x[0], x[1]);
       }
     }
+    B2_T(2);
     __syncthreads();
+    B2_T(3);
     // trailing tiles in registers
 #pragma unroll
     for (int s = 0; s < TPW; ++s) {
@@ -229,6 +244,7 @@ __device__ void b2_cholesky(double* As, double* Dinv, int* fail) {
       dmma(c[s], -pa[t], pb[t]);
       dmma(c[s], -pa[4 + t], pb[4 + t]);
     }
+    B2_T(4);
   }
   __syncthreads();
 }
@@ -245,10 +261,11 @@ __device__ __forceinline__ void b2_solve_tiles(const double* As, const double* D
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
   for (int ct0 = warp * CT; ct0 < nct; ct0 += kB2Warps * CT) {
-    // a slot beyond the last tile repeats the last tile (same warp, same data, same result: harmless)
+    // a slot beyond the last tile reads the last tile (so the code stays branch-free up to the stores) but never writes
     double* col[CT];
+    bool on[CT];
 #pragma unroll
-    for (int q = 0; q < CT; ++q) col[q] = Ws + 8 * min(ct0 + q, nct - 1);
+    for (int q = 0; q < CT; ++q) { on[q] = ct0 + q < nct; col[q] = Ws + 8 * min(ct0 + q, nct - 1); }
 #pragma unroll 1
     for (int dir = 0; dir < 2; ++dir) {
       // dir 0: forward, L y = w (J ascending, rows below J updated); dir 1: backward, L^T x = y
@@ -271,7 +288,7 @@ __device__ __forceinline__ void b2_solve_tiles(const double* As, const double* D
         __syncwarp();
 #pragma unroll
         for (int q = 0; q < CT; ++q)
-          *reinterpret_cast<double2*>(col[q] + (8 * J + g) * ldw + 2 * t) = make_double2(x[q][0], x[q][1]);
+          if (on[q]) *reinterpret_cast<double2*>(col[q] + (8 * J + g) * ldw + 2 * t) = make_double2(x[q][0], x[q][1]);
         __syncwarp();
 #pragma unroll
         for (int q = 0; q < CT; ++q) {
@@ -297,7 +314,7 @@ __device__ __forceinline__ void b2_solve_tiles(const double* As, const double* D
             double c[2] = {v.x, v.y};
             dmma(c, a0, xb0[q]);
             dmma(c, a1, xb1[q]);
-            *cp = make_double2(c[0], c[1]);
+            if (on[q]) *cp = make_double2(c[0], c[1]);
           }
         }
         __syncwarp();
@@ -367,7 +384,10 @@ __global__ void __launch_bounds__(kB2Threads, 1) k_b2_fs(B2Level lv, int nct_cta
   b2_cholesky<NBK>(As, Dinv, fail);
   cp_wait<0>();
   __syncthreads();
-  b2_solve_tiles<NBK, Cfg::CT>(As, Dinv, Ws, ldw, nct);
+  // one column tile per warp while there are warps to spare (a warp's DMMAs serialise on its scheduler's FP64
+  // pipe: 264 per tile and sweep pair, 16 cycles each), three in lockstep otherwise
+  if (nct <= kB2Warps) b2_solve_tiles<NBK, 1>(As, Dinv, Ws, ldw, nct);
+  else b2_solve_tiles<NBK, Cfg::CT>(As, Dinv, Ws, ldw, nct);
   __syncthreads();
   // solution columns -> Uh | Vh | yh (16-byte stores, rows contiguous)
   double* Uq = lv.Uh + size_t(q) * MM;
@@ -396,14 +416,18 @@ __global__ void __launch_bounds__(kB2Threads, 1) k_b2_top(B2Level lv, double* __
   double* As = b2_sm;
   double* Dinv = As + Mp * LD;
   double* Ws = Dinv + NBK * 64;  // [Mp][12]: column 0 = b
+  B2_T0();
   b2_stage(As, LD, lv.A, Mp);
   cp_commit();
   for (int i = threadIdx.x; i < Mp * 8; i += kB2Threads) Ws[(i >> 3) * ldw + (i & 7)] = (i & 7) == 0 ? lv.b[i >> 3] : 0.0;
   cp_wait<0>();
   __syncthreads();
+  B2_T(8);
   b2_cholesky<NBK>(As, Dinv, fail);
+  B2_T(9);
   b2_solve_tiles<NBK, 1>(As, Dinv, Ws, ldw, 1);
   __syncthreads();
+  B2_T(10);
   for (int i = threadIdx.x; i < Mp; i += kB2Threads) x[i] = Ws[i * ldw];
 }
 
@@ -610,7 +634,7 @@ pba_status b2_launch_level(Handle* h, const B2Level& lv, const B2Level& nx, int 
   // FP64-bound on one SM (1.4 M FMAs at 64 per clock = 11 us for 88 x 88), so the SMs a sparse level leaves idle
   // take a share; R grows until the level fills the GPU once.
   const int NCT = 2 * NBK + 1, n_odd = lv.n / 2;
-  int R = std::max(R_min, std::min(8, n_sm / std::max(1, n_odd)));
+  int R = std::max(R_min, n_sm / std::max(1, n_odd));
   R = std::min(R, NCT);
   const int nct_cta = (NCT + R - 1) / R;
   R = (NCT + nct_cta - 1) / nct_cta;
@@ -618,7 +642,8 @@ pba_status b2_launch_level(Handle* h, const B2Level& lv, const B2Level& nx, int 
              h->chol_fail.p);
   // products: parts per next-level block chosen so that a level is about one wave of CTAs
   int PA = 1, PB = 1;
-  if (nx.n * 11 <= n_sm) { PA = 4; PB = 6; }
+  if (nx.n * 24 <= n_sm) { PA = 9; PB = 14; }
+  else if (nx.n * 11 <= n_sm) { PA = 4; PB = 6; }
   else if (nx.n * 6 <= n_sm) { PA = 2; PB = 3; }
   const size_t smem_r = size_t(2) * (8 * NBK) * b2_ld(8 * NBK) * sizeof(double);
   PBA_LAUNCH(h, K_BCR, k_b2_reduce<NBK>, dim3(nx.n, PA + PB + 1), dim3(kB2RedThreads), smem_r, lv, nx, PA, PB);
@@ -727,6 +752,22 @@ pba_status launch_bcr2_rcs(Handle* h) {
     if (e != cudaSuccess) return map_cuda(e);
   }
   PBA_LAUNCH(h, K_BCR, k_b2_unpad, dim3((z.dim + 255) / 256), dim3(256), 0, M, Mp, z.dim, x, h->y_cam.p);
+#ifdef PBA_B2_TIMING
+  {
+    static int calls = 0;
+    if (++calls == 6) {
+      cudaStreamSynchronize(h->stream);
+      long long t[32];
+      cudaMemcpyFromSymbol(t, g_b2_t, sizeof(t));
+      // phases 0..4 are accumulated by every k_b2_fs (CTA 0) and k_b2_top call: per Cholesky = / (calls * (levels))
+      const double nchol = double(calls) * nl;
+      fprintf(stderr, "[b2] per Cholesky (cycles): diag+stores %.0f | barrier %.0f | panel %.0f | barrier %.0f | trailing %.0f ;  "
+              "top kernel (per call): stage %.0f chol %.0f solve %.0f\n",
+              t[0] / nchol, t[1] / nchol, t[2] / nchol, t[3] / nchol, t[4] / nchol, t[8] / double(calls), t[9] / double(calls),
+              t[10] / double(calls));
+    }
+  }
+#endif
   return PBA_OK;
 }
 

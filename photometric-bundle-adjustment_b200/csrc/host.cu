@@ -131,10 +131,30 @@ NcclApi g_nccl;
 constexpr int kNcclDouble = 8, kNcclSum = 0, kNcclMax = 2;
 }  // namespace
 
+// small pinned blocks (the handle's scalar mirror) are recycled: cudaMallocHost / cudaFreeHost cost a millisecond each
+namespace {
+std::mutex g_scalar_mu;
+std::vector<double*> g_scalar_blocks;  // each kScalarBlock doubles
+constexpr size_t kScalarBlock = 64;
+double* acquire_scalar_block() {
+  {
+    std::lock_guard<std::mutex> lock(g_scalar_mu);
+    if (!g_scalar_blocks.empty()) { double* p = g_scalar_blocks.back(); g_scalar_blocks.pop_back(); return p; }
+  }
+  double* p = nullptr;
+  if (cudaHostAlloc(&p, sizeof(double) * kScalarBlock, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+void release_scalar_block(double* p) {
+  std::lock_guard<std::mutex> lock(g_scalar_mu);
+  g_scalar_blocks.push_back(p);
+}
+}  // namespace
+
 Handle::~Handle() {
   // nccl_comm is owned by the process-wide cache (pba_comm_init), not by the handle
   if (stream) cudaStreamSynchronize(stream);  // nothing may still run on memory that goes back to the cache
-  if (h_scalars) cudaFreeHost(h_scalars);
+  if (h_scalars) release_scalar_block(h_scalars);
   if (own_stream && stream) cudaStreamDestroy(stream);
 }
 
@@ -455,6 +475,14 @@ std::vector<int> rcm_order(const std::vector<std::vector<int>>& nb) {
 }
 
 void analyze_cameras(const pba_problem* p, int nthr, int max_band_blocks, CameraLayout* L) {
+  const bool timing = getenv("PBA_TIMING") != nullptr;
+  double t_mark = wall();
+  auto mark = [&](const char* what) {
+    if (!timing) return;
+    const double now = wall();
+    fprintf(stderr, "[analyze_cameras] %-24s %8.1f ms\n", what, 1e3 * (now - t_mark));
+    t_mark = now;
+  };
   const bool photo = p->mode == PBA_MODE_PHOTOMETRIC;
   const int np = p->n_poses;
   std::vector<uint8_t> used(np, 0), is_target(np, 0);
@@ -484,6 +512,7 @@ void analyze_cameras(const pba_problem* p, int nthr, int max_band_blocks, Camera
       host_targets[i].insert(host_targets[i].end(), mine[i].begin(), mine[i].end());
     }
   }
+  mark("observation scan");
   for (auto& v : host_targets) { std::sort(v.begin(), v.end()); v.erase(std::unique(v.begin(), v.end()), v.end()); }
   L->n_active_lm = n_active;
   L->slot.assign(np, -1);
@@ -512,6 +541,7 @@ void analyze_cameras(const pba_problem* p, int nthr, int max_band_blocks, Camera
     nb[a].erase(std::unique(nb[a].begin(), nb[a].end()), nb[a].end());
     for (int b : nb[a]) bw_nat = std::max(bw_nat, std::abs(a - b));
   }
+  mark("covisibility graph");
   L->bandwidth_natural = bw_nat;
   L->bandwidth = bw_nat;
   L->reordered = false;
@@ -542,6 +572,7 @@ void analyze_cameras(const pba_problem* p, int nthr, int max_band_blocks, Camera
     }
   }
   for (auto& v : L->adj) std::sort(v.begin(), v.end());
+  mark("ordering + pattern");
 }
 
 constexpr int kChunkObs = 1024;
@@ -844,10 +875,17 @@ pba_status create_impl(const pba_problem* p, const pba_options* o, int rank, int
       for (size_t i = 0; i < v.size(); ++i) { ++ptr[v[i].key + 1]; src[i] = v[i].off; }
       for (int64_t i = 0; i < nkeys; ++i) ptr[i + 1] += ptr[i];
     };
-    build(d, z.n_blocks, dir_ptr, dir_src);
-    build(s, z.n_blocks, sch_ptr, sch_src);
-    build(vd, z.n_slots, vdir_ptr, vdir_src);
-    build(vs, z.n_slots, vsch_ptr, vsch_src);
+#pragma omp parallel sections num_threads(4)
+    {
+#pragma omp section
+      build(d, z.n_blocks, dir_ptr, dir_src);
+#pragma omp section
+      build(s, z.n_blocks, sch_ptr, sch_src);
+#pragma omp section
+      build(vd, z.n_slots, vdir_ptr, vdir_src);
+#pragma omp section
+      build(vs, z.n_slots, vsch_ptr, vsch_src);
+    }
   }
   // symmetric block-row CSR for the PCG
   std::vector<int> row_ptr(z.n_slots + 1, 0), row_blk, row_col;
@@ -964,7 +1002,9 @@ pba_status create_impl(const pba_problem* p, const pba_options* o, int rank, int
   PBA_CUDA_OK(h->scalars.alloc(S_NUM)); PBA_CUDA_OK(h->chol_fail.alloc(1));
   PBA_CUDA_OK(cudaMemsetAsync(h->scalars.p, 0, sizeof(double) * S_NUM, s));
   PBA_CUDA_OK(cudaMemsetAsync(h->chol_fail.p, 0, sizeof(int), s));
-  PBA_CUDA_OK(cudaMallocHost(&h->h_scalars, sizeof(double) * (S_NUM + 2)));
+  static_assert(S_NUM + 2 <= int(kScalarBlock), "scalar mirror block too small");
+  h->h_scalars = acquire_scalar_block();
+  if (!h->h_scalars) return PBA_ERR_OUT_OF_MEMORY;
   mark("allocate work buffers");
   if (image_thread.joinable()) image_thread.join();  // quads are complete (the helper synchronised its stream)
   if (image_status != PBA_OK) return image_status;

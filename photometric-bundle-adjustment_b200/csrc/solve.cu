@@ -13,6 +13,10 @@
 #include <cooperative_groups.h>
 #include <stdio.h>
 
+#include <mutex>
+#include <utility>
+#include <vector>
+
 #include "launch.h"
 #include "pba_internal.h"
 
@@ -467,11 +471,17 @@ pba_status launch_pcg_rcs(Handle* h) {
 }
 
 int pcg_max_grid(int device) {
+  // the occupancy query costs a good fraction of a millisecond; the answer is a property of the device
+  static std::mutex mu;
+  static std::vector<std::pair<int, int>> cache;
+  std::lock_guard<std::mutex> lock(mu);
+  for (auto& kv : cache) if (kv.first == device) return kv.second;
   int sms = 0, per_sm = 0;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg, 256, 0);
   if (per_sm < 1) per_sm = 1;
   if (per_sm > 2) per_sm = 2;
+  cache.emplace_back(device, sms * per_sm);
   return sms * per_sm;
 }
 
