@@ -422,6 +422,12 @@ def main():
         if single_process and rank == 0:
             pb.multi_gpu_init(0, world)  # NCCL communicators: process set-up, cached (like torch.distributed's)
             o2.device, o2.num_gpus = 0, world
+        # steady state, as in the SfM loop's repeated optimize() calls (src/sfm.cpp:1153-1155): one untimed
+        # one-iteration solve first, so the device arena / pinned staging pools hold this problem's sizes
+        if world == 1 or (single_process and rank == 0):
+            o_w = pb.BundleAdjustmentOptions(verbosity_level=0, huber_parameter=hub, device=o2.device, solver=a.solver,
+                                             max_num_iterations=1, num_gpus=o2.num_gpus)
+            pb.bundle_adjustment(prob.copy(), o_w)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -462,6 +468,8 @@ def main():
                "bytes_are_per": "solve: one call = set-up + %d LM iterations; the copies happen once per call, "
                                 "not once per iteration" % lm_its,
                "excludes": None if world == 1 else "NCCL communicator creation (cached per process: pba_multi_gpu_init / pba_comm_init)",
+               "state": "steady: one untimed one-iteration solve precedes the timed call (device arena and pinned staging "
+                        "pools warm, as in the SfM loop's repeated optimize() calls)",
                "lm_iterations": lm_its, "wall_s": float(t_e2e.item()), "setup_s": s2.setup_time_in_seconds,
                "minimizer_s": s2.minimizer_time_in_seconds, "solve_total_s": s2.total_time_in_seconds,
                "final_cost": s2.final_cost, "initial_cost": s2.initial_cost,

@@ -107,6 +107,8 @@ struct NcclApi {
   int (*GetUniqueId)(NcclId*) = nullptr;
   int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
   int (*CommInitAll)(void**, int, const int*) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
   int (*CommDestroy)(void*) = nullptr;
   bool load() {
@@ -124,7 +126,9 @@ struct NcclApi {
     AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(lib, "ncclAllReduce");
     CommDestroy = (int (*)(void*))dlsym(lib, "ncclCommDestroy");
     CommInitAll = (int (*)(void**, int, const int*))dlsym(lib, "ncclCommInitAll");
-    return GetUniqueId && CommInitRank && AllReduce && CommDestroy && CommInitAll;
+    GroupStart = (int (*)())dlsym(lib, "ncclGroupStart");
+    GroupEnd = (int (*)())dlsym(lib, "ncclGroupEnd");
+    return GetUniqueId && CommInitRank && AllReduce && CommDestroy && CommInitAll && GroupStart && GroupEnd;
   }
 };
 NcclApi g_nccl;
@@ -1726,6 +1730,35 @@ pba_status multi_comms(int device0, int n, std::vector<void*>* out) {
   for (int i = 0; i < n; ++i) devs[i] = device0 + i;
   std::vector<void*> comms(n, nullptr);
   if (g_nccl.CommInitAll(comms.data(), n, devs.data()) != 0) return PBA_ERR_NCCL;
+  // NCCL sets its channels / peer connections up lazily, on the first collective: run one here (a grouped
+  // all-reduce of a few doubles on every device) so that it is part of the communicator set-up, not of a solve
+  {
+    int cur = 0;
+    cudaGetDevice(&cur);
+    std::vector<double*> buf(n, nullptr);
+    std::vector<cudaStream_t> st(n, nullptr);
+    bool ok = true;
+    for (int i = 0; i < n && ok; ++i) {
+      ok = cudaSetDevice(devs[i]) == cudaSuccess && cudaMalloc(&buf[i], 64 * sizeof(double)) == cudaSuccess &&
+           cudaMemset(buf[i], 0, 64 * sizeof(double)) == cudaSuccess &&
+           cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking) == cudaSuccess;
+    }
+    if (ok) {
+      g_nccl.GroupStart();
+      for (int i = 0; i < n; ++i) {
+        cudaSetDevice(devs[i]);
+        ok = ok && g_nccl.AllReduce(buf[i], buf[i], 64, kNcclDouble, kNcclSum, comms[i], st[i]) == 0;
+      }
+      ok = g_nccl.GroupEnd() == 0 && ok;
+    }
+    for (int i = 0; i < n; ++i) {
+      cudaSetDevice(devs[i]);
+      if (st[i]) { cudaStreamSynchronize(st[i]); cudaStreamDestroy(st[i]); }
+      if (buf[i]) cudaFree(buf[i]);
+    }
+    cudaSetDevice(cur);
+    if (!ok) return PBA_ERR_NCCL;
+  }
   g_multi.push_back(MultiComms{device0, n, comms});
   *out = comms;
   return PBA_OK;
