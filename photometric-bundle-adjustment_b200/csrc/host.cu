@@ -1022,7 +1022,11 @@ pba_status create_impl(const pba_problem* p, const pba_options* o, int rank, int
   return PBA_OK;
 }
 
+// PBA_TIMING: host seconds spent waiting for the device in read_scalars (per handle, reset by minimize_impl);
+// the rest of the minimizer's wall time is enqueue work on the host
 pba_status read_scalars(Handle* h) {
+  const double t_wait0 = wall();
+  struct Acc { Handle* h; double t0; ~Acc() { h->t_wait += wall() - t0; } } acc{h, t_wait0};
   PBA_CUDA_OK(cudaMemcpyAsync(h->h_scalars, h->scalars.p, sizeof(double) * S_NUM, cudaMemcpyDeviceToHost, h->stream));
   int* fail = reinterpret_cast<int*>(h->h_scalars + S_NUM);
   PBA_CUDA_OK(cudaMemcpyAsync(fail, h->chol_fail.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
@@ -1118,6 +1122,7 @@ pba_status minimize_impl(Handle* h, pba_summary* sum) {
   const int* chol_fail = reinterpret_cast<const int*>(hs + S_NUM);
 
   h->scale_ready = false;  // Jacobi scaling is computed at iteration 0 of every solve
+  h->t_wait = 0.0;
   pba_iteration it;
   memset(&it, 0, sizeof(it));
   if ((st = eval_jacobian_and_build(h, radius)) != PBA_OK) return st;
@@ -1287,6 +1292,10 @@ pba_status minimize_impl(Handle* h, pba_summary* sum) {
     sum->linear_solver_time_in_seconds = 1e-3 * lin;
     sum->minimizer_time_in_seconds = wall() - t_start;
     sum->total_time_in_seconds = sum->minimizer_time_in_seconds;
+    if (getenv("PBA_TIMING"))
+      fprintf(stderr, "[pba_minimize] rank %d/%d: %d iterations, wall %.1f ms, waiting for the device %.1f ms, host enqueue %.1f ms\n",
+              h->rank, h->world, n_it, 1e3 * sum->minimizer_time_in_seconds, 1e3 * h->t_wait,
+              1e3 * (sum->minimizer_time_in_seconds - h->t_wait));
     if (n_inexact > 0)
       snprintf(sum->message, sizeof(sum->message), "%.180s [%d PCG solve(s) stopped above pcg_tolerance]", message, n_inexact);
     else

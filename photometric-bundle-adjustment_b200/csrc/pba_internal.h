@@ -287,6 +287,7 @@ struct Handle {
   DevBuf<double> scalars;      // small device scalar bank
   double* h_scalars = nullptr; // pinned mirror
 
+  double t_wait = 0.0;         // host seconds spent waiting for the device (diagnostics, PBA_TIMING)
   bool have_jac = false;
   bool have_rcs = false;
   bool scale_ready = false;
