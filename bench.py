@@ -432,6 +432,11 @@ def main():
             pb.bundle_adjustment(prob.copy(), pb.BundleAdjustmentOptions(
                 verbosity_level=0, huber_parameter=hub, device=local_rank, solver=a.solver, max_num_iterations=1))
         else:
+            p_keep = p2
+            p2 = prob.copy()
+            run_per_rank(pb.BundleAdjustmentOptions(verbosity_level=0, huber_parameter=hub, device=local_rank,
+                                                    solver=a.solver, max_num_iterations=1))
+            p2 = p_keep
             dist.barrier()
         torch.cuda.synchronize()
         t0 = time.time()

@@ -96,8 +96,10 @@ __device__ __forceinline__ void b2_stage(double* dst, int ld, const double* __re
 __global__ void k_b2_build(int cd, int m, int M, int Mp, int64_t n_blocks, int dim, const int* __restrict__ blk_row,
                            const int* __restrict__ blk_col, const double* __restrict__ S, const double* __restrict__ rhs,
                            int n_super, double* __restrict__ A, double* __restrict__ B, double* __restrict__ b) {
-  const int64_t blk = blockIdx.x;
-  const int e = threadIdx.x;
+  // four RCS blocks (or right-hand-side segments) per 256-thread CTA: one 64-thread CTA each was 24 k CTAs
+  // = 15 us of pure launch overhead at 2,000 keyframes
+  const int64_t blk = int64_t(blockIdx.x) * 4 + (threadIdx.x >> 6);
+  const int e = threadIdx.x & 63;
   const size_t MM = size_t(Mp) * Mp;
   if (blk < n_blocks) {
     if (e >= cd * cd) return;
@@ -117,7 +119,7 @@ __global__ void k_b2_build(int cd, int m, int M, int Mp, int64_t n_blocks, int d
     // last super block beyond the system's dimension)
     const int s = int(blk - n_blocks);
     if (s >= n_super) return;
-    for (int i = e; i < Mp; i += blockDim.x) {
+    for (int i = e; i < Mp; i += 64) {
       const int gi = s * M + i;
       const bool real = i < M && gi < dim;
       b[size_t(s) * Mp + i] = real ? rhs[gi] : 0.0;
@@ -703,7 +705,7 @@ pba_status launch_bcr2_rcs(Handle* h) {
   const double* rhs = Sblk + z.n_blocks * z.cd * z.cd;
   double* x = ws + h->b2_x_off;
   PBA_CUDA_OK(cudaMemsetAsync(h->chol_fail.p, 0, sizeof(int), h->stream));
-  PBA_LAUNCH(h, K_BCR, k_b2_build, dim3((unsigned)(z.n_blocks + S)), dim3(64), 0, z.cd, m, M, Mp, z.n_blocks, z.dim,
+  PBA_LAUNCH(h, K_BCR, k_b2_build, dim3((unsigned)((z.n_blocks + S + 3) / 4)), dim3(256), 0, z.cd, m, M, Mp, z.n_blocks, z.dim,
              h->d_blk_row.p, h->d_blk_col.p, Sblk, rhs, S, pk.lv[0].A, pk.lv[0].B, pk.lv[0].b);
   // fewest CTAs per odd block of the factor + solve kernel whose share of the right-hand sides fits shared memory
   const int NCT = 2 * nbk + 1;

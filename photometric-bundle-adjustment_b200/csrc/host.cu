@@ -581,8 +581,11 @@ void analyze_cameras(const pba_problem* p, int nthr, int max_band_blocks, Camera
 
 constexpr int kChunkObs = 1024;
 
-pba_status create_impl(const pba_problem* p, const pba_options* o, int rank, int world, Handle** out) {
-  pba_status st = validate(p, o);
+// `shared` (single-process multi-GPU): the global camera layout, computed once by the caller with all host
+// cores instead of once per rank thread; the problem has been validated by the caller as well.
+pba_status create_impl(const pba_problem* p, const pba_options* o, int rank, int world, Handle** out,
+                       const CameraLayout* shared = nullptr) {
+  pba_status st = shared ? PBA_OK : validate(p, o);
   if (st != PBA_OK) return st;
   if (world < 1 || rank < 0 || rank >= world) return PBA_ERR_INVALID_ARGUMENT;
   int ndev = 0;
@@ -683,7 +686,8 @@ pba_status create_impl(const pba_problem* p, const pba_options* o, int rank, int
   // ---- global layout (identical on every rank): which parameter blocks survive Ceres' reduced program,
   //      the order of the free cameras, the RCS block pattern ----
   CameraLayout layout;
-  analyze_cameras(p, nthr, 128 / cd, &layout);
+  if (shared) layout = *shared;
+  else analyze_cameras(p, nthr, 128 / cd, &layout);
   h->n_active_lm += layout.n_active_lm;
   h->n_obs_global = p->n_obs;
   h->slot = layout.slot;
@@ -1795,6 +1799,10 @@ pba_status solve_multi_gpu(pba_problem* problem, const pba_options* options, int
   std::vector<void*> comms;
   pba_status st = multi_comms(options->device, n_gpus, &comms);
   if (st != PBA_OK) return st;
+  // the global part of the set-up (camera layout, RCS pattern) once, with every core; the rank threads then
+  // order their own shards with their share of the cores
+  CameraLayout layout;
+  analyze_cameras(problem, std::max(1, omp_get_num_procs()), 128 / (problem->mode == PBA_MODE_PHOTOMETRIC ? 8 : 6), &layout);
   StatusBarrier barrier(n_gpus);
   std::vector<pba_status> status(n_gpus, PBA_OK);
   std::vector<double> t_setup(n_gpus, 0.0);
@@ -1805,7 +1813,7 @@ pba_status solve_multi_gpu(pba_problem* problem, const pba_options* options, int
     o.device = options->device + r;
     o.num_gpus = 1;
     Handle* h = nullptr;
-    pba_status s = create_impl(problem, &o, r, n_gpus, &h);
+    pba_status s = create_impl(problem, &o, r, n_gpus, &h, &layout);
     std::unique_ptr<Handle> guard(h);
     t_setup[r] = wall() - t0;
     if (barrier.wait(s) != PBA_OK) { status[r] = s; return; }
