@@ -55,7 +55,10 @@ enum { PBA_CAM_PINHOLE = 0, PBA_CAM_DS = 1, PBA_CAM_KB4 = 2, PBA_CAM_EUCM = 3 };
  * solvers for block-banded systems (windowed covisibility): BAND = sequential block-banded
  * Cholesky on one SM, BCR = parallel block cyclic reduction on dense super blocks.
  * AUTO = BCR when applicable (BAND for chains of <= 64 free keyframes), else BAND, else CHOLESKY while
- * dim <= cholesky_max_dim, else PCG. */
+ * dim <= cholesky_max_dim, else PCG.  The free cameras are renumbered by reverse Cuthill-McKee when their own
+ * order is not banded (loop closures, unordered maps: pba_analyze_structure), so the banded solvers cover
+ * maps whose keyframes arrive in any order; PCG is the last resort, and a PCG solve that stops above
+ * pcg_tolerance counts as an invalid step (pba_summary.num_inexact_linear_solves). */
 enum { PBA_SOLVER_AUTO = 0, PBA_SOLVER_CHOLESKY = 1, PBA_SOLVER_PCG = 2, PBA_SOLVER_BAND = 3, PBA_SOLVER_BCR = 4 };
 
 /* Ceres termination types (include/ceres/types.h) kept so reports line up. */
@@ -112,7 +115,7 @@ typedef struct pba_options {
   int32_t max_num_iterations;
 
   int32_t solver;              /* PBA_SOLVER_* (see above) */
-  int32_t cholesky_max_dim;    /* default 4096 */
+  int32_t cholesky_max_dim;    /* default 16384 (2.1 GB of dense workspace, allocated on first use) */
   int32_t pcg_max_iterations;  /* default 500 */
   double pcg_tolerance;        /* relative residual ||r||/||b||, default 1e-10 */
   double initial_trust_region_radius; /* 1e4 */
@@ -379,6 +382,18 @@ pba_status pba_compute_projections(const pba_problem* p, const pba_projection_th
                                    int32_t device, double* point_reprojected, double* point_3d_c,
                                    double* reprojection_error, uint32_t* outlier_flags,
                                    uint8_t* landmark_remove, int32_t* any_severe_outliers);
+
+/* add_new_landmarks_between_cams() (include/visnav/map_utils.h:121-195), the step right BEFORE bundle_adjustment()
+ * in the SfM loop: for n feature tracks shared by cameras 0 and 1 (corner pixels uv0 / uv1 [n*2], HOST memory),
+ * v = normalize(unproject(z)) in each camera, p = opengv::triangulation::triangulate in camera 0's frame with
+ * T_c0_c1 = T_w_c0^-1 T_w_c1 (thirdparty/opengv/src/triangulation/methods.cpp:36-64: null vector of the 4x4 DLT
+ * matrix), and the new landmark's inverse distance 1 / |p| (map_utils.h:190, kept as the reference computes it,
+ * including its own "TODO check correctness": the distance is measured in camera 0 even when the landmark's host,
+ * obs.begin(), is another camera).  Outputs (HOST): p_c0 [n*3] (may be NULL), inv_depth [n]. */
+pba_status pba_triangulate_inverse_depth(int32_t model0, const double intr0[8], int32_t model1, const double intr1[8],
+                                         const double T_w_c0[7], const double T_w_c1[7], int64_t n,
+                                         const double* uv0, const double* uv1, int32_t device, double* p_c0,
+                                         double* inv_depth);
 
 #ifdef __cplusplus
 }

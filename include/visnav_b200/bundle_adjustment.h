@@ -240,4 +240,58 @@ pba_status compute_projections(const CornersT& feature_corners, CalibrationT& ca
   return PBA_OK;
 }
 
+// Drop-in for the reference's
+//
+//   int add_new_landmarks_between_cams(const FrameCamId& fcid0, const FrameCamId& fcid1,
+//                                      const Calibration&, const Corners&, const FeatureTracks&,
+//                                      const Cameras&, Landmarks&)
+//   (include/visnav/map_utils.h:121-195; called by initialize_scene_from_stereo_pair and by the
+//   "add landmarks" stage of the SfM loop, right before optimize())
+//
+// Same semantics: every feature track seen in BOTH images that is not a landmark yet is triangulated in
+// camera 0's frame from the two unit bearings (opengv's linear method) and becomes a landmark with inverse
+// distance 1 / |p| and the observations of all cameras already in the map.  The bearings + triangulation of
+// all new tracks run in one GPU pass (pba_triangulate_inverse_depth).  Returns the number of new landmarks,
+// or -1 if the GPU call failed.
+template <class FrameCamIdT, class CalibrationT, class CornersT, class FeatureTracksT, class CamerasT, class LandmarksT>
+int add_new_landmarks_between_cams(const FrameCamIdT& fcid0, const FrameCamIdT& fcid1, const CalibrationT& calib_cam,
+                                   const CornersT& feature_corners, const FeatureTracksT& feature_tracks,
+                                   const CamerasT& cameras, LandmarksT& landmarks, int device = 0) {
+  using TrackIdT = typename FeatureTracksT::key_type;
+  std::vector<TrackIdT> new_track_ids;
+  std::vector<double> uv0, uv1;
+  const auto& corners0 = feature_corners.at(fcid0).corners;
+  const auto& corners1 = feature_corners.at(fcid1).corners;
+  for (const auto& kv : feature_tracks) {  // GetTracksInImages (tracks.h:175-197) + "not a landmark yet"
+    const auto it0 = kv.second.find(fcid0), it1 = kv.second.find(fcid1);
+    if (it0 == kv.second.end() || it1 == kv.second.end() || landmarks.count(kv.first) > 0) continue;
+    const auto& z0 = corners0[it0->second];
+    const auto& z1 = corners1[it1->second];
+    uv0.push_back(z0[0]); uv0.push_back(z0[1]);
+    uv1.push_back(z1[0]); uv1.push_back(z1[1]);
+    new_track_ids.push_back(kv.first);
+  }
+  if (new_track_ids.empty()) return 0;
+  const auto& cam0 = calib_cam.intrinsics[fcid0.cam_id];
+  const auto& cam1 = calib_cam.intrinsics[fcid1.cam_id];
+  const int64_t n = int64_t(new_track_ids.size());
+  std::vector<double> rho(size_t(n), 0.0);
+  const pba_status st = pba_triangulate_inverse_depth(
+      camera_model_id(cam0->name()), cam0->data(), camera_model_id(cam1->name()), cam1->data(),
+      cameras.at(fcid0).T_w_c.data(), cameras.at(fcid1).T_w_c.data(), n, uv0.data(), uv1.data(), device, nullptr,
+      rho.data());
+  if (st != PBA_OK) {
+    std::fprintf(stderr, "visnav_b200::add_new_landmarks_between_cams: %s\n", pba_status_string(st));
+    return -1;
+  }
+  for (int64_t i = 0; i < n; ++i) {
+    typename LandmarksT::mapped_type lm;
+    lm.inv_depth = rho[size_t(i)];
+    for (const auto& track_kv : feature_tracks.at(new_track_ids[size_t(i)]))
+      if (cameras.count(track_kv.first) > 0) lm.obs[track_kv.first] = track_kv.second;
+    landmarks[new_track_ids[size_t(i)]] = lm;
+  }
+  return int(n);
+}
+
 }  // namespace visnav_b200

@@ -1113,3 +1113,77 @@ ORACLE_API int pba_oracle_compute_projections(const pba_problem* p, const pba_pr
   }
   return 0;
 }
+
+// ---- add_new_landmarks_between_cams (include/visnav/map_utils.h:121-195) ----
+// Bearings (map_utils.h:150-160), relative pose T_c0_c1 = T_w_c0^-1 T_w_c1 (:166-170), the linear triangulation
+// of opengv (thirdparty/opengv/src/triangulation/methods.cpp:36-64) and inv_depth = 1 / |p| (map_utils.h:190).
+// opengv takes the right singular vector of the smallest singular value of the 4x4 DLT matrix A (Eigen
+// JacobiSVD); here it is the eigenvector of the smallest eigenvalue of A^T A by cyclic Jacobi rotations — a
+// different route to the same vector than the CUDA kernel's one-sided iteration on A's columns.
+static void smallest_right_singular_vector(const double A[4][4], double v[4]) {
+  double S[4][4], V[4][4];
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) {
+      double s = 0.0;
+      for (int k = 0; k < 4; ++k) s += A[k][i] * A[k][j];
+      S[i][j] = s;
+      V[i][j] = i == j ? 1.0 : 0.0;
+    }
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    double off = 0.0, diag = 0.0;
+    for (int i = 0; i < 4; ++i) { diag += fabs(S[i][i]); for (int j = i + 1; j < 4; ++j) off += fabs(S[i][j]); }
+    if (off <= 1e-32 * diag) break;
+    for (int p = 0; p < 3; ++p)
+      for (int q = p + 1; q < 4; ++q) {
+        if (S[p][q] == 0.0) continue;
+        const double theta = (S[q][q] - S[p][p]) / (2.0 * S[p][q]);
+        const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+        for (int k = 0; k < 4; ++k) { const double a = S[k][p], b = S[k][q]; S[k][p] = c * a - sn * b; S[k][q] = sn * a + c * b; }
+        for (int k = 0; k < 4; ++k) { const double a = S[p][k], b = S[q][k]; S[p][k] = c * a - sn * b; S[q][k] = sn * a + c * b; }
+        for (int k = 0; k < 4; ++k) { const double a = V[k][p], b = V[k][q]; V[k][p] = c * a - sn * b; V[k][q] = sn * a + c * b; }
+      }
+  }
+  int best = 0;
+  for (int i = 1; i < 4; ++i) if (S[i][i] < S[best][best]) best = i;
+  for (int k = 0; k < 4; ++k) v[k] = V[k][best];
+}
+
+ORACLE_API int pba_oracle_triangulate(int model0, const double* intr0, int model1, const double* intr1, const double* T_w_c0,
+                                      const double* T_w_c1, int64_t n, const double* uv0, const double* uv1, double* p_c0,
+                                      double* inv_depth) {
+  const SE3<double> T0 = map_se3(T_w_c0), T1 = map_se3(T_w_c1);
+  const SE3<double> T01 = mul(inverse(T0), T1);
+  // rotation matrix of T01 and P2 = [R^T | -R^T t]
+  double R[3][3];
+  for (int c = 0; c < 3; ++c) {
+    V3<double> e{c == 0 ? 1.0 : 0.0, c == 1 ? 1.0 : 0.0, c == 2 ? 1.0 : 0.0};
+    const V3<double> r = rotate(T01.q, e);
+    R[0][c] = r.x; R[1][c] = r.y; R[2][c] = r.z;
+  }
+  double P2[3][4];
+  const double t[3] = {T01.t.x, T01.t.y, T01.t.z};
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) P2[i][j] = R[j][i];
+    P2[i][3] = -(R[0][i] * t[0] + R[1][i] * t[1] + R[2][i] * t[2]);
+  }
+  for (int64_t i = 0; i < n; ++i) {
+    const V3<double> f1 = unit(unproject<double>(model0, intr0, uv0[2 * i], uv0[2 * i + 1]));
+    const V3<double> f2 = unit(unproject<double>(model1, intr1, uv1[2 * i], uv1[2 * i + 1]));
+    double A[4][4];
+    for (int c = 0; c < 4; ++c) {
+      const double p10 = c == 0, p11 = c == 1, p12 = c == 2;
+      A[0][c] = f1.x * p12 - f1.z * p10;
+      A[1][c] = f1.y * p12 - f1.z * p11;
+      A[2][c] = f2.x * P2[2][c] - f2.z * P2[0][c];
+      A[3][c] = f2.y * P2[2][c] - f2.z * P2[1][c];
+    }
+    double v[4];
+    smallest_right_singular_vector(A, v);
+    const double x = v[0] / v[3], y = v[1] / v[3], z = v[2] / v[3];
+    if (p_c0) { p_c0[3 * i] = x; p_c0[3 * i + 1] = y; p_c0[3 * i + 2] = z; }
+    inv_depth[i] = 1.0 / sqrt(x * x + y * y + z * z);
+  }
+  return 0;
+}
+

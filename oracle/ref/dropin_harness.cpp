@@ -180,3 +180,55 @@ extern "C" __attribute__((visibility("default"))) int pba_dropin_compute_project
   }
   return 0;
 }
+
+// add_new_landmarks_between_cams() drop-in proof: the reference's containers (two cameras,
+// n shared feature tracks, every third track already a landmark) through either the reference's own function
+// (use_b200 = 0; opengv triangulation compiled from the vendored sources) or visnav_b200's (CUDA).  Outputs per
+// track: inv_depth (or -1 where no landmark was added / the old one kept) and the number of observations stored.
+extern "C" __attribute__((visibility("default"))) int pba_dropin_add_new_landmarks(
+    int model0, const double* intr0, int model1, const double* intr1, const double* T_w_c0, const double* T_w_c1,
+    int64_t n, const double* uv0, const double* uv1, int use_b200, double* inv_depth, int32_t* n_obs, int32_t* added) {
+  using namespace visnav;
+  static const char* const names[] = {"pinhole", "ds", "kb4", "eucm"};
+  Calibration calib;
+  calib.intrinsics.push_back(AbstractCamera<double>::from_data(names[model0], intr0));
+  calib.intrinsics.push_back(AbstractCamera<double>::from_data(names[model1], intr1));
+  calib.T_i_c.push_back(Sophus::SE3d());
+  calib.T_i_c.push_back(Sophus::SE3d());
+  const FrameCamId fcid0(0, 0), fcid1(0, 1), other(7, 0);  // `other` is in the tracks but not in the map
+  Cameras cameras;
+  Camera c0, c1;
+  std::memcpy(c0.T_w_c.data(), T_w_c0, 7 * sizeof(double));
+  std::memcpy(c1.T_w_c.data(), T_w_c1, 7 * sizeof(double));
+  cameras[fcid0] = c0;
+  cameras[fcid1] = c1;
+  Corners corners;
+  FeatureTracks tracks;
+  Landmarks landmarks;
+  for (int64_t i = 0; i < n; ++i) {
+    corners[fcid0].corners.emplace_back(uv0[2 * i], uv0[2 * i + 1]);
+    corners[fcid1].corners.emplace_back(uv1[2 * i], uv1[2 * i + 1]);
+    FeatureTrack t;
+    t[fcid0] = FeatureId(i);
+    if (i % 5 != 4) t[fcid1] = FeatureId(i);  // every fifth track is not shared
+    t[other] = FeatureId(0);
+    tracks[TrackId(i)] = t;
+    if (i % 3 == 0) {  // already in the map: must be left alone
+      Landmark lm;
+      lm.inv_depth = -1.0;
+      lm.obs[fcid0] = FeatureId(i);
+      landmarks[TrackId(i)] = lm;
+    }
+  }
+  const int cnt = use_b200 ? visnav_b200::add_new_landmarks_between_cams(fcid0, fcid1, calib, corners, tracks, cameras, landmarks)
+                           : add_new_landmarks_between_cams(fcid0, fcid1, calib, corners, tracks, cameras, landmarks);
+  if (cnt < 0) return 30;
+  *added = cnt;
+  for (int64_t i = 0; i < n; ++i) {
+    const auto it = landmarks.find(TrackId(i));
+    inv_depth[i] = it == landmarks.end() ? -2.0 : it->second.inv_depth;
+    n_obs[i] = it == landmarks.end() ? 0 : int32_t(it->second.obs.size());
+  }
+  return 0;
+}
+

@@ -645,3 +645,56 @@ REF_API int pba_ref_map_roundtrip(const char* in_path, const char* out_path, int
 }
 
 }  // extern "C"
+
+// add_new_landmarks_between_cams (include/visnav/map_utils.h:121-195) through the reference's OWN function:
+// two cameras, n feature tracks shared by them, no landmarks yet -> the reference triangulates every track
+// (opengv::triangulation::triangulate, compiled from thirdparty/opengv/src by oracle/ref/Makefile) and sets
+// inv_depth = 1 / |p|.  p_c0 (optional) comes from opengv's triangulate called the same way.
+extern "C" REF_API int pba_ref_add_new_landmarks(int model0, const double* intr0, int model1, const double* intr1,
+                                      const double* T_w_c0, const double* T_w_c1, int64_t n, const double* uv0,
+                                      const double* uv1, double* p_c0, double* inv_depth) {
+  using namespace visnav;
+  Calibration calib;
+  calib.intrinsics.push_back(AbstractCamera<double>::from_data(model_name(model0), intr0));
+  calib.intrinsics.push_back(AbstractCamera<double>::from_data(model_name(model1), intr1));
+  calib.T_i_c.push_back(Sophus::SE3d());
+  calib.T_i_c.push_back(Sophus::SE3d());
+  const FrameCamId fcid0(0, 0), fcid1(1, 1);
+  Cameras cameras;
+  Camera c0, c1;
+  std::memcpy(c0.T_w_c.data(), T_w_c0, 7 * sizeof(double));
+  std::memcpy(c1.T_w_c.data(), T_w_c1, 7 * sizeof(double));
+  cameras[fcid0] = c0;
+  cameras[fcid1] = c1;
+  Corners corners;
+  FeatureTracks tracks;
+  for (int64_t i = 0; i < n; ++i) {
+    corners[fcid0].corners.emplace_back(uv0[2 * i], uv0[2 * i + 1]);
+    corners[fcid1].corners.emplace_back(uv1[2 * i], uv1[2 * i + 1]);
+    FeatureTrack t;
+    t[fcid0] = FeatureId(i);
+    t[fcid1] = FeatureId(i);
+    tracks[TrackId(i)] = t;
+  }
+  Landmarks landmarks;
+  const int added = add_new_landmarks_between_cams(fcid0, fcid1, calib, corners, tracks, cameras, landmarks);
+  if (added != int(n)) return 2;
+  for (int64_t i = 0; i < n; ++i) inv_depth[i] = landmarks.at(TrackId(i)).inv_depth;
+  if (p_c0) {
+    opengv::bearingVectors_t b0, b1;
+    for (int64_t i = 0; i < n; ++i) {
+      Eigen::Vector3d v0 = calib.intrinsics[0]->unproject(corners[fcid0].corners[i]);
+      Eigen::Vector3d v1 = calib.intrinsics[1]->unproject(corners[fcid1].corners[i]);
+      b0.push_back(v0.normalized());
+      b1.push_back(v1.normalized());
+    }
+    const Sophus::SE3d T01 = c0.T_w_c.inverse() * c1.T_w_c;
+    opengv::relative_pose::CentralRelativeAdapter adapter(b0, b1, T01.translation(), T01.rotationMatrix());
+    for (int64_t i = 0; i < n; ++i) {
+      const Eigen::Vector3d p = opengv::triangulation::triangulate(adapter, i);
+      p_c0[3 * i] = p[0]; p_c0[3 * i + 1] = p[1]; p_c0[3 * i + 2] = p[2];
+    }
+  }
+  return 0;
+}
+

@@ -13,12 +13,13 @@ from .calibration import Calibration, initialize_from_double_sphere, load_calibr
 from .engine import BundleAdjustmentOptions, Engine, Summary, analyze_structure, bundle_adjustment, device_count, multi_gpu_init
 from .map_io import Map, load_map_file, save_map_file
 from .problem import Problem, partition_landmarks
-from .projections import ProjectionThresholds, Projections, compute_projections, landmark_positions
+from .projections import (ProjectionThresholds, Projections, compute_projections, landmark_positions,
+                          triangulate_inverse_depth)
 from .synth import make_scene
 
 __all__ = [
     "Calibration", "load_calibration", "save_calibration", "initialize_from_double_sphere",
-    "BundleAdjustmentOptions", "Engine", "Summary", "bundle_adjustment", "device_count", "multi_gpu_init", "analyze_structure", "Problem",
+    "BundleAdjustmentOptions", "Engine", "Summary", "bundle_adjustment", "device_count", "multi_gpu_init", "analyze_structure", "triangulate_inverse_depth", "Problem",
     "partition_landmarks", "make_scene", "MODE_GEOMETRIC", "MODE_PHOTOMETRIC", "CAM_PINHOLE", "CAM_DS",
     "CAM_KB4", "CAM_EUCM", "SOLVER_AUTO", "SOLVER_CHOLESKY", "SOLVER_PCG", "SOLVER_BAND", "SOLVER_BCR", "CONVERGENCE", "NO_CONVERGENCE",
     "FAILURE", "ExtensionMissing", "ProjectionThresholds", "Projections", "compute_projections",

@@ -122,7 +122,7 @@ PBA_SYMBOLS = [
     "pba_lm_iterate",
     "pba_set_state", "pba_get_state", "pba_get_sizes", "pba_reset_kernel_stats", "pba_set_profile", "pba_get_kernel_stats",
     "pba_nccl_unique_id", "pba_comm_init", "pba_camera_project", "pba_camera_unproject", "pba_se3_plus",
-    "pba_cholesky_solve", "pba_projection_thresholds_init", "pba_landmark_positions", "pba_compute_projections",
+    "pba_cholesky_solve", "pba_projection_thresholds_init", "pba_landmark_positions", "pba_compute_projections", "pba_triangulate_inverse_depth",
 ]
 
 _lib = None
@@ -185,6 +185,8 @@ def load_lib():
         "pba_se3_plus": [C.c_int64, c_double_p, c_double_p, c_double_p],
         "pba_cholesky_solve": [C.c_int32, c_double_p, c_double_p, c_double_p],
         "pba_landmark_positions": [C.POINTER(pba_problem), C.c_int32, c_double_p],
+        "pba_triangulate_inverse_depth": [C.c_int32, c_double_p, C.c_int32, c_double_p, c_double_p, c_double_p, C.c_int64,
+                                          c_double_p, c_double_p, C.c_int32, c_double_p, c_double_p],
         "pba_compute_projections": [C.POINTER(pba_problem), C.POINTER(pba_projection_thresholds), C.c_int32,
                                     c_double_p, c_double_p, c_double_p, c_u32_p, c_u8_p, c_i32_p],
     }

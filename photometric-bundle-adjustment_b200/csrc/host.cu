@@ -1377,7 +1377,7 @@ PBA_API void pba_options_init(pba_options* o) {
   if (!o) return;
   memset(o, 0, sizeof(*o));
   o->verbosity_level = 1; o->optimize_intrinsics = 0; o->use_huber = 1; o->huber_parameter = 1.0; o->max_num_iterations = 20;
-  o->solver = PBA_SOLVER_AUTO; o->cholesky_max_dim = 4096; o->pcg_max_iterations = 500; o->pcg_tolerance = 1e-10;
+  o->solver = PBA_SOLVER_AUTO; o->cholesky_max_dim = 16384; o->pcg_max_iterations = 500; o->pcg_tolerance = 1e-10;
   o->initial_trust_region_radius = 1e4; o->max_trust_region_radius = 1e16; o->min_trust_region_radius = 1e-32;
   o->min_relative_decrease = 1e-3; o->min_lm_diagonal = 1e-6; o->max_lm_diagonal = 1e32;
   o->function_tolerance = 1e-6; o->gradient_tolerance = 1e-10; o->parameter_tolerance = 1e-8;

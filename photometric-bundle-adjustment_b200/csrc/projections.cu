@@ -209,6 +209,124 @@ pba_status upload_view(const pba_problem* p, bool with_obs, cudaStream_t st, Pro
 
 using namespace pba;
 
+namespace pba {
+namespace {
+
+// add_new_landmarks_between_cams (include/visnav/map_utils.h:121-195): a thread per shared track.
+// v0 / v1 = unit bearings of the two corners; the point is opengv's linear triangulation in camera 0's frame
+// (thirdparty/opengv/src/triangulation/methods.cpp:36-64): rows f_x P_2 - f_z P_0, f_y P_2 - f_z P_1 of the two
+// projection matrices P1 = [I | 0], P2 = [R12^T | -R12^T t12], the null vector of that 4x4 matrix by SVD.  Here
+// the SVD is a one-sided (Hestenes) Jacobi iteration on the columns, which is as accurate as Eigen's two-sided
+// JacobiSVD for the small singular vector; the landmark's inverse distance is 1 / |p| (map_utils.h:190).
+struct TriArgs {
+  int64_t n;
+  int model0, model1;
+  double intr0[8], intr1[8];
+  double Rt[9];   // R12^T
+  double mt[3];   // -R12^T t12
+};
+
+__global__ void k_triangulate(TriArgs a, const double* __restrict__ uv0, const double* __restrict__ uv1,
+                              double* __restrict__ p_out, double* __restrict__ inv_depth) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= a.n) return;
+  double f1[3], f2[3];
+  cam_bearing(a.model0, a.intr0, uv0[2 * i], uv0[2 * i + 1], f1);
+  cam_bearing(a.model1, a.intr1, uv1[2 * i], uv1[2 * i + 1], f2);
+  // U = A (row-major 4x4), V = I
+  double U[4][4], V[4][4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const double p10 = c == 0 ? 1.0 : 0.0, p11 = c == 1 ? 1.0 : 0.0, p12 = c == 2 ? 1.0 : 0.0;
+    const double p20 = c < 3 ? a.Rt[c] : a.mt[0], p21 = c < 3 ? a.Rt[3 + c] : a.mt[1], p22 = c < 3 ? a.Rt[6 + c] : a.mt[2];
+    U[0][c] = f1[0] * p12 - f1[2] * p10;
+    U[1][c] = f1[1] * p12 - f1[2] * p11;
+    U[2][c] = f2[0] * p22 - f2[2] * p20;
+    U[3][c] = f2[1] * p22 - f2[2] * p21;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) V[r][c] = r == c ? 1.0 : 0.0;
+  }
+  for (int sweep = 0; sweep < 30; ++sweep) {
+    double off = 0.0;
+#pragma unroll
+    for (int p = 0; p < 3; ++p)
+#pragma unroll
+      for (int q = p + 1; q < 4; ++q) {
+        double al = 0.0, be = 0.0, ga = 0.0;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) { al += U[r][p] * U[r][p]; be += U[r][q] * U[r][q]; ga += U[r][p] * U[r][q]; }
+        const double lim = 1e-16 * sqrt(al * be);
+        if (fabs(ga) <= lim || ga == 0.0) continue;
+        off = fmax(off, fabs(ga) / fmax(lim * 1e16, 1e-300));
+        const double zeta = (be - al) / (2.0 * ga);
+        const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+        const double c = 1.0 / sqrt(1.0 + t * t), sn = c * t;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const double up = U[r][p], uq = U[r][q];
+          U[r][p] = c * up - sn * uq; U[r][q] = sn * up + c * uq;
+          const double vp = V[r][p], vq = V[r][q];
+          V[r][p] = c * vp - sn * vq; V[r][q] = sn * vp + c * vq;
+        }
+      }
+    if (off < 1e-15) break;
+  }
+  int best = 0;
+  double smin = 1e300;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    double s2 = 0.0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) s2 += U[r][c] * U[r][c];
+    if (s2 < smin) { smin = s2; best = c; }
+  }
+  double v[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) v[r] = best == 0 ? V[r][0] : best == 1 ? V[r][1] : best == 2 ? V[r][2] : V[r][3];
+  const double px = v[0] / v[3], py = v[1] / v[3], pz = v[2] / v[3];
+  if (p_out) { p_out[3 * i] = px; p_out[3 * i + 1] = py; p_out[3 * i + 2] = pz; }
+  inv_depth[i] = 1.0 / sqrt(px * px + py * py + pz * pz);
+}
+
+}  // namespace
+}  // namespace pba
+
+PBA_API pba_status pba_triangulate_inverse_depth(int32_t model0, const double intr0[8], int32_t model1, const double intr1[8],
+                                                 const double T_w_c0[7], const double T_w_c1[7], int64_t n,
+                                                 const double* uv0, const double* uv1, int32_t device, double* p_c0,
+                                                 double* inv_depth) {
+  if (!intr0 || !intr1 || !T_w_c0 || !T_w_c1 || n < 0 || (n > 0 && (!uv0 || !uv1 || !inv_depth))) return PBA_ERR_INVALID_ARGUMENT;
+  if (model0 < 0 || model0 > PBA_CAM_EUCM || model1 < 0 || model1 > PBA_CAM_EUCM) return PBA_ERR_UNSUPPORTED;
+  if (!have_device()) return PBA_ERR_NO_DEVICE;
+  PBA_CUDA_OK(cudaSetDevice(device));
+  if (n == 0) return PBA_OK;
+  TriArgs a;
+  a.n = n; a.model0 = model0; a.model1 = model1;
+  memcpy(a.intr0, intr0, sizeof(a.intr0)); memcpy(a.intr1, intr1, sizeof(a.intr1));
+  // T_c0_c1 = T_w_c0^-1 T_w_c1: R12 = R0^T R1, t12 = R0^T (t1 - t0); P2 = [R12^T | -R12^T t12]
+  double R0[9], R1[9], R12[9], t12[3];
+  quat_to_rot(T_w_c0, R0);
+  quat_to_rot(T_w_c1, R1);
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) R12[3 * i + j] = R0[i] * R1[j] + R0[3 + i] * R1[3 + j] + R0[6 + i] * R1[6 + j];
+  const double d[3] = {T_w_c1[4] - T_w_c0[4], T_w_c1[5] - T_w_c0[5], T_w_c1[6] - T_w_c0[6]};
+  for (int i = 0; i < 3; ++i) t12[i] = R0[i] * d[0] + R0[3 + i] * d[1] + R0[6 + i] * d[2];
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) a.Rt[3 * i + j] = R12[3 * j + i];
+    a.mt[i] = -(R12[i] * t12[0] + R12[3 + i] * t12[1] + R12[6 + i] * t12[2]);
+  }
+  DevBuf<double> d0, d1, dp, dr;
+  PBA_CUDA_OK(d0.alloc(size_t(2) * n)); PBA_CUDA_OK(d1.alloc(size_t(2) * n));
+  PBA_CUDA_OK(dp.alloc(size_t(3) * n)); PBA_CUDA_OK(dr.alloc(size_t(n)));
+  PBA_CUDA_OK(cudaMemcpy(d0.p, uv0, sizeof(double) * 2 * n, cudaMemcpyHostToDevice));
+  PBA_CUDA_OK(cudaMemcpy(d1.p, uv1, sizeof(double) * 2 * n, cudaMemcpyHostToDevice));
+  k_triangulate<<<unsigned((n + 127) / 128), 128>>>(a, d0.p, d1.p, dp.p, dr.p);
+  PBA_CUDA_OK(cudaGetLastError());
+  if (p_c0) PBA_CUDA_OK(cudaMemcpy(p_c0, dp.p, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost));
+  PBA_CUDA_OK(cudaMemcpy(inv_depth, dr.p, sizeof(double) * n, cudaMemcpyDeviceToHost));
+  return PBA_OK;
+}
+
 PBA_API void pba_projection_thresholds_init(pba_projection_thresholds* t) {
   if (!t) return;
   t->reprojection_error_huge_pixel = 40.0;   // src/sfm.cpp:256-257

@@ -76,3 +76,21 @@ def compute_projections(problem: Problem, thresholds: ProjectionThresholds = Non
         "pba_compute_projections")
     slot_ptr = problem.lm_obs_ptr + np.arange(nl + 1, dtype=np.int64)
     return Projections(slot_ptr, repro, p3c, err, flags, remove, bool(severe.value))
+
+
+def triangulate_inverse_depth(model0, intr0, model1, intr1, T_w_c0, T_w_c1, uv0, uv1, device=0):
+    """add_new_landmarks_between_cams (include/visnav/map_utils.h:121-195) for n shared tracks: returns
+    (p in camera 0's frame [n,3], initial inverse distance [n])."""
+    m0 = _ffi.CAM_NAMES[model0] if isinstance(model0, str) else int(model0)
+    m1 = _ffi.CAM_NAMES[model1] if isinstance(model1, str) else int(model1)
+    i0, i1 = np.ascontiguousarray(intr0, np.float64), np.ascontiguousarray(intr1, np.float64)
+    T0, T1 = np.ascontiguousarray(T_w_c0, np.float64), np.ascontiguousarray(T_w_c1, np.float64)
+    uv0, uv1 = np.ascontiguousarray(uv0, np.float64).reshape(-1, 2), np.ascontiguousarray(uv1, np.float64).reshape(-1, 2)
+    n = uv0.shape[0]
+    p = np.zeros((n, 3))
+    rho = np.zeros(n)
+    _ffi.check(_ffi.load_lib().pba_triangulate_inverse_depth(
+        m0, _ffi.ptr(i0, C.c_double), m1, _ffi.ptr(i1, C.c_double), _ffi.ptr(T0, C.c_double), _ffi.ptr(T1, C.c_double), n,
+        _ffi.ptr(uv0, C.c_double), _ffi.ptr(uv1, C.c_double), device, _ffi.ptr(p, C.c_double), _ffi.ptr(rho, C.c_double)),
+        "pba_triangulate_inverse_depth")
+    return p, rho

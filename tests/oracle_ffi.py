@@ -87,7 +87,7 @@ def default_options(**kw):
     """pba_options with BundleAdjustmentOptions + Ceres defaults (no CUDA library needed)."""
     o = _ffi.pba_options()
     o.verbosity_level, o.optimize_intrinsics, o.use_huber, o.huber_parameter, o.max_num_iterations = 0, 0, 1, 1.0, 20
-    o.solver, o.cholesky_max_dim, o.pcg_max_iterations, o.pcg_tolerance = 0, 4096, 500, 1e-10
+    o.solver, o.cholesky_max_dim, o.pcg_max_iterations, o.pcg_tolerance = 0, 16384, 500, 1e-10
     o.initial_trust_region_radius, o.max_trust_region_radius, o.min_trust_region_radius = 1e4, 1e16, 1e-32
     o.min_relative_decrease, o.min_lm_diagonal, o.max_lm_diagonal = 1e-3, 1e-6, 1e32
     o.function_tolerance, o.gradient_tolerance, o.parameter_tolerance = 1e-6, 1e-10, 1e-8
@@ -203,3 +203,22 @@ def compute_projections(lib_kind, prob, thresholds=None):
                 _ffi.ptr(out["outlier_flags"], C.c_uint32))
     assert rc == 0, rc
     return out
+
+
+def triangulate(lib_kind, model0, intr0, model1, intr1, T_w_c0, T_w_c1, uv0, uv1):
+    """add_new_landmarks_between_cams: (p in camera 0's frame [n,3], inverse distance [n]) from the oracle port or
+    from the reference's own function (+ opengv's triangulate for p)."""
+    lib = oracle() if lib_kind == "oracle" else ref()
+    fn = lib.pba_oracle_triangulate if lib_kind == "oracle" else lib.pba_ref_add_new_landmarks
+    fn.argtypes = [C.c_int, _d, C.c_int, _d, _d, _d, C.c_int64, _d, _d, _d, _d]
+    fn.restype = C.c_int
+    i0, i1 = np.ascontiguousarray(intr0, np.float64), np.ascontiguousarray(intr1, np.float64)
+    T0, T1 = np.ascontiguousarray(T_w_c0, np.float64), np.ascontiguousarray(T_w_c1, np.float64)
+    uv0, uv1 = np.ascontiguousarray(uv0, np.float64).reshape(-1, 2), np.ascontiguousarray(uv1, np.float64).reshape(-1, 2)
+    n = uv0.shape[0]
+    p, rho = np.zeros((n, 3)), np.zeros(n)
+    rc = fn(int(model0), _ffi.ptr(i0, C.c_double), int(model1), _ffi.ptr(i1, C.c_double), _ffi.ptr(T0, C.c_double),
+            _ffi.ptr(T1, C.c_double), n, _ffi.ptr(uv0, C.c_double), _ffi.ptr(uv1, C.c_double), _ffi.ptr(p, C.c_double),
+            _ffi.ptr(rho, C.c_double))
+    assert rc == 0, rc
+    return p, rho
