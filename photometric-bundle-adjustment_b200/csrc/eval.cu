@@ -331,6 +331,7 @@ __global__ void __launch_bounds__(kPhotoThreads, MINB) k_eval_photo(const EvalAr
     // ---- phase 1: warp the 8 pixels, branch-free; then gather the 8 quads together ----
     double fx[8], fy[8];
     int off[8];
+    int cell[8];  // (y0 << 16 | x0): pass 2 needs the integer cell, not the offset (no integer division by the pitch there)
     const double umax = double(a.width - 1), vmax = double(a.height - 1);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -351,6 +352,7 @@ __global__ void __launch_bounds__(kPhotoThreads, MINB) k_eval_photo(const EvalAr
       const double x0 = floor(u), y0 = floor(v);
       fx[k] = u - x0; fy[k] = v - y0;
       off[k] = int(y0) * a.pitch + int(x0);
+      cell[k] = (int(y0) << 16) | int(x0);
     }
     uint32_t quad[8];
 #pragma unroll
@@ -382,7 +384,7 @@ __global__ void __launch_bounds__(kPhotoThreads, MINB) k_eval_photo(const EvalAr
           s_pat[(4 * k + 3) * 32] = Ih[k];
         }
         s_quad[k * kPhotoThreads + tid] = quad[k];
-        s_off[k * kPhotoThreads + tid] = off[k];
+        s_off[k * kPhotoThreads + tid] = cell[k];
       }
       // ---- phase 2: one pixel at a time: recompute the warp with its projection Jacobian
       //      (no global loads), weight, stream the row out ----
@@ -406,7 +408,7 @@ __global__ void __launch_bounds__(kPhotoThreads, MINB) k_eval_photo(const EvalAr
         double uv[2], Jp[6];
         cam_project<true>(c.model, c.in, ok ? xt : 0.0, ok ? yt : 0.0, ok ? zt : 1.0, uv, Jp);
         // same integer cell as pass 1 (a recomputed floor could differ by one ulp of u)
-        const int y0 = ofk / a.pitch, x0 = ofk - y0 * a.pitch;
+        const int y0 = ofk >> 16, x0 = ofk & 0xffff;
         const double fxk = ok ? uv[0] - x0 : 0.0, fyk = ok ? uv[1] - y0 : 0.0;
         const double i00 = double(q & 0xffu), i10 = double((q >> 8) & 0xffu), i01 = double((q >> 16) & 0xffu),
                      i11 = double(q >> 24);

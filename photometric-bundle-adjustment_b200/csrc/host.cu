@@ -330,6 +330,7 @@ pba_status validate(const pba_problem* p, const pba_options* o) {
   } else {
     if (p->n_poses > 0 && !p->images && !p->image_ptrs) return PBA_ERR_INVALID_ARGUMENT;
     if (p->width < 2 || p->height < 2 || p->pitch < p->width) return PBA_ERR_INVALID_ARGUMENT;
+    if (p->width > 65535 || p->height > 32767) return PBA_ERR_UNSUPPORTED;  // the kernels pack a pixel cell into 32 bits
   }
   return PBA_OK;
 }
