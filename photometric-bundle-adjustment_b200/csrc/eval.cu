@@ -520,15 +520,21 @@ void (*photo_kernel(int model, bool rc))(const EvalArgs) {
 // reprojection.h:82-112: r = z_t - pi_t(T_t^-1 T_h (b / rho)).  Both cameras
 // use the HOST's model (the reference passes the host's model name for both,
 // map_utils.h:363-364) with the target's intrinsic values.
-template <bool WITH_J>
-__global__ void __launch_bounds__(kEvalThreads) k_eval_geom(const EvalArgs a) {
+// MINB: CTAs per SM the register allocation is bounded for (0 = unbounded: 90 registers, 5 CTAs per SM).  ncu
+// (profiles/r02a_k1_geom_details.txt) shows the unbounded kernel latency-bound: IPC 0.63, 84 % of the cycles
+// without an eligible warp at 31 % occupancy; PBA_K1G_VARIANT switches the bound for A/B runs.
+template <bool WITH_J, int MINB = 0>
+__global__ void __launch_bounds__(kEvalThreads, MINB > 0 ? MINB : 1) k_eval_geom(const EvalArgs a) {
   __shared__ double s_red[kEvalThreads / 32];
   const int64_t i = int64_t(blockIdx.x) * kEvalThreads + threadIdx.x;
   double cost = 0.0;
   if (i < a.n) {
     const int e = a.obs_edge[i];
     const int l = a.obs_lm[i];
-    const double* T = a.edge_T + kEdgeStride * int64_t(e);
+    const double2* T2 = reinterpret_cast<const double2*>(a.edge_T + kEdgeStride * int64_t(e));
+    double T[24];  // the record's first 24 doubles, 16 bytes per load
+#pragma unroll
+    for (int k = 0; k < 12; ++k) { const double2 v = T2[k]; T[2 * k] = v.x; T[2 * k + 1] = v.y; }
     const int model = int(T[15]);  // both cameras use the HOST's model (map_utils.h:363-364)
     double A[9], in[8];
 #pragma unroll
@@ -768,8 +774,17 @@ pba_status launch_evaluate(Handle* h, bool with_jacobian, const double* poses, c
       }
       else { PBA_LAUNCH(h, K_COST, photo_kernel<false>(h->uniform_model, rc), dim3(grid), dim3(kPhotoThreads), 0, a); }
     } else {
-      if (with_jacobian) { PBA_LAUNCH(h, K_RESJAC, k_eval_geom<true>, dim3(grid), dim3(kEvalThreads), 0, a); }
-      else { PBA_LAUNCH(h, K_COST, k_eval_geom<false>, dim3(grid), dim3(kEvalThreads), 0, a); }
+      static const int gvar = [] { const char* e = getenv("PBA_K1G_VARIANT"); return e ? atoi(e) : 0; }();
+      if (with_jacobian) {
+        if (gvar == 1) { PBA_LAUNCH(h, K_RESJAC, (k_eval_geom<true, 6>), dim3(grid), dim3(kEvalThreads), 0, a); }
+        else if (gvar == 2) { PBA_LAUNCH(h, K_RESJAC, (k_eval_geom<true, 8>), dim3(grid), dim3(kEvalThreads), 0, a); }
+        else if (gvar == 3) { PBA_LAUNCH(h, K_RESJAC, (k_eval_geom<true, 10>), dim3(grid), dim3(kEvalThreads), 0, a); }
+        else { PBA_LAUNCH(h, K_RESJAC, (k_eval_geom<true, 0>), dim3(grid), dim3(kEvalThreads), 0, a); }
+      } else {
+        if (gvar == 1) { PBA_LAUNCH(h, K_COST, (k_eval_geom<false, 6>), dim3(grid), dim3(kEvalThreads), 0, a); }
+        else if (gvar == 2) { PBA_LAUNCH(h, K_COST, (k_eval_geom<false, 8>), dim3(grid), dim3(kEvalThreads), 0, a); }
+        else { PBA_LAUNCH(h, K_COST, (k_eval_geom<false, 0>), dim3(grid), dim3(kEvalThreads), 0, a); }
+      }
     }
   }
   launch_reduce_sum(h, h->red_ws.p, int64_t(grid), cost_out);
