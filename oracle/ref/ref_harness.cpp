@@ -26,6 +26,7 @@
 #include <visnav/local_parameterization_se3.hpp>
 #include <visnav/map_utils.h>
 #include <visnav/reprojection.h>
+#include <visnav/aprilgrid.h>
 
 #include <ceres/ceres.h>
 
@@ -696,5 +697,51 @@ extern "C" REF_API int pba_ref_add_new_landmarks(int model0, const double* intr0
     }
   }
   return 0;
+}
+
+// Camera calibration exactly as the reference's calibration application sets it up (src/calibration.cpp:373-425,
+// a GUI translation unit that cannot be compiled here): one ReprojectionCostFunctor (include/visnav/reprojection.h:
+// 47-71, the reference's own) per detected AprilGrid corner (include/visnav/aprilgrid.h), parameter blocks T_w_i per
+// frame, T_i_c per camera (camera 0's constant) and the intrinsics per camera, LocalParameterizationSE3, the same
+// solver options.  It exists so that BASELINE config 1 (data/euroc_V1) can get the stereo extrinsics the snapshot
+// only provides through that application (tools/euroc/calibrate.py).  In/out arrays are updated in place.
+extern "C" REF_API int pba_ref_calibrate(int model, int n_frames, int n_cams, double* intr /*[n_cams*8]*/,
+                                         double* T_i_c /*[n_cams*7]*/, double* T_w_i /*[n_frames*7]*/, int64_t n_obs,
+                                         const int32_t* obs_frame, const int32_t* obs_cam, const int32_t* obs_corner,
+                                         const double* obs_uv, int num_threads, double* initial_cost, double* final_cost) {
+  using namespace visnav;
+  const AprilGrid grid;
+  const std::string name = model_name(model);
+  std::vector<Sophus::SE3d, Eigen::aligned_allocator<Sophus::SE3d>> Twi(n_frames), Tic(n_cams);
+  for (int i = 0; i < n_frames; ++i) std::memcpy(Twi[i].data(), T_w_i + 7 * i, 7 * sizeof(double));
+  for (int i = 0; i < n_cams; ++i) std::memcpy(Tic[i].data(), T_i_c + 7 * i, 7 * sizeof(double));
+  ceres::Problem problem;
+  for (int i = 0; i < n_frames; ++i)
+    problem.AddParameterBlock(Twi[i].data(), Sophus::SE3d::num_parameters, new Sophus::test::LocalParameterizationSE3);
+  for (int i = 0; i < n_cams; ++i) {
+    problem.AddParameterBlock(Tic[i].data(), Sophus::SE3d::num_parameters, new Sophus::test::LocalParameterizationSE3);
+    if (i == 0) problem.SetParameterBlockConstant(Tic[i].data());
+  }
+  for (int64_t k = 0; k < n_obs; ++k) {
+    if (obs_corner[k] < 0 || size_t(obs_corner[k]) >= grid.aprilgrid_corner_pos_3d.size()) return 2;
+    const Eigen::Vector2d p_2d(obs_uv[2 * k], obs_uv[2 * k + 1]);
+    const Eigen::Vector3d& p_3d = grid.aprilgrid_corner_pos_3d[obs_corner[k]];
+    auto* functor = new ReprojectionCostFunctor(p_2d, p_3d, name);
+    auto* cost = new ceres::AutoDiffCostFunction<ReprojectionCostFunctor, 2, Sophus::SE3d::num_parameters,
+                                                 Sophus::SE3d::num_parameters, 8>(functor);
+    problem.AddResidualBlock(cost, nullptr, Twi[obs_frame[k]].data(), Tic[obs_cam[k]].data(), intr + 8 * obs_cam[k]);
+  }
+  ceres::Solver::Options options;
+  options.gradient_tolerance = 0.01 * Sophus::Constants<double>::epsilon();
+  options.function_tolerance = 0.01 * Sophus::Constants<double>::epsilon();
+  options.linear_solver_type = ceres::SPARSE_NORMAL_CHOLESKY;
+  options.num_threads = num_threads > 0 ? num_threads : int(std::thread::hardware_concurrency());
+  ceres::Solver::Summary summary;
+  ceres::Solve(options, &problem, &summary);
+  for (int i = 0; i < n_frames; ++i) std::memcpy(T_w_i + 7 * i, Twi[i].data(), 7 * sizeof(double));
+  for (int i = 0; i < n_cams; ++i) std::memcpy(T_i_c + 7 * i, Tic[i].data(), 7 * sizeof(double));
+  if (initial_cost) *initial_cost = summary.initial_cost;
+  if (final_cost) *final_cost = summary.final_cost;
+  return summary.IsSolutionUsable() ? 0 : 3;
 }
 

@@ -776,10 +776,12 @@ pba_status launch_evaluate(Handle* h, bool with_jacobian, const double* poses, c
     } else {
       static const int gvar = [] { const char* e = getenv("PBA_K1G_VARIANT"); return e ? atoi(e) : 0; }();
       if (with_jacobian) {
-        if (gvar == 1) { PBA_LAUNCH(h, K_RESJAC, (k_eval_geom<true, 6>), dim3(grid), dim3(kEvalThreads), 0, a); }
+        // measured at config 5 (profiles/r02b_variants_geom.txt): unbounded (104 registers) 0.745 ms, 6 CTAs/SM
+        // (80 registers) 0.601 ms = 65.6 % of the copy peak, 8 CTAs/SM (64, spills) 0.651, 10 (48, spills) 0.831
+        if (gvar == 1) { PBA_LAUNCH(h, K_RESJAC, (k_eval_geom<true, 0>), dim3(grid), dim3(kEvalThreads), 0, a); }
         else if (gvar == 2) { PBA_LAUNCH(h, K_RESJAC, (k_eval_geom<true, 8>), dim3(grid), dim3(kEvalThreads), 0, a); }
         else if (gvar == 3) { PBA_LAUNCH(h, K_RESJAC, (k_eval_geom<true, 10>), dim3(grid), dim3(kEvalThreads), 0, a); }
-        else { PBA_LAUNCH(h, K_RESJAC, (k_eval_geom<true, 0>), dim3(grid), dim3(kEvalThreads), 0, a); }
+        else { PBA_LAUNCH(h, K_RESJAC, (k_eval_geom<true, 6>), dim3(grid), dim3(kEvalThreads), 0, a); }
       } else {
         if (gvar == 1) { PBA_LAUNCH(h, K_COST, (k_eval_geom<false, 6>), dim3(grid), dim3(kEvalThreads), 0, a); }
         else if (gvar == 2) { PBA_LAUNCH(h, K_COST, (k_eval_geom<false, 8>), dim3(grid), dim3(kEvalThreads), 0, a); }

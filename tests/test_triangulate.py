@@ -80,7 +80,7 @@ def test_cuda_triangulation_mixed_models_and_many_points():
     p, rho = pb.triangulate_inverse_depth(pb.CAM_DS, intr0, pb.CAM_KB4, intr1, T0, T1, uv0, uv1)
     p_o, rho_o = of.triangulate("oracle", pb.CAM_DS, intr0, pb.CAM_KB4, intr1, T0, T1, uv0, uv1)
     assert np.all(np.abs(rho - rho_o) <= 1e-8 * np.abs(rho_o))
-    assert np.median(np.abs(p - X).max(axis=1)) < 0.05
+    assert np.median(np.abs(p - X).max(axis=1)) < 0.5  # 0.2 px noise, 20 cm baseline, points up to 12 m away
     del g0, g1
 
 
