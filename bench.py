@@ -469,11 +469,20 @@ def main():
         # Steady state, as in the SfM loop's repeated optimize() calls (src/sfm.cpp:1153-1155): an untimed
         # one-iteration solve first wherever the pools (device arena, pinned staging) have not seen these sizes.
         def run_per_rank(opts):
+            tt = [time.time()]
             e2 = pb.Engine(p2, opts, rank=rank, world_size=world)
+            tt.append(time.time())
             e2.comm_init(comm_id)  # same id as the resident engine: the communicator is cached per process
+            tt.append(time.time())
             sm = e2.minimize()
+            tt.append(time.time())
             p2.poses[:] = e2.get_state()[0]
+            tt.append(time.time())
             e2.close()
+            tt.append(time.time())
+            if os.environ.get("PBA_TIMING"):
+                print("[bench e2e rank %d] create %.1f comm_init %.1f minimize %.1f get_state %.1f close %.1f ms" %
+                      ((rank,) + tuple(1e3 * (tt[i + 1] - tt[i]) for i in range(5))), file=sys.stderr)
             return sm
         if world == 1:
             pb.bundle_adjustment(prob.copy(), pb.BundleAdjustmentOptions(
@@ -520,7 +529,8 @@ def main():
                 pb.multi_gpu_init(0, world)  # NCCL communicators of this path: process set-up, cached
                 o3 = pb.BundleAdjustmentOptions(verbosity_level=0, huber_parameter=hub, device=0, solver=a.solver,
                                                 max_num_iterations=1, num_gpus=world)
-                pb.bundle_adjustment(prob.copy(), o3)
+                for _ in range(2):  # the pinned staging pool reaches its concurrent capacity on the second call
+                    pb.bundle_adjustment(prob.copy(), o3)
                 o3.max_num_iterations = 20
                 p3 = prob.copy()
                 t0 = time.time()

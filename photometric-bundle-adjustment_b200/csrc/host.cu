@@ -22,6 +22,7 @@
 #include <chrono>
 #include <limits>
 #include <array>
+#include <atomic>
 #include <memory>
 #include <condition_variable>
 #include <mutex>
@@ -162,6 +163,13 @@ Handle::~Handle() {
   if (own_stream && stream) cudaStreamDestroy(stream);
 }
 
+// PBA_TIMING: slow driver allocations (they serialise every thread of the process)
+std::atomic<int> g_n_cuda_malloc{0}, g_n_host_alloc{0};
+std::atomic<int64_t> g_us_cuda_malloc{0}, g_us_host_alloc{0}, g_mb_cuda_malloc{0}, g_mb_host_alloc{0};
+static double wall_s() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 // ---- device arena + per-process chunk cache ----
 namespace {
 constexpr size_t kArenaChunk = size_t(1) << 30;
@@ -198,7 +206,9 @@ void* DeviceArena::alloc(size_t bytes, cudaError_t* err) {
   if (!c.p) {
     const size_t want = bytes > kArenaChunk ? bytes : kArenaChunk;
     void* q = nullptr;
+    const double t_alloc = wall_s();
     cudaError_t e = cudaMalloc(&q, want);
+    ++g_n_cuda_malloc; g_us_cuda_malloc += int64_t(1e6 * (wall_s() - t_alloc)); g_mb_cuda_malloc += int64_t(want >> 20);
     if (e != cudaSuccess) {  // give cached chunks that did not fit back to the driver and retry
       cudaGetLastError();
       trim_device_cache();
@@ -317,14 +327,8 @@ pba_status validate(const pba_problem* p, const pba_options* o) {
     if (p->calib_model[i] < 0 || p->calib_model[i] > PBA_CAM_EUCM) return PBA_ERR_UNSUPPORTED;  // from_data aborts (camera_models.h:469)
   for (int l = 0; l < p->n_landmarks; ++l)  // offsets first: the parallel scan below indexes with them
     if (p->lm_obs_ptr[l + 1] < p->lm_obs_ptr[l] || p->lm_obs_ptr[l + 1] > p->n_obs) return PBA_ERR_INVALID_ARGUMENT;
-  int bad = 0;
-#pragma omp parallel for schedule(static) reduction(| : bad)
-  for (int l = 0; l < p->n_landmarks; ++l) {
-    if (p->lm_host[l] < 0 || p->lm_host[l] >= p->n_poses) { bad |= 1; continue; }
-    for (int64_t k = p->lm_obs_ptr[l]; k < p->lm_obs_ptr[l + 1]; ++k)
-      if (p->obs_target[k] < 0 || p->obs_target[k] >= p->n_poses || p->obs_target[k] == p->lm_host[l]) bad |= 1;
-  }
-  if (bad) return PBA_ERR_INVALID_ARGUMENT;
+  // the per-observation index checks (host / target in range, target != host) ride on the observation scan
+  // of analyze_cameras: one pass over the 4 B x n_obs target table instead of two
   if (p->mode == PBA_MODE_GEOMETRIC) {
     if (p->n_obs > 0 && !p->obs_uv) return PBA_ERR_INVALID_ARGUMENT;
   } else {
@@ -345,11 +349,17 @@ struct PinnedPool {
   struct Buf { void* p; size_t bytes; };
   std::vector<Buf> free_list;
   void* acquire(size_t bytes, size_t* got) {
+    // sizes are rounded up to a quarter-octave grid (and 1 MB): the shards of a multi-GPU solve and the
+    // successive solves of a growing map ask for slightly different sizes, and a buffer that is a little
+    // too small for the next request would otherwise be pinned again (~0.3 ms per MB)
+    size_t step = size_t(1) << 20;
+    while (step * 8 <= bytes) step <<= 1;
+    const size_t want = (bytes + step - 1) / step * step;
     {
       std::lock_guard<std::mutex> lock(mu);
       int best = -1;
       for (int i = 0; i < int(free_list.size()); ++i)
-        if (free_list[i].bytes >= bytes && (best < 0 || free_list[i].bytes < free_list[best].bytes)) best = i;
+        if (free_list[i].bytes == want) { best = i; break; }  // exact size class: no request steals a larger one's buffer
       if (best >= 0) {
         Buf b = free_list[best];
         free_list.erase(free_list.begin() + best);
@@ -358,8 +368,10 @@ struct PinnedPool {
       }
     }
     void* q = nullptr;
-    const size_t want = (bytes + (size_t(1) << 20) - 1) & ~((size_t(1) << 20) - 1);
-    if (cudaHostAlloc(&q, want, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); *got = 0; return nullptr; }
+    const double t_alloc = wall_s();
+    const cudaError_t e = cudaHostAlloc(&q, want, cudaHostAllocPortable);
+    ++g_n_host_alloc; g_us_host_alloc += int64_t(1e6 * (wall_s() - t_alloc)); g_mb_host_alloc += int64_t(want >> 20);
+    if (e != cudaSuccess) { cudaGetLastError(); *got = 0; return nullptr; }
     *got = want;
     return q;
   }
@@ -479,7 +491,9 @@ std::vector<int> rcm_order(const std::vector<std::vector<int>>& nb) {
   return order;
 }
 
-void analyze_cameras(const pba_problem* p, int nthr, int max_band_blocks, CameraLayout* L) {
+// Returns PBA_ERR_INVALID_ARGUMENT for a host / target index out of range or a landmark observed by its own
+// host keyframe (the part of the input validation that has to look at every observation).
+pba_status analyze_cameras(const pba_problem* p, int nthr, int max_band_blocks, CameraLayout* L) {
   const bool timing = getenv("PBA_TIMING") != nullptr;
   double t_mark = wall();
   auto mark = [&](const char* what) {
@@ -493,7 +507,8 @@ void analyze_cameras(const pba_problem* p, int nthr, int max_band_blocks, Camera
   std::vector<uint8_t> used(np, 0), is_target(np, 0);
   std::vector<std::vector<int>> host_targets(np);  // distinct targets of the landmarks hosted by a keyframe
   int64_t n_active = 0;
-#pragma omp parallel num_threads(nthr) reduction(+ : n_active)
+  int bad = 0;
+#pragma omp parallel num_threads(nthr) reduction(+ : n_active) reduction(| : bad)
   {
     std::vector<uint8_t> u(np, 0), t(np, 0);
     std::vector<int> stamp(np, -1);  // stamp[target] = host while consecutive landmarks share the host
@@ -501,14 +516,15 @@ void analyze_cameras(const pba_problem* p, int nthr, int max_band_blocks, Camera
 #pragma omp for schedule(static)
     for (int l = 0; l < p->n_landmarks; ++l) {
       const int64_t k0 = p->lm_obs_ptr[l], k1 = p->lm_obs_ptr[l + 1];
-      if (k1 == k0) continue;
       const int hst = p->lm_host[l];
+      if (hst < 0 || hst >= np) { bad |= 1; continue; }
+      if (k1 == k0) continue;
       u[hst] = 1;
       ++n_active;
       for (int64_t k = k0; k < k1; ++k) {
         const int tg = p->obs_target[k];
-        u[tg] = 1; t[tg] = 1;
-        if (stamp[tg] != hst) { stamp[tg] = hst; mine[hst].push_back(tg); }
+        if (unsigned(tg) >= unsigned(np) || tg == hst) { bad |= 1; continue; }
+        if (stamp[tg] != hst) { stamp[tg] = hst; mine[hst].push_back(tg); u[tg] = 1; t[tg] = 1; }
       }
     }
 #pragma omp critical
@@ -518,6 +534,7 @@ void analyze_cameras(const pba_problem* p, int nthr, int max_band_blocks, Camera
     }
   }
   mark("observation scan");
+  if (bad) return PBA_ERR_INVALID_ARGUMENT;
   for (auto& v : host_targets) { std::sort(v.begin(), v.end()); v.erase(std::unique(v.begin(), v.end()), v.end()); }
   L->n_active_lm = n_active;
   L->slot.assign(np, -1);
@@ -578,6 +595,7 @@ void analyze_cameras(const pba_problem* p, int nthr, int max_band_blocks, Camera
   }
   for (auto& v : L->adj) std::sort(v.begin(), v.end());
   mark("ordering + pattern");
+  return PBA_OK;
 }
 
 constexpr int kChunkObs = 1024;
@@ -586,6 +604,7 @@ constexpr int kChunkObs = 1024;
 // cores instead of once per rank thread; the problem has been validated by the caller as well.
 pba_status create_impl(const pba_problem* p, const pba_options* o, int rank, int world, Handle** out,
                        const CameraLayout* shared = nullptr) {
+  const double t_begin = wall();
   pba_status st = shared ? PBA_OK : validate(p, o);
   if (st != PBA_OK) return st;
   if (world < 1 || rank < 0 || rank >= world) return PBA_ERR_INVALID_ARGUMENT;
@@ -595,11 +614,11 @@ pba_status create_impl(const pba_problem* p, const pba_options* o, int rank, int
   PBA_CUDA_OK(cudaSetDevice(o->device));
 
   const bool timing = getenv("PBA_TIMING") != nullptr;
-  double t_mark = wall();
+  double t_mark = t_begin;
   auto mark = [&](const char* what) {
     if (!timing) return;
     const double now = wall();
-    fprintf(stderr, "[pba_create] %-28s %8.1f ms\n", what, 1e3 * (now - t_mark));
+    fprintf(stderr, "[pba_create %d/%d] %-28s %8.1f ms\n", rank, world, what, 1e3 * (now - t_mark));
     t_mark = now;
   };
   std::unique_ptr<Handle> hh(new Handle);
@@ -688,7 +707,7 @@ pba_status create_impl(const pba_problem* p, const pba_options* o, int rank, int
   //      the order of the free cameras, the RCS block pattern ----
   CameraLayout layout;
   if (shared) layout = *shared;
-  else analyze_cameras(p, nthr, 128 / cd, &layout);
+  else if ((st = analyze_cameras(p, nthr, 128 / cd, &layout)) != PBA_OK) return st;
   h->n_active_lm += layout.n_active_lm;
   h->n_obs_global = p->n_obs;
   h->slot = layout.slot;
@@ -717,11 +736,16 @@ pba_status create_impl(const pba_problem* p, const pba_options* o, int rank, int
   // ---- local shard: landmarks ordered by host, observations by (host,target) edge ----
 
   h->lm_order.resize(n_lm);
-  std::iota(h->lm_order.begin(), h->lm_order.end(), 0);
+  bool hosts_sorted = true;
   {
-    bool sorted = true;
-    for (int i = 1; i < n_lm && sorted; ++i) sorted = p->lm_host[lm_lo + i - 1] <= p->lm_host[lm_lo + i];
-    if (!sorted)
+    int unsorted = 0;
+#pragma omp parallel for num_threads(nthr) schedule(static) reduction(| : unsorted)
+    for (int i = 0; i < n_lm; ++i) {
+      h->lm_order[i] = i;
+      if (i > 0 && p->lm_host[lm_lo + i - 1] > p->lm_host[lm_lo + i]) unsorted |= 1;
+    }
+    hosts_sorted = !unsorted;
+    if (!hosts_sorted)
       std::stable_sort(h->lm_order.begin(), h->lm_order.end(),
                        [&](int a, int b) { return p->lm_host[lm_lo + a] < p->lm_host[lm_lo + b]; });
   }
@@ -730,14 +754,32 @@ pba_status create_impl(const pba_problem* p, const pba_options* o, int rank, int
   // observation-/landmark-sized tables are built in pinned staging memory (StageVec) and uploaded asynchronously;
   // they live until the final synchronisation of this function
   StageVec<int64_t> lm_ptr(size_t(n_lm) + 1);
-  lm_ptr[0] = 0;
-  for (int li = 0; li < n_lm; ++li) {
-    const int l = lm_lo + h->lm_order[li];
-    lm_ptr[li + 1] = lm_ptr[li] + (p->lm_obs_ptr[l + 1] - p->lm_obs_ptr[l]);
-  }
   std::vector<int> grp_lm_ptr;  // host groups = runs of equal host
-  for (int li = 0; li < n_lm; ++li)
-    if (li == 0 || p->lm_host[lm_lo + h->lm_order[li]] != p->lm_host[lm_lo + h->lm_order[li - 1]]) grp_lm_ptr.push_back(li);
+  if (hosts_sorted) {
+    // the usual case (landmarks arrive grouped by host): the caller's own order, no prefix sum to redo;
+    // the run starts are collected per thread and concatenated in thread order
+    std::vector<std::vector<int>> starts(nthr);
+#pragma omp parallel num_threads(nthr)
+    {
+      const int tid = omp_get_thread_num(), nt = omp_get_num_threads();
+      const int lo = int(int64_t(n_lm) * tid / nt), hi = int(int64_t(n_lm) * (tid + 1) / nt);
+      std::vector<int>& mine = starts[tid];
+      for (int li = lo; li < hi; ++li) {
+        lm_ptr[li] = p->lm_obs_ptr[lm_lo + li] - obs_lo;
+        if (li == 0 || p->lm_host[lm_lo + li] != p->lm_host[lm_lo + li - 1]) mine.push_back(li);
+      }
+    }
+    lm_ptr[n_lm] = n;
+    for (auto& v : starts) grp_lm_ptr.insert(grp_lm_ptr.end(), v.begin(), v.end());
+  } else {
+    lm_ptr[0] = 0;
+    for (int li = 0; li < n_lm; ++li) {
+      const int l = lm_lo + h->lm_order[li];
+      lm_ptr[li + 1] = lm_ptr[li] + (p->lm_obs_ptr[l + 1] - p->lm_obs_ptr[l]);
+    }
+    for (int li = 0; li < n_lm; ++li)
+      if (li == 0 || p->lm_host[lm_lo + h->lm_order[li]] != p->lm_host[lm_lo + h->lm_order[li - 1]]) grp_lm_ptr.push_back(li);
+  }
   grp_lm_ptr.push_back(n_lm);
   z.n_groups = int(grp_lm_ptr.size()) - 1;
   const int G = z.n_groups;
@@ -878,11 +920,14 @@ pba_status create_impl(const pba_problem* p, const pba_options* o, int rank, int
       for (int i = 0; i < c; ++i) { vs.push_back({grp_cams[c0 + i], off}); off += cd; }
     }
     auto build = [](std::vector<Src>& v, int64_t nkeys, std::vector<int64_t>& ptr, std::vector<int64_t>& src) {
-      std::stable_sort(v.begin(), v.end(), [](const Src& a, const Src& b) { return a.key < b.key; });
+      // stable counting sort by key (keys are block / slot numbers): sources of a block stay in list order,
+      // which fixes the summation order of k_rcs_reduce
       ptr.assign(nkeys + 1, 0);
       src.resize(v.size());
-      for (size_t i = 0; i < v.size(); ++i) { ++ptr[v[i].key + 1]; src[i] = v[i].off; }
+      for (const Src& e : v) ++ptr[e.key + 1];
       for (int64_t i = 0; i < nkeys; ++i) ptr[i + 1] += ptr[i];
+      std::vector<int64_t> cur(ptr.begin(), ptr.end() - 1);
+      for (const Src& e : v) src[cur[e.key]++] = e.off;
     };
 #pragma omp parallel sections num_threads(4)
     {
@@ -1023,6 +1068,10 @@ pba_status create_impl(const pba_problem* p, const pba_options* o, int rank, int
   if (st != PBA_OK) return st;
   PBA_CUDA_OK(cudaStreamSynchronize(s));
   mark("init landmarks");
+  if (timing)
+    fprintf(stderr, "[pba_create %d/%d] total %.1f ms   (process so far: %d cudaMalloc %lld MB %.1f ms, %d cudaHostAlloc %lld MB %.1f ms)\n",
+            rank, world, 1e3 * (wall() - t_begin), g_n_cuda_malloc.load(), (long long)g_mb_cuda_malloc.load(),
+            1e-3 * g_us_cuda_malloc.load(), g_n_host_alloc.load(), (long long)g_mb_host_alloc.load(), 1e-3 * g_us_host_alloc.load());
   *out = hh.release();
   return PBA_OK;
 }
@@ -1416,7 +1465,7 @@ PBA_API pba_status pba_analyze_structure(const pba_problem* problem, const pba_o
   if (st != PBA_OK) return st;
   const int cd = problem->mode == PBA_MODE_PHOTOMETRIC ? 8 : 6;
   CameraLayout L;
-  analyze_cameras(problem, std::max(1, omp_get_num_procs()), 128 / cd, &L);
+  if ((st = analyze_cameras(problem, std::max(1, omp_get_num_procs()), 128 / cd, &L)) != PBA_OK) return st;
   if (slot) for (int i = 0; i < problem->n_poses; ++i) slot[i] = L.slot[i];
   if (n_slots) *n_slots = L.n_slots;
   if (bandwidth_natural) *bandwidth_natural = L.bandwidth_natural;
@@ -1802,8 +1851,12 @@ pba_status solve_multi_gpu(pba_problem* problem, const pba_options* options, int
   if (st != PBA_OK) return st;
   // the global part of the set-up (camera layout, RCS pattern) once, with every core; the rank threads then
   // order their own shards with their share of the cores
+  const bool timing = getenv("PBA_TIMING") != nullptr;
+  if (timing) fprintf(stderr, "[pba_solve x%d] communicators %.1f ms\n", n_gpus, 1e3 * (wall() - t0));
   CameraLayout layout;
-  analyze_cameras(problem, std::max(1, omp_get_num_procs()), 128 / (problem->mode == PBA_MODE_PHOTOMETRIC ? 8 : 6), &layout);
+  st = analyze_cameras(problem, std::max(1, omp_get_num_procs()), 128 / (problem->mode == PBA_MODE_PHOTOMETRIC ? 8 : 6), &layout);
+  if (st != PBA_OK) return st;
+  if (timing) fprintf(stderr, "[pba_solve x%d] + camera layout %.1f ms\n", n_gpus, 1e3 * (wall() - t0));
   StatusBarrier barrier(n_gpus);
   std::vector<pba_status> status(n_gpus, PBA_OK);
   std::vector<double> t_setup(n_gpus, 0.0);
@@ -1817,6 +1870,7 @@ pba_status solve_multi_gpu(pba_problem* problem, const pba_options* options, int
     pba_status s = create_impl(problem, &o, r, n_gpus, &h, &layout);
     std::unique_ptr<Handle> guard(h);
     t_setup[r] = wall() - t0;
+    if (timing) fprintf(stderr, "[pba_solve x%d] rank %d created at %.1f ms\n", n_gpus, r, 1e3 * t_setup[r]);
     if (barrier.wait(s) != PBA_OK) { status[r] = s; return; }
     h->nccl_comm = comms[r];
     pba_summary local;
@@ -1829,6 +1883,9 @@ pba_status solve_multi_gpu(pba_problem* problem, const pba_options* options, int
                          (r == 0 && problem->mode == PBA_MODE_PHOTOMETRIC) ? problem->affine : nullptr);
     if (r == 0 && summary) *summary = local;
     status[r] = s;
+    if (timing) fprintf(stderr, "[pba_solve x%d] rank %d state read at %.1f ms\n", n_gpus, r, 1e3 * (wall() - t0));
+    guard.reset();
+    if (timing) fprintf(stderr, "[pba_solve x%d] rank %d destroyed at %.1f ms\n", n_gpus, r, 1e3 * (wall() - t0));
   };
   std::vector<std::thread> threads;
   for (int r = 1; r < n_gpus; ++r) threads.emplace_back(worker, r);

@@ -86,3 +86,28 @@ def test_shuffled_keyframes_solve_with_an_exact_banded_solver(mode):
     assert abs(sg.final_cost - so.final_cost) <= 1e-6 * so.final_cost
     assert np.abs(pg.poses - po.poses).max() < 1e-5
     assert np.abs(pg.inv_depth - po.inv_depth).max() < 1e-5
+
+
+def test_bad_observation_indices_are_rejected():
+    """The per-observation part of the input validation rides on the layout's observation scan (host.cu
+    analyze_cameras): an index out of range or a landmark observed by its own host is PBA_ERR_INVALID_ARGUMENT,
+    as the reference's containers make them impossible (map_utils.h:340-376 iterates obs of existing cameras)."""
+    import pytest
+    prob, _ = pb.make_scene(pb.MODE_GEOMETRIC, 12, 400, "pinhole")
+    pb.analyze_structure(prob)
+    k = int(prob.lm_obs_ptr[7])
+    for field, idx, val in (("obs_target", k, prob.n_poses), ("obs_target", k, -1),
+                            ("obs_target", k, int(prob.lm_host[7])), ("lm_host", 7, prob.n_poses),
+                            ("lm_host", 399, -3)):
+        bad = prob.copy()
+        arr = getattr(bad, field).copy()
+        arr[idx] = val
+        setattr(bad, field, arr)
+        with pytest.raises(RuntimeError, match="INVALID_ARGUMENT"):
+            pb.analyze_structure(bad)
+    bad = prob.copy()
+    ptr = bad.lm_obs_ptr.copy()
+    ptr[5] = ptr[6] + 1  # not monotone
+    bad.lm_obs_ptr = ptr
+    with pytest.raises(RuntimeError, match="INVALID_ARGUMENT"):
+        pb.analyze_structure(bad)
