@@ -134,24 +134,36 @@ __global__ void k_b2_unpad(int M, int Mp, int dim, const double* __restrict__ x,
   if (i < dim) y[i] = x[size_t(i / M) * Mp + i % M];
 }
 
-// ---- 8x8 diagonal block, factored IN REGISTERS by the warp that owns the tile.  The tile sits in the DMMA
-// accumulator layout (lane (g, t) holds A[g][2t], A[g][2t+1]); the warp runs the square-root form of
-// Gaussian elimination on [A | I] with row operations: step j scales row j by 1 / sqrt(a_jj) and subtracts
-// multiples of it from the rows below, so that A becomes L^T and the identity becomes W = L^-1 — the only
-// thing the panel and the triangular solves need.  Per pivot the dependent chain is shuffle -> rsqrt ->
-// multiply -> FMA (~110 cycles), every lane issues ~20 instructions; the single-thread version of the first
-// generation (factor, then invert) took ~2,100 cycles per block and was the longest item of a level.
+// ---- 8x8 diagonal block, factored IN REGISTERS by one warp.  The tile sits in the DMMA accumulator layout
+// (lane (g, t) holds A[g][2t], A[g][2t+1]); the warp runs Gaussian elimination on [A | I] with row operations
+// and WITHOUT scaling the pivot rows: step j subtracts (a_gj / a_jj) x row j from the rows g > j, so that the
+// identity becomes W~ = D^1/2 L^-1; the rows are scaled by 1 / sqrt(pivot) once, after the loop, which gives
+// W = L^-1 — the only thing the panel and the triangular solves need (L^T itself is never formed).
+// The dependent chain per pivot is: shuffle (pivot) -> reciprocal -> one FMA.  The reciprocal is the hardware
+// approximation (rcp.approx.ftz.f64, ~20 bits) with two Newton steps (full double precision), four dependent
+// FMAs; the products a_gj x (row j) it multiplies are formed meanwhile.  The first version of this function
+// (scale row j by rsqrt(a_jj), then multiply, then FMA: library rsqrt + two more multiplies on the chain)
+// measured ~2,400 cycles per tile, two thirds of the factorisation's critical path
+// (profiles/r02a_b2_cholesky_phases.txt); the single-thread version of the first generation ~2,100.
 // Returns W in (w0, w1) = W[g][2t], W[g][2t+1]. ----
-//
-// NOT inlined: the factorisation calls it from every slot of its unrolled tile loop, and these kernels run
-// through their code once per launch — the first version (everything unrolled: 13,700 instructions = 219 KB
-// for k_b2_fs<11>, more than the instruction cache) was bound by instruction fetch, 45 us a level whatever
-// the amount of arithmetic.
+__device__ __forceinline__ double b2_rcp(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  return fma(y, e, y);
+}
+
+// NOT inlined: these kernels run through their code once per launch — the first version (everything
+// unrolled: 13,700 instructions = 219 KB for k_b2_fs<11>, more than the instruction cache) was bound by
+// instruction fetch, 45 us a level whatever the amount of arithmetic.
 __device__ __noinline__ double2 b2_diag_factor(double a0, double a1, int* fail) {
   const int lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   double w0 = g == 2 * t ? 1.0 : 0.0;
   double w1 = g == 2 * t + 1 ? 1.0 : 0.0;
+  double mypiv = 1.0;
   bool bad = false;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -162,165 +174,370 @@ __device__ __noinline__ double2 b2_diag_factor(double a0, double a1, int* fail) 
     const double p0 = __shfl_sync(0xffffffffu, a0, 4 * j + t), p1 = __shfl_sync(0xffffffffu, a1, 4 * j + t);  // pivot row,
     const double q0 = __shfl_sync(0xffffffffu, w0, 4 * j + t), q1 = __shfl_sync(0xffffffffu, w1, 4 * j + t);  // my columns
     if (!(ajj > 0.0)) { bad = true; ajj = 1.0; }
-    const double inv = rsqrt(ajj);
-    const double m = arj * inv;
-    const double u0 = p0 * inv, u1 = p1 * inv, v0 = q0 * inv, v1 = q1 * inv;
-    if (g > j) { a0 -= m * u0; a1 -= m * u1; w0 -= m * v0; w1 -= m * v1; }
-    else if (g == j) { a0 = u0; a1 = u1; w0 = v0; w1 = v1; }
+    if (g == j) mypiv = ajj;
+    const double r = b2_rcp(ajj);
+    const double t0 = arj * p0, t1 = arj * p1, s0 = arj * q0, s1 = arj * q1;  // off the chain: no dependence on r
+    if (g > j) { a0 = fma(-t0, r, a0); a1 = fma(-t1, r, a1); w0 = fma(-s0, r, w0); w1 = fma(-s1, r, w1); }
   }
   if (bad && lane == 0) *fail = 1;
-  return make_double2(w0, w1);
+  const double inv = rsqrt(mypiv);
+  return make_double2(w0 * inv, w1 * inv);
 }
 
 // ---- A (Mp x Mp, shared, lower 8x8 tiles valid) <- the panels of its lower Cholesky factor (tiles (I, J),
 // I > J); Dinv[J] = inverse of the J-th diagonal block of the factor (the diagonal tiles themselves are
-// not stored: nothing reads them).  Right-looking, block size 8.  The whole matrix lives in registers as
-// DMMA accumulator fragments (tile u = I (I + 1) / 2 + K is owned by warp u % 8 for the whole
-// factorisation); per block column J: the owners write the column's sub-diagonal tiles to shared memory
-// while the owner of (J, J) factors it in registers and publishes W_J; barrier; the warps scale the panel
-// P_I = A_IJ W_J^T (one DMMA pair per tile); barrier; every owned trailing tile takes C -= P_I P_K^T (one
-// DMMA pair, A and B fragments straight from the panel). ----
+// not stored: nothing reads them).  Right-looking, block size 8, and the DIAGONAL CHAIN HAS ITS OWN WARP:
+//   * the trailing matrix lives in registers as DMMA accumulator fragments, spread over the first 7 warps
+//     (tile u = I (I + 1) / 2 + K is owned by warp u % 7 until it is due);
+//   * a sub-diagonal tile (I, K) is due — written back to shared memory — after the update with block column
+//     K - 1 (it is then the input of panel K); a diagonal tile (I, I) one step EARLIER, after column I - 2;
+//   * the last warp does nothing but the chain: in step J it scales the one panel tile the next diagonal block
+//     needs, P_{J+1,J} = A_{J+1,J} W_J^T, applies the missing update A_{J+1,J+1} -= P P^T and factors the
+//     tile in registers (b2_diag_factor) WHILE the other warps update their trailing tiles with column J.
+// Two block-wide barriers per step (W_J + the due tiles are visible; panel J is complete).  The critical path
+// of a step is barrier + one panel tile + barrier + 2 DMMAs + the 8x8 factor; in the first version the factor,
+// the whole panel and the whole trailing update were serialised (~3,600 cycles a step, 40 k for 88 x 88). ----
 template <int NBK>
 __device__ void b2_cholesky(double* As, double* Dinv, int* fail) {
   constexpr int LD = 8 * NBK + 4;
   constexpr int NT = NBK * (NBK + 1) / 2;
-  constexpr int TPW = (NT + kB2Warps - 1) / kB2Warps;
+  constexpr int NW = kB2Warps - 1;  // trailing warps; warp NW runs the diagonal chain
+  constexpr int TPW = (NT + NW - 1) / NW;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
-  int ti[TPW], tk[TPW];
+  const bool chain = warp == NW;
+  int ti[TPW], tk[TPW], due[TPW];
   double c[TPW][2];
 #pragma unroll
   for (int s = 0; s < TPW; ++s) {
-    const int u = warp + s * kB2Warps;
+    const int u = warp + s * NW;
     int I = -1, K = 0;
-    if (u < NT) {
+    if (!chain && u < NT) {
       I = int((sqrtf(8.0f * float(u) + 1.0f) - 1.0f) * 0.5f);
       while (I * (I + 1) / 2 > u) --I;
       while ((I + 1) * (I + 2) / 2 <= u) ++I;
       K = u - I * (I + 1) / 2;
     }
     ti[s] = I; tk[s] = K;
+    due[s] = I < 0 ? -1 : (I == K ? I - 2 : K - 1);  // last block column this warp applies; < 0: never touched here
     c[s][0] = 0.0; c[s][1] = 0.0;
-    if (I >= 0 && (K >= 1 || I == 0)) {  // the sub-diagonal tiles of block column 0 are the first panel: they stay in shared memory
+    if (due[s] >= 0) {
       const double2 v = *reinterpret_cast<const double2*>(As + (8 * I + g) * LD + 8 * K + 2 * t);
       c[s][0] = v.x; c[s][1] = v.y;
     }
   }
   B2_T0();
-#pragma unroll 1
-  for (int J = 0; J < NBK; ++J) {
-#pragma unroll
-    for (int s = 0; s < TPW; ++s) {
-      if (ti[s] < 0 || tk[s] != J) continue;
-      if (ti[s] == J) {  // warp-uniform: this warp owns the diagonal tile
-        *reinterpret_cast<double2*>(Dinv + 64 * J + g * 8 + 2 * t) = b2_diag_factor(c[s][0], c[s][1], fail);
-      } else if (J > 0) {
-        *reinterpret_cast<double2*>(As + (8 * ti[s] + g) * LD + 8 * J + 2 * t) = make_double2(c[s][0], c[s][1]);
-      }
-    }
-    B2_T(0);
-    __syncthreads();
-    B2_T(1);
-    // panel: P_I = A_IJ W^T  (W = inverse of the diagonal factor)
-    {
-      const double w0 = Dinv[64 * J + g * 8 + t], w1 = Dinv[64 * J + g * 8 + 4 + t];
-      for (int I = J + 1 + warp; I < NBK; I += kB2Warps) {
-        double* tile = As + (8 * I + g) * LD + 8 * J;
-        const double a0 = tile[t], a1 = tile[4 + t];
-        double x[2] = {0.0, 0.0};
-        dmma(x, a0, w0);
-        dmma(x, a1, w1);
-        __syncwarp();
-        *reinterpret_cast<double2*>(tile + 2 * t) = make_double2(x[0], x[1]);
-      }
-    }
-    B2_T(2);
-    __syncthreads();
-    B2_T(3);
-    // trailing tiles in registers
-#pragma unroll
-    for (int s = 0; s < TPW; ++s) {
-      if (ti[s] < 0 || tk[s] <= J) continue;
-      const double* pa = As + (8 * ti[s] + g) * LD + 8 * J;
-      const double* pb = As + (8 * tk[s] + g) * LD + 8 * J;
-      dmma(c[s], -pa[t], pb[t]);
-      dmma(c[s], -pa[4 + t], pb[4 + t]);
-    }
-    B2_T(4);
+  if (chain) {
+    const double2 v = *reinterpret_cast<const double2*>(As + g * LD + 2 * t);
+    *reinterpret_cast<double2*>(Dinv + g * 8 + 2 * t) = b2_diag_factor(v.x, v.y, fail);
   }
   __syncthreads();
+  B2_T(0);
+#pragma unroll 1
+  for (int J = 0; J + 1 < NBK; ++J) {
+    // panel: P_I = A_IJ W_J^T  (W_J = inverse of the diagonal factor); tile (J + 1, J) belongs to the chain warp
+    {
+      const double w0 = Dinv[64 * J + g * 8 + t], w1 = Dinv[64 * J + g * 8 + 4 + t];
+      for (int I = chain ? J + 1 : J + 2 + warp; I < (chain ? J + 2 : NBK); I += NW) {
+        double* tile = As + (8 * I + g) * LD + 8 * J;
+        const double a0 = tile[t], a1 = tile[4 + t];
+        // two independent DMMAs and an add: a DMMA's result is ~160 cycles away (its four k-steps are dependent
+        // FMAs), so chaining the second one on the first's accumulator would double the latency of the tile
+        double x[2] = {0.0, 0.0}, x2[2] = {0.0, 0.0};
+        dmma(x, a0, w0);
+        dmma(x2, a1, w1);
+        __syncwarp();
+        *reinterpret_cast<double2*>(tile + 2 * t) = make_double2(x[0] + x2[0], x[1] + x2[1]);
+      }
+    }
+    B2_T(1);
+    // panel J complete: the trailing warps wait for it; the chain warp only needs its own tile, so it signals
+    // and goes on (named barrier 1; barrier 0 = __syncthreads stays the step barrier)
+    if (chain) {
+      __syncwarp();
+      asm volatile("bar.arrive 1, %0;" ::"n"(kB2Threads) : "memory");  // orders this warp's prior shared-memory writes
+    } else {
+      asm volatile("bar.sync 1, %0;" ::"n"(kB2Threads) : "memory");
+    }
+    B2_T(2);
+    if (chain) {
+      // next diagonal tile: every update but column J's is already in it (its owner wrote it back a step ago)
+      const double2 v = *reinterpret_cast<const double2*>(As + (8 * (J + 1) + g) * LD + 8 * (J + 1) + 2 * t);
+      double d[2] = {v.x, v.y}, d2[2] = {0.0, 0.0};
+      const double* pa = As + (8 * (J + 1) + g) * LD + 8 * J;
+      const double p0 = pa[t], p1 = pa[4 + t];
+      dmma(d, -p0, p0);
+      dmma(d2, -p1, p1);
+      *reinterpret_cast<double2*>(Dinv + 64 * (J + 1) + g * 8 + 2 * t) = b2_diag_factor(d[0] + d2[0], d[1] + d2[1], fail);
+    } else {
+      // trailing tiles in registers; the ones that are due go back to shared memory
+#pragma unroll
+      for (int s = 0; s < TPW; ++s) {
+        if (due[s] < J) continue;
+        const double* pa = As + (8 * ti[s] + g) * LD + 8 * J;
+        const double* pb = As + (8 * tk[s] + g) * LD + 8 * J;
+        dmma(c[s], -pa[t], pb[t]);
+        dmma(c[s], -pa[4 + t], pb[4 + t]);
+        if (due[s] == J)
+          *reinterpret_cast<double2*>(As + (8 * ti[s] + g) * LD + 8 * tk[s] + 2 * t) = make_double2(c[s][0], c[s][1]);
+      }
+    }
+    B2_T(3);
+    __syncthreads();
+    B2_T(4);
+  }
+}
+
+// accumulator layout (lane (g, t): X[g][2t], X[g][2t+1]) -> the two B-operand fragments of the same 8x8 tile
+// (k-slice 0: X[t][g], k-slice 1: X[4+t][g]), with shuffles instead of a round trip through shared memory
+__device__ __forceinline__ void b2_acc_to_b(double c0, double c1, int g, int t, double& b0, double& b1) {
+  const int s0 = 4 * t + (g >> 1), s1 = 4 * (4 + t) + (g >> 1);
+  const double l0 = __shfl_sync(0xffffffffu, c0, s0), h0 = __shfl_sync(0xffffffffu, c1, s0);
+  const double l1 = __shfl_sync(0xffffffffu, c0, s1), h1 = __shfl_sync(0xffffffffu, c1, s1);
+  b0 = (g & 1) ? h0 : l0;
+  b1 = (g & 1) ? h1 : l1;
 }
 
 // ---- W (Mp x 8 nct, shared, leading dimension ldw) <- A^-1 W = L^-T L^-1 W, in place.  A warp owns CT column
-// tiles (8 columns each) at a time and sweeps them forward and backward on its own: the only
-// synchronisation is __syncwarp (no block-wide barrier).  Tiles stay in shared memory in the accumulator
-// layout (one 16-byte load / store per lane and update) and the loops are NOT unrolled over the block rows:
-// the straight-line version with the strip in registers was 2.4 k instructions per sweep and column-tile
-// count, executed once — instruction fetch, not arithmetic, set its time. ----
+// tiles (8 columns each) at a time and sweeps them forward and backward on its own (no block-wide barrier).
+// The whole strip (NBK tiles per column tile) stays in REGISTERS as accumulator fragments; the loop over the
+// block steps J is rolled, the loop over the strip's tiles is unrolled and predicated (I > J / I < J), so that
+// every tile has a compile-time register and the code stays small (the fully unrolled first version — 2.4 k
+// instructions per sweep and column-tile count, executed once — was bound by instruction fetch).  All the
+// factor-fragment loads of a step are independent of its arithmetic; the dependent chain of a step is
+//     X_J = W_J x_J (2 DMMAs) -> shuffle to operand layout -> update of the NEXT tile (2 DMMAs) -> shuffle,
+// the updates of the other tiles fill the FP64 pipe behind it.  (The second version kept the strip in shared
+// memory and re-read every tile around each update: ~870 cycles per block step, 19 k cycles per sweep pair,
+// and 48 us for the 23 column tiles of a level-0 block on one SM against 13 us of FP64 pipe time.) ----
 template <int NBK, int CT>
 __device__ __forceinline__ void b2_solve_tiles(const double* As, const double* Dinv, double* Ws, int ldw, int nct) {
   constexpr int LD = 8 * NBK + 4;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
   for (int ct0 = warp * CT; ct0 < nct; ct0 += kB2Warps * CT) {
-    // a slot beyond the last tile reads the last tile (so the code stays branch-free up to the stores) but never writes
+    // a slot beyond the last tile computes on the last tile (the code stays branch-free) but never writes
     double* col[CT];
     bool on[CT];
+    double x[CT][NBK][2];
+    double n0[CT], n1[CT];  // the tile the next step finishes, picked out of the strip (runtime index)
 #pragma unroll
-    for (int q = 0; q < CT; ++q) { on[q] = ct0 + q < nct; col[q] = Ws + 8 * min(ct0 + q, nct - 1); }
+    for (int q = 0; q < CT; ++q) {
+      on[q] = ct0 + q < nct;
+      col[q] = Ws + 8 * min(ct0 + q, nct - 1);
+#pragma unroll
+      for (int I = 0; I < NBK; ++I) {
+        const double2 v = *reinterpret_cast<const double2*>(col[q] + (8 * I + g) * ldw + 2 * t);
+        x[q][I][0] = v.x; x[q][I][1] = v.y;
+      }
+      n0[q] = x[q][0][0]; n1[q] = x[q][0][1];
+    }
+    // ---- forward: L y = w ----
 #pragma unroll 1
-    for (int dir = 0; dir < 2; ++dir) {
-      // dir 0: forward, L y = w (J ascending, rows below J updated); dir 1: backward, L^T x = y
-#pragma unroll 1
-      for (int jj = 0; jj < NBK; ++jj) {
-        const int J = dir == 0 ? jj : NBK - 1 - jj;
-        // diagonal block: X_J = W_J tile (forward) or W_J^T tile (backward)
-        const double d0 = dir == 0 ? Dinv[64 * J + g * 8 + t] : Dinv[64 * J + t * 8 + g];
-        const double d1 = dir == 0 ? Dinv[64 * J + g * 8 + 4 + t] : Dinv[64 * J + (4 + t) * 8 + g];
-        double xb0[CT], xb1[CT];
-        double x[CT][2];
+    for (int J = 0; J < NBK; ++J) {
+      const double d0 = Dinv[64 * J + g * 8 + t], d1 = Dinv[64 * J + g * 8 + 4 + t];
+      double xb0[CT], xb1[CT];
 #pragma unroll
-        for (int q = 0; q < CT; ++q) {
-          const double* tile = col[q] + 8 * J * ldw;
-          const double b0 = tile[t * ldw + g], b1 = tile[(4 + t) * ldw + g];
-          x[q][0] = 0.0; x[q][1] = 0.0;
-          dmma(x[q], d0, b0);
-          dmma(x[q], d1, b1);
-        }
-        __syncwarp();
+      for (int q = 0; q < CT; ++q) {
+        double b0, b1;
+        b2_acc_to_b(n0[q], n1[q], g, t, b0, b1);
+        double y[2] = {0.0, 0.0}, y2[2] = {0.0, 0.0};  // independent DMMAs + add: see b2_cholesky
+        dmma(y, d0, b0);
+        dmma(y2, d1, b1);
+        y[0] += y2[0]; y[1] += y2[1];
 #pragma unroll
-        for (int q = 0; q < CT; ++q)
-          if (on[q]) *reinterpret_cast<double2*>(col[q] + (8 * J + g) * ldw + 2 * t) = make_double2(x[q][0], x[q][1]);
-        __syncwarp();
+        for (int I = 0; I < NBK; ++I)
+          if (I == J) { x[q][I][0] = y[0]; x[q][I][1] = y[1]; }
+        b2_acc_to_b(y[0], y[1], g, t, xb0[q], xb1[q]);
+      }
 #pragma unroll
-        for (int q = 0; q < CT; ++q) {
-          const double* tile = col[q] + 8 * J * ldw;
-          xb0[q] = tile[t * ldw + g]; xb1[q] = tile[(4 + t) * ldw + g];
-        }
-        // other block rows: tile_I -= L_IJ X_J (forward, I > J) or (L_JI)^T X_J (backward, I < J)
-        const int i_lo = dir == 0 ? J + 1 : 0, i_hi = dir == 0 ? NBK : J;
-#pragma unroll 2
-        for (int I = i_lo; I < i_hi; ++I) {
-          double a0, a1;
-          if (dir == 0) {
-            const double* la = As + (8 * I + g) * LD + 8 * J;
-            a0 = -la[t]; a1 = -la[4 + t];
-          } else {
-            const double* la = As + (8 * J) * LD + 8 * I + g;  // element (g, k) = L[8 J + k][8 I + g]
-            a0 = -la[t * LD]; a1 = -la[(4 + t) * LD];
-          }
+      for (int I = 1; I < NBK; ++I) {  // ascending: the next step's tile (J + 1) first
+        if (I > J) {
+          const double* la = As + (8 * I + g) * LD + 8 * J;
+          const double a0 = -la[t], a1 = -la[4 + t];
 #pragma unroll
           for (int q = 0; q < CT; ++q) {
-            double2* cp = reinterpret_cast<double2*>(col[q] + (8 * I + g) * ldw + 2 * t);
-            const double2 v = *cp;
-            double c[2] = {v.x, v.y};
-            dmma(c, a0, xb0[q]);
-            dmma(c, a1, xb1[q]);
-            if (on[q]) *cp = make_double2(c[0], c[1]);
+            double u[2] = {0.0, 0.0};
+            dmma(x[q][I], a0, xb0[q]);
+            dmma(u, a1, xb1[q]);
+            x[q][I][0] += u[0]; x[q][I][1] += u[1];
           }
         }
-        __syncwarp();
       }
+#pragma unroll
+      for (int q = 0; q < CT; ++q) {
+#pragma unroll
+        for (int I = 1; I < NBK; ++I)
+          if (I == J + 1) { n0[q] = x[q][I][0]; n1[q] = x[q][I][1]; }
+      }
+    }
+    // ---- backward: L^T x = y ----
+#pragma unroll
+    for (int q = 0; q < CT; ++q) { n0[q] = x[q][NBK - 1][0]; n1[q] = x[q][NBK - 1][1]; }
+#pragma unroll 1
+    for (int J = NBK - 1; J >= 0; --J) {
+      const double d0 = Dinv[64 * J + t * 8 + g], d1 = Dinv[64 * J + (4 + t) * 8 + g];  // W_J^T
+      double xb0[CT], xb1[CT];
+#pragma unroll
+      for (int q = 0; q < CT; ++q) {
+        double b0, b1;
+        b2_acc_to_b(n0[q], n1[q], g, t, b0, b1);
+        double y[2] = {0.0, 0.0}, y2[2] = {0.0, 0.0};
+        dmma(y, d0, b0);
+        dmma(y2, d1, b1);
+        y[0] += y2[0]; y[1] += y2[1];
+        if (on[q]) *reinterpret_cast<double2*>(col[q] + (8 * J + g) * ldw + 2 * t) = make_double2(y[0], y[1]);
+        b2_acc_to_b(y[0], y[1], g, t, xb0[q], xb1[q]);
+      }
+#pragma unroll
+      for (int I = NBK - 2; I >= 0; --I) {  // descending: the next step's tile (J - 1) first
+        if (I < J) {
+          const double* la = As + (8 * J) * LD + 8 * I + g;  // element (g, k) = L[8 J + k][8 I + g]
+          const double a0 = -la[t * LD], a1 = -la[(4 + t) * LD];
+#pragma unroll
+          for (int q = 0; q < CT; ++q) {
+            double u[2] = {0.0, 0.0};
+            dmma(x[q][I], a0, xb0[q]);
+            dmma(u, a1, xb1[q]);
+            x[q][I][0] += u[0]; x[q][I][1] += u[1];
+          }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < CT; ++q) {
+#pragma unroll
+        for (int I = 0; I < NBK - 1; ++I)
+          if (I == J - 1) { n0[q] = x[q][I][0]; n1[q] = x[q][I][1]; }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ---- the same solve for FEW column tiles per CTA (the sparse upper levels: the column tiles of an odd block are
+// spread over up to 23 CTAs): a GROUP of WPT warps shares one column tile, warp wi of the group owns the strip
+// tiles wi, wi + WPT, ... in registers.  Per block step the owner of tile J multiplies it by W_J and publishes
+// X_J in shared memory (double-buffered, one named barrier of the group per step); every warp then updates its
+// own tiles.  With one warp per column tile a block step costs ~770 cycles of in-order issue (the warp runs ~160
+// instructions, most of them bookkeeping for the 10 other tiles); here the dependent chain is
+//     select + shuffle -> 2 DMMAs -> add -> store | barrier | load -> 2 DMMAs -> add        (~250 cycles). ----
+template <int NBK, int WPT>
+__device__ __forceinline__ void b2_solve_group(const double* As, const double* Dinv, double* Ws, int ldw, int nct,
+                                               double* xbuf_all) {
+  constexpr int LD = 8 * NBK + 4;
+  constexpr int SL = (NBK + WPT - 1) / WPT;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int grp = warp / WPT, wi = warp % WPT;
+  if (grp >= nct) return;  // no block-wide barrier below
+  double* col = Ws + 8 * grp + g * ldw + 2 * t;   // + 8 I ldw: this lane's accumulator pair of strip tile I
+  double* xbuf = xbuf_all + grp * 128;
+  const int bar_id = 2 + grp;
+  // Everything that depends on the step is kept as a running pointer / counter: the straightforward index
+  // arithmetic (tile -> address, clamping of the inactive slots) compiled to ~180 instructions per block step,
+  // and a lone warp issues them at ~3.6 cycles each — the arithmetic itself is 4 DMMAs.
+  double x[SL][2];
+  int Is[SL];
+#pragma unroll
+  for (int s = 0; s < SL; ++s) {
+    const int I = wi + s * WPT;
+    Is[s] = I < NBK ? I : NBK + 64;  // a slot without a tile: never active in either direction (I > J false, see below)
+    x[s][0] = 0.0; x[s][1] = 0.0;
+    if (I < NBK) {
+      const double2 v = *reinterpret_cast<const double2*>(col + 8 * I * ldw);
+      x[s][0] = v.x; x[s][1] = v.y;
+    }
+  }
+  const double* dfw = Dinv + g * 8 + t;   // W_J   fragments: + 64 J, + 4
+  const double* dbw = Dinv + t * 8 + g;   // W_J^T fragments: + 64 J, + 32
+  double* xst = xbuf + g * 8 + 2 * t;     // publish (accumulator layout), + 64 parity
+  const double* xld = xbuf + t * 8 + g;   // read as B operand, + 32 for the second k-slice
+  int par = 0;
+  // ---- forward: L y = w.  la[s] -> L tile (I_s, J), A-operand fragment of this lane; slots without a tile read
+  // tile (NBK - 1, J) and discard the product ----
+  {
+    const double* la[SL];
+#pragma unroll
+    for (int s = 0; s < SL; ++s) la[s] = As + (8 * min(wi + s * WPT, NBK - 1) + g) * LD + t;
+    int own = 0, sj = 0;  // owner warp of tile J (= J % WPT) and its slot (= J / WPT)
+#pragma unroll 1
+    for (int J = 0; J < NBK; ++J) {
+      double a0[SL], a1[SL];
+#pragma unroll
+      for (int s = 0; s < SL; ++s) { a0[s] = la[s][0]; a1[s] = la[s][4]; la[s] += 8; }
+      if (wi == own) {  // warp-uniform
+        double c0 = x[0][0], c1 = x[0][1];
+#pragma unroll
+        for (int s = 1; s < SL; ++s)
+          if (s == sj) { c0 = x[s][0]; c1 = x[s][1]; }
+        double b0, b1;
+        b2_acc_to_b(c0, c1, g, t, b0, b1);
+        double y[2] = {0.0, 0.0}, y2[2] = {0.0, 0.0};
+        dmma(y, dfw[0], b0);
+        dmma(y2, dfw[4], b1);
+        y[0] += y2[0]; y[1] += y2[1];
+        *reinterpret_cast<double2*>(xst + par) = make_double2(y[0], y[1]);
+#pragma unroll
+        for (int s = 0; s < SL; ++s)
+          if (s == sj) { x[s][0] = y[0]; x[s][1] = y[1]; }
+        }
+      asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(WPT * 32) : "memory");
+      const double xb0 = xld[par], xb1 = xld[par + 32];
+#pragma unroll
+      for (int s = 0; s < SL; ++s) {
+        if (Is[s] > J && Is[s] < NBK) {  // warp-uniform; an idle slot's DMMAs would still occupy the FP64 pipe
+          double u[2] = {0.0, 0.0}, v[2] = {0.0, 0.0};
+          dmma(u, a0[s], xb0);
+          dmma(v, a1[s], xb1);
+          x[s][0] -= u[0] + v[0]; x[s][1] -= u[1] + v[1];
+        }
+      }
+      dfw += 64;
+      par ^= 64;
+      if (++own == WPT) { own = 0; ++sj; }
+    }
+  }
+  // ---- backward: L^T x = y.  la[s] -> element (g, k) = L[8 J + k][8 I_s + g] ----
+  {
+    const double* la[SL];
+#pragma unroll
+    for (int s = 0; s < SL; ++s) la[s] = As + (8 * (NBK - 1) + t) * LD + 8 * min(wi + s * WPT, NBK - 1) + g;
+    int own = (NBK - 1) % WPT, sj = (NBK - 1) / WPT;
+    dbw += 64 * (NBK - 1);
+    double* cst = col + 8 * (NBK - 1) * ldw;
+#pragma unroll 1
+    for (int J = NBK - 1; J >= 0; --J) {
+      double a0[SL], a1[SL];
+#pragma unroll
+      for (int s = 0; s < SL; ++s) { a0[s] = la[s][0]; a1[s] = la[s][4 * LD]; la[s] -= 8 * LD; }
+      if (wi == own) {
+        double c0 = x[0][0], c1 = x[0][1];
+#pragma unroll
+        for (int s = 1; s < SL; ++s)
+          if (s == sj) { c0 = x[s][0]; c1 = x[s][1]; }
+        double b0, b1;
+        b2_acc_to_b(c0, c1, g, t, b0, b1);
+        double y[2] = {0.0, 0.0}, y2[2] = {0.0, 0.0};
+        dmma(y, dbw[0], b0);
+        dmma(y2, dbw[32], b1);
+        y[0] += y2[0]; y[1] += y2[1];
+        *reinterpret_cast<double2*>(xst + par) = make_double2(y[0], y[1]);
+        *reinterpret_cast<double2*>(cst) = make_double2(y[0], y[1]);
+      }
+      asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(WPT * 32) : "memory");
+      const double xb0 = xld[par], xb1 = xld[par + 32];
+#pragma unroll
+      for (int s = 0; s < SL; ++s) {
+        if (Is[s] < J) {
+          double u[2] = {0.0, 0.0}, v[2] = {0.0, 0.0};
+          dmma(u, a0[s], xb0);
+          dmma(v, a1[s], xb1);
+          x[s][0] -= u[0] + v[0]; x[s][1] -= u[1] + v[1];
+        }
+      }
+      dbw -= 64;
+      cst -= 8 * ldw;
+      par ^= 64;
+      if (--own < 0) { own = WPT - 1; --sj; }
     }
   }
 }
@@ -345,6 +562,7 @@ __global__ void __launch_bounds__(kB2Threads, 1) k_b2_fs(B2Level lv, int nct_cta
   double* As = b2_sm;                // [Mp][LD]
   double* Dinv = As + Mp * LD;       // [NBK][64]
   double* Ws = Dinv + NBK * 64;      // [Mp][ldw]
+  double* xbuf = Ws + Mp * ldw;      // [8 groups][2][64]: b2_solve_group
   const int q = blockIdx.x, p = 2 * q + 1;
   const int ct_first = blockIdx.y * nct_cta;
   const int nct = min(nct_cta, NCT - ct_first);
@@ -388,7 +606,10 @@ __global__ void __launch_bounds__(kB2Threads, 1) k_b2_fs(B2Level lv, int nct_cta
   __syncthreads();
   // one column tile per warp while there are warps to spare (a warp's DMMAs serialise on its scheduler's FP64
   // pipe: 264 per tile and sweep pair, 16 cycles each), three in lockstep otherwise
-  if (nct <= kB2Warps) b2_solve_tiles<NBK, 1>(As, Dinv, Ws, ldw, nct);
+  if (nct == 1) b2_solve_group<NBK, 8>(As, Dinv, Ws, ldw, nct, xbuf);
+  else if (nct == 2) b2_solve_group<NBK, 4>(As, Dinv, Ws, ldw, nct, xbuf);
+  else if (nct <= 4) b2_solve_group<NBK, 2>(As, Dinv, Ws, ldw, nct, xbuf);
+  else if (nct <= kB2Warps) b2_solve_tiles<NBK, 1>(As, Dinv, Ws, ldw, nct);
   else b2_solve_tiles<NBK, Cfg::CT>(As, Dinv, Ws, ldw, nct);
   __syncthreads();
   // solution columns -> Uh | Vh | yh (16-byte stores, rows contiguous)
@@ -418,6 +639,7 @@ __global__ void __launch_bounds__(kB2Threads, 1) k_b2_top(B2Level lv, double* __
   double* As = b2_sm;
   double* Dinv = As + Mp * LD;
   double* Ws = Dinv + NBK * 64;  // [Mp][12]: column 0 = b
+  double* xbuf = Ws + Mp * ldw;
   B2_T0();
   b2_stage(As, LD, lv.A, Mp);
   cp_commit();
@@ -427,10 +649,52 @@ __global__ void __launch_bounds__(kB2Threads, 1) k_b2_top(B2Level lv, double* __
   B2_T(8);
   b2_cholesky<NBK>(As, Dinv, fail);
   B2_T(9);
-  b2_solve_tiles<NBK, 1>(As, Dinv, Ws, ldw, 1);
+  b2_solve_group<NBK, 8>(As, Dinv, Ws, ldw, 1, xbuf);
   __syncthreads();
   B2_T(10);
   for (int i = threadIdx.x; i < Mp; i += kB2Threads) x[i] = Ws[i * ldw];
+}
+
+// ---- rows [8 I, 8 I + 8) of b' = b_e - B_e^T yh_r - B_{e-1} yh_l, by ONE warp, as a DMMA tile whose B operand is the
+// vector in column 0 (fragments straight from L2, all loads of a product in flight).  The first version gave a warp
+// 6-11 whole rows, one after the other, each a strided dot product with its own load latency: 7-14 us, the longest
+// role of the update kernels at the sparse levels. ----
+template <int NBK>
+__device__ __forceinline__ void b2_rhs_tile(const B2Level& lv, const B2Level& nx, int pe, int I) {
+  constexpr int Mp = 8 * NBK;
+  const int e = 2 * pe;
+  const bool has_l = e - 1 >= 0, has_r = e + 1 < lv.n;
+  const size_t MM = size_t(Mp) * Mp;
+  const int lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int qr = e / 2, ql = e / 2 - 1;
+  double c[2] = {t == 0 ? lv.b[size_t(e) * Mp + 8 * I + g] : 0.0, 0.0};
+  double c2[2] = {0.0, 0.0};
+  if (has_r) {
+    const double* xa = lv.B + size_t(e) * MM + size_t(t) * Mp + 8 * I + g;  // (B_e^T)[8 I + g][k] = B_e[k][8 I + g]
+    const double* yv = lv.yh + size_t(qr) * Mp + t;
+    double a[Mp / 4], b[Mp / 4];
+#pragma unroll
+    for (int j = 0; j < Mp / 4; ++j) { a[j] = __ldg(xa + size_t(4 * j) * Mp); b[j] = g == 0 ? __ldg(yv + 4 * j) : 0.0; }
+#pragma unroll
+    for (int j = 0; j < Mp / 4; j += 2) {
+      dmma(c, -a[j], b[j]);
+      if (j + 1 < Mp / 4) dmma(c2, -a[j + 1], b[j + 1]);
+    }
+  }
+  if (has_l) {
+    const double* xa = lv.B + size_t(e - 1) * MM + size_t(8 * I + g) * Mp + t;  // B_{e-1}[8 I + g][k]
+    const double* yv = lv.yh + size_t(ql) * Mp + t;
+    double a[Mp / 4], b[Mp / 4];
+#pragma unroll
+    for (int j = 0; j < Mp / 4; ++j) { a[j] = __ldg(xa + 4 * j); b[j] = g == 0 ? __ldg(yv + 4 * j) : 0.0; }
+#pragma unroll
+    for (int j = 0; j < Mp / 4; j += 2) {
+      dmma(c, -a[j], b[j]);
+      if (j + 1 < Mp / 4) dmma(c2, -a[j + 1], b[j + 1]);
+    }
+  }
+  if (t == 0) nx.b[size_t(pe) * Mp + 8 * I + g] = c[0] + c2[0];
 }
 
 // ---- even super blocks of a level -> next level.  grid (n_next, 3):
@@ -459,24 +723,7 @@ __global__ void __launch_bounds__(kB2RedThreads, 1) k_b2_reduce(B2Level lv, B2Le
   const int g = lane >> 2, t = lane & 3;
   const int qr = e / 2, ql = e / 2 - 1;  // odd-block indices of e + 1 and e - 1
   if (role == 2) {
-    // b': warp per row; lanes stride the 8 Mp-long dot products
-    double* red = b2_sm;
-    for (int i = threadIdx.x; i < 2 * Mp; i += kB2RedThreads) {
-      const bool left = i >= Mp;
-      red[i] = (left ? has_l : has_r) ? lv.yh[size_t(left ? ql : qr) * Mp + (left ? i - Mp : i)] : 0.0;
-    }
-    __syncthreads();
-    const double* Be = has_r ? lv.B + size_t(e) * MM : nullptr;
-    const double* Bl = has_l ? lv.B + size_t(e - 1) * MM : nullptr;
-    for (int i = warp; i < Mp; i += kB2RedWarps) {
-      double s = 0.0;
-      for (int k = lane; k < Mp; k += 32) {
-        if (has_r) s += Be[size_t(k) * Mp + i] * red[k];        // (B_e^T yh_r)[i]
-        if (has_l) s += Bl[size_t(i) * Mp + k] * red[Mp + k];   // (B_{e-1} yh_l)[i]
-      }
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (lane == 0) nx.b[size_t(pe) * Mp + i] = lv.b[size_t(e) * Mp + i] - s;
-    }
+    if (warp < NBK) b2_rhs_tile<NBK>(lv, nx, pe, warp);
     return;
   }
   if (role == 1) {
@@ -577,6 +824,63 @@ __global__ void __launch_bounds__(kB2RedThreads, 1) k_b2_reduce(B2Level lv, B2Le
       *reinterpret_cast<double2*>(An + size_t(8 * tI[s] + g) * Mp + 8 * tK[s] + 2 * t) = make_double2(c[s][0], c[s][1]);
 }
 
+// ---- the same update for the SPARSE upper levels (few even blocks): no shared-memory staging.  The staged kernel
+// above spends its time bringing two full operand matrices in (twice, for the right and the left neighbour) before
+// a few warps multiply for a microsecond: 12-14 us per level whatever the level's size.  Here a warp owns ONE
+// output tile and loads its DMMA fragments straight from L2 (a fragment is 8 full 32-byte sectors), all 2 x 22 of
+// a product in flight at once, then runs two independent accumulator chains.  Without the shared-memory reuse
+// a level moves 187 tiles x 2 products x 11 KB per even block through L2, which is why the dense lower levels
+// keep the staged kernel.  grid (n_next, ceil((66 + 121 + 11) / 8)) for 88 x 88 blocks. ----
+template <int NBK>
+__global__ void __launch_bounds__(kB2Threads, 1) k_b2_reduce_direct(B2Level lv, B2Level nx) {
+  constexpr int Mp = 8 * NBK;
+  constexpr int NTL = NBK * (NBK + 1) / 2, NTF = NBK * NBK;
+  const int pe = blockIdx.x, e = 2 * pe;
+  const bool has_l = e - 1 >= 0, has_r = e + 1 < lv.n;
+  const size_t MM = size_t(Mp) * Mp;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int qr = e / 2, ql = e / 2 - 1;  // odd-block indices of e + 1 and e - 1
+  // [0, NTL): lower tiles of A';  [NTL, NTL + NTF): tiles of B';  then NBK row tiles of b'
+  const int u = int(blockIdx.y) * kB2Warps + warp;
+  if (u >= NTL + NTF + NBK) return;
+  if (u >= NTL + NTF) { b2_rhs_tile<NBK>(lv, nx, pe, u - NTL - NTF); return; }
+  // one product: c -= X(I-rows) * Y(K-cols) with the fragment addressing of the caller
+  auto product = [&](double (&c)[2], const double* xa, size_t xa_k, const double* yb) {
+    // xa + kk * xa_k: this lane's A-operand element of k-slice kk / 4 ; yb + kk * Mp: B-operand element
+    double a[Mp / 4], b[Mp / 4];
+#pragma unroll
+    for (int j = 0; j < Mp / 4; ++j) { a[j] = __ldg(xa + size_t(4 * j) * xa_k); b[j] = __ldg(yb + size_t(4 * j) * Mp); }
+    double c2[2] = {0.0, 0.0};
+#pragma unroll
+    for (int j = 0; j < Mp / 4; j += 2) {
+      dmma(c, -a[j], b[j]);
+      if (j + 1 < Mp / 4) dmma(c2, -a[j + 1], b[j + 1]);
+    }
+    c[0] += c2[0]; c[1] += c2[1];
+  };
+  if (u < NTL) {
+    int I = int((sqrtf(8.0f * float(u) + 1.0f) - 1.0f) * 0.5f);
+    while (I * (I + 1) / 2 > u) --I;
+    while ((I + 1) * (I + 2) / 2 <= u) ++I;
+    const int K = u - I * (I + 1) / 2;
+    const double2 v = *reinterpret_cast<const double2*>(lv.A + size_t(e) * MM + size_t(8 * I + g) * Mp + 8 * K + 2 * t);
+    double c[2] = {v.x, v.y};
+    // B_e^T Uh_r: A-operand element (row g of tile I, k) = B_e[k][8 I + g]
+    if (has_r) product(c, lv.B + size_t(e) * MM + size_t(t) * Mp + 8 * I + g, Mp, lv.Uh + size_t(qr) * MM + size_t(t) * Mp + 8 * K + g);
+    // B_{e-1} Vh_l: A-operand element = B_{e-1}[8 I + g][k]
+    if (has_l) product(c, lv.B + size_t(e - 1) * MM + size_t(8 * I + g) * Mp + t, 1, lv.Vh + size_t(ql) * MM + size_t(t) * Mp + 8 * K + g);
+    *reinterpret_cast<double2*>(nx.A + size_t(pe) * MM + size_t(8 * I + g) * Mp + 8 * K + 2 * t) = make_double2(c[0], c[1]);
+  } else {
+    if (e + 2 >= lv.n) return;  // no block beyond e + 1: no coupling at the next level
+    const int w = u - NTL, I = w / NBK, K = w % NBK;
+    double c[2] = {0.0, 0.0};
+    // B' = -B_{e+1} Uh_r
+    product(c, lv.B + size_t(e + 1) * MM + size_t(8 * I + g) * Mp + t, 1, lv.Uh + size_t(qr) * MM + size_t(t) * Mp + 8 * K + g);
+    *reinterpret_cast<double2*>(nx.B + size_t(pe) * MM + size_t(8 * I + g) * Mp + 8 * K + 2 * t) = make_double2(c[0], c[1]);
+  }
+}
+
 // ---- back-substitution: x_p = yh_p - Uh_p x_{p-1} - Vh_p x_{p+1} for the odd blocks of every level, top down,
 // in ONE cooperative kernel (a grid-wide barrier between levels instead of a launch per level; the first
 // version's single-CTA kernel for the upper levels took 185 us, a launch per level 21 us each).  x is indexed
@@ -625,7 +929,7 @@ __global__ void __launch_bounds__(256) k_b2_back_all(int Mp, B2LevelPack pk, int
 
 size_t b2_fs_smem(int nbk, int nct_cta) {
   const int Mp = 8 * nbk;
-  return (size_t(Mp) * b2_ld(Mp) + size_t(nbk) * 64 + size_t(Mp) * (8 * nct_cta + 4)) * sizeof(double);
+  return (size_t(Mp) * b2_ld(Mp) + size_t(nbk) * 64 + size_t(Mp) * (8 * nct_cta + 4) + 8 * 128) * sizeof(double);
 }
 
 constexpr size_t kB2SmemCap = 225 * 1024;
@@ -647,13 +951,19 @@ pba_status b2_launch_level(Handle* h, const B2Level& lv, const B2Level& nx, int 
   if (nx.n * 24 <= n_sm) { PA = 9; PB = 14; }
   else if (nx.n * 11 <= n_sm) { PA = 4; PB = 6; }
   else if (nx.n * 6 <= n_sm) { PA = 2; PB = 3; }
+  static const bool no_direct = getenv("PBA_B2_NO_DIRECT") != nullptr;
+  if (nx.n <= 12 && !no_direct) {
+    constexpr int NCTA = (NBK * (NBK + 1) / 2 + NBK * NBK + NBK + kB2Warps - 1) / kB2Warps;
+    PBA_LAUNCH(h, K_BCR, k_b2_reduce_direct<NBK>, dim3(nx.n, NCTA), dim3(kB2Threads), 0, lv, nx);
+    return PBA_OK;
+  }
   const size_t smem_r = size_t(2) * (8 * NBK) * b2_ld(8 * NBK) * sizeof(double);
   PBA_LAUNCH(h, K_BCR, k_b2_reduce<NBK>, dim3(nx.n, PA + PB + 1), dim3(kB2RedThreads), smem_r, lv, nx, PA, PB);
   return PBA_OK;
 }
 template <int NBK>
 pba_status b2_launch_top(Handle* h, const B2Level& lv, double* x) {
-  const size_t smem = (size_t(8 * NBK) * b2_ld(8 * NBK) + size_t(NBK) * 64 + size_t(8 * NBK) * 12) * sizeof(double);
+  const size_t smem = (size_t(8 * NBK) * b2_ld(8 * NBK) + size_t(NBK) * 64 + size_t(8 * NBK) * 12 + 8 * 128) * sizeof(double);
   PBA_LAUNCH(h, K_BCR, k_b2_top<NBK>, dim3(1), dim3(kB2Threads), smem, lv, x, h->chol_fail.p);
   return PBA_OK;
 }
