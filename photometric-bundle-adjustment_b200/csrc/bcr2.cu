@@ -309,7 +309,7 @@ __device__ __forceinline__ void b2_acc_to_b(double c0, double c1, int g, int t, 
 // the updates of the other tiles fill the FP64 pipe behind it.  (The second version kept the strip in shared
 // memory and re-read every tile around each update: ~870 cycles per block step, 19 k cycles per sweep pair,
 // and 48 us for the 23 column tiles of a level-0 block on one SM against 13 us of FP64 pipe time.) ----
-template <int NBK, int CT>
+template <int NBK, int CT, int UNR = 1>
 __device__ __forceinline__ void b2_solve_tiles(const double* As, const double* Dinv, double* Ws, int ldw, int nct) {
   constexpr int LD = 8 * NBK + 4;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -332,7 +332,10 @@ __device__ __forceinline__ void b2_solve_tiles(const double* As, const double* D
       n0[q] = x[q][0][0]; n1[q] = x[q][0][1];
     }
     // ---- forward: L y = w ----
-#pragma unroll 1
+    // UNR = NBK: the block steps are unrolled too — straight-line code without the tile selects (2 NBK per column
+    // tile and step, ~70 % of the rolled loop's instructions).  Used where the sweeps are throughput-bound (dense
+    // lower levels: every warp has tiles); ~3 k instructions for CT = 3, executed once.
+#pragma unroll UNR
     for (int J = 0; J < NBK; ++J) {
       const double d0 = Dinv[64 * J + g * 8 + t], d1 = Dinv[64 * J + g * 8 + 4 + t];
       double xb0[CT], xb1[CT];
@@ -373,7 +376,7 @@ __device__ __forceinline__ void b2_solve_tiles(const double* As, const double* D
     // ---- backward: L^T x = y ----
 #pragma unroll
     for (int q = 0; q < CT; ++q) { n0[q] = x[q][NBK - 1][0]; n1[q] = x[q][NBK - 1][1]; }
-#pragma unroll 1
+#pragma unroll UNR
     for (int J = NBK - 1; J >= 0; --J) {
       const double d0 = Dinv[64 * J + t * 8 + g], d1 = Dinv[64 * J + (4 + t) * 8 + g];  // W_J^T
       double xb0[CT], xb1[CT];
@@ -609,8 +612,8 @@ __global__ void __launch_bounds__(kB2Threads, 1) k_b2_fs(B2Level lv, int nct_cta
   if (nct == 1) b2_solve_group<NBK, 8>(As, Dinv, Ws, ldw, nct, xbuf);
   else if (nct == 2) b2_solve_group<NBK, 4>(As, Dinv, Ws, ldw, nct, xbuf);
   else if (nct <= 4) b2_solve_group<NBK, 2>(As, Dinv, Ws, ldw, nct, xbuf);
-  else if (nct <= kB2Warps) b2_solve_tiles<NBK, 1>(As, Dinv, Ws, ldw, nct);
-  else b2_solve_tiles<NBK, Cfg::CT>(As, Dinv, Ws, ldw, nct);
+  else if (nct <= kB2Warps) b2_solve_tiles<NBK, 1, NBK>(As, Dinv, Ws, ldw, nct);
+  else b2_solve_tiles<NBK, Cfg::CT, NBK>(As, Dinv, Ws, ldw, nct);
   __syncthreads();
   // solution columns -> Uh | Vh | yh (16-byte stores, rows contiguous)
   double* Uq = lv.Uh + size_t(q) * MM;
