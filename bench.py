@@ -591,6 +591,9 @@ def main():
                 "step": "pba_lm_iterate: J+r eval (K1), Schur/RCS build, solve, back-substitution, model cost, "
                         "candidate cost (K2); state not advanced, so every step does identical work",
                 "rcs_solver": solver_used, "partition": "landmarks by observation count, %d shard(s)" % world,
+                "collective": {"none": "none (one rank)", "nccl": "ncclAllReduce of the partial RCS + scalars",
+                               "peer": "own NVLink kernels over peer-mapped buffers (csrc/peer.cu): reduce-scatter + "
+                                       "push all-gather of the partial RCS, scalar table; NCCL only for set-up"}[eng.collective],
                 "scene_s": t_scene, "create_s": t_create,
             },
             "resjac_obs_per_s": prob.n_obs / (k1_ms * 1e-3) if k1_ms > 0 else None,

@@ -322,6 +322,12 @@ int32_t pba_get_kernel_stats(pba_handle* h, pba_kernel_stat* out, int32_t cap);
 #define PBA_NCCL_ID_BYTES 128
 pba_status pba_nccl_unique_id(uint8_t id[PBA_NCCL_ID_BYTES]);
 pba_status pba_comm_init(pba_handle* h, const uint8_t id[PBA_NCCL_ID_BYTES]);
+/* Which implementation carries the handle's data-path collectives (the sum of the partial reduced camera
+ * systems, the candidate-cost scalars): 0 = none (one rank), 1 = ncclAllReduce, 2 = the library's own
+ * peer-memory kernels over NVLink (csrc/peer.cu: every rank's buffer is mapped by its peers — cudaIpc* between
+ * processes, peer access inside one; PBA_NO_PEER=1 in the environment keeps NCCL).  pba_comm_init sets the
+ * exchange up collectively and falls back to NCCL on every rank if any rank cannot map its peers. */
+int32_t pba_collective_kind(pba_handle* h);
 
 /* ---- stand-alone primitives exposed for parity tests ---- */
 /* Camera models on the device (camera_models.h project/unproject), n points. */

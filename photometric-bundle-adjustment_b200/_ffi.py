@@ -116,7 +116,7 @@ def ptr(a, ctype):
 
 # Every symbol include/pba.h declares (checked by tests/test_abi.py).
 PBA_SYMBOLS = [
-    "pba_abi_version", "pba_status_string", "pba_device_count", "pba_options_init", "pba_solve", "pba_multi_gpu_init", "pba_analyze_structure",
+    "pba_abi_version", "pba_status_string", "pba_device_count", "pba_options_init", "pba_solve", "pba_multi_gpu_init", "pba_analyze_structure", "pba_collective_kind",
     "pba_create", "pba_destroy", "pba_trim_device_cache", "pba_set_stream", "pba_synchronize", "pba_evaluate", "pba_get_residuals",
     "pba_get_jacobians", "pba_get_blocks", "pba_build_rcs", "pba_get_rcs_dim", "pba_get_rcs", "pba_solve_rcs", "pba_minimize",
     "pba_lm_iterate",
@@ -158,6 +158,7 @@ def load_lib():
     sigs = {
         "pba_solve": [C.POINTER(pba_problem), C.POINTER(pba_options), C.POINTER(pba_summary)],
         "pba_multi_gpu_init": [C.c_int32, C.c_int32],
+        "pba_collective_kind": [C.c_void_p],
         "pba_analyze_structure": [C.POINTER(pba_problem), C.POINTER(pba_options), c_i32_p, c_i32_p, c_i32_p, c_i32_p,
                                   c_i64_p],
         "pba_create": [C.POINTER(pba_problem), C.POINTER(pba_options), C.c_int32, C.c_int32, C.POINTER(H)],

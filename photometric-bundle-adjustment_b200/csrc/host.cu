@@ -111,6 +111,7 @@ struct NcclApi {
   int (*GroupStart)() = nullptr;
   int (*GroupEnd)() = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;  // optional: peer-memory set-up
   int (*CommDestroy)(void*) = nullptr;
   bool load() {
     if (lib) return true;
@@ -125,6 +126,7 @@ struct NcclApi {
     GetUniqueId = (int (*)(NcclId*))dlsym(lib, "ncclGetUniqueId");
     CommInitRank = (int (*)(void**, int, NcclId, int))dlsym(lib, "ncclCommInitRank");
     AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(lib, "ncclAllReduce");
+    AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(lib, "ncclAllGather");
     CommDestroy = (int (*)(void*))dlsym(lib, "ncclCommDestroy");
     CommInitAll = (int (*)(void**, int, const int*))dlsym(lib, "ncclCommInitAll");
     GroupStart = (int (*)())dlsym(lib, "ncclGroupStart");
@@ -276,6 +278,7 @@ pba_status allreduce_rcs(Handle* h, bool with_scalars) {
   if (!h->nccl_comm) return PBA_ERR_NCCL;
   const Sizes& z = h->sz;
   const size_t count = size_t(z.n_blocks) * z.cd * z.cd + 3 * size_t(z.dim) + (with_scalars ? size_t(2 + h->world) : 0);
+  if (h->peer) return launch_peer_allreduce(h, count);  // our own NVLink kernel (peer.cu); `rcs` lives in the exchange buffer
   h->stats.begin(K_COPY, h->stream);
   const int rc = g_nccl.AllReduce(h->rcs.p, h->rcs.p, count, kNcclDouble, kNcclSum, h->nccl_comm, h->stream);
   h->stats.end(h->stream);
@@ -285,9 +288,130 @@ pba_status allreduce_rcs(Handle* h, bool with_scalars) {
 pba_status allreduce_scalars(Handle* h, double* dev, int n, bool max_op) {
   if (h->world <= 1) return PBA_OK;
   if (!h->nccl_comm) return PBA_ERR_NCCL;
+  if (h->peer && !max_op && n <= kPeerSmall) return launch_peer_allreduce_small(h, dev, n);
   const int rc = g_nccl.AllReduce(dev, dev, size_t(n), kNcclDouble, max_op ? kNcclMax : kNcclSum, h->nccl_comm, h->stream);
   return rc == 0 ? PBA_OK : PBA_ERR_NCCL;
 }
+
+// ---- exchange allocations of the peer-memory collectives (peer.cu) ----
+// One per communicator and rank, created collectively, kept for the life of the process (like the communicator)
+// and re-created only when a problem needs a larger payload.  PBA_NO_PEER=1 keeps every collective on NCCL.
+namespace {
+
+bool peer_enabled() {
+  static const bool off = getenv("PBA_NO_PEER") != nullptr;
+  return !off;
+}
+
+void peer_release(PeerExchange* px) {
+  if (!px) return;
+  int cur = 0;
+  cudaGetDevice(&cur);
+  cudaSetDevice(px->device);
+  for (int p = 0; p < px->world; ++p) {
+    if (!px->base[p]) continue;
+    if (p == px->rank) cudaFree(px->base[p]);
+    else if (px->ipc) cudaIpcCloseMemHandle(px->base[p]);
+  }
+  cudaGetLastError();
+  cudaSetDevice(cur);
+  delete px;
+}
+
+// one process per GPU: allocate, exchange the IPC handles through the communicator, map the peers.  COLLECTIVE:
+// every rank calls it with the same `payload` (the RCS layout is global).  On any failure EVERY rank ends up
+// without an exchange (the status is all-reduced), so that nobody takes the peer path alone.
+PeerExchange* peer_create_ipc(void* comm, int rank, int world, int device, size_t payload, cudaStream_t stream) {
+  if (!peer_enabled() || world > kMaxPeers || !g_nccl.AllGather) return nullptr;
+  PeerExchange* px = new PeerExchange;
+  px->world = world; px->rank = rank; px->device = device; px->bytes = payload; px->ipc = true;
+  bool ok = true;
+  const size_t total = peer_alloc_bytes(payload);
+  ok = cudaMalloc(reinterpret_cast<void**>(&px->base[rank]), total) == cudaSuccess;
+  if (ok) ok = cudaMemset(px->base[rank], 0, total) == cudaSuccess;
+  cudaIpcMemHandle_t mine;
+  memset(&mine, 0, sizeof(mine));
+  if (ok) ok = cudaIpcGetMemHandle(&mine, px->base[rank]) == cudaSuccess;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  // [world handles | world status doubles] on the device; the gather runs even after a local failure (collective)
+  char* d = nullptr;
+  std::vector<cudaIpcMemHandle_t> all(world);
+  bool comm_ok = cudaMalloc(reinterpret_cast<void**>(&d), size_t(64) * (world + 1) + 64) == cudaSuccess;
+  if (comm_ok) {
+    comm_ok = cudaMemcpyAsync(d + size_t(64) * world, &mine, 64, cudaMemcpyHostToDevice, stream) == cudaSuccess &&
+              g_nccl.AllGather(d + size_t(64) * world, d, 64, /*ncclInt8*/ 0, comm, stream) == 0 &&
+              cudaMemcpyAsync(all.data(), d, size_t(64) * world, cudaMemcpyDeviceToHost, stream) == cudaSuccess &&
+              cudaStreamSynchronize(stream) == cudaSuccess;
+  }
+  ok = ok && comm_ok;
+  if (ok) {
+    for (int p = 0; p < world && ok; ++p) {
+      if (p == rank) continue;
+      void* q = nullptr;
+      ok = cudaIpcOpenMemHandle(&q, all[p], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+      px->base[p] = static_cast<char*>(q);
+    }
+  }
+  cudaGetLastError();
+  // agree: the number of ranks that failed
+  double bad = ok ? 0.0 : 1.0;
+  if (comm_ok) {
+    double* ds = reinterpret_cast<double*>(d + size_t(64) * (world + 1));
+    const bool s_ok = cudaMemcpyAsync(ds, &bad, sizeof(double), cudaMemcpyHostToDevice, stream) == cudaSuccess &&
+                      g_nccl.AllReduce(ds, ds, 1, kNcclDouble, kNcclSum, comm, stream) == 0 &&
+                      cudaMemcpyAsync(&bad, ds, sizeof(double), cudaMemcpyDeviceToHost, stream) == cudaSuccess &&
+                      cudaStreamSynchronize(stream) == cudaSuccess;
+    if (!s_ok) bad = 1.0;
+  }
+  if (d) cudaFree(d);
+  if (bad != 0.0) { peer_release(px); cudaGetLastError(); return nullptr; }
+  for (int p = 0; p < world; ++p) peer_set_layout(px, p);
+  return px;
+}
+
+// one process, n devices starting at device0 (the caller serialises): plain peer access
+bool peer_create_local(int device0, int n, size_t payload, std::vector<PeerExchange*>* out) {
+  out->assign(n, nullptr);
+  if (!peer_enabled() || n > kMaxPeers) return false;
+  int cur = 0;
+  cudaGetDevice(&cur);
+  bool ok = true;
+  for (int i = 0; i < n && ok; ++i)
+    for (int j = 0; j < n && ok; ++j) {
+      if (i == j) continue;
+      int can = 0;
+      ok = cudaDeviceCanAccessPeer(&can, device0 + i, device0 + j) == cudaSuccess && can;
+    }
+  std::vector<char*> base(n, nullptr);
+  const size_t total = peer_alloc_bytes(payload);
+  for (int i = 0; i < n && ok; ++i) {
+    ok = cudaSetDevice(device0 + i) == cudaSuccess;
+    for (int j = 0; j < n && ok; ++j) {
+      if (i == j) continue;
+      const cudaError_t e = cudaDeviceEnablePeerAccess(device0 + j, 0);
+      if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+      else ok = e == cudaSuccess;
+    }
+    if (ok) ok = cudaMalloc(reinterpret_cast<void**>(&base[i]), total) == cudaSuccess && cudaMemset(base[i], 0, total) == cudaSuccess;
+  }
+  for (int i = 0; i < n && ok; ++i) { cudaSetDevice(device0 + i); ok = cudaDeviceSynchronize() == cudaSuccess; }
+  if (!ok) {
+    for (int i = 0; i < n; ++i) if (base[i]) { cudaSetDevice(device0 + i); cudaFree(base[i]); }
+    cudaGetLastError();
+    cudaSetDevice(cur);
+    return false;
+  }
+  for (int r = 0; r < n; ++r) {
+    PeerExchange* px = new PeerExchange;
+    px->world = n; px->rank = r; px->device = device0 + r; px->bytes = payload; px->ipc = false;
+    for (int p = 0; p < n; ++p) { px->base[p] = base[p]; peer_set_layout(px, p); }
+    (*out)[r] = px;
+  }
+  cudaSetDevice(cur);
+  return true;
+}
+
+}  // namespace
 
 namespace {
 
@@ -1245,6 +1369,7 @@ pba_status minimize_impl(Handle* h, pba_summary* sum) {
     // linear-solver failure (invalid step: the radius shrinks, which also improves the conditioning).
     const bool pcg_short = h->last_solver == PBA_SOLVER_PCG && !(hs[S_PCG_RES] <= opt.pcg_tolerance);
     if (pcg_short) ++n_inexact;
+    if (*chol_fail == 3) return PBA_ERR_NCCL;  // a peer-memory collective timed out (peer.cu): a rank is missing
     const bool solved = !(h->last_solver != PBA_SOLVER_PCG && *chol_fail) && !pcg_short && std::isfinite(model_cost_change) &&
                         std::isfinite(hs[S_STEP2]);
     it.model_cost_change = model_cost_change;
@@ -1758,18 +1883,48 @@ PBA_API pba_status pba_comm_init(pba_handle* hh, const uint8_t id[PBA_NCCL_ID_BY
   // Communicators are cached per process, keyed by (id, world, rank, device): ncclCommInitRank
   // costs seconds at 8 ranks, a solve milliseconds, so every later handle given the same id
   // (the SfM loop calls optimize() again and again) reuses the first one.
+  struct Entry { std::string key; void* comm; PeerExchange* px; };
   static std::mutex mu;
-  static std::vector<std::pair<std::string, void*>> cache;
+  static std::vector<Entry> cache;
   std::string key(reinterpret_cast<const char*>(id), PBA_NCCL_ID_BYTES);
   key += "/" + std::to_string(h->world) + "/" + std::to_string(h->rank) + "/" + std::to_string(h->device);
   std::lock_guard<std::mutex> lock(mu);
-  for (auto& kv : cache)
-    if (kv.first == key) { h->nccl_comm = kv.second; return PBA_OK; }
-  void* comm = nullptr;
-  if (g_nccl.CommInitRank(&comm, h->world, nid, h->rank) != 0) return PBA_ERR_NCCL;
-  cache.emplace_back(key, comm);
-  h->nccl_comm = comm;
+  Entry* ent = nullptr;
+  for (auto& e : cache)
+    if (e.key == key) ent = &e;
+  if (!ent) {
+    void* comm = nullptr;
+    if (g_nccl.CommInitRank(&comm, h->world, nid, h->rank) != 0) return PBA_ERR_NCCL;
+    cache.push_back(Entry{key, comm, nullptr});
+    ent = &cache.back();
+  }
+  h->nccl_comm = ent->comm;
+  // the exchange buffer of the peer-memory collectives: every rank sees the same payload size (the RCS layout is
+  // global), so every rank takes the same branch here
+  const size_t payload = h->rcs.n * sizeof(double);
+  if (h->world > 1 && (!ent->px || ent->px->bytes < payload)) {
+    // a larger problem than before: the old mappings go first; the gather inside peer_create_ipc is the
+    // point after which no rank can still be using them
+    PeerExchange* old = ent->px;
+    ent->px = nullptr;
+    if (old) {
+      for (int p = 0; p < old->world; ++p)
+        if (p != old->rank && old->base[p]) { cudaIpcCloseMemHandle(old->base[p]); old->base[p] = nullptr; }
+    }
+    ent->px = peer_create_ipc(ent->comm, h->rank, h->world, h->device, payload + payload / 4, h->stream);
+    if (old) peer_release(old);
+  }
+  if (ent->px) {
+    h->peer = ent->px;
+    h->rcs.p = ent->px->buf[h->rank];  // arena memory is not freed per buffer: the handle's own block simply stays unused
+  }
   return PBA_OK;
+}
+
+PBA_API int32_t pba_collective_kind(pba_handle* hh) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h || h->world <= 1) return 0;
+  return h->peer ? 2 : 1;
 }
 
 // ---- single-process multi-GPU (pba_options.num_gpus) ----
@@ -1781,7 +1936,7 @@ namespace pba {
 namespace {
 
 std::mutex g_multi_mu;
-struct MultiComms { int device0, n; std::vector<void*> comms; };
+struct MultiComms { int device0, n; std::vector<void*> comms; std::vector<PeerExchange*> px; size_t px_bytes = 0; };
 std::vector<MultiComms> g_multi;
 
 pba_status multi_comms(int device0, int n, std::vector<void*>* out) {
@@ -1822,9 +1977,38 @@ pba_status multi_comms(int device0, int n, std::vector<void*>* out) {
     cudaSetDevice(cur);
     if (!ok) return PBA_ERR_NCCL;
   }
-  g_multi.push_back(MultiComms{device0, n, comms});
+  g_multi.push_back(MultiComms{device0, n, comms, {}, 0});
   *out = comms;
   return PBA_OK;
+}
+
+// the exchange buffers of the cached communicators, (re)created when a problem needs a larger payload; no solve
+// may be running on these devices (pba_solve calls are serial in the caller's thread)
+void multi_exchange(int device0, int n, size_t payload, std::vector<PeerExchange*>* out) {
+  out->assign(n, nullptr);
+  std::lock_guard<std::mutex> lock(g_multi_mu);
+  for (MultiComms& m : g_multi) {
+    if (m.device0 != device0 || m.n != n) continue;
+    if (m.px.empty() || m.px_bytes < payload) {
+      if (!m.px.empty()) {
+        int cur = 0;
+        cudaGetDevice(&cur);
+        for (int r = 0; r < n; ++r) {
+          if (!m.px[r]) continue;
+          cudaSetDevice(device0 + r);
+          cudaDeviceSynchronize();
+          cudaFree(m.px[r]->base[r]);
+          delete m.px[r];
+        }
+        cudaSetDevice(cur);
+        m.px.clear();
+      }
+      m.px_bytes = payload + payload / 4;
+      if (!peer_create_local(device0, n, m.px_bytes, &m.px)) { m.px.assign(n, nullptr); }
+    }
+    *out = m.px;
+    return;
+  }
 }
 
 // all threads arrive, then everyone learns whether anyone failed (no rank may enter a collective alone)
@@ -1857,6 +2041,14 @@ pba_status solve_multi_gpu(pba_problem* problem, const pba_options* options, int
   st = analyze_cameras(problem, std::max(1, omp_get_num_procs()), 128 / (problem->mode == PBA_MODE_PHOTOMETRIC ? 8 : 6), &layout);
   if (st != PBA_OK) return st;
   if (timing) fprintf(stderr, "[pba_solve x%d] + camera layout %.1f ms\n", n_gpus, 1e3 * (wall() - t0));
+  std::vector<PeerExchange*> px;
+  {
+    const int cd = problem->mode == PBA_MODE_PHOTOMETRIC ? 8 : 6;
+    int64_t n_blocks = 0;
+    for (const auto& a : layout.adj) n_blocks += int64_t(a.size());
+    const size_t count = size_t(n_blocks) * cd * cd + 3 * size_t(layout.n_slots) * cd + 2 + size_t(n_gpus);
+    multi_exchange(options->device, n_gpus, count * sizeof(double), &px);
+  }
   StatusBarrier barrier(n_gpus);
   std::vector<pba_status> status(n_gpus, PBA_OK);
   std::vector<double> t_setup(n_gpus, 0.0);
@@ -1873,6 +2065,10 @@ pba_status solve_multi_gpu(pba_problem* problem, const pba_options* options, int
     if (timing) fprintf(stderr, "[pba_solve x%d] rank %d created at %.1f ms\n", n_gpus, r, 1e3 * t_setup[r]);
     if (barrier.wait(s) != PBA_OK) { status[r] = s; return; }
     h->nccl_comm = comms[r];
+    if (px[r] && px[r]->bytes >= h->rcs.n * sizeof(double)) {
+      h->peer = px[r];
+      h->rcs.p = px[r]->buf[r];
+    }
     pba_summary local;
     memset(&local, 0, sizeof(local));
     if (r == 0) { local.iterations = its; local.iterations_capacity = cap; }

@@ -318,6 +318,9 @@ struct Handle {
 
   // NCCL
   void* nccl_comm = nullptr;
+  // exchange allocation mapped by every rank (peer.cu): when set, `rcs` points into it and the collectives of the
+  // data path run as our own NVLink kernels instead of ncclAllReduce.  Owned by the communicator cache.
+  struct PeerExchange* peer = nullptr;
   // Tail of the all-reduce buffer `rcs` (world > 1): [0] cost, [1] sum of squared landmark gradients,
   // [2 + r] max |landmark gradient| of rank r (every rank writes its own slot, the others stay 0, so the SUM
   // all-reduce gathers them): one collective per Jacobian evaluation carries the RCS and every scalar.
@@ -371,6 +374,38 @@ int pcg_max_grid(int device);
 int schur_tile_l(int max_stride);
 int eval_grid(int64_t n);
 // host.cu
+// ---- peer-memory collectives (peer.cu) ----
+constexpr int kMaxPeers = 8;     // ranks of one NVSwitch domain
+constexpr int kPeerSmall = 16;   // doubles per rank in the scalar table
+struct PeerExchange {
+  int world = 1, rank = 0, device = 0;
+  size_t bytes = 0;                          // payload capacity of every rank's allocation
+  char* base[kMaxPeers] = {};                // base[rank]: own cudaMalloc; the others: peer mappings
+  double* buf[kMaxPeers] = {};               // payload
+  unsigned long long* flags[kMaxPeers] = {}; // [3][kMaxPeers] epoch counters: barrier A, barrier B, scalar table
+  double* small[kMaxPeers] = {};             // [2][kMaxPeers][kPeerSmall] scalar table, double-buffered by epoch parity
+  unsigned long long epoch = 0, epoch_small = 0;
+  bool ipc = false;                          // peers opened with cudaIpcOpenMemHandle (one process per GPU)
+};
+struct PeerArgs {
+  double* buf[kMaxPeers];
+  unsigned long long* flags[kMaxPeers];
+  double* small[kMaxPeers];
+  int rank, world;
+  size_t count;
+  unsigned long long epoch;
+  int* fail;
+};
+inline size_t peer_alloc_bytes(size_t payload) { return ((payload + 255) & ~size_t(255)) + 256 + 2 * kMaxPeers * kPeerSmall * sizeof(double); }
+inline void peer_set_layout(PeerExchange* px, int p) {
+  char* b = px->base[p];
+  px->buf[p] = reinterpret_cast<double*>(b);
+  px->flags[p] = reinterpret_cast<unsigned long long*>(b + ((px->bytes + 255) & ~size_t(255)));
+  px->small[p] = reinterpret_cast<double*>(b + ((px->bytes + 255) & ~size_t(255)) + 256);
+}
+pba_status launch_peer_allreduce(Handle* h, size_t count);
+pba_status launch_peer_allreduce_small(Handle* h, double* dev, int n);
+
 pba_status allreduce_rcs(Handle* h, bool with_scalars);
 pba_status allreduce_scalars(Handle* h, double* dev, int n, bool max_op);
 

@@ -218,6 +218,11 @@ class Engine:
         n = self.lib.pba_get_kernel_stats(self._h, buf, 64)
         return {buf[i].name.decode(): (buf[i].launches, buf[i].total_ms) for i in range(n)}
 
+    @property
+    def collective(self):
+        """'none' | 'nccl' | 'peer' (include/pba.h: pba_collective_kind)."""
+        return {0: "none", 1: "nccl", 2: "peer"}[int(self.lib.pba_collective_kind(self._h))]
+
     def comm_init(self, nccl_id: bytes):
         arr = (C.c_uint8 * _ffi.NCCL_ID_BYTES).from_buffer_copy(nccl_id)
         _ffi.check(self.lib.pba_comm_init(self._h, arr), "pba_comm_init")

@@ -44,7 +44,7 @@ def main():
         poses, rho, aff = eng.get_state()
         np.savez(os.path.join(outdir, "rank%d.npz" % rank), poses=poses, rho=rho, first=eng.first_landmark,
                  cost0=cost0, initial_cost=s.initial_cost, final_cost=s.final_cost, iterations=s.num_iterations,
-                 costs=np.array([i["cost"] for i in s.iterations]))
+                 costs=np.array([i["cost"] for i in s.iterations]), collective=eng.collective)
         eng.close()
     else:
         import oracle_ffi as of

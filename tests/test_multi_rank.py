@@ -58,11 +58,19 @@ def test_two_rank_sharding_gloo(tmp_path):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("collective", ["peer", "nccl"])
 @pytest.mark.parametrize("mode", [pb.MODE_GEOMETRIC, pb.MODE_PHOTOMETRIC])
-def test_two_gpu_sharded_lm_matches_single_gpu(tmp_path, mode):
+def test_two_gpu_sharded_lm_matches_single_gpu(tmp_path, mode, collective):
+    """One process per GPU.  `peer`: the library's own NVLink collectives over cudaIpc-mapped buffers (csrc/peer.cu,
+    the default); `nccl`: PBA_NO_PEER=1 keeps ncclAllReduce.  Both must reproduce the one-GPU solve."""
     if pb.device_count() < 2:
         pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
-    procs = [subprocess.Popen([sys.executable, WORKER, "gpu", str(r), "2", str(tmp_path), str(mode)]) for r in range(2)]
+    env = dict(os.environ)
+    env.pop("PBA_NO_PEER", None)
+    if collective == "nccl":
+        env["PBA_NO_PEER"] = "1"
+    procs = [subprocess.Popen([sys.executable, WORKER, "gpu", str(r), "2", str(tmp_path), str(mode)], env=env)
+             for r in range(2)]
     for p in procs:
         assert p.wait(timeout=600) == 0
     prob, _ = pb.make_scene(mode, 14, 900, "pinhole")
@@ -70,6 +78,9 @@ def test_two_gpu_sharded_lm_matches_single_gpu(tmp_path, mode):
     ref = prob.copy()
     s = pb.bundle_adjustment(ref, pb.BundleAdjustmentOptions(verbosity_level=0, huber_parameter=hub))
     r0, r1 = np.load(tmp_path / "rank0.npz"), np.load(tmp_path / "rank1.npz")
+    assert str(r0["collective"]) == str(r1["collective"])  # the choice is collective
+    if collective == "nccl":
+        assert str(r0["collective"]) == "nccl"
     for r in (r0, r1):  # every rank reports the global cost trace
         assert int(r["iterations"]) == s.num_iterations
         assert abs(float(r["cost0"]) - s.initial_cost) <= 1e-12 * s.initial_cost

@@ -9,7 +9,7 @@ python -c "
 import json
 d=json.loads(open('gpurun_out/b16.json').read().strip().splitlines()[-1])
 print(d['value'], d['ms_per_step'], 'bcr', d['kernels_ms_per_step']['bcr'])"
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name regex:k_b2 -s 60 -c 20 --csv --log-file $O/bcr2_launches.csv $B > $O/ncu_bcr2.log 2>&1
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name regex:k_b2 -s 66 -c 22 --csv --log-file $O/bcr2_launches.csv $B > $O/ncu_bcr2.log 2>&1
 python - <<'PY'
 import csv
 rows=[r for r in csv.reader(open('gpurun_out/bcr2_launches.csv')) if len(r)>10 and r[0].isdigit()]
