@@ -15,12 +15,12 @@ from .map_io import Map, load_map_file, save_map_file
 from .problem import Problem, partition_landmarks
 from .projections import (ProjectionThresholds, Projections, compute_projections, landmark_positions,
                           triangulate_inverse_depth)
-from .synth import make_scene
+from .synth import make_grid_scene, make_scene
 
 __all__ = [
     "Calibration", "load_calibration", "save_calibration", "initialize_from_double_sphere",
     "BundleAdjustmentOptions", "Engine", "Summary", "bundle_adjustment", "device_count", "multi_gpu_init", "analyze_structure", "triangulate_inverse_depth", "Problem",
-    "partition_landmarks", "make_scene", "MODE_GEOMETRIC", "MODE_PHOTOMETRIC", "CAM_PINHOLE", "CAM_DS",
+    "partition_landmarks", "make_scene", "make_grid_scene", "MODE_GEOMETRIC", "MODE_PHOTOMETRIC", "CAM_PINHOLE", "CAM_DS",
     "CAM_KB4", "CAM_EUCM", "SOLVER_AUTO", "SOLVER_CHOLESKY", "SOLVER_PCG", "SOLVER_BAND", "SOLVER_BCR", "CONVERGENCE", "NO_CONVERGENCE",
     "FAILURE", "ExtensionMissing", "ProjectionThresholds", "Projections", "compute_projections",
     "landmark_positions", "Map", "load_map_file", "save_map_file",

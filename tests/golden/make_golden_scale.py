@@ -34,7 +34,11 @@ CASES = {
     "cfg3_kb4": (pb.MODE_PHOTOMETRIC, 200, 100000, "kb4", 20),
     "cfg4": (pb.MODE_PHOTOMETRIC, 2000, 2000000, "pinhole", 3),
     "cfg5": (pb.MODE_GEOMETRIC, 1000, 1000000, "pinhole", 20),
+    # NOT banded under any camera order: 27 x 27 keyframes of a lawn-mower flight, covisible along
+    # both grid directions; 727 free cameras = 4,362 unknowns, half-bandwidth 113 cameras after reverse Cuthill-McKee
+    "grid": (pb.MODE_GEOMETRIC, 729, 30000, "pinhole", 20),
 }
+GRID = (27, 27)
 RHO_STRIDE = 97  # final inverse distances kept: every 97th landmark
 
 
@@ -44,7 +48,7 @@ def main(names):
         mode, kf, pts, model, iters = CASES[name]
         hub = 9.0 if mode == pb.MODE_PHOTOMETRIC else 1.0
         t0 = time.time()
-        prob, _ = pb.make_scene(mode, kf, pts, model)
+        prob, _ = pb.make_grid_scene(GRID[0], GRID[1], pts) if name == "grid" else pb.make_scene(mode, kf, pts, model)
         # cfg4: the vendored Ceres aborts above 2^31 - 1 Jacobian entries (oracle_ffi.CERES_MAX_NONZEROS); the
         # fixture is made on the longest keyframe prefix it can hold (99.6 % of the observations) and the GPU
         # test solves that same prefix

@@ -67,7 +67,10 @@ def check_against(g, prob, s):
 def run_case(name):
     g = golden(name)
     mode, kf, pts = int(g["mode"]), int(g["n_kf"]), int(g["n_pts"])
-    prob, _ = pb.make_scene(mode, kf, pts, model_name(g))  # CPU renderer: the bytes the fixture was made from
+    if name == "grid":
+        prob, _ = pb.make_grid_scene(27, 27, pts)
+    else:
+        prob, _ = pb.make_scene(mode, kf, pts, model_name(g))  # CPU renderer: the bytes the fixture was made from
     if "n_kf_prefix" in g.files and int(g["n_kf_prefix"]) < kf:
         # config 4: the reference's Ceres cannot hold the whole Jacobian (oracle_ffi.CERES_MAX_NONZEROS);
         # fixture and test use the longest keyframe prefix it can
@@ -97,6 +100,32 @@ def test_config5_full_lm_vs_reference_golden():
 
 def test_config4_three_iterations_vs_reference_golden():
     run_case("cfg4")
+
+
+def test_non_banded_rcs_above_4096_unknowns_vs_reference_golden():
+    """a map whose reduced camera system is not banded under any camera order (27 x 27
+    keyframes of a lawn-mower flight, covisible along both grid directions: 4,362 unknowns, half-bandwidth 113
+    cameras after reverse Cuthill-McKee).  AUTO must take an EXACT solver (the dense tiled Cholesky with the DMMA
+    trailing update) and reproduce the reference's SPARSE_SCHUR run: iteration trace, costs 1e-6, states 1e-5."""
+    prob, s = run_case("grid")
+    assert s.rcs_dim == 4362 and s.rcs_dim > 4096
+    assert s.linear_solver == pb.SOLVER_CHOLESKY
+    assert s.num_inexact_linear_solves == 0
+
+
+def test_non_banded_rcs_with_pcg_reports_what_it_did():
+    """The same map forced onto the iterative solver (what AUTO falls back to above cholesky_max_dim): either
+    every solve reached pcg_tolerance and the run matches the reference, or the summary says how many did not
+    (a truncated solve is never silent)."""
+    g = golden("grid")
+    prob, _ = pb.make_grid_scene(27, 27, int(g["n_pts"]))
+    s = pb.bundle_adjustment(prob, pb.BundleAdjustmentOptions(verbosity_level=0, huber_parameter=1.0, solver=pb.SOLVER_PCG))
+    assert s.linear_solver == pb.SOLVER_PCG
+    if s.num_inexact_linear_solves == 0:
+        assert abs(s.final_cost - float(g["final_cost"])) <= 1e-5 * float(g["final_cost"])
+    else:
+        assert "PCG" in s.message
+    assert s.final_cost < float(g["initial_cost"])
 
 
 def test_config2_full_lm_vs_live_reference():

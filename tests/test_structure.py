@@ -63,6 +63,31 @@ def test_loop_closure_stays_banded():
     assert bw1 <= 2 * bw_chain + 4
 
 
+def test_grid_flight_is_not_banded_under_any_order():
+    """Lawn-mower flight (make_grid_scene): covisibility is a 2-D mesh, so reverse Cuthill-McKee cannot do better
+    than ~ one flight line of keyframes; the layout keeps the narrower of the two orders and reports it."""
+    prob, _ = pb.make_grid_scene(12, 12, 3000)
+    slot, ns, bw0, bw1, nb = pb.analyze_structure(prob)
+    assert ns == 142 and bw1 <= bw0
+    assert bw1 >= 12                                          # wider than the banded solvers take
+    assert nb < ns * (ns + 1) // 2                            # but far from dense
+
+
+def test_grid_flight_oracle_matches_the_reference_golden():
+    """The CPU restatement on the non-banded 27 x 27 flight (4,362 unknowns) against the real reference's run
+    (tests/golden/scale_grid.npz, made by make_golden_scale.py grid)."""
+    import os
+    import oracle_ffi as of
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "scale_grid.npz"))
+    prob, _ = pb.make_grid_scene(27, 27, int(g["n_pts"]))
+    assert prob.n_obs == int(g["n_obs"])
+    s = of.solve("oracle", prob, of.default_options(huber_parameter=1.0, max_num_iterations=20))
+    cost = np.array([i["cost"] for i in s.iterations])
+    assert len(cost) == len(g["iter_cost"])
+    assert np.all(np.abs(cost - g["iter_cost"]) <= 1e-9 * np.abs(g["iter_cost"]))
+    assert np.abs(prob.poses - g["sol_poses"]).max() < 1e-9
+
+
 import pytest  # noqa: E402
 
 
