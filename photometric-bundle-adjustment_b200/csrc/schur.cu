@@ -716,6 +716,113 @@ __global__ void __launch_bounds__(256) k_backsub(int n_lm, int cd, const int* __
   }
 }
 
+// The same computation as a STREAMING mat-vec (the default whenever every host group has at most 31 cameras):
+// the rows of W are contiguous per landmark and all landmarks of a host group multiply the same vector
+// (d_cam of the group's cameras), so
+//   * a warp owns 32 consecutive landmarks; lane j loads landmark j's descriptors once (coalesced),
+//   * the group's vector sits in registers, laid out like the row (lane q holds elements 2q, 2q+1 (+64 per step))
+//     and is reloaded only when the group changes (~1,000 landmarks per group),
+//   * rows are read as 16-byte loads, four landmarks (4 x S independent loads per lane) in flight.
+// k_backsub above chases lm_ptr -> lm_group -> grp_cam_ptr -> grp_cams -> d_cam per landmark and element; ncu
+// (profiles/r02a_backsub_details.txt) showed it at 41 % of the DRAM peak, 77 % of the warp cycles waiting on
+// L1TEX scoreboards.  S = double2 steps per row: row length <= 64 S doubles.
+template <int S>
+__global__ void __launch_bounds__(128, S <= 2 ? 4 : 2) k_backsub_stream(int n_lm, int cd, const int* __restrict__ lm_group,
+                                                         const int* __restrict__ grp_cam_ptr,
+                                                         const int* __restrict__ grp_cams,
+                                                         const int64_t* __restrict__ lm_w_off,
+                                                         const int* __restrict__ lm_w_stride,
+                                                         const int64_t* __restrict__ lm_ptr, const double* __restrict__ W,
+                                                         const double* __restrict__ lm_scale,
+                                                         const double* __restrict__ lm_iete,
+                                                         const double* __restrict__ d_cam, double* __restrict__ d_rho,
+                                                         double* __restrict__ part_model) {
+  __shared__ double sm[4];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int l0 = blockIdx.x * 128 + warp * 32;
+  const int my_l = l0 + lane;
+  const bool my_live = my_l < n_lm && lm_ptr[my_l + 1] > lm_ptr[my_l];
+  const int my_g = my_live ? lm_group[my_l] : -1;
+  const int64_t my_off = my_live ? lm_w_off[my_l] : 0;
+  const int my_stride = my_live ? lm_w_stride[my_l] : 0;
+  const double my_scale = my_live ? lm_scale[my_l] : 0.0, my_iete = my_live ? lm_iete[my_l] : 0.0;
+  double mc = 0.0;
+  int cur_g = -1, cur_c = 0;
+  (void)cur_c;
+  double2 dv[S];
+#pragma unroll
+  for (int s = 0; s < S; ++s) dv[s] = make_double2(0.0, 0.0);
+  // Software pipeline over the eight batches of four landmarks: batch b + 1's loads are issued before batch b's
+  // arithmetic (the group-change branch in the arithmetic keeps the compiler from hoisting them itself).
+  struct Batch { double2 v[4][S], gc[4]; int g[4]; };  // gc (lane 0): [g_l, c_l] = the first two of the row's last eight
+  auto load_batch = [&](int j0, Batch& B) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      B.g[u] = __shfl_sync(0xffffffffu, my_g, j0 + u);
+      const int64_t off = __shfl_sync(0xffffffffu, my_off, j0 + u);
+      const int st = __shfl_sync(0xffffffffu, my_stride, j0 + u);
+      const double2* row = reinterpret_cast<const double2*>(W + off);
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        const int e2 = lane + 32 * s;
+        B.v[u][s] = (B.g[u] >= 0 && 2 * e2 < st) ? __ldcs(row + e2) : make_double2(0.0, 0.0);  // streamed once
+      }
+      B.gc[u] = (B.g[u] >= 0 && lane == 0) ? __ldcs(row + ((st - 8) >> 1)) : make_double2(0.0, 0.0);
+    }
+  };
+  Batch cur;
+  load_batch(0, cur);
+#pragma unroll
+  for (int j0 = 0; j0 < 32; j0 += 4) {
+    Batch nxt;
+    if (j0 + 4 < 32) load_batch(j0 + 4, nxt);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int l = l0 + j0 + u;
+      if (cur.g[u] < 0) {  // warp-uniform: no observations (or beyond the last landmark)
+        if (lane == 0 && l < n_lm) d_rho[l] = 0.0;
+      } else {
+        if (cur.g[u] != cur_g) {
+          cur_g = cur.g[u];
+          const int c0 = grp_cam_ptr[cur_g];
+          cur_c = grp_cam_ptr[cur_g + 1] - c0;
+#pragma unroll
+          for (int s = 0; s < S; ++s) {
+            const int e = 2 * (lane + 32 * s);
+            const int j = e >> 3, i = e & 7;  // i is even: i and i + 1 belong to the same camera
+            double a = 0.0, b = 0.0;
+            if (j < cur_c) {
+              const double* d = d_cam + grp_cams[c0 + j] * cd;
+              if (i < cd) a = d[i];
+              if (i + 1 < cd) b = d[i + 1];
+            }
+            dv[s] = make_double2(a, b);
+          }
+        }
+        // d_cam = -sigma y  =>  sum_a w_la . (sigma_a y_a) = -sum_a w_la . d_a
+        double t = 0.0;
+#pragma unroll
+        for (int s = 0; s < S; ++s) t = fma(cur.v[u][s].x, dv[s].x, fma(cur.v[u][s].y, dv[s].y, t));
+        const double gl = cur.gc[u].x, cl = cur.gc[u].y;  // lane 0 only
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        const double sc = __shfl_sync(0xffffffffu, my_scale, j0 + u), ie = __shfl_sync(0xffffffffu, my_iete, j0 + u);
+        if (lane == 0) {
+          const double y = ie * sc * (gl + t);
+          const double dl = -sc * y;
+          d_rho[l] = dl;
+          mc += -dl * (gl + t + 0.5 * cl * dl);
+        }
+      }
+    }
+    if (j0 + 4 < 32) cur = nxt;
+  }
+  if (lane == 0) sm[warp] = mc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    part_model[blockIdx.x] = (sm[0] + sm[1]) + (sm[2] + sm[3]);
+  }
+}
+
 // Camera part of the model cost change: one thread per RCS block of the raw (unscaled,
 // undamped, this rank's) direct part B:  -d_a^T B_ab d_b (x1/2 on the diagonal), plus
 // -d_a . g_a from the diagonal block's thread.
@@ -1006,9 +1113,22 @@ pba_status launch_backsub(Handle* h) {
   const int g_cam = int((z.n_blocks + 127) / 128);
   double* part = h->red_ws.p;
   if (g_lm > 0) {
-    PBA_LAUNCH(h, K_BACKSUB, k_backsub, dim3(g_lm), dim3(256), 0, z.n_lm, z.cd, h->lm_group.p, h->grp_cam_ptr.p,
-               h->grp_cams.p, h->lm_w_off.p, h->lm_w_stride.p, h->lm_ptr.p, h->W.p, h->lm_scale.p, h->lm_iete.p,
-               h->d_cam.p, h->d_rho.p, part);
+    // streaming mat-vec while a row fits 2 / 4 double2 steps per lane (<= 15 / 31 cameras per host group);
+    // PBA_BACKSUB_V1=1 keeps the per-element kernel for A/B runs
+    static const bool force_v1 = getenv("PBA_BACKSUB_V1") != nullptr;
+    if (!force_v1 && h->max_w_stride <= 128) {
+      PBA_LAUNCH(h, K_BACKSUB, k_backsub_stream<2>, dim3(g_lm), dim3(128), 0, z.n_lm, z.cd, h->lm_group.p, h->grp_cam_ptr.p,
+                 h->grp_cams.p, h->lm_w_off.p, h->lm_w_stride.p, h->lm_ptr.p, h->W.p, h->lm_scale.p, h->lm_iete.p,
+                 h->d_cam.p, h->d_rho.p, part);
+    } else if (!force_v1 && h->max_w_stride <= 256) {
+      PBA_LAUNCH(h, K_BACKSUB, k_backsub_stream<4>, dim3(g_lm), dim3(128), 0, z.n_lm, z.cd, h->lm_group.p, h->grp_cam_ptr.p,
+                 h->grp_cams.p, h->lm_w_off.p, h->lm_w_stride.p, h->lm_ptr.p, h->W.p, h->lm_scale.p, h->lm_iete.p,
+                 h->d_cam.p, h->d_rho.p, part);
+    } else {
+      PBA_LAUNCH(h, K_BACKSUB, k_backsub, dim3(g_lm), dim3(256), 0, z.n_lm, z.cd, h->lm_group.p, h->grp_cam_ptr.p,
+                 h->grp_cams.p, h->lm_w_off.p, h->lm_w_stride.p, h->lm_ptr.p, h->W.p, h->lm_scale.p, h->lm_iete.p,
+                 h->d_cam.p, h->d_rho.p, part);
+    }
   }
   if (g_cam > 0) {
     PBA_LAUNCH(h, K_MODEL_COST, k_model_cost_cam, dim3(g_cam), dim3(128), 0, z.cd, z.n_blocks, h->d_blk_row.p,
