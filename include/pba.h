@@ -401,6 +401,44 @@ pba_status pba_triangulate_inverse_depth(int32_t model0, const double intr0[8], 
                                          const double* uv0, const double* uv1, int32_t device, double* p_c0,
                                          double* inv_depth);
 
+/* ---- the feature front-end that produces the BA problem ----
+ * The SfM pipeline in front of bundle_adjustment() (src/sfm.cpp:1191-1330): per image
+ * detectKeypointsAndDescriptors() (include/visnav/keypoints.h:133-245), then matchDescriptors()
+ * (keypoints.h:248-300) for the stereo pairs (match_stereo, src/sfm.cpp:1216-1262, followed by
+ * findInliersEssential, include/visnav/matching_utils.h:62-79) and for ALL image pairs (match_all,
+ * src/sfm.cpp:1286-1330).  Corner DETECTION stays with the caller (the reference calls
+ * cv::goodFeaturesToTrack); everything after it is byte / integer work and is bit-exact here. */
+
+/* computeAngles() + computeDescriptors() (keypoints.h:182-245) for the corners of n_images images of one size.
+ * images: HOST, n_images x image_stride bytes, row pitch `pitch`; corner_ptr [n_images + 1] (CSR into corners);
+ * corners [n][2] = (x, y) doubles, each at least 19 pixels (EDGE_THRESHOLD, keypoints.h:50) inside its image,
+ * as detectKeypoints() guarantees (keypoints.h:146-150) — anything else is PBA_ERR_INVALID_ARGUMENT.
+ * rotate_features = 0: all angles 0 (keypoints.h:194).  Outputs (HOST): angles [n] (radians, atan2 of the patch's
+ * intensity centroid), descriptors [n][32]: bit d of the reference's std::bitset<256> is bit d % 8 of byte d / 8. */
+pba_status pba_corner_descriptors(const uint8_t* images, int32_t n_images, int64_t image_stride, int32_t width,
+                                  int32_t height, int32_t pitch, const int32_t* corner_ptr, const double* corners,
+                                  int32_t rotate_features, int32_t device, double* angles, uint8_t* descriptors);
+
+/* matchDescriptors() (keypoints.h:248-300) for a LIST of image pairs in one call: brute-force Hamming distance in
+ * both directions, best match kept when its distance < threshold and the second best >= best * dist_2_best
+ * (ties: the lowest index wins, as the reference's strict comparisons do), and a match (i, j) survives when
+ * i -> j and j -> i agree.  set_ptr [n_sets + 1]: CSR into descriptors [.][32] (one set per image); pairs
+ * [n_pairs][2] = set indices (first, second).  Outputs (HOST): match_ptr [n_pairs + 1], matches [capacity][2] =
+ * (index in the first set, index in the second set) per pair, ascending in the first index (the reference's own
+ * order is its unordered_map's, keypoints.h:291-297).  capacity >= sum over pairs of min(|first|, |second|) always
+ * suffices; a smaller buffer that overflows returns PBA_ERR_INVALID_ARGUMENT with match_ptr filled in. */
+pba_status pba_match_descriptors(int32_t n_sets, const int32_t* set_ptr, const uint8_t* descriptors, int32_t n_pairs,
+                                 const int32_t* pairs, int32_t threshold, double dist_2_best, int32_t device,
+                                 int64_t* match_ptr, int32_t* matches, int64_t capacity);
+
+/* computeEssential() + findInliersEssential() (matching_utils.h:50-79): E = [t / |t|]x R of T_0_1 (7 doubles, Sophus
+ * order) — returned in E_out [9] (row-major, may be NULL) — and inlier[k] = |x0^T E x1| <= threshold for match k,
+ * x = unproject(corner) with each camera's model (camera_models.h).  All pointers HOST. */
+pba_status pba_epipolar_inliers(int32_t model0, const double intr0[8], int32_t model1, const double intr1[8],
+                                const double T_0_1[7], double threshold, int64_t n_matches, const int32_t* matches,
+                                const double* corners0, const double* corners1, int32_t device, double* E_out,
+                                uint8_t* inlier);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1187,3 +1187,157 @@ ORACLE_API int pba_oracle_triangulate(int model0, const double* intr0, int model
   return 0;
 }
 
+
+// ===================================================================== front-end ====
+// CPU restatement of the reference's descriptor / matching / epipolar functions, pinned by
+// tests/golden/frontend_euroc.npz (made by tests/golden/make_golden_frontend.py from the reference's own
+// functions, oracle/ref/frontend_harness.cpp) and, when oracle/_ref travelled, against that library live.
+//   computeAngles ........ include/visnav/keypoints.h:182-212
+//   computeDescriptors ... include/visnav/keypoints.h:214-245
+//   matchSets / matchDescriptors ... include/visnav/keypoints.h:248-300
+//   computeEssential / findInliersEssential ... include/visnav/matching_utils.h:50-79
+namespace {
+// the reference's four point tables (keypoints.h:54-131), one array per coordinate as there
+const signed char kXa[256] = {
+    8,4,-11,7,2,1,-2,-13,-13,10,-13,-11,7,-4,-13,-9,12,-3,-6,11,4,5,3,-8,-2,-13,-7,-4,-10,5,5,1,
+    9,4,2,-4,-8,4,0,-13,-3,-6,8,0,7,-13,10,-6,10,-13,-13,3,5,-1,3,2,-13,-13,-13,-7,6,-9,-2,-12,
+    3,-7,-3,2,-11,-1,5,-4,-9,-12,10,7,-7,-4,7,-7,-13,-3,7,-13,1,2,-4,-1,7,1,9,-1,-13,7,12,6,
+    5,2,3,2,9,-8,-11,1,6,2,6,3,7,-11,-10,-5,-10,8,4,-10,4,-2,-5,7,-9,-5,8,-9,1,7,-2,11,
+    -12,3,5,0,-9,0,-1,5,3,-13,-5,-4,6,-7,-13,1,4,-2,2,-2,4,-6,-3,7,4,-13,7,7,-7,-8,-13,2,
+    10,-6,8,2,-11,-12,-11,5,-2,-1,-13,-10,-3,2,-9,-4,-4,-6,6,-13,11,7,-1,-4,-7,-13,-7,-8,-5,-13,1,1,
+    9,5,-1,-9,-1,-13,8,2,7,-10,-10,4,3,-4,5,4,-9,0,-12,3,-10,8,-8,2,10,6,-7,-3,-1,-3,-8,4,
+    2,6,3,11,-3,4,2,-10,-13,-13,6,0,-13,-9,-13,5,2,-1,9,11,3,-1,3,-13,5,8,7,-10,7,9,7,-1
+};
+const signed char kYa[256] = {
+    -3,2,9,-12,-13,-7,-10,-13,-3,4,-8,7,7,-5,2,0,-6,6,-13,-13,7,-3,-7,-7,11,12,3,2,-12,-12,-6,0,
+    11,7,-1,-12,-5,11,-8,-2,-2,9,12,9,-5,-6,7,-3,-9,8,0,3,7,7,-10,-4,0,-7,3,12,-10,-1,-5,5,
+    -10,-7,-2,9,-13,6,-3,-13,-6,-10,2,12,-13,9,-1,6,11,7,-8,-7,-3,-6,3,-13,1,-1,1,-9,-13,7,-5,3,
+    -13,-12,8,6,-12,4,12,12,-9,3,3,-3,8,-5,11,-8,5,-1,-6,12,-2,0,-8,-6,-13,-13,-8,-11,-8,-4,1,-6,
+    -9,7,5,-4,12,7,2,11,5,-4,9,-7,5,6,6,-10,1,-2,-12,-13,1,-10,-13,5,-2,9,1,-8,-4,11,6,4,
+    -5,-5,-3,-12,-2,-13,0,-3,-13,-8,-11,-2,9,-3,-13,6,12,-11,-3,11,11,-5,12,-8,1,-12,-2,5,-1,7,5,0,
+    12,-8,11,-3,-10,1,-11,-13,-13,-10,-8,-6,12,2,-13,-13,9,3,1,2,-10,-13,-12,2,6,8,10,-9,-13,-7,-2,2,
+    -5,-9,-1,-1,0,-11,-4,-6,7,12,0,-1,3,8,-6,-9,7,-6,5,-3,0,4,-6,0,8,9,-4,4,3,-7,0,-6
+};
+const signed char kXb[256] = {
+    9,7,-8,12,2,1,-2,-11,-12,11,-8,-9,12,-3,-12,-7,12,-2,-4,12,5,10,6,-6,-1,-8,-5,-3,-6,6,7,4,
+    11,4,4,-2,-7,9,1,-8,-2,-4,10,1,11,-11,12,-6,12,-8,-8,7,10,1,5,3,-13,-12,-11,-4,12,-7,0,-7,
+    8,-4,-1,5,-5,0,5,-4,-9,-8,12,12,-6,-3,12,-5,-12,-2,12,-11,12,3,-2,1,8,3,12,-1,-10,10,12,7,
+    6,2,4,12,10,-7,-4,2,7,3,11,8,9,-6,-5,-3,-9,12,6,-8,6,-2,-5,10,-8,-5,9,-9,1,9,-1,12,
+    -6,7,10,2,-5,2,1,7,6,-8,-3,-3,8,-6,-5,3,8,2,12,0,9,-3,-1,12,5,-9,8,7,-7,-7,-12,3,
+    12,-6,9,2,-10,-7,-10,11,-1,0,-12,-10,-2,3,-4,-3,-2,-4,6,-5,12,12,0,-3,-6,-8,-6,-6,-4,-8,5,10,
+    10,10,1,-6,1,-8,10,3,12,-5,-8,8,8,-3,10,5,-4,3,-6,4,-10,12,-6,3,11,8,-6,-3,-1,-3,-8,12,
+    3,11,7,12,-3,4,2,-8,-11,-11,11,1,-9,-6,-8,8,3,-1,11,12,3,0,4,-10,12,9,8,-10,12,10,12,0
+};
+const signed char kYb[256] = {
+    5,-12,2,-13,12,6,-4,-8,-9,9,-9,12,6,0,-3,5,-1,12,-8,-8,1,-3,12,-2,-10,10,-3,7,11,-7,-1,-5,
+    -13,12,4,7,-10,12,-13,2,3,-9,7,3,-10,0,1,12,-4,-12,-4,8,-7,-12,6,-10,5,12,8,7,8,-6,12,5,
+    -13,5,-7,-11,-13,-1,2,12,6,-4,-3,12,5,4,2,1,5,-6,-7,-12,12,0,-13,9,-6,12,6,3,5,12,9,11,
+    10,3,-6,-13,3,9,-6,-8,-4,-2,0,-8,3,-4,10,12,0,-6,-11,7,7,12,2,12,-8,-2,-13,0,-2,1,-4,-11,
+    4,12,8,8,-13,12,7,-9,-8,9,-3,-12,0,12,-2,10,-4,-13,12,-6,3,-5,1,-11,-7,-5,6,6,1,-8,-8,9,
+    3,7,-8,8,3,-9,-5,8,12,9,-5,11,-13,2,0,-10,-7,9,11,5,6,-2,7,-2,7,-13,-8,-9,5,10,-13,-13,
+    -1,-9,-13,2,12,-10,-6,-6,-9,-7,-13,5,-13,-3,-12,-1,3,-9,1,-8,9,12,-5,7,-8,-12,5,9,5,4,3,12,
+    11,-13,12,4,6,12,1,1,1,-13,-13,4,-2,-3,-2,10,-9,-1,-2,-8,5,10,5,5,11,-6,-12,9,4,-2,-2,-11
+};
+
+inline int px(const uint8_t* img, int pitch, int x, int y) { return img[int64_t(y) * pitch + x]; }
+}  // namespace
+
+ORACLE_API int pba_oracle_corner_descriptors(const uint8_t* image, int w, int h, int pitch, int n, const double* corners,
+                                             int rotate_features, double* angles, uint8_t* descriptors) {
+  (void)w; (void)h;
+  for (int i = 0; i < n; ++i) {
+    const int cx = int(corners[2 * i]), cy = int(corners[2 * i + 1]);
+    double angle = 0.0;
+    if (rotate_features) {
+      double m01 = 0.0, m10 = 0.0;
+      for (int x = -15; x <= 15; ++x) {
+        const int yb = int(sqrt(double(15 * 15 - x * x)));
+        for (int y = -yb; y <= yb; ++y) {
+          const int v = px(image, pitch, cx + x, cy + y);
+          m01 += y * v;
+          m10 += x * v;
+        }
+      }
+      angle = atan2(m01, m10);
+    }
+    angles[i] = angle;
+    const double cs = cos(angle), sn = sin(angle);
+    uint8_t* d = descriptors + 32 * int64_t(i);
+    memset(d, 0, 32);
+    for (int b = 0; b < 256; ++b) {
+      const int xa = int(round(cs * kXa[b] - sn * kYa[b])), ya = int(round(sn * kXa[b] + cs * kYa[b]));
+      const int xb = int(round(cs * kXb[b] - sn * kYb[b])), yb = int(round(sn * kXb[b] + cs * kYb[b]));
+      if (px(image, pitch, cx + xa, cy + ya) < px(image, pitch, cx + xb, cy + yb)) d[b / 8] |= uint8_t(1u << (b % 8));
+    }
+  }
+  return 0;
+}
+
+namespace {
+int hamming256(const uint8_t* a, const uint8_t* b) {
+  int d = 0;
+  for (int k = 0; k < 32; ++k) d += __builtin_popcount(unsigned(a[k] ^ b[k]));
+  return d;
+}
+void match_sets(int n1, const uint8_t* d1, int n2, const uint8_t* d2, int threshold, double ratio, std::vector<int>& out) {
+  out.assign(n1, -1);
+  for (int i = 0; i < n1; ++i) {
+    int smallest = 256, second = 256, best = 0;
+    for (int j = 0; j < n2; ++j) {
+      const int dist = hamming256(d1 + 32 * int64_t(i), d2 + 32 * int64_t(j));
+      if (dist < smallest) { second = smallest; smallest = dist; best = j; }
+      else if (dist < second) second = dist;
+    }
+    if (smallest >= threshold) best = -1;
+    if (second < smallest * ratio) best = -1;
+    if (n2 == 0) best = -1;
+    out[i] = best;
+  }
+}
+}  // namespace
+
+// matches [min(n1, n2)][2], ascending in the first index; returns the count
+ORACLE_API int pba_oracle_match_descriptors(int n1, const uint8_t* d1, int n2, const uint8_t* d2, int threshold,
+                                            double dist_2_best, int32_t* matches) {
+  std::vector<int> pq, qp;
+  match_sets(n1, d1, n2, d2, threshold, dist_2_best, pq);
+  match_sets(n2, d2, n1, d1, threshold, dist_2_best, qp);
+  int n = 0;
+  for (int i = 0; i < n1; ++i)
+    if (pq[i] != -1 && qp[pq[i]] == i) { matches[2 * n] = i; matches[2 * n + 1] = pq[i]; ++n; }
+  return n;
+}
+
+ORACLE_API int pba_oracle_epipolar_inliers(int model0, const double* intr0, int model1, const double* intr1,
+                                           const double* T_0_1, double threshold, int64_t n_matches, const int32_t* matches,
+                                           const double* corners0, const double* corners1, double* E_out, uint8_t* inlier) {
+  // E = [t / |t|]x R  (matching_utils.h:50-60)
+  const Q4<double> q{T_0_1[0], T_0_1[1], T_0_1[2], T_0_1[3]};
+  double R[3][3];
+  for (int c = 0; c < 3; ++c) {
+    V3<double> e{c == 0 ? 1.0 : 0.0, c == 1 ? 1.0 : 0.0, c == 2 ? 1.0 : 0.0};
+    const V3<double> r = rotate(q, e);
+    R[0][c] = r.x; R[1][c] = r.y; R[2][c] = r.z;
+  }
+  const double nt = sqrt(T_0_1[4] * T_0_1[4] + T_0_1[5] * T_0_1[5] + T_0_1[6] * T_0_1[6]);
+  const double t[3] = {T_0_1[4] / nt, T_0_1[5] / nt, T_0_1[6] / nt};
+  const double S[3][3] = {{0.0, -t[2], t[1]}, {t[2], 0.0, -t[0]}, {-t[1], t[0], 0.0}};
+  double E[3][3];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) E[i][j] = S[i][0] * R[0][j] + S[i][1] * R[1][j] + S[i][2] * R[2][j];
+  if (E_out)
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) E_out[3 * i + j] = E[i][j];
+  int n_in = 0;
+  for (int64_t k = 0; k < n_matches; ++k) {
+    const int i = matches[2 * k], j = matches[2 * k + 1];
+    const V3<double> xl = unproject<double>(model0, intr0, corners0[2 * i], corners0[2 * i + 1]);
+    const V3<double> xr = unproject<double>(model1, intr1, corners1[2 * j], corners1[2 * j + 1]);
+    const double e0 = E[0][0] * xr.x + E[0][1] * xr.y + E[0][2] * xr.z;
+    const double e1 = E[1][0] * xr.x + E[1][1] * xr.y + E[1][2] * xr.z;
+    const double e2 = E[2][0] * xr.x + E[2][1] * xr.y + E[2][2] * xr.z;
+    inlier[k] = fabs(xl.x * e0 + xl.y * e1 + xl.z * e2) <= threshold ? 1 : 0;
+    n_in += inlier[k];
+  }
+  return n_in;
+}

@@ -222,3 +222,80 @@ def triangulate(lib_kind, model0, intr0, model1, intr1, T_w_c0, T_w_c1, uv0, uv1
             _ffi.ptr(rho, C.c_double))
     assert rc == 0, rc
     return p, rho
+
+
+# ---- front-end checkers: oracle restatement and the reference's own functions ----
+REF_FRONTEND_SO = os.path.join(_ROOT, "oracle", "_ref", "libpba_ref_frontend.so")
+_ref_fe = None
+
+
+def have_ref_frontend():
+    return os.path.exists(REF_FRONTEND_SO)
+
+
+def _frontend_lib(kind):
+    global _ref_fe
+    if kind == "oracle":
+        return oracle(), "pba_oracle"
+    if _ref_fe is None:
+        _ref_fe = C.CDLL(REF_FRONTEND_SO)
+    return _ref_fe, "pba_ref"
+
+
+def corner_descriptors(kind, image, corners, rotate_features=True):
+    """computeAngles + computeDescriptors of one image: (angles [n], descriptors [n, 32])."""
+    lib, pre = _frontend_lib(kind)
+    image = np.ascontiguousarray(image, np.uint8)
+    corners = np.ascontiguousarray(corners, np.float64).reshape(-1, 2)
+    h, w = image.shape
+    n = len(corners)
+    ang = np.zeros(n)
+    desc = np.zeros((n, 32), np.uint8)
+    f = getattr(lib, pre + "_corner_descriptors")
+    f.argtypes = [C.POINTER(C.c_uint8), C.c_int, C.c_int, C.c_int, C.c_int, _d, C.c_int, _d, C.POINTER(C.c_uint8)]
+    f(_ffi.ptr(image, C.c_uint8), w, h, w, n, _ffi.ptr(corners, C.c_double), int(bool(rotate_features)),
+      _ffi.ptr(ang, C.c_double), _ffi.ptr(desc, C.c_uint8))
+    return ang, desc
+
+
+def match_descriptors(kind, d1, d2, threshold=70, dist_2_best=1.2):
+    """matchDescriptors: [q, 2] int32, ascending in the first index."""
+    lib, pre = _frontend_lib(kind)
+    d1 = np.ascontiguousarray(d1, np.uint8).reshape(-1, 32)
+    d2 = np.ascontiguousarray(d2, np.uint8).reshape(-1, 32)
+    out = np.zeros((max(min(len(d1), len(d2)), 1), 2), np.int32)
+    f = getattr(lib, pre + "_match_descriptors")
+    f.argtypes = [C.c_int, C.POINTER(C.c_uint8), C.c_int, C.POINTER(C.c_uint8), C.c_int, C.c_double, C.POINTER(C.c_int32)]
+    f.restype = C.c_int
+    n = f(len(d1), _ffi.ptr(d1, C.c_uint8), len(d2), _ffi.ptr(d2, C.c_uint8), int(threshold), float(dist_2_best),
+          _ffi.ptr(out, C.c_int32))
+    return out[:n].copy()
+
+
+def epipolar_inliers(kind, model0, intr0, model1, intr1, T_0_1, matches, corners0, corners1, threshold=1e-3):
+    """(E [3, 3], inlier mask) from computeEssential + findInliersEssential."""
+    lib, pre = _frontend_lib(kind)
+    i0 = np.ascontiguousarray(intr0, np.float64).reshape(8)
+    i1 = np.ascontiguousarray(intr1, np.float64).reshape(8)
+    T = np.ascontiguousarray(T_0_1, np.float64).reshape(7)
+    matches = np.ascontiguousarray(matches, np.int32).reshape(-1, 2)
+    c0 = np.ascontiguousarray(corners0, np.float64).reshape(-1, 2)
+    c1 = np.ascontiguousarray(corners1, np.float64).reshape(-1, 2)
+    E = np.zeros(9)
+    inl = np.zeros(max(len(matches), 1), np.uint8)
+    u8 = C.POINTER(C.c_uint8)
+    if kind == "oracle":
+        f = lib.pba_oracle_epipolar_inliers
+        f.argtypes = [C.c_int, _d, C.c_int, _d, _d, C.c_double, C.c_int64, C.POINTER(C.c_int32), _d, _d, _d, u8]
+        f(int(model0), _ffi.ptr(i0, C.c_double), int(model1), _ffi.ptr(i1, C.c_double), _ffi.ptr(T, C.c_double),
+          float(threshold), len(matches), _ffi.ptr(matches, C.c_int32), _ffi.ptr(c0, C.c_double), _ffi.ptr(c1, C.c_double),
+          _ffi.ptr(E, C.c_double), _ffi.ptr(inl, C.c_uint8))
+    else:
+        lib.pba_ref_compute_essential.argtypes = [_d, _d]
+        lib.pba_ref_compute_essential(_ffi.ptr(T, C.c_double), _ffi.ptr(E, C.c_double))
+        f = lib.pba_ref_epipolar_inliers
+        f.argtypes = [C.c_int, C.POINTER(C.c_int32), C.c_int, _d, C.c_int, _d, C.c_int, _d, C.c_int, _d, _d, C.c_double, u8]
+        f(len(matches), _ffi.ptr(matches, C.c_int32), len(c0), _ffi.ptr(c0, C.c_double), len(c1), _ffi.ptr(c1, C.c_double),
+          int(model0), _ffi.ptr(i0, C.c_double), int(model1), _ffi.ptr(i1, C.c_double), _ffi.ptr(E, C.c_double),
+          float(threshold), _ffi.ptr(inl, C.c_uint8))
+    return E.reshape(3, 3), inl[:len(matches)].astype(bool)

@@ -1,0 +1,168 @@
+"""Feature front-end: orientation + rotated-BRIEF descriptors, mutual descriptor matching and
+the stereo pairs' epipolar inlier test — the steps of the reference's SfM pipeline between corner detection and the
+BA problem (include/visnav/keypoints.h:182-300, include/visnav/matching_utils.h:50-79, callers
+src/sfm.cpp:1191-1330).
+
+Golden vectors: tests/golden/frontend_euroc.npz, produced by the reference's OWN functions (compiled unmodified,
+oracle/ref/frontend_harness.cpp) on real EuRoC stereo images (tests/golden/make_golden_frontend.py).
+CPU tests pin the oracle restatement to them (and to the reference library live, when it is present);
+GPU tests compare the CUDA kernels (through the C ABI) with both.  Bar: descriptors, matches and inlier flags
+BIT-EXACT; the orientation angle (fp64 atan2) and E within 1e-14.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_ffi as of
+import pba_b200 as pb
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+ANGLE_TOL = 1e-14
+
+
+@pytest.fixture(scope="module")
+def g():
+    return np.load(os.path.join(GOLDEN, "frontend_euroc.npz"))
+
+
+@pytest.fixture(scope="module")
+def images(g):
+    return np.load(os.path.join(GOLDEN, "euroc_v1_photo.npz"))["images"][: len(g["image_index"])]
+
+
+def random_descriptors(rng, n, pool=None, flip=0):
+    """n descriptors; with `pool`, noisy copies of pool rows (so that real matches, ties and near-ties exist)."""
+    if pool is None or len(pool) == 0:
+        return rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    d = pool[rng.integers(0, len(pool), n)].copy()
+    for i in range(n):
+        for _ in range(int(rng.integers(0, flip + 1))):
+            b = int(rng.integers(0, 256))
+            d[i, b // 8] ^= np.uint8(1 << (b % 8))
+    return d
+
+
+# ------------------------------------------------------------------------------------------------ CPU: the oracle
+def test_oracle_descriptors_match_the_reference_golden(g, images):
+    for i in range(len(images)):
+        ang, d = of.corner_descriptors("oracle", images[i], g["corners_%d" % i], True)
+        assert np.abs(ang - g["angles_%d" % i]).max() <= ANGLE_TOL
+        assert np.array_equal(d, g["descriptors_%d" % i])
+        ang0, d0 = of.corner_descriptors("oracle", images[i], g["corners_%d" % i], False)
+        assert (ang0 == 0).all() and np.array_equal(d0, g["descriptors_norot_%d" % i])
+
+
+def test_oracle_matches_and_inliers_match_the_reference_golden(g):
+    for k, (a, b) in enumerate(g["pairs"]):
+        m = of.match_descriptors("oracle", g["descriptors_%d" % a], g["descriptors_%d" % b], int(g["threshold"]),
+                                 float(g["dist_2_best"]))
+        assert np.array_equal(m, g["matches_%d" % k])
+        if "inliers_%d" % k in g.files:
+            E, inl = of.epipolar_inliers("oracle", g["calib_model"][0], g["intrinsics"][0], g["calib_model"][1],
+                                         g["intrinsics"][1], g["T_0_1"], m, g["corners_%d" % a], g["corners_%d" % b],
+                                         float(g["epipolar_threshold"]))
+            assert np.abs(E - g["E"]).max() <= 1e-15
+            assert np.array_equal(inl, g["inliers_%d" % k])
+            assert 0 < inl.sum() < len(inl)
+
+
+@pytest.mark.skipif(not of.have_ref_frontend(), reason="oracle/_ref/libpba_ref_frontend.so not built")
+def test_oracle_matching_equals_the_reference_on_ties_and_edge_cases():
+    """Crafted sets: duplicated descriptors (distance-0 ties: the lowest index wins and the ratio test 0 < 0 * 1.2
+    keeps the match), near-ties, an empty set, thresholds at the distance itself."""
+    rng = np.random.default_rng(5)
+    pool = random_descriptors(rng, 40)
+    for n1, n2, flip, thr, ratio in [(60, 70, 0, 70, 1.2), (130, 90, 3, 70, 1.2), (257, 300, 40, 70, 1.2),
+                                     (50, 0, 0, 70, 1.2), (0, 50, 0, 70, 1.2), (64, 64, 60, 40, 1.0),
+                                     (64, 64, 60, 256, 4.0), (33, 47, 20, 1, 1.2)]:
+        d1, d2 = random_descriptors(rng, n1, pool, flip), random_descriptors(rng, n2, pool, flip)
+        mo = of.match_descriptors("oracle", d1, d2, thr, ratio)
+        mr = of.match_descriptors("ref", d1, d2, thr, ratio)
+        assert np.array_equal(mo, mr), (n1, n2, flip, thr, ratio)
+
+
+def test_corners_outside_the_reference_bounds_are_rejected(images):
+    """detectKeypoints only keeps corners InBounds(x, y, 19) (keypoints.h:146-150); the C ABI refuses anything else
+    before touching the device."""
+    for bad in ([18.9, 100.0], [100.0, 480 - 19.0], [752 - 19.0, 50.0], [np.nan, 50.0]):
+        with pytest.raises(RuntimeError, match="INVALID_ARGUMENT"):
+            pb.corner_descriptors(images[:1], [np.array([[100.0, 100.0], bad])])
+
+
+@pytest.mark.skipif(pb.device_count() > 0, reason="only meaningful on a box without a GPU")
+def test_front_end_has_no_cpu_fallback(g, images):
+    with pytest.raises(RuntimeError, match="PBA_ERR_NO_DEVICE"):
+        pb.corner_descriptors(images[:1], [g["corners_0"]])
+    with pytest.raises(RuntimeError, match="PBA_ERR_NO_DEVICE"):
+        pb.match_descriptors([g["descriptors_0"], g["descriptors_1"]], [(0, 1)])
+    with pytest.raises(RuntimeError, match="PBA_ERR_NO_DEVICE"):
+        pb.epipolar_inliers(1, g["intrinsics"][0], 1, g["intrinsics"][1], g["T_0_1"], g["matches_0"], g["corners_0"],
+                            g["corners_1"])
+
+
+# ------------------------------------------------------------------------------------------------ GPU: the kernels
+@pytest.mark.gpu
+def test_cuda_descriptors_bit_exact_on_real_images(g, images):
+    corners = [g["corners_%d" % i] for i in range(len(images))]
+    ang, desc = pb.corner_descriptors(images, corners, True)            # all images in one call
+    for i in range(len(images)):
+        assert np.abs(ang[i] - g["angles_%d" % i]).max() <= ANGLE_TOL
+        assert np.array_equal(desc[i], g["descriptors_%d" % i])
+    ang0, desc0 = pb.corner_descriptors(images, corners, False)
+    for i in range(len(images)):
+        assert (ang0[i] == 0).all() and np.array_equal(desc0[i], g["descriptors_norot_%d" % i])
+    a1, d1 = pb.corner_descriptors(images[3], [corners[3]], True)        # one image, 2-D input
+    assert np.array_equal(d1[0], g["descriptors_3"])
+
+
+@pytest.mark.gpu
+def test_cuda_matches_and_inliers_bit_exact_on_real_images(g):
+    descs = [g["descriptors_%d" % i] for i in range(len(g["image_index"]))]
+    ms = pb.match_descriptors(descs, g["pairs"], int(g["threshold"]), float(g["dist_2_best"]))  # all pairs, one call
+    for k, (a, b) in enumerate(g["pairs"]):
+        assert np.array_equal(ms[k], g["matches_%d" % k]), k
+        if "inliers_%d" % k in g.files:
+            E, inl = pb.epipolar_inliers(int(g["calib_model"][0]), g["intrinsics"][0], int(g["calib_model"][1]),
+                                         g["intrinsics"][1], g["T_0_1"], ms[k], g["corners_%d" % a], g["corners_%d" % b],
+                                         float(g["epipolar_threshold"]))
+            assert np.abs(E - g["E"]).max() <= 1e-14
+            assert np.array_equal(inl, g["inliers_%d" % k])
+
+
+@pytest.mark.gpu
+def test_cuda_matching_equals_the_oracle_on_ties_ragged_and_large_sets():
+    """Empty sets, sizes around the CTA (128) and staging (512) granularities, duplicates (ties), many pairs in one
+    call including a set matched against itself."""
+    rng = np.random.default_rng(17)
+    pool = random_descriptors(rng, 64)
+    sizes = [0, 1, 127, 128, 129, 511, 512, 513, 1500, 1300, 700]
+    sets = [random_descriptors(rng, n, pool, 30) for n in sizes]
+    pairs = [(a, b) for a in range(len(sizes)) for b in range(len(sizes)) if (a + 2 * b) % 3 == 0]
+    for thr, ratio in [(70, 1.2), (256, 1.0)]:
+        ms = pb.match_descriptors(sets, pairs, thr, ratio)
+        for k, (a, b) in enumerate(pairs):
+            mo = of.match_descriptors("oracle", sets[a], sets[b], thr, ratio)
+            assert np.array_equal(ms[k], mo), (sizes[a], sizes[b], thr, ratio)
+    assert pb.match_descriptors(sets, []) == []
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("model", ["pinhole", "ds", "kb4", "eucm"])
+def test_cuda_epipolar_inliers_equal_the_oracle_for_every_camera_model(model):
+    rng = np.random.default_rng(23)
+    prob, _ = pb.make_scene(pb.MODE_GEOMETRIC, 4, 10, model)
+    intr = prob.intrinsics[0]
+    mid = int(prob.calib_model[0])
+    c0 = np.stack([rng.uniform(30, 720, 400), rng.uniform(30, 450, 400)], 1)
+    c1 = c0 + rng.normal(0, 1.5, c0.shape) + [-20.0, 0.0]
+    m = np.stack([rng.permutation(400)[:300], rng.permutation(400)[:300]], 1).astype(np.int32)
+    m[:150, 1] = m[:150, 0]                                             # half of them true correspondences
+    T = np.array([0.004, -0.002, 0.001, 0.99999, 0.11, 0.001, -0.002])
+    T[:4] /= np.linalg.norm(T[:4])
+    for thr in (1e-3, 5e-3):
+        Eg, ig = pb.epipolar_inliers(mid, intr, mid, intr, T, m, c0, c1, thr)
+        Eo, io = of.epipolar_inliers("oracle", mid, intr, mid, intr, T, m, c0, c1, thr)
+        assert np.abs(Eg - Eo).max() <= 1e-15
+        assert np.array_equal(ig, io)
+        assert 0 < ig.sum() < len(ig)
