@@ -12,14 +12,18 @@
 
 #include <visnav/calibration.h>
 #include <visnav/camera_models.h>
+#include <visnav/keypoints.h>
 #include <visnav/map_utils.h>
+#include <visnav/matching_utils.h>
 
+#include <algorithm>
 #include <cstring>
 #include <set>
 #include <vector>
 
 #include "pba.h"
 #include "visnav_b200/bundle_adjustment.h"
+#include "visnav_b200/frontend.h"
 
 namespace {
 
@@ -232,3 +236,69 @@ extern "C" __attribute__((visibility("default"))) int pba_dropin_add_new_landmar
   return 0;
 }
 
+
+// Front-end drop-in proof: one stereo pair through the reference's containers (KeypointsData,
+// MatchData, Corners, Matches, the calibration's camera objects) with either the reference's own functions
+// (use_b200 = 0: computeAngles, computeDescriptors, matchDescriptors, computeEssential, findInliersEssential —
+// keypoints.h:182-300, matching_utils.h:50-79, exactly the calls of src/sfm.cpp:1197-1250) or visnav_b200's
+// (CUDA).  Outputs: angles / descriptors of both images, the matches (sorted) and the epipolar inliers.
+extern "C" __attribute__((visibility("default"))) int pba_dropin_frontend_stereo(
+    const uint8_t* image0, const uint8_t* image1, int w, int h, int pitch, int n0, const double* corners0, int n1,
+    const double* corners1, int model0, const double* intr0, int model1, const double* intr1, const double* T_0_1,
+    int threshold, double dist_2_best, double epipolar_threshold, int use_b200, double* angles0, uint8_t* desc0,
+    double* angles1, uint8_t* desc1, int32_t* matches, int32_t* n_matches, int32_t* inliers, int32_t* n_inliers) {
+  using namespace visnav;
+  static const char* const names[] = {"pinhole", "ds", "kb4", "eucm"};
+  const FrameCamId fcid0(0, 0), fcid1(0, 1);
+  pangolin::ManagedImage<uint8_t> img0(const_cast<uint8_t*>(image0), w, h, pitch), img1(const_cast<uint8_t*>(image1), w, h, pitch);
+  Corners feature_corners;
+  for (int i = 0; i < n0; ++i) feature_corners[fcid0].corners.emplace_back(corners0[2 * i], corners0[2 * i + 1]);
+  for (int i = 0; i < n1; ++i) feature_corners[fcid1].corners.emplace_back(corners1[2 * i], corners1[2 * i + 1]);
+  KeypointsData& kd0 = feature_corners[fcid0];
+  KeypointsData& kd1 = feature_corners[fcid1];
+  Calibration calib;
+  calib.intrinsics.push_back(AbstractCamera<double>::from_data(names[model0], intr0));
+  calib.intrinsics.push_back(AbstractCamera<double>::from_data(names[model1], intr1));
+  const Sophus::SE3d T01(Eigen::Quaterniond(T_0_1[3], T_0_1[0], T_0_1[1], T_0_1[2]), Eigen::Vector3d(T_0_1[4], T_0_1[5], T_0_1[6]));
+  MatchData md;
+  md.T_i_j = T01;
+  if (use_b200) {
+    if (visnav_b200::computeAnglesAndDescriptors(img0, kd0, true) != PBA_OK) return 40;
+    if (visnav_b200::computeAnglesAndDescriptors(img1, kd1, true) != PBA_OK) return 41;
+    Matches feature_matches;
+    const std::vector<std::pair<FrameCamId, FrameCamId>> pairs = {{fcid0, fcid1}};
+    if (visnav_b200::matchImagePairs(feature_corners, pairs, threshold, dist_2_best, feature_matches) != PBA_OK) return 42;
+    md.matches = feature_matches.at(std::make_pair(fcid0, fcid1)).matches;
+    std::vector<std::pair<int, int>> again;  // the two-set form gives the same list
+    if (visnav_b200::matchDescriptors(kd0.corner_descriptors, kd1.corner_descriptors, again, threshold, dist_2_best) != PBA_OK) return 43;
+    if (again.size() != md.matches.size()) return 44;
+    for (size_t k = 0; k < again.size(); ++k)
+      if (again[k].first != md.matches[k].first || again[k].second != md.matches[k].second) return 45;
+    if (visnav_b200::findInliersEssential(kd0, kd1, calib.intrinsics[0], calib.intrinsics[1], T01, epipolar_threshold, md) != PBA_OK) return 46;
+  } else {
+    computeAngles(img0, kd0, true);
+    computeDescriptors(img0, kd0);
+    computeAngles(img1, kd1, true);
+    computeDescriptors(img1, kd1);
+    matchDescriptors(kd0.corner_descriptors, kd1.corner_descriptors, md.matches, threshold, dist_2_best);
+    std::sort(md.matches.begin(), md.matches.end());
+    Eigen::Matrix3d E;
+    computeEssential(T01, E);
+    findInliersEssential(kd0, kd1, calib.intrinsics[0], calib.intrinsics[1], E, epipolar_threshold, md);
+  }
+  auto dump = [](const KeypointsData& kd, double* ang, uint8_t* d) {
+    std::memset(d, 0, kd.corners.size() * 32);
+    for (size_t i = 0; i < kd.corners.size(); ++i) {
+      ang[i] = kd.corner_angles[i];
+      for (size_t b = 0; b < 256; ++b)
+        if (kd.corner_descriptors[i][b]) d[32 * i + b / 8] |= uint8_t(1u << (b % 8));
+    }
+  };
+  dump(kd0, angles0, desc0);
+  dump(kd1, angles1, desc1);
+  *n_matches = int32_t(md.matches.size());
+  for (size_t k = 0; k < md.matches.size(); ++k) { matches[2 * k] = md.matches[k].first; matches[2 * k + 1] = md.matches[k].second; }
+  *n_inliers = int32_t(md.inliers.size());
+  for (size_t k = 0; k < md.inliers.size(); ++k) { inliers[2 * k] = md.inliers[k].first; inliers[2 * k + 1] = md.inliers[k].second; }
+  return 0;
+}

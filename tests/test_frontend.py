@@ -166,3 +166,45 @@ def test_cuda_epipolar_inliers_equal_the_oracle_for_every_camera_model(model):
         assert np.abs(Eg - Eo).max() <= 1e-15
         assert np.array_equal(ig, io)
         assert 0 < ig.sum() < len(ig)
+
+
+@pytest.mark.gpu
+def test_reference_containers_drive_both_front_ends(g, images):
+    """Drop-in proof: one stereo pair through the reference's own containers (KeypointsData, Corners, Matches,
+    MatchData, the calibration's camera objects), once with the reference's functions — the calls of
+    src/sfm.cpp:1197-1250 — and once with include/visnav_b200/frontend.h on the CUDA kernels; identical outputs."""
+    import ctypes as C
+    base = os.path.dirname(of.REF_SO)
+    path = os.path.join(base, "libpba_dropin_v4.so" if of.REF_SO.endswith("_v4.so") else "libpba_dropin.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libpba_dropin.so not built on this box")
+    lib = C.CDLL(path)
+    u8, d, i32 = C.POINTER(C.c_uint8), C.POINTER(C.c_double), C.POINTER(C.c_int32)
+    lib.pba_dropin_frontend_stereo.argtypes = [u8, u8, C.c_int, C.c_int, C.c_int, C.c_int, d, C.c_int, d, C.c_int, d, C.c_int, d,
+                                               d, C.c_int, C.c_double, C.c_double, C.c_int, d, u8, d, u8, i32, i32, i32, i32]
+    c0, c1 = np.ascontiguousarray(g["corners_2"]), np.ascontiguousarray(g["corners_3"])
+    im0, im1 = np.ascontiguousarray(images[2]), np.ascontiguousarray(images[3])
+    h, w = im0.shape
+    intr = np.ascontiguousarray(g["intrinsics"])
+    T = np.ascontiguousarray(g["T_0_1"])
+    res = []
+    for use_b200 in (0, 1):
+        a0, a1 = np.zeros(len(c0)), np.zeros(len(c1))
+        d0, d1 = np.zeros((len(c0), 32), np.uint8), np.zeros((len(c1), 32), np.uint8)
+        m, inl = np.zeros((len(c0), 2), np.int32), np.zeros((len(c0), 2), np.int32)
+        nm, ni = C.c_int32(), C.c_int32()
+        P = pb._ffi.ptr
+        rc = lib.pba_dropin_frontend_stereo(P(im0, C.c_uint8), P(im1, C.c_uint8), w, h, w, len(c0), P(c0, C.c_double), len(c1),
+                                            P(c1, C.c_double), int(g["calib_model"][0]), P(intr[0], C.c_double),
+                                            int(g["calib_model"][1]), P(intr[1], C.c_double), P(T, C.c_double),
+                                            int(g["threshold"]), float(g["dist_2_best"]), float(g["epipolar_threshold"]),
+                                            use_b200, P(a0, C.c_double), P(d0, C.c_uint8), P(a1, C.c_double), P(d1, C.c_uint8),
+                                            P(m, C.c_int32), C.byref(nm), P(inl, C.c_int32), C.byref(ni))
+        assert rc == 0, rc
+        res.append((a0, d0, a1, d1, m[:nm.value].copy(), inl[:ni.value].copy()))
+    ref, gpu = res
+    assert np.abs(ref[0] - gpu[0]).max() <= ANGLE_TOL and np.abs(ref[2] - gpu[2]).max() <= ANGLE_TOL
+    assert np.array_equal(ref[1], gpu[1]) and np.array_equal(ref[3], gpu[3])
+    assert np.array_equal(ref[4], gpu[4]) and np.array_equal(ref[5], gpu[5])
+    assert np.array_equal(gpu[4], g["matches_1"])                       # pair (2, 3) of the fixture
+    assert np.array_equal(gpu[5], g["matches_1"][g["inliers_1"]])
