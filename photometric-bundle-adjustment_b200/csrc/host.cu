@@ -966,6 +966,9 @@ pba_status create_impl(const pba_problem* p, const pba_options* o, int rank, int
     part_total += int64_t(c) * (c + 1) / 2 * cd * cd + int64_t(c) * cd;
   }
   h->schur_tile_l = schur_tile_l(h->max_w_stride);
+  std::vector<int> syrk_work;
+  schur_syrk_work(grp_cam_ptr, &syrk_work);
+  h->n_syrk_work = int(syrk_work.size() / 2);
 
   // pass B (parallel over groups): place every observation at its edge-order position
   StageVec<int> obs_lm(n);  // every entry is written in pass B
@@ -1107,6 +1110,7 @@ pba_status create_impl(const pba_problem* p, const pba_options* o, int rank, int
   PBA_CUDA_OK(up(h->chunk_edge, chunk_edge)); PBA_CUDA_OK(up(h->chunk_begin, chunk_begin)); PBA_CUDA_OK(up(h->chunk_end, chunk_end));
   PBA_CUDA_OK(up(h->grp_lm_ptr, grp_lm_ptr)); PBA_CUDA_OK(up(h->grp_cam_ptr, grp_cam_ptr)); PBA_CUDA_OK(up(h->grp_cams, grp_cams));
   PBA_CUDA_OK(up(h->grp_w_off, grp_w_off)); PBA_CUDA_OK(up(h->grp_part_off, grp_part_off));
+  PBA_CUDA_OK(up(h->syrk_work, syrk_work));
   PBA_CUDA_OK(up(h->lm_w_off, lm_w_off)); PBA_CUDA_OK(up(h->lm_w_stride, lm_w_stride));
   PBA_CUDA_OK(up(h->d_blk_row, h->blk_row)); PBA_CUDA_OK(up(h->d_blk_col, h->blk_col)); PBA_CUDA_OK(up(h->d_diag_blk, h->diag_blk));
   PBA_CUDA_OK(up(h->blk_dir_ptr, dir_ptr)); PBA_CUDA_OK(up(h->blk_dir_src, dir_src));

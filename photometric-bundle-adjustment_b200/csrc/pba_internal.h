@@ -240,6 +240,8 @@ struct Handle {
   DevBuf<int> grp_cams;            // slots, ascending
   DevBuf<int64_t> grp_w_off;       // [G] offset of the group's W rows (doubles)
   DevBuf<int64_t> grp_part_off;    // [G] offset of the group's Schur partial blocks (blocks of 64)
+  DevBuf<int> syrk_work;           // [n_syrk_work][2] (group, first tile) of the generic Schur product's passes
+  int n_syrk_work = 0;
   DevBuf<int64_t> lm_w_off;        // [n_lm] offset of the landmark's W row
   DevBuf<int> lm_w_stride;         // [n_lm] row length = 8*(c_g+1)
   // RCS structure
@@ -368,10 +370,12 @@ pba_status bcr_setup(Handle* h);
 pba_status bcr2_setup(Handle* h);
 pba_status launch_bcr2_rcs(Handle* h);
 int band_max_bw(int cd);
-pba_status dense_cholesky_solve(Handle* h, double* A, double* b, int ld, int* fail_dev);
+pba_status dense_cholesky_solve(Handle* h, double* A, double* b, int ld, int* fail_dev, double* work);
+size_t dense_work_size(int ld);
 int dense_ld(int n);
 int pcg_max_grid(int device);
 int schur_tile_l(int max_stride);
+void schur_syrk_work(const std::vector<int>& grp_cam_ptr, std::vector<int>* work);  // (group, first tile) per pass
 int eval_grid(int64_t n);
 // host.cu
 // ---- peer-memory collectives (peer.cu) ----

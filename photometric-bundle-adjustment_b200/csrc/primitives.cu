@@ -112,11 +112,12 @@ PBA_API pba_status pba_se3_plus(int64_t n, const double* poses7, const double* d
 PBA_API pba_status pba_cholesky_solve(int32_t n, const double* A, const double* b, double* x) {
   if (!A || !b || !x || n <= 0) return PBA_ERR_INVALID_ARGUMENT;
   if (!have_device()) return PBA_ERR_NO_DEVICE;
-  Handle h;  // only its stream (default) and launch counters are used
+  Handle h;  // only its stream (default), device and launch counters are used
+  PBA_CUDA_OK(cudaGetDevice(&h.device));
   const int ld = dense_ld(n);
   DevBuf<double> dA, db, dAp;
   DevBuf<int> fail;
-  PBA_CUDA_OK(dA.alloc(size_t(n) * n)); PBA_CUDA_OK(db.alloc(n)); PBA_CUDA_OK(dAp.alloc(size_t(ld) * ld + ld));
+  PBA_CUDA_OK(dA.alloc(size_t(n) * n)); PBA_CUDA_OK(db.alloc(n)); PBA_CUDA_OK(dAp.alloc(size_t(ld) * ld + ld + dense_work_size(ld)));
   PBA_CUDA_OK(fail.alloc(1));
   PBA_CUDA_OK(cudaMemset(fail.p, 0, sizeof(int)));
   PBA_CUDA_OK(cudaMemcpy(dA.p, A, sizeof(double) * size_t(n) * n, cudaMemcpyHostToDevice));
@@ -125,7 +126,7 @@ PBA_API pba_status pba_cholesky_solve(int32_t n, const double* A, const double* 
   const int64_t tot = int64_t(ld) * ld;
   k_pad_dense<<<unsigned((tot + 255) / 256), 256>>>(n, ld, dA.p, db.p, dAp.p, bp);
   PBA_CUDA_OK(cudaGetLastError());
-  pba_status st = dense_cholesky_solve(&h, dAp.p, bp, ld, fail.p);
+  pba_status st = dense_cholesky_solve(&h, dAp.p, bp, ld, fail.p, bp + ld);
   if (st != PBA_OK) return st;
   int f = 0;
   PBA_CUDA_OK(cudaMemcpy(&f, fail.p, sizeof(int), cudaMemcpyDeviceToHost));

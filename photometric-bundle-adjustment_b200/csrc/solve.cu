@@ -212,6 +212,261 @@ __global__ void __launch_bounds__(NB) k_tri_update(int ld, int k, int transpose,
   }
 }
 
+// ---------------------------------------------------- one-launch Cholesky ---
+// The whole factorisation + both triangular solves as ONE cooperative kernel (r02d).  The multi-launch version
+// above costs three launches per 64-wide tile column plus four per column for the solves (profiles/r02b: at the
+// 900 unknowns of the EuRoC map, panel 0.99 ms + triangular solves 0.82 ms + TRSM 0.53 ms of a 3.4 ms LM step, all
+// launch / barrier latency).  Here, per tile column k:
+//   * the diagonal tile is factored by ONE CTA in shared memory as an unscaled elimination of [A_kk | I] with one
+//     block barrier per pivot; it yields L_kk AND W_k = L_kk^-1 (rows scaled by 1 / sqrt(pivot) at the end);
+//   * with W_k explicit, the panel is a GEMM, L_ik = A_ik W_k^T, on the FP64 tensor cores — no per-row substitution
+//     chain — and the forward substitution rides along: y_k = W_k b_k, b_i -= L_ik y_k from the accumulators;
+//   * the trailing update A_ij -= L_ik L_jk^T (DMMA) is spread over the grid; the CTA that owns tile (k+1, k+1)
+//     factors it right behind its update, so a column costs two grid barriers, not three;
+//   * the backward substitution is mat-vecs with W_k^T, one grid barrier per column.
+// Everything other CTAs produced is read with ld.global.cg (L1 is not coherent across SMs).
+constexpr int kCoopThreads = 256;
+constexpr int TLD = NB + 1;  // row stride of the diagonal-phase tiles
+constexpr size_t kCoopSmem = (2 * NB * LDS + 2 * NB) * sizeof(double);  // two operand tiles (>= two TLD tiles) + 2 vectors
+
+struct CholCoopArgs {
+  double* A;   // [ld][ld], lower tiles used
+  double* b;   // [ld] right-hand side in, solution out
+  double* W;   // [nt][64][64] inverses of the diagonal factor tiles
+  double* y;   // [ld] forward-substituted right-hand side
+  int ld, nt;
+  int* fail;
+};
+
+__device__ __forceinline__ void coop_stage(double* dst, const double* __restrict__ src, int src_ld) {
+  for (int x = threadIdx.x; x < NB * NB / 2; x += kCoopThreads) {
+    const int r = x >> 5, c2 = x & 31;
+    const double2 v = __ldcg(reinterpret_cast<const double2*>(src + int64_t(r) * src_ld) + c2);
+    *reinterpret_cast<double2*>(dst + r * LDS + 2 * c2) = v;
+  }
+}
+
+// acc = P Q^T for two 64 x 64 row-major tiles in shared memory (stride LDS); warp w owns rows 8 w .. 8 w + 7,
+// lane (g, t) ends with C[8 w + g][8 b + 2 t + {0, 1}] in acc[b]
+__device__ __forceinline__ void coop_pqt(const double* P, const double* Q, double (&acc)[8][2]) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int fr = lane >> 2, fc = lane & 3;
+#pragma unroll
+  for (int b = 0; b < 8; ++b) { acc[b][0] = 0.0; acc[b][1] = 0.0; }
+#pragma unroll 4
+  for (int k0 = 0; k0 < NB; k0 += 4) {
+    const double af = P[(8 * warp + fr) * LDS + k0 + fc];
+#pragma unroll
+    for (int b = 0; b < 8; ++b) dmma8x8x4(acc[b][0], acc[b][1], af, Q[(8 * b + fr) * LDS + k0 + fc]);
+  }
+}
+
+// Diagonal tile k: A_kk = L L^T; L goes back to A, W = L^-1 to a.W.
+// Unscaled Gaussian elimination on [A_kk | I] with the rows in REGISTERS: thread (r, ph) owns the 16 columns
+// c = ph + 4 q of row r of ONE merged 64 x 64 array — column c holds the A part while c > j (kept symmetric, so
+// "column j" is simply row j) and the I part once c <= j.  Per pivot j the four owners of row j publish it to
+// shared memory (double-buffered: one block barrier per pivot), every row r > j subtracts (a_rj / a_jj) x row j,
+// and the slot of column j — final, L_rj = a_rj / sqrt(a_jj) goes to the output tile — is re-used for the I part
+// (-a_rj / a_jj).  At the end row r of the I part scaled by 1 / sqrt(pivot_r) is row r of W = L^-1.  Shared-memory
+// traffic per pivot: 64 stores + broadcast loads (the first version kept both arrays in shared memory and
+// read-modify-wrote them: ~0.4 M accesses per tile, 33 us; fully predicated 16-slot loops were slower still).
+__device__ void coop_diag(const CholCoopArgs& a, int k, double* sm) {
+  double* Lout = sm;             // [64][TLD]
+  double* prow = sm + NB * TLD;  // [2][64]
+  double* piv = prow + 2 * NB;   // [64]
+  double* Akk = a.A + (int64_t(k) * NB) * a.ld + k * NB;
+  const int r = threadIdx.x >> 2, ph = threadIdx.x & 3;
+  double t[16];
+#pragma unroll
+  for (int q = 0; q < 16; ++q) {
+    const int c = ph + 4 * q;  // the lower triangle is the reference copy: (r, c) or its mirror
+    t[q] = __ldcg(c <= r ? Akk + int64_t(r) * a.ld + c : Akk + int64_t(c) * a.ld + r);
+  }
+  for (int j = 0; j < NB; ++j) {
+    double* pr = prow + (j & 1) * NB;
+    if (r == j) {
+#pragma unroll
+      for (int q = 0; q < 16; ++q) pr[ph + 4 * q] = t[q];
+    }
+    __syncthreads();
+    double d = pr[j];
+    const bool bad = !(d > 0.0);
+    if (bad) d = 1.0;
+    const double is = 1.0 / sqrt(d);
+    if (threadIdx.x == 0) { piv[j] = d; if (bad) *a.fail = 1; }
+    if (r == j && ph == (j & 3)) Lout[j * TLD + j] = d * is;
+    if (r > j) {
+      const double f = pr[r] * (1.0 / d);
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const int c = ph + 4 * q;
+        if (c == j) {
+          Lout[r * TLD + j] = t[q] * is;
+          t[q] = -f;
+        } else {
+          t[q] = fma(-f, pr[c], t[q]);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  double* Wk = a.W + int64_t(k) * NB * NB;
+  {
+    const double isr = 1.0 / sqrt(piv[r]);
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const int c = ph + 4 * q;
+      Wk[r * NB + c] = c < r ? t[q] * isr : (c == r ? isr : 0.0);
+    }
+  }
+  for (int x = threadIdx.x; x < NB * NB; x += kCoopThreads) {
+    const int rr = x >> 6, c = x & 63;
+    Akk[int64_t(rr) * a.ld + c] = c <= rr ? Lout[rr * TLD + c] : 0.0;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kCoopThreads) k_chol_coop(const CholCoopArgs a) {
+  extern __shared__ __align__(16) double coop_sm[];
+  cg::grid_group grid = cg::this_grid();
+  double* P = coop_sm;
+  double* Q = coop_sm + NB * LDS;
+  double* vec = coop_sm + 2 * NB * LDS;  // [64] y_k / x_k, [64] scratch
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int fr = lane >> 2, fc = lane & 3;
+  const int G = gridDim.x, cta = blockIdx.x;
+  const int nt = a.nt;
+  if (cta == 0) coop_diag(a, 0, coop_sm);
+  __threadfence();
+  grid.sync();
+  for (int k = 0; k < nt; ++k) {
+    const int m = nt - k - 1;
+    // ---- panel + forward substitution ----
+    if (cta == 0 || cta < m) {
+      for (int x = threadIdx.x; x < NB * NB / 2; x += kCoopThreads) {  // W_k: dense [64][64]
+        const int r = x >> 5, c2 = x & 31;
+        *reinterpret_cast<double2*>(Q + r * LDS + 2 * c2) = __ldcg(reinterpret_cast<const double2*>(a.W + int64_t(k) * NB * NB + r * NB) + c2);
+      }
+      if (threadIdx.x < NB) vec[NB + threadIdx.x] = __ldcg(a.b + k * NB + threadIdx.x);
+      __syncthreads();
+      if (threadIdx.x < NB) {
+        double s = 0.0;
+        for (int c = 0; c <= int(threadIdx.x); ++c) s += Q[threadIdx.x * LDS + c] * vec[NB + c];
+        vec[threadIdx.x] = s;
+        if (cta == 0) a.y[k * NB + threadIdx.x] = s;
+      }
+      for (int i = k + 1 + cta; i < nt; i += G) {
+        __syncthreads();  // y_k visible; P free again
+        double* Aik = a.A + (int64_t(i) * NB) * a.ld + k * NB;
+        coop_stage(P, Aik, a.ld);
+        __syncthreads();
+        double acc[8][2];
+        coop_pqt(P, Q, acc);  // L_ik = A_ik W_k^T
+        double part = 0.0;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+          *reinterpret_cast<double2*>(Aik + int64_t(8 * warp + fr) * a.ld + 8 * b + 2 * fc) = make_double2(acc[b][0], acc[b][1]);
+          part += acc[b][0] * vec[8 * b + 2 * fc] + acc[b][1] * vec[8 * b + 2 * fc + 1];
+        }
+        part += __shfl_xor_sync(0xffffffffu, part, 1);
+        part += __shfl_xor_sync(0xffffffffu, part, 2);
+        if (fc == 0) a.b[i * NB + 8 * warp + fr] = __ldcg(a.b + i * NB + 8 * warp + fr) - part;
+      }
+    }
+    __threadfence();
+    grid.sync();
+    // ---- trailing update; CTA 0 takes tile (k+1, k+1) and factors it right away ----
+    if (m > 0) {
+      const int n_tiles = m * (m + 1) / 2;
+      const int first = G > 1 ? (cta == 0 ? 0 : cta) : 0;            // tile 0 belongs to CTA 0; the others share 1..
+      const int stride = G > 1 ? (cta == 0 ? n_tiles : G - 1) : 1;   // (a single-CTA grid walks all of them)
+      for (int t = first; t < n_tiles; t += stride) {
+        int ii = int((sqrtf(8.0f * float(t) + 1.0f) - 1.0f) * 0.5f);
+        while (ii * (ii + 1) / 2 > t) --ii;
+        while ((ii + 1) * (ii + 2) / 2 <= t) ++ii;
+        const int jj = t - ii * (ii + 1) / 2;
+        const int i = k + 1 + ii, j = k + 1 + jj;
+        __syncthreads();
+        coop_stage(P, a.A + (int64_t(i) * NB) * a.ld + k * NB, a.ld);
+        coop_stage(Q, a.A + (int64_t(j) * NB) * a.ld + k * NB, a.ld);
+        __syncthreads();
+        double acc[8][2];
+        coop_pqt(P, Q, acc);
+        double* Aij = a.A + (int64_t(i) * NB) * a.ld + j * NB;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+          double2* q = reinterpret_cast<double2*>(Aij + int64_t(8 * warp + fr) * a.ld + 8 * b + 2 * fc);
+          double2 v = __ldcg(q);
+          v.x -= acc[b][0]; v.y -= acc[b][1];
+          *q = v;
+        }
+        if (G == 1 && t == 0) { __threadfence(); __syncthreads(); coop_diag(a, k + 1, coop_sm); }
+      }
+      if (G > 1 && cta == 0) { __threadfence(); __syncthreads(); coop_diag(a, k + 1, coop_sm); }
+    }
+    __threadfence();
+    grid.sync();
+  }
+  // ---- backward substitution: x_k = W_k^T y_k, y_i -= L_ki^T x_k for i < k ----
+  for (int k = nt - 1; k >= 0; --k) {
+    if (cta == 0 || cta < k) {
+      __syncthreads();
+      for (int x = threadIdx.x; x < NB * NB / 2; x += kCoopThreads) {
+        const int r = x >> 5, c2 = x & 31;
+        *reinterpret_cast<double2*>(Q + r * LDS + 2 * c2) = __ldcg(reinterpret_cast<const double2*>(a.W + int64_t(k) * NB * NB + r * NB) + c2);
+      }
+      if (threadIdx.x < NB) vec[NB + threadIdx.x] = __ldcg(a.y + k * NB + threadIdx.x);
+      __syncthreads();
+      if (threadIdx.x < NB) {
+        double s = 0.0;
+        for (int r = threadIdx.x; r < NB; ++r) s += Q[r * LDS + threadIdx.x] * vec[NB + r];
+        vec[threadIdx.x] = s;
+        if (cta == 0) a.b[k * NB + threadIdx.x] = s;
+      }
+      for (int i = cta; i < k; i += G) {
+        __syncthreads();
+        coop_stage(P, a.A + (int64_t(k) * NB) * a.ld + i * NB, a.ld);  // L_ki
+        __syncthreads();
+        // 4 partial sums per column, combined in fixed order
+        const int c = threadIdx.x & 63, q = threadIdx.x >> 6;
+        double s = 0.0;
+#pragma unroll 4
+        for (int r = 16 * q; r < 16 * q + 16; ++r) s += P[r * LDS + c] * vec[r];
+        __syncthreads();
+        P[threadIdx.x] = s;  // P is consumed: reuse its first 256 doubles
+        __syncthreads();
+        if (threadIdx.x < NB) {
+          const double tot = (P[threadIdx.x] + P[64 + threadIdx.x]) + (P[128 + threadIdx.x] + P[192 + threadIdx.x]);
+          a.y[i * NB + threadIdx.x] = __ldcg(a.y + i * NB + threadIdx.x) - tot;
+        }
+      }
+    }
+    __threadfence();
+    grid.sync();
+  }
+}
+
+int chol_coop_grid(int device, int nt) {
+  static std::mutex mu;
+  static std::vector<std::pair<int, int>> cache;  // (device, CTAs that can be co-resident)
+  int cap = 0;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    for (auto& c : cache) if (c.first == device) cap = c.second;
+    if (!cap) {
+      int n_sm = 0, per_sm = 0;
+      cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
+      ensure_dynamic_smem((const void*)k_chol_coop, kCoopSmem, device);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_chol_coop, kCoopThreads, kCoopSmem);
+      cap = n_sm * (per_sm > 0 ? 1 : 0);  // one CTA per SM: a grid barrier costs less with fewer CTAs
+      cache.emplace_back(device, cap);
+    }
+  }
+  const int m = nt - 1;
+  const int want = std::max(1, m * (m + 1) / 2 + 1);
+  return std::max(1, std::min(cap, want));
+}
+
 // ------------------------------------------------------------------- PCG ---
 // Inverse of the (SPD) diagonal blocks: the block-Jacobi preconditioner.
 __global__ void k_block_inverse(int cd, int n_slots, const int* __restrict__ diag_blk, const double* __restrict__ S,
@@ -395,9 +650,29 @@ __global__ void __launch_bounds__(256) k_pcg(const PcgArgs a) {
 
 }  // namespace
 
-// In-place tiled Cholesky + solve of the padded dense system (ld = multiple of 64).
-pba_status dense_cholesky_solve(Handle* h, double* A, double* b, int ld, int* fail_dev) {
+// In-place tiled Cholesky + solve of the padded dense system (ld = multiple of 64).  `work` holds
+// dense_work_size(ld) doubles (inverse diagonal tiles + the forward-substituted right-hand side).
+// One cooperative launch (k_chol_coop); PBA_CHOL_V1=1 keeps the multi-launch version for A/B runs.
+size_t dense_work_size(int ld) { return size_t(ld / NB) * NB * NB + size_t(ld); }
+
+pba_status dense_cholesky_solve(Handle* h, double* A, double* b, int ld, int* fail_dev, double* work) {
   const int nt = ld / NB;
+  static const bool force_v1 = getenv("PBA_CHOL_V1") != nullptr;
+  int device = h->device;
+  if (!force_v1 && work) {
+    const int grid = chol_coop_grid(device, nt);
+    if (grid > 0) {
+      CholCoopArgs a;
+      a.A = A; a.b = b; a.W = work; a.y = work + size_t(nt) * NB * NB; a.ld = ld; a.nt = nt; a.fail = fail_dev;
+      void* args[] = {(void*)&a};
+      PBA_CUDA_OK(ensure_dynamic_smem((const void*)k_chol_coop, kCoopSmem, device));
+      h->stats.begin(K_CHOL_SYRK, h->stream);
+      const cudaError_t e = cudaLaunchCooperativeKernel((void*)k_chol_coop, dim3(grid), dim3(kCoopThreads), args, kCoopSmem, h->stream);
+      h->stats.end(h->stream);
+      if (e != cudaSuccess) return map_cuda(e);
+      return PBA_OK;
+    }
+  }
   constexpr size_t kSyrkSmem = 2 * NB * LDS * sizeof(double);  // 69,632 B: needs the opt-in limit
   for (int k = 0; k < nt; ++k) {
     PBA_LAUNCH(h, K_CHOL_PANEL, k_chol_diag, dim3(1), dim3(256), 0, ld, k, A, fail_dev);
@@ -424,8 +699,8 @@ pba_status launch_cholesky_rcs(Handle* h) {
   const Sizes& z = h->sz;
   if (z.dim == 0) return PBA_OK;
   const int ld = dense_ld(z.dim);
-  if (h->dense.n < size_t(ld) * ld + ld) {
-    PBA_CUDA_OK(h->dense.alloc(size_t(ld) * ld + ld));
+  if (h->dense.n < size_t(ld) * ld + ld + dense_work_size(ld)) {
+    PBA_CUDA_OK(h->dense.alloc(size_t(ld) * ld + ld + dense_work_size(ld)));
   }
   double* A = h->dense.p;
   double* b = A + size_t(ld) * ld;
@@ -437,7 +712,7 @@ pba_status launch_cholesky_rcs(Handle* h) {
              h->d_blk_row.p, h->d_blk_col.p, S, A);
   PBA_CUDA_OK(cudaMemcpyAsync(b, rhs, sizeof(double) * z.dim, cudaMemcpyDeviceToDevice, h->stream));
   PBA_CUDA_OK(cudaMemsetAsync(h->chol_fail.p, 0, sizeof(int), h->stream));
-  pba_status st = dense_cholesky_solve(h, A, b, ld, h->chol_fail.p);
+  pba_status st = dense_cholesky_solve(h, A, b, ld, h->chol_fail.p, b + ld);
   if (st != PBA_OK) return st;
   PBA_CUDA_OK(cudaMemcpyAsync(h->y_cam.p, b, sizeof(double) * z.dim, cudaMemcpyDeviceToDevice, h->stream));
   return PBA_OK;
