@@ -261,6 +261,15 @@ __device__ __forceinline__ void coop_pqt(const double* P, const double* Q, doubl
   }
 }
 
+__device__ __forceinline__ double coop_rcp(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  return fma(y, e, y);
+}
+
 // Diagonal tile k: A_kk = L L^T; L goes back to A, W = L^-1 to a.W.
 // Unscaled Gaussian elimination on [A_kk | I] with the rows in REGISTERS: thread (r, ph) owns the 16 columns
 // c = ph + 4 q of row r of ONE merged 64 x 64 array — column c holds the A part while c > j (kept symmetric, so
@@ -292,27 +301,33 @@ __device__ void coop_diag(const CholCoopArgs& a, int k, double* sm) {
     double d = pr[j];
     const bool bad = !(d > 0.0);
     if (bad) d = 1.0;
-    const double is = 1.0 / sqrt(d);
     if (threadIdx.x == 0) { piv[j] = d; if (bad) *a.fail = 1; }
-    if (r == j && ph == (j & 3)) Lout[j * TLD + j] = d * is;
     if (r > j) {
-      const double f = pr[r] * (1.0 / d);
+      // the only non-trivial operation on the per-pivot chain is this reciprocal (hardware approximation + two
+      // Newton steps); the square roots wait until the end.  With 1 / sqrt(d) and 1 / d as library calls per pivot
+      // a tile took 96 k cycles (in-kernel stamps), 90 % of the whole factorisation.
+      // row j first, all 16 loads in flight (left to itself the compiler alternated load -> dependent FMA through
+      // two registers: sixteen shared-memory latencies in series, ~1,000 cycles per pivot)
+      double p[16];
+#pragma unroll
+      for (int q = 0; q < 16; ++q) p[q] = pr[ph + 4 * q];
+      const double f = pr[r] * coop_rcp(d);
 #pragma unroll
       for (int q = 0; q < 16; ++q) {
         const int c = ph + 4 * q;
-        if (c == j) {
-          Lout[r * TLD + j] = t[q] * is;
-          t[q] = -f;
-        } else {
-          t[q] = fma(-f, pr[c], t[q]);
-        }
+        const double u = fma(-f, p[q], t[q]);
+        if (c == j) Lout[r * TLD + j] = t[q];  // a_rj of the j-th Schur complement: L_rj = a_rj / sqrt(pivot_j), scaled below
+        t[q] = c == j ? -f : u;
       }
     }
   }
   __syncthreads();
+  double* isv = prow;  // 1 / sqrt(pivot), per column
+  if (threadIdx.x < NB) isv[threadIdx.x] = 1.0 / sqrt(piv[threadIdx.x]);
+  __syncthreads();
   double* Wk = a.W + int64_t(k) * NB * NB;
   {
-    const double isr = 1.0 / sqrt(piv[r]);
+    const double isr = isv[r];
 #pragma unroll
     for (int q = 0; q < 16; ++q) {
       const int c = ph + 4 * q;
@@ -321,10 +336,19 @@ __device__ void coop_diag(const CholCoopArgs& a, int k, double* sm) {
   }
   for (int x = threadIdx.x; x < NB * NB; x += kCoopThreads) {
     const int rr = x >> 6, c = x & 63;
-    Akk[int64_t(rr) * a.ld + c] = c <= rr ? Lout[rr * TLD + c] : 0.0;
+    Akk[int64_t(rr) * a.ld + c] = c < rr ? Lout[rr * TLD + c] * isv[c] : (c == rr ? piv[c] * isv[c] : 0.0);
   }
   __syncthreads();
 }
+
+#ifdef PBA_CHOL_TIMING
+__device__ long long g_chol_t[8];
+#define CT0() long long _ct = clock64()
+#define CT(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) { const long long _n = clock64(); g_chol_t[i] += _n - _ct; _ct = _n; } } while (0)
+#else
+#define CT0()
+#define CT(i)
+#endif
 
 __global__ void __launch_bounds__(kCoopThreads) k_chol_coop(const CholCoopArgs a) {
   extern __shared__ __align__(16) double coop_sm[];
@@ -336,9 +360,11 @@ __global__ void __launch_bounds__(kCoopThreads) k_chol_coop(const CholCoopArgs a
   const int fr = lane >> 2, fc = lane & 3;
   const int G = gridDim.x, cta = blockIdx.x;
   const int nt = a.nt;
+  CT0();
   if (cta == 0) coop_diag(a, 0, coop_sm);
   __threadfence();
   grid.sync();
+  CT(0);
   for (int k = 0; k < nt; ++k) {
     const int m = nt - k - 1;
     // ---- panel + forward substitution ----
@@ -373,8 +399,10 @@ __global__ void __launch_bounds__(kCoopThreads) k_chol_coop(const CholCoopArgs a
         if (fc == 0) a.b[i * NB + 8 * warp + fr] = __ldcg(a.b + i * NB + 8 * warp + fr) - part;
       }
     }
+    CT(1);
     __threadfence();
     grid.sync();
+    CT(2);
     // ---- trailing update; CTA 0 takes tile (k+1, k+1) and factors it right away ----
     if (m > 0) {
       const int n_tiles = m * (m + 1) / 2;
@@ -402,10 +430,13 @@ __global__ void __launch_bounds__(kCoopThreads) k_chol_coop(const CholCoopArgs a
         }
         if (G == 1 && t == 0) { __threadfence(); __syncthreads(); coop_diag(a, k + 1, coop_sm); }
       }
+      CT(3);
       if (G > 1 && cta == 0) { __threadfence(); __syncthreads(); coop_diag(a, k + 1, coop_sm); }
+      CT(4);
     }
     __threadfence();
     grid.sync();
+    CT(5);
   }
   // ---- backward substitution: x_k = W_k^T y_k, y_i -= L_ki^T x_k for i < k ----
   for (int k = nt - 1; k >= 0; --k) {
@@ -441,8 +472,10 @@ __global__ void __launch_bounds__(kCoopThreads) k_chol_coop(const CholCoopArgs a
         }
       }
     }
+    CT(6);
     __threadfence();
     grid.sync();
+    CT(7);
   }
 }
 
@@ -670,6 +703,19 @@ pba_status dense_cholesky_solve(Handle* h, double* A, double* b, int ld, int* fa
       const cudaError_t e = cudaLaunchCooperativeKernel((void*)k_chol_coop, dim3(grid), dim3(kCoopThreads), args, kCoopSmem, h->stream);
       h->stats.end(h->stream);
       if (e != cudaSuccess) return map_cuda(e);
+#ifdef PBA_CHOL_TIMING
+      {
+        static int calls = 0;
+        if (++calls == 40) {
+          cudaStreamSynchronize(h->stream);
+          long long t[8];
+          cudaMemcpyFromSymbol(t, g_chol_t, sizeof(t));
+          const char* names[8] = {"diag0+sync", "panel", "sync1", "trailing(tile)", "diag(k+1)", "sync2", "backward", "sync3"};
+          for (int i = 0; i < 8; ++i) fprintf(stderr, "[chol] %-16s %10.1f cycles/solve\n", names[i], double(t[i]) / calls);
+          fprintf(stderr, "[chol] nt %d grid %d\n", nt, grid);
+        }
+      }
+#endif
       return PBA_OK;
     }
   }
