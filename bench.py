@@ -59,7 +59,7 @@ def parse():
     ap.add_argument("--model", default="pinhole")
     ap.add_argument("--mode", type=int, default=1, help="1 photometric (headline), 0 geometric")
     ap.add_argument("--solver", type=int, default=0, help="0 auto, 1 cholesky, 2 pcg")
-    ap.add_argument("--workload", default="synthetic", choices=["synthetic", "euroc_geom", "euroc_photo"],
+    ap.add_argument("--workload", default="synthetic", choices=["synthetic", "euroc_geom", "euroc_photo", "grid"],
                     help="euroc_*: BASELINE config 1, the map built from data/euroc_V1 by tools/euroc/ (fixtures under "
                          "tests/golden/): geometric BA of the whole map / photometric BA on its first 12 keyframes")
     ap.add_argument("--sample-kf", type=int, default=48, help="keyframes in the CPU-baseline sample")
@@ -73,8 +73,11 @@ def parse():
 
 
 def load_euroc(a):
-    """BASELINE config 1 fixtures (tools/euroc/build_map.py)."""
+    """BASELINE config 1 fixtures (tools/euroc/build_map.py); `grid`: the non-banded lawn-mower flight of
+    tests/golden/scale_grid.npz (27 x 27 keyframes, 4,362 unknowns in the reduced camera system)."""
     import pba_b200 as pb
+    if a.workload == "grid":
+        return pb.make_grid_scene(27, 27, 30000)[0]
     g = np.load(os.path.join(ROOT, "tests", "golden", "euroc_v1_map.npz" if a.workload == "euroc_geom" else "euroc_v1_photo.npz"))
     photo = a.workload == "euroc_photo"
     return pb.Problem(int(g["mode"]), g["poses"], g["pose_fixed"], g["pose_calib"], g["calib_model"], g["intrinsics"],
@@ -83,6 +86,10 @@ def load_euroc(a):
 
 
 def workload_name(a, n_obs):
+    if a.workload == "grid":
+        return ("geometric reprojection (Huber 1) BA on a lawn-mower flight, 27 x 27 keyframes x 30000 landmarks (%d residual "
+                "blocks): reduced camera system NOT banded under any camera order (4,362 unknowns, half-bandwidth 113 "
+                "cameras after reverse Cuthill-McKee), solved by the exact dense Cholesky" % n_obs)
     if a.workload != "synthetic":
         return ("BASELINE config 1: %s BA on the map built from the bundled data/euroc_V1 stereo keyframes (%s, %d residual "
                 "blocks, double-sphere model calibrated from data/euroc_calib; tools/euroc/)" %

@@ -13,7 +13,8 @@ def last_json(path):
 
 for src, dst in (("bench_full.json", "bench_cfg4_n1.json"), ("bench_cfg2.json", "bench_cfg2.json"),
                  ("bench_cfg3_ds.json", "bench_cfg3_ds.json"), ("bench_cfg3_kb4.json", "bench_cfg3_kb4.json"),
-                 ("bench_cfg5.json", "bench_cfg5.json")):
+                 ("bench_cfg5.json", "bench_cfg5.json"), ("bench_cfg1_euroc_geom.json", "bench_cfg1_euroc_geom.json"),
+                 ("bench_cfg1_euroc_photo.json", "bench_cfg1_euroc_photo.json"), ("bench_grid.json", "bench_grid.json")):
     p = os.path.join(go, src)
     if os.path.exists(p):
         d = last_json(p)
@@ -47,13 +48,17 @@ KEEP = re.compile(r"Duration|Elapsed Cycles|DRAM Throughput|Memory Throughput|Co
                   r"Dynamic Shared Memory|Issue Slots Busy")
 traffic = {}
 for name in ("k1_full", "k2_full", "gram_full", "syrk_full", "gather_full", "backsub_full", "b2_fs_l0_full", "b2_fs_l3_full",
-             "b2_reduce_l0_full", "k1_geom_full", "chol_syrk_full"):
+             "b2_reduce_l0_full", "k1_geom_full", "chol_syrk_full", "chol_coop_full", "chol_coop_grid_full"):
     rep = os.path.join(go, name + ".ncu-rep")
-    if not os.path.exists(rep):
+    if os.path.exists(rep):
+        det = subprocess.run(["ncu", "-i", rep, "--page", "details"], capture_output=True, text=True).stdout
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    elif os.path.exists(os.path.join(go, name + ".details.txt")):  # extracted on the GPU box (r02d_profile.sh)
+        det = open(os.path.join(go, name + ".details.txt")).read()
+        raw = open(os.path.join(go, name + ".raw.csv")).read()
+    else:
         continue
-    det = subprocess.run(["ncu", "-i", rep, "--page", "details"], capture_output=True, text=True).stdout
     open(os.path.join(out, "%s_%s_details.txt" % (tag, name.replace("_full", ""))), "w").write(det)
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     h = rows[0]
 
