@@ -261,6 +261,17 @@ __device__ __forceinline__ void coop_pqt(const double* P, const double* Q, doubl
   }
 }
 
+#ifdef PBA_CHOL_TIMING
+__device__ long long g_chol_t[12];
+#define CT0() long long _ct = clock64()
+#define CT(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) { const long long _n = clock64(); g_chol_t[i] += _n - _ct; _ct = _n; } } while (0)
+#define CTP(i) do { if (threadIdx.x == 252 && blockIdx.x == 0) { const long long _n = clock64(); g_chol_t[i] += _n - _cp; _cp = _n; } } while (0)
+#else
+#define CT0()
+#define CT(i)
+#define CTP(i)
+#endif
+
 __device__ __forceinline__ double coop_rcp(double x) {
   double y;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
@@ -291,13 +302,18 @@ __device__ void coop_diag(const CholCoopArgs& a, int k, double* sm) {
     const int c = ph + 4 * q;  // the lower triangle is the reference copy: (r, c) or its mirror
     t[q] = __ldcg(c <= r ? Akk + int64_t(r) * a.ld + c : Akk + int64_t(c) * a.ld + r);
   }
+#ifdef PBA_CHOL_TIMING
+  long long _cp = clock64();
+#endif
   for (int j = 0; j < NB; ++j) {
     double* pr = prow + (j & 1) * NB;
     if (r == j) {
 #pragma unroll
       for (int q = 0; q < 16; ++q) pr[ph + 4 * q] = t[q];
     }
+    CTP(8);
     __syncthreads();
+    CTP(9);
     double d = pr[j];
     const bool bad = !(d > 0.0);
     if (bad) d = 1.0;
@@ -312,6 +328,7 @@ __device__ void coop_diag(const CholCoopArgs& a, int k, double* sm) {
 #pragma unroll
       for (int q = 0; q < 16; ++q) p[q] = pr[ph + 4 * q];
       const double f = pr[r] * coop_rcp(d);
+      CTP(10);
 #pragma unroll
       for (int q = 0; q < 16; ++q) {
         const int c = ph + 4 * q;
@@ -319,6 +336,7 @@ __device__ void coop_diag(const CholCoopArgs& a, int k, double* sm) {
         if (c == j) Lout[r * TLD + j] = t[q];  // a_rj of the j-th Schur complement: L_rj = a_rj / sqrt(pivot_j), scaled below
         t[q] = c == j ? -f : u;
       }
+      CTP(11);
     }
   }
   __syncthreads();
@@ -340,15 +358,6 @@ __device__ void coop_diag(const CholCoopArgs& a, int k, double* sm) {
   }
   __syncthreads();
 }
-
-#ifdef PBA_CHOL_TIMING
-__device__ long long g_chol_t[8];
-#define CT0() long long _ct = clock64()
-#define CT(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) { const long long _n = clock64(); g_chol_t[i] += _n - _ct; _ct = _n; } } while (0)
-#else
-#define CT0()
-#define CT(i)
-#endif
 
 __global__ void __launch_bounds__(kCoopThreads) k_chol_coop(const CholCoopArgs a) {
   extern __shared__ __align__(16) double coop_sm[];
@@ -708,10 +717,11 @@ pba_status dense_cholesky_solve(Handle* h, double* A, double* b, int ld, int* fa
         static int calls = 0;
         if (++calls == 40) {
           cudaStreamSynchronize(h->stream);
-          long long t[8];
+          long long t[12];
           cudaMemcpyFromSymbol(t, g_chol_t, sizeof(t));
-          const char* names[8] = {"diag0+sync", "panel", "sync1", "trailing(tile)", "diag(k+1)", "sync2", "backward", "sync3"};
-          for (int i = 0; i < 8; ++i) fprintf(stderr, "[chol] %-16s %10.1f cycles/solve\n", names[i], double(t[i]) / calls);
+          const char* names[12] = {"diag0+sync", "panel", "sync1", "trailing(tile)", "diag(k+1)", "sync2", "backward", "sync3",
+                                   "pivot: publish", "pivot: barrier", "pivot: d, rcp, loads", "pivot: update"};
+          for (int i = 0; i < 12; ++i) fprintf(stderr, "[chol] %-16s %10.1f cycles/solve\n", names[i], double(t[i]) / calls);
           fprintf(stderr, "[chol] nt %d grid %d\n", nt, grid);
         }
       }
