@@ -485,6 +485,76 @@ __global__ void __launch_bounds__(kPhotoThreads, MINB) k_eval_photo(const EvalAr
   if (threadIdx.x == 0) a.block_cost[blockIdx.x] = bs;
 }
 
+// K2 for the pinhole / recomputed-bearing path with the eight pattern pixels in TWO HALVES (project 4 -> gather 4 ->
+// sample 4, twice): the live ranges of (fx, fy, offset, quad, I_h) halve, the kernel fits 5 / 6 CTAs per SM without
+// spills (the template above needs 128 registers for its 8-deep batch; bounding IT to 5 / 6 CTAs spilled and ran
+// slower, profiles/r02a_variants.txt).  Same arithmetic as k_eval_photo<false, pinhole, true>, pixel by pixel.
+template <int MINB>
+__global__ void __launch_bounds__(kPhotoThreads, MINB) k_cost_photo_halves(const EvalArgs a) {
+  __shared__ double s_red[kPhotoThreads / 32];
+  const int64_t i = int64_t(blockIdx.x) * kPhotoThreads + threadIdx.x;
+  double cost = 0.0;
+  if (i < a.n) {
+    const int e = a.obs_edge[i];
+    const int l = a.obs_lm[i];
+    const int t = a.edge_t[e];
+    const double2* T2 = reinterpret_cast<const double2*>(a.edge_T + kEdgeStride * int64_t(e));
+    PhotoCtx c;
+    c.model = PBA_CAM_PINHOLE;
+    const double2 huv = reinterpret_cast<const double2*>(a.lm_uv)[l];
+    const double2 hif = T2[12], hcxy = T2[13];
+    const double2 t0 = T2[0], t1 = T2[1], t2 = T2[2], t3 = T2[3], t4 = T2[4], t5 = T2[5], t6 = T2[6];
+    c.A[0] = t0.x; c.A[1] = t0.y; c.A[2] = t1.x; c.A[3] = t1.y; c.A[4] = t2.x; c.A[5] = t2.y; c.A[6] = t3.x;
+    c.A[7] = t3.y; c.A[8] = t4.x; c.tr[0] = t4.y; c.tr[1] = t5.x; c.tr[2] = t5.y; c.ea = t6.x; c.bb = t6.y;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) { const double2 v = T2[8 + q]; c.in[2 * q] = v.x; c.in[2 * q + 1] = v.y; }
+    const double ifx = hif.x, ify = hif.y;
+    const double mx0 = (huv.x - hcxy.x) * ifx, my0 = (huv.y - hcxy.y) * ify;
+    c.irho = 1.0 / a.rho[l];
+    const uint32_t* img = a.quads + int64_t(t) * a.image_stride;
+    bool ok = a.lm_ok[l] != 0;
+    const double umax = double(a.width - 1), vmax = double(a.height - 1);
+    const double* pk = a.lm_pat + l;
+    const int64_t nl = a.n_lm;
+    double s = 0.0;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      double fx[4], fy[4], Ih[4];
+      int off[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        Ih[k] = __ldg(pk + int64_t(4 * (4 * h + k) + 3) * nl);
+        double xh, yh, zh;
+        pinhole_host_point(mx0, my0, ifx, ify, 4 * h + k, c.irho, xh, yh, zh);
+        const double xt = c.A[0] * xh + c.A[1] * yh + c.A[2] * zh + c.tr[0];
+        const double yt = c.A[3] * xh + c.A[4] * yh + c.A[5] * zh + c.tr[1];
+        const double zt = c.A[6] * xh + c.A[7] * yh + c.A[8] * zh + c.tr[2];
+        double uv[2];
+        cam_project<false>(PBA_CAM_PINHOLE, c.in, xt, yt, zt, uv, nullptr);
+        const bool inb = uv[0] >= 0.0 && uv[1] >= 0.0 && uv[0] < umax && uv[1] < vmax;
+        ok &= inb;
+        const double u = inb ? uv[0] : 0.0, v = inb ? uv[1] : 0.0;
+        const double x0 = floor(u), y0 = floor(v);
+        fx[k] = u - x0; fy[k] = v - y0;
+        off[k] = int(y0) * a.pitch + int(x0);
+      }
+      uint32_t quad[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) quad[k] = __ldg(img + off[k]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const double rk = quad_sample(quad[k], fx[k], fy[k]) - (c.ea * Ih[k] + c.bb);
+        s += rk * rk;
+      }
+    }
+    if (!ok) s = 0.0;
+    double w;
+    cost = huber(s, a.use_huber, a.huber, &w);
+  }
+  const double bs = block_sum(cost, s_red);
+  if (threadIdx.x == 0) a.block_cost[blockIdx.x] = bs;
+}
+
 // rc: recompute the pattern bearings (all cameras pinhole); see the kernel's comment.
 // PBA_K1_VARIANT / PBA_K2_VARIANT pick the occupancy / unroll variants kept for A/B measurements.
 template <bool WITH_J>
@@ -503,6 +573,9 @@ void (*photo_kernel(int model, bool rc))(const EvalArgs) {
       switch (var) {  // measured (profiles/r02a_variants.txt): 4 CTAs/SM 1.055 ms, 5 (spills) 1.080, 6 1.131; table path 1.041
         case 1: return k_eval_photo<WITH_J, PBA_CAM_PINHOLE, true, 5, 2>;
         case 2: return k_eval_photo<WITH_J, PBA_CAM_PINHOLE, true, 6, 2>;
+        case 3: return k_cost_photo_halves<5>;
+        case 4: return k_cost_photo_halves<6>;
+        case 5: return k_cost_photo_halves<8>;
         default: return k_eval_photo<WITH_J, PBA_CAM_PINHOLE, true, 4, 2>;
       }
     }
