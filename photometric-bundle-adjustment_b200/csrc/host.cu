@@ -1178,7 +1178,7 @@ pba_status create_impl(const pba_problem* p, const pba_options* o, int rank, int
   h->pcg_grid = pcg_max_grid(h->device);
   PBA_CUDA_OK(h->pcg_ws.alloc(4 * size_t(z.dim) + 3 * size_t(h->pcg_grid) + 8));
   const size_t red = std::max<size_t>({size_t(eval_grid(n)) + 8, 2 * ((size_t(p->n_poses) + n_lm + 255) / 256) + 8,
-                                       size_t(n_lm + 127) / 128 + size_t(z.n_blocks + 127) / 128 + 8});
+                                       size_t(n_lm + 127) / 128 + size_t(z.n_blocks + 15) / 16 + 8});
   PBA_CUDA_OK(h->red_ws.alloc(std::max<size_t>(red, (nn + 255) / 256 + 8)));
   PBA_CUDA_OK(h->red_mid.alloc(kReduceMid));
   PBA_CUDA_OK(h->scalars.alloc(S_NUM)); PBA_CUDA_OK(h->chol_fail.alloc(1));

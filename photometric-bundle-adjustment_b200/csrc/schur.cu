@@ -829,35 +829,28 @@ __global__ void __launch_bounds__(128, S <= 2 ? 4 : 2) k_backsub_stream(int n_lm
   }
 }
 
-// Camera part of the model cost change: one thread per RCS block of the raw (unscaled,
-// undamped, this rank's) direct part B:  -d_a^T B_ab d_b (x1/2 on the diagonal), plus
-// -d_a . g_a from the diagonal block's thread.
+// Camera part of the model cost change: EIGHT lanes per RCS block of the raw (unscaled, undamped, this rank's)
+// direct part B (lane i takes row i: consecutive lanes read consecutive rows, the block is one contiguous run):
+// -d_a^T B_ab d_b (x1/2 on the diagonal), plus -d_a . g_a from the diagonal block.  One thread per block read its
+// 64 doubles alone, 512 bytes apart from its neighbour's: 17 us per launch for 24 k blocks.
 __global__ void __launch_bounds__(128) k_model_cost_cam(int cd, int64_t n_blocks, const int* __restrict__ blk_row,
                                                          const int* __restrict__ blk_col,
                                                          const double* __restrict__ B_local,
                                                          const double* __restrict__ g_local,
                                                          const double* __restrict__ d_cam, double* __restrict__ part) {
   __shared__ double sm[4];
-  const int64_t b = int64_t(blockIdx.x) * 128 + threadIdx.x;
+  const int64_t b = int64_t(blockIdx.x) * 16 + (threadIdx.x >> 3);
+  const int i = threadIdx.x & 7;
   double mc = 0.0;
-  if (b < n_blocks) {
+  if (b < n_blocks && i < cd) {
     const int a = blk_row[b], c = blk_col[b];
-    const double* Bb = B_local + b * cd * cd;
-    const double* da = d_cam + a * cd;
+    const double* Bb = B_local + b * cd * cd + i * cd;
     const double* dc = d_cam + c * cd;
-    double q = 0.0;
-    for (int i = 0; i < cd; ++i) {
-      double s = 0.0;
-      for (int j = 0; j < cd; ++j) s += Bb[i * cd + j] * dc[j];
-      q += da[i] * s;
-    }
-    if (a == c) {
-      double dg = 0.0;
-      for (int i = 0; i < cd; ++i) dg += da[i] * g_local[a * cd + i];
-      mc = -dg - 0.5 * q;
-    } else {
-      mc = -q;
-    }
+    double s = 0.0;
+    for (int j = 0; j < cd; ++j) s += Bb[j] * dc[j];
+    const double da = d_cam[a * cd + i];
+    const double q = da * s;
+    mc = a == c ? -da * g_local[a * cd + i] - 0.5 * q : -q;
   }
   for (int o = 16; o > 0; o >>= 1) mc += __shfl_down_sync(0xffffffffu, mc, o);
   if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = mc;
@@ -1127,7 +1120,7 @@ pba_status launch_backsub(Handle* h) {
                h->d_cam.p);
   }
   const int g_lm = (z.n_lm + 127) / 128;
-  const int g_cam = int((z.n_blocks + 127) / 128);
+  const int g_cam = int((z.n_blocks + 15) / 16);  // 16 RCS blocks per CTA (eight lanes each)
   double* part = h->red_ws.p;
   if (g_lm > 0) {
     // streaming mat-vec while a row fits 2 / 4 double2 steps per lane (<= 15 / 31 cameras per host group);
