@@ -439,6 +439,20 @@ pba_status pba_epipolar_inliers(int32_t model0, const double intr0[8], int32_t m
                                 const double* corners0, const double* corners1, int32_t device, double* E_out,
                                 uint8_t* inlier);
 
+/* TrackBuilder::Build + Filter + Export (include/visnav/tracks.h:53-160; caller build_tracks, src/sfm.cpp:1511-1520):
+ * feature tracks = connected components of the graph whose nodes are (image, feature) pairs and whose edges are the
+ * inlier matches of the image pairs; a track is dropped when it holds two features of the same image or fewer than
+ * min_length features.  feat_ptr [n_images + 1]: CSR of the images' feature counts, node id = feat_ptr[image] + feature;
+ * pairs [n_pairs][2] = image indices; match_ptr [n_pairs + 1] / matches [.][2] = (feature in the first image, feature in
+ * the second image) per pair — the layout pba_match_descriptors produces.  Outputs (HOST): track_of [n_nodes] = the
+ * track's id, which is the SMALLEST node id of the component (the reference's ids are the roots of its union-find forest
+ * and depend on the insertion order; only the partition is defined), or -1 for a node in no match or in a dropped track;
+ * n_tracks [1] (may be NULL) = tracks kept.  More than 8,192 features in one image is PBA_ERR_UNSUPPORTED (the reference's
+ * own limit is 5,000, src/sfm.cpp:197-198). */
+pba_status pba_build_tracks(int32_t n_images, const int32_t* feat_ptr, int32_t n_pairs, const int32_t* pairs,
+                            const int64_t* match_ptr, const int32_t* matches, int32_t min_length, int32_t device,
+                            int32_t* track_of, int32_t* n_tracks);
+
 #ifdef __cplusplus
 }
 #endif

@@ -9,14 +9,16 @@
 //   void computeEssential(const Sophus::SE3d& T_0_1, Eigen::Matrix3d& E)
 //   void findInliersEssential(kd1, kd2, cam1, cam2, E, epipolar_error_threshold, MatchData&)
 //                                                                              matching_utils.h:50-79
+//   TrackBuilder::Build / Filter / Export                                      tracks.h:53-160
 //
 // Header-only C++14 templates over the reference's own types (they compile unchanged against
 // include/visnav/common_types.h, keypoints.h and camera_models.h: oracle/ref/dropin_harness.cpp), on top of the C ABI
-// (include/pba.h: pba_corner_descriptors, pba_match_descriptors, pba_epipolar_inliers).  Corner DETECTION
+// (include/pba.h: pba_corner_descriptors, pba_match_descriptors, pba_epipolar_inliers, pba_build_tracks).  Corner DETECTION
 // (detectKeypoints: cv::goodFeaturesToTrack, keypoints.h:133-151) stays where it is.  Every function returns a
 // pba_status (the reference's return void); on an error the outputs are left cleared.
 #pragma once
 
+#include <algorithm>
 #include <cstdint>
 #include <cstdio>
 #include <utility>
@@ -163,6 +165,52 @@ pba_status findInliersEssential(const KeypointsDataT& kd1, const KeypointsDataT&
   }
   for (int64_t k = 0; k < n; ++k)
     if (inl[size_t(k)]) md.inliers.emplace_back(md.matches[size_t(k)].first, md.matches[size_t(k)].second);
+  return PBA_OK;
+}
+
+// TrackBuilder::Build + Filter + Export as build_tracks() uses them (src/sfm.cpp:1511-1520; include/visnav/tracks.h:53-160):
+// feature tracks = connected components of the inlier-match graph, minus the tracks with two features of one image
+// or fewer than min_length features.  feature_corners supplies the images and their feature counts.  TrackIds are
+// the smallest node (image, feature) of the track in FrameCamId order — the reference's are the roots of its
+// union-find forest; both are opaque keys.
+template <class MatchesT, class CornersT, class FeatureTracksT>
+pba_status buildTracks(const MatchesT& feature_matches, const CornersT& feature_corners, size_t min_length,
+                       FeatureTracksT& feature_tracks, int device = 0) {
+  using FrameCamIdT = typename CornersT::key_type;
+  using TrackIdT = typename FeatureTracksT::key_type;
+  feature_tracks.clear();
+  std::vector<FrameCamIdT> ids;
+  for (const auto& kv : feature_corners) ids.push_back(kv.first);
+  std::sort(ids.begin(), ids.end());
+  std::vector<int32_t> feat_ptr(1, 0);
+  for (const auto& id : ids) feat_ptr.push_back(feat_ptr.back() + int32_t(feature_corners.at(id).corners.size()));
+  auto index_of = [&](const FrameCamIdT& id) {
+    const auto it = std::lower_bound(ids.begin(), ids.end(), id);
+    return (it != ids.end() && !(id < *it)) ? int32_t(it - ids.begin()) : int32_t(-1);
+  };
+  std::vector<int32_t> pairs, matches;
+  std::vector<int64_t> match_ptr(1, 0);
+  for (const auto& kv : feature_matches) {
+    const int32_t a = index_of(kv.first.first), b = index_of(kv.first.second);
+    if (a < 0 || b < 0) return PBA_ERR_INVALID_ARGUMENT;
+    pairs.push_back(a); pairs.push_back(b);
+    for (const auto& m : kv.second.inliers) { matches.push_back(int32_t(m.first)); matches.push_back(int32_t(m.second)); }
+    match_ptr.push_back(int64_t(matches.size() / 2));
+  }
+  matches.push_back(0); matches.push_back(0);  // never an empty buffer
+  pairs.push_back(0); pairs.push_back(0);
+  std::vector<int32_t> track_of(size_t(feat_ptr.back()) + 1, -1);
+  const pba_status st = pba_build_tracks(int32_t(ids.size()), feat_ptr.data(), int32_t(match_ptr.size() - 1), pairs.data(),
+                                         match_ptr.data(), matches.data(), int32_t(min_length), device, track_of.data(), nullptr);
+  if (st != PBA_OK) {
+    std::fprintf(stderr, "visnav_b200::buildTracks: %s\n", pba_status_string(st));
+    return st;
+  }
+  for (size_t im = 0; im < ids.size(); ++im)
+    for (int32_t f = 0; f < feat_ptr[im + 1] - feat_ptr[im]; ++f) {
+      const int32_t t = track_of[size_t(feat_ptr[im] + f)];
+      if (t >= 0) feature_tracks[TrackIdT(t)].emplace(ids[im], f);
+    }
   return PBA_OK;
 }
 

@@ -1341,3 +1341,44 @@ ORACLE_API int pba_oracle_epipolar_inliers(int model0, const double* intr0, int 
   }
   return n_in;
 }
+
+// TrackBuilder::Build / Filter / Export (include/visnav/tracks.h:53-160), restated with a plain sequential
+// union-find.  Node id = feat_ptr[image] + feature; track id = smallest node id of the component (the reference's ids
+// are the roots of ITS forest; the partition and the filter decisions are what is defined).
+ORACLE_API int pba_oracle_build_tracks(int n_images, const int32_t* feat_ptr, int n_pairs, const int32_t* pairs,
+                                       const int64_t* match_ptr, const int32_t* matches, int min_length, int32_t* track_of) {
+  const int n = n_images > 0 ? feat_ptr[n_images] : 0;
+  std::vector<int> parent(n), image(n);
+  std::vector<char> touched(n, 0);
+  for (int i = 0; i < n; ++i) parent[i] = i;
+  for (int im = 0; im < n_images; ++im)
+    for (int i = feat_ptr[im]; i < feat_ptr[im + 1]; ++i) image[i] = im;
+  auto find = [&](int x) { while (parent[x] != x) { parent[x] = parent[parent[x]]; x = parent[x]; } return x; };
+  for (int k = 0; k < n_pairs; ++k)
+    for (int64_t e = match_ptr[k]; e < match_ptr[k + 1]; ++e) {
+      const int u = feat_ptr[pairs[2 * k]] + matches[2 * e], v = feat_ptr[pairs[2 * k + 1]] + matches[2 * e + 1];
+      touched[u] = touched[v] = 1;
+      const int ru = find(u), rv = find(v);
+      if (ru != rv) parent[std::max(ru, rv)] = std::min(ru, rv);
+    }
+  // a component's nodes in ascending id are ascending in image: two equal consecutive images = a conflict
+  std::vector<int> count(n, 0), last_image(n, -1);
+  std::vector<char> bad(n, 0);
+  for (int i = 0; i < n; ++i) {
+    if (!touched[i]) continue;
+    const int r = find(i);
+    ++count[r];
+    if (last_image[r] == image[i]) bad[r] = 1;
+    last_image[r] = image[i];
+  }
+  int kept = 0;
+  for (int i = 0; i < n; ++i) {
+    int t = -1;
+    if (touched[i]) {
+      const int r = find(i);
+      if (count[r] >= min_length && !bad[r]) { t = r; kept += r == i; }
+    }
+    track_of[i] = t;
+  }
+  return kept;
+}

@@ -15,6 +15,7 @@
 #include <visnav/keypoints.h>
 #include <visnav/map_utils.h>
 #include <visnav/matching_utils.h>
+#include <visnav/tracks.h>
 
 #include <algorithm>
 #include <cstring>
@@ -300,5 +301,45 @@ extern "C" __attribute__((visibility("default"))) int pba_dropin_frontend_stereo
   for (size_t k = 0; k < md.matches.size(); ++k) { matches[2 * k] = md.matches[k].first; matches[2 * k + 1] = md.matches[k].second; }
   *n_inliers = int32_t(md.inliers.size());
   for (size_t k = 0; k < md.inliers.size(); ++k) { inliers[2 * k] = md.inliers[k].first; inliers[2 * k + 1] = md.inliers[k].second; }
+  return 0;
+}
+
+// build_tracks() drop-in proof (src/sfm.cpp:1511-1520): the reference's Corners / Matches / FeatureTracks through
+// either the reference's TrackBuilder (use_b200 = 0) or visnav_b200::buildTracks (CUDA).  Image i is
+// FrameCamId(i / 2, i % 2) (stereo frames).  Output per node (image offset + feature): the smallest node of its
+// track, -1 for none — comparable whatever the TrackIds are.
+extern "C" __attribute__((visibility("default"))) int pba_dropin_build_tracks(
+    int n_images, const int32_t* feat_ptr, int n_pairs, const int32_t* pairs, const int64_t* match_ptr,
+    const int32_t* matches, int min_length, int use_b200, int32_t* track_of, int32_t* n_tracks) {
+  using namespace visnav;
+  std::vector<FrameCamId> ids;
+  Corners feature_corners;
+  for (int i = 0; i < n_images; ++i) {
+    ids.emplace_back(i / 2, size_t(i % 2));
+    feature_corners[ids.back()].corners.resize(size_t(feat_ptr[i + 1] - feat_ptr[i]));
+  }
+  Matches feature_matches;
+  for (int k = 0; k < n_pairs; ++k) {
+    MatchData md;
+    for (int64_t e = match_ptr[k]; e < match_ptr[k + 1]; ++e) md.inliers.emplace_back(matches[2 * e], matches[2 * e + 1]);
+    feature_matches[std::make_pair(ids[pairs[2 * k]], ids[pairs[2 * k + 1]])] = md;
+  }
+  FeatureTracks tracks;
+  if (use_b200) {
+    if (visnav_b200::buildTracks(feature_matches, feature_corners, size_t(min_length), tracks) != PBA_OK) return 50;
+  } else {
+    TrackBuilder tb;
+    tb.Build(feature_matches);
+    tb.Filter(size_t(min_length));
+    tb.Export(tracks);
+  }
+  const int n = feat_ptr[n_images];
+  for (int i = 0; i < n; ++i) track_of[i] = -1;
+  for (const auto& kv : tracks) {
+    int lo = n;
+    for (const auto& f : kv.second) lo = std::min(lo, int(feat_ptr[f.first.frame_id * 2 + int(f.first.cam_id)] + f.second));
+    for (const auto& f : kv.second) track_of[feat_ptr[f.first.frame_id * 2 + int(f.first.cam_id)] + f.second] = lo;
+  }
+  *n_tracks = int32_t(tracks.size());
   return 0;
 }

@@ -3,6 +3,7 @@
 // (include/visnav/keypoints.h:182-300), visnav::computeEssential / findInliersEssential
 // (include/visnav/matching_utils.h:50-79).
 //
+// and visnav::TrackBuilder (include/visnav/tracks.h:53-160).
 // TEST INFRASTRUCTURE ONLY: built by oracle/ref/Makefile into oracle/_ref/libpba_ref_frontend.so, loaded only
 // by tests/ (golden-vector generation and live parity).  Pangolin and OpenCV are replaced by the two shims
 // under oracle/ref/shim (an image view and never-called declarations); nothing of the reference is copied.
@@ -11,6 +12,7 @@
 #include <visnav/camera_models.h>
 #include <visnav/keypoints.h>
 #include <visnav/matching_utils.h>
+#include <visnav/tracks.h>
 
 #include <algorithm>
 #include <cstdint>
@@ -97,4 +99,31 @@ FE_API int pba_ref_epipolar_inliers(int n_matches, const int32_t* matches, int n
   for (int k = 0; k < n_matches && q < md.inliers.size(); ++k)
     if (md.matches[k] == md.inliers[q]) { inlier[k] = 1; ++q; }
   return int(md.inliers.size());
+}
+
+// The reference's TrackBuilder on the inlier matches of a list of image pairs (image i = FrameCamId(i, 0)).
+// track_of [n_nodes]: the SMALLEST node id of the exported track a node belongs to (the reference's own TrackIds are
+// the roots of its union-find forest), -1 for nodes in no exported track.  Returns the number of exported tracks.
+FE_API int pba_ref_build_tracks(int n_images, const int32_t* feat_ptr, int n_pairs, const int32_t* pairs,
+                                const int64_t* match_ptr, const int32_t* matches, int min_length, int32_t* track_of) {
+  using namespace visnav;
+  Matches feature_matches;
+  for (int k = 0; k < n_pairs; ++k) {
+    MatchData md;
+    for (int64_t e = match_ptr[k]; e < match_ptr[k + 1]; ++e) md.inliers.emplace_back(matches[2 * e], matches[2 * e + 1]);
+    feature_matches[std::make_pair(FrameCamId(pairs[2 * k], 0), FrameCamId(pairs[2 * k + 1], 0))] = md;
+  }
+  TrackBuilder tb;
+  tb.Build(feature_matches);
+  tb.Filter(size_t(min_length));
+  FeatureTracks tracks;
+  tb.Export(tracks);
+  const int n = n_images > 0 ? feat_ptr[n_images] : 0;
+  for (int i = 0; i < n; ++i) track_of[i] = -1;
+  for (const auto& kv : tracks) {
+    int lo = n;
+    for (const auto& f : kv.second) lo = std::min(lo, int(feat_ptr[f.first.frame_id] + f.second));
+    for (const auto& f : kv.second) track_of[feat_ptr[f.first.frame_id] + f.second] = lo;
+  }
+  return int(tracks.size());
 }

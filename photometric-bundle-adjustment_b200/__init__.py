@@ -11,7 +11,7 @@ from ._ffi import (CAM_DS, CAM_EUCM, CAM_KB4, CAM_PINHOLE, CONVERGENCE, FAILURE,
                    MODE_PHOTOMETRIC, NO_CONVERGENCE, SOLVER_AUTO, SOLVER_BAND, SOLVER_BCR, SOLVER_CHOLESKY, SOLVER_PCG, ExtensionMissing)
 from .calibration import Calibration, initialize_from_double_sphere, load_calibration, save_calibration
 from .engine import BundleAdjustmentOptions, Engine, Summary, analyze_structure, bundle_adjustment, device_count, multi_gpu_init
-from .frontend import corner_descriptors, epipolar_inliers, match_descriptors
+from .frontend import build_tracks, corner_descriptors, epipolar_inliers, match_descriptors
 from .map_io import Map, load_map_file, save_map_file
 from .problem import Problem, partition_landmarks
 from .projections import (ProjectionThresholds, Projections, compute_projections, landmark_positions,
@@ -24,5 +24,5 @@ __all__ = [
     "partition_landmarks", "make_scene", "make_grid_scene", "MODE_GEOMETRIC", "MODE_PHOTOMETRIC", "CAM_PINHOLE", "CAM_DS",
     "CAM_KB4", "CAM_EUCM", "SOLVER_AUTO", "SOLVER_CHOLESKY", "SOLVER_PCG", "SOLVER_BAND", "SOLVER_BCR", "CONVERGENCE", "NO_CONVERGENCE",
     "FAILURE", "ExtensionMissing", "ProjectionThresholds", "Projections", "compute_projections",
-    "landmark_positions", "corner_descriptors", "match_descriptors", "epipolar_inliers", "Map", "load_map_file", "save_map_file",
+    "landmark_positions", "corner_descriptors", "match_descriptors", "epipolar_inliers", "build_tracks", "Map", "load_map_file", "save_map_file",
 ]

@@ -123,7 +123,7 @@ PBA_SYMBOLS = [
     "pba_set_state", "pba_get_state", "pba_get_sizes", "pba_reset_kernel_stats", "pba_set_profile", "pba_get_kernel_stats",
     "pba_nccl_unique_id", "pba_comm_init", "pba_camera_project", "pba_camera_unproject", "pba_se3_plus",
     "pba_cholesky_solve", "pba_projection_thresholds_init", "pba_landmark_positions", "pba_compute_projections", "pba_triangulate_inverse_depth",
-    "pba_corner_descriptors", "pba_match_descriptors", "pba_epipolar_inliers",
+    "pba_corner_descriptors", "pba_match_descriptors", "pba_epipolar_inliers", "pba_build_tracks",
 ]
 
 _lib = None

@@ -256,6 +256,109 @@ __global__ void k_epipolar(const EpiArgs a, const int* __restrict__ matches, con
   inlier[k] = fabs(xl[0] * e0 + xl[1] * e1 + xl[2] * e2) <= a.threshold ? 1 : 0;
 }
 
+
+// ---- feature tracks (tracks.h:53-160): connected components of the match graph ----
+// Label propagation with the smaller-root-wins hook and pointer jumping: every edge (u, v) hooks the larger of the two
+// current roots under the smaller one (atomicMin on the root's parent: integer, so the fixed point — every node
+// labelled with the smallest node id of its component — does not depend on the order), a compress pass points every
+// node at its root, and the pair repeats until no edge joins two roots any more (a handful of rounds).
+constexpr int kTrackMaxFeat = 8192;
+
+__device__ __forceinline__ int track_root(const int* parent, int x) {
+  int p = parent[x];
+  while (p != x) { x = p; p = parent[x]; }
+  return x;
+}
+
+struct TrackEdges {
+  int n_pairs;
+  int64_t n_edges;
+  const int* feat_ptr;
+  const int* pairs;
+  const int64_t* match_ptr;
+  const int* matches;
+};
+
+__device__ __forceinline__ void track_edge(const TrackEdges& g, int64_t e, int& u, int& v) {
+  int lo = 0, hi = g.n_pairs - 1;  // the pair of edge e: last k with match_ptr[k] <= e
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (g.match_ptr[mid] <= e) lo = mid; else hi = mid - 1;
+  }
+  u = g.feat_ptr[g.pairs[2 * lo]] + g.matches[2 * e];
+  v = g.feat_ptr[g.pairs[2 * lo + 1]] + g.matches[2 * e + 1];
+}
+
+__global__ void k_track_init(int n, int* __restrict__ parent) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) parent[i] = i;
+}
+
+__global__ void k_track_hook(const TrackEdges g, int first, int* parent, uint8_t* __restrict__ touched, int* __restrict__ changed) {
+  const int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (e >= g.n_edges) return;
+  int u, v;
+  track_edge(g, e, u, v);
+  if (first) { touched[u] = 1; touched[v] = 1; }
+  const int ru = track_root(parent, u), rv = track_root(parent, v);
+  if (ru != rv) {
+    atomicMin(parent + max(ru, rv), min(ru, rv));
+    *changed = 1;
+  }
+}
+
+__global__ void k_track_compress(int n, int* parent) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) parent[i] = track_root(parent, i);
+}
+
+__global__ void k_track_count(int n, const int* __restrict__ parent, const uint8_t* __restrict__ touched, int* __restrict__ count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && touched[i]) atomicAdd(count + parent[i], 1);
+}
+
+// One CTA per image: two features of the image in one track <=> two equal labels among the image's nodes.  The labels
+// are sorted in shared memory (bitonic, padded with distinct sentinels) and neighbours compared.
+__global__ void __launch_bounds__(256) k_track_conflict(const int* __restrict__ feat_ptr, const int* __restrict__ parent,
+                                                         const uint8_t* __restrict__ touched, uint8_t* __restrict__ conflict) {
+  extern __shared__ int s_lab[];
+  const int i0 = feat_ptr[blockIdx.x], n = feat_ptr[blockIdx.x + 1] - i0;
+  int m = 1;
+  while (m < n) m <<= 1;
+  for (int x = threadIdx.x; x < m; x += blockDim.x)
+    s_lab[x] = (x < n && touched[i0 + x]) ? parent[i0 + x] : -1 - x;  // untouched / padding: all different, all negative
+  __syncthreads();
+  for (int k = 2; k <= m; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int x = threadIdx.x; x < m; x += blockDim.x) {
+        const int y = x ^ j;
+        if (y > x) {
+          const int a = s_lab[x], b = s_lab[y];
+          if (((x & k) == 0) ? (a > b) : (a < b)) { s_lab[x] = b; s_lab[y] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  for (int x = threadIdx.x; x + 1 < m; x += blockDim.x)
+    if (s_lab[x] >= 0 && s_lab[x] == s_lab[x + 1]) conflict[s_lab[x]] = 1;
+}
+
+__global__ void k_track_finish(int n, int min_length, const int* __restrict__ parent, const uint8_t* __restrict__ touched,
+                               const int* __restrict__ count, const uint8_t* __restrict__ conflict, int* __restrict__ track_of,
+                               int* __restrict__ n_tracks) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int t = -1;
+  if (touched[i]) {
+    const int r = parent[i];
+    if (count[r] >= min_length && !conflict[r]) {
+      t = r;
+      if (r == i) atomicAdd(n_tracks, 1);
+    }
+  }
+  track_of[i] = t;
+}
+
 }  // namespace
 }  // namespace pba
 
@@ -397,5 +500,80 @@ PBA_API pba_status pba_epipolar_inliers(int32_t model0, const double intr0[8], i
   k_epipolar<<<unsigned((n_matches + 127) / 128), 128>>>(a, d_m.p, d_c0.p, d_c1.p, d_in.p);
   PBA_CUDA_OK(cudaGetLastError());
   PBA_CUDA_OK(cudaMemcpy(inlier, d_in.p, size_t(n_matches), cudaMemcpyDeviceToHost));
+  return PBA_OK;
+}
+
+PBA_API pba_status pba_build_tracks(int32_t n_images, const int32_t* feat_ptr, int32_t n_pairs, const int32_t* pairs,
+                                    const int64_t* match_ptr, const int32_t* matches, int32_t min_length, int32_t device,
+                                    int32_t* track_of, int32_t* n_tracks) {
+  if (n_images < 0 || n_pairs < 0 || !feat_ptr || (n_pairs > 0 && (!pairs || !match_ptr))) return PBA_ERR_INVALID_ARGUMENT;
+  if (feat_ptr[0] != 0) return PBA_ERR_INVALID_ARGUMENT;
+  int max_feat = 0;
+  for (int i = 0; i < n_images; ++i) {
+    if (feat_ptr[i + 1] < feat_ptr[i]) return PBA_ERR_INVALID_ARGUMENT;
+    max_feat = std::max(max_feat, feat_ptr[i + 1] - feat_ptr[i]);
+  }
+  const int n = n_images > 0 ? feat_ptr[n_images] : 0;
+  if (n > 0 && !track_of) return PBA_ERR_INVALID_ARGUMENT;
+  const int64_t n_edges = n_pairs > 0 ? match_ptr[n_pairs] : 0;
+  if (n_pairs > 0 && match_ptr[0] != 0) return PBA_ERR_INVALID_ARGUMENT;
+  if (n_edges > 0 && !matches) return PBA_ERR_INVALID_ARGUMENT;
+  for (int k = 0; k < n_pairs; ++k) {
+    if (match_ptr[k + 1] < match_ptr[k]) return PBA_ERR_INVALID_ARGUMENT;
+    const int a = pairs[2 * k], b = pairs[2 * k + 1];
+    if (a < 0 || a >= n_images || b < 0 || b >= n_images) return PBA_ERR_INVALID_ARGUMENT;
+    const int na = feat_ptr[a + 1] - feat_ptr[a], nb = feat_ptr[b + 1] - feat_ptr[b];
+    for (int64_t e = match_ptr[k]; e < match_ptr[k + 1]; ++e)
+      if (matches[2 * e] < 0 || matches[2 * e] >= na || matches[2 * e + 1] < 0 || matches[2 * e + 1] >= nb) return PBA_ERR_INVALID_ARGUMENT;
+  }
+  if (max_feat > kTrackMaxFeat) return PBA_ERR_UNSUPPORTED;
+  if (!have_device()) return PBA_ERR_NO_DEVICE;
+  PBA_CUDA_OK(cudaSetDevice(device));
+  if (n_tracks) *n_tracks = 0;
+  if (n == 0) return PBA_OK;
+  DevBuf<int> d_fp, d_pairs, d_m, d_parent, d_count, d_track, d_flag;
+  DevBuf<int64_t> d_mp;
+  DevBuf<uint8_t> d_touched, d_conf;
+  PBA_CUDA_OK(d_fp.alloc(size_t(n_images) + 1)); PBA_CUDA_OK(d_pairs.alloc(size_t(2) * std::max(n_pairs, 1)));
+  PBA_CUDA_OK(d_mp.alloc(size_t(n_pairs) + 1)); PBA_CUDA_OK(d_m.alloc(size_t(2) * std::max<int64_t>(n_edges, 1)));
+  PBA_CUDA_OK(d_parent.alloc(n)); PBA_CUDA_OK(d_count.alloc(n)); PBA_CUDA_OK(d_track.alloc(n)); PBA_CUDA_OK(d_flag.alloc(2));
+  PBA_CUDA_OK(d_touched.alloc(n)); PBA_CUDA_OK(d_conf.alloc(n));
+  PBA_CUDA_OK(cudaMemcpy(d_fp.p, feat_ptr, sizeof(int) * (size_t(n_images) + 1), cudaMemcpyHostToDevice));
+  if (n_pairs > 0) {
+    PBA_CUDA_OK(cudaMemcpy(d_pairs.p, pairs, sizeof(int) * 2 * n_pairs, cudaMemcpyHostToDevice));
+    PBA_CUDA_OK(cudaMemcpy(d_mp.p, match_ptr, sizeof(int64_t) * (size_t(n_pairs) + 1), cudaMemcpyHostToDevice));
+  }
+  if (n_edges > 0) PBA_CUDA_OK(cudaMemcpy(d_m.p, matches, sizeof(int) * 2 * n_edges, cudaMemcpyHostToDevice));
+  PBA_CUDA_OK(cudaMemset(d_touched.p, 0, n)); PBA_CUDA_OK(cudaMemset(d_conf.p, 0, n));
+  PBA_CUDA_OK(cudaMemset(d_count.p, 0, sizeof(int) * n)); PBA_CUDA_OK(cudaMemset(d_flag.p, 0, sizeof(int) * 2));
+  const unsigned gn = unsigned((n + 255) / 256);
+  k_track_init<<<gn, 256>>>(n, d_parent.p);
+  PBA_CUDA_OK(cudaGetLastError());
+  if (n_edges > 0) {
+    TrackEdges g;
+    g.n_pairs = n_pairs; g.n_edges = n_edges; g.feat_ptr = d_fp.p; g.pairs = d_pairs.p; g.match_ptr = d_mp.p; g.matches = d_m.p;
+    const unsigned ge = unsigned((n_edges + 255) / 256);
+    for (int round = 0; round < 64; ++round) {  // a component of diameter D settles in O(log D) rounds
+      PBA_CUDA_OK(cudaMemset(d_flag.p, 0, sizeof(int)));
+      k_track_hook<<<ge, 256>>>(g, round == 0 ? 1 : 0, d_parent.p, d_touched.p, d_flag.p);
+      k_track_compress<<<gn, 256>>>(n, d_parent.p);
+      PBA_CUDA_OK(cudaGetLastError());
+      int changed = 0;
+      PBA_CUDA_OK(cudaMemcpy(&changed, d_flag.p, sizeof(int), cudaMemcpyDeviceToHost));
+      if (!changed) break;
+      if (round == 63) return PBA_ERR_NUMERICAL_FAILURE;
+    }
+  }
+  k_track_count<<<gn, 256>>>(n, d_parent.p, d_touched.p, d_count.p);
+  int m = 1;
+  while (m < max_feat) m <<= 1;
+  if (n_images > 0 && max_feat > 0) {
+    PBA_CUDA_OK(ensure_dynamic_smem((const void*)k_track_conflict, sizeof(int) * size_t(m), device));
+    k_track_conflict<<<n_images, 256, sizeof(int) * size_t(m)>>>(d_fp.p, d_parent.p, d_touched.p, d_conf.p);
+  }
+  k_track_finish<<<gn, 256>>>(n, min_length, d_parent.p, d_touched.p, d_count.p, d_conf.p, d_track.p, d_flag.p + 1);
+  PBA_CUDA_OK(cudaGetLastError());
+  PBA_CUDA_OK(cudaMemcpy(track_of, d_track.p, sizeof(int) * n, cudaMemcpyDeviceToHost));
+  if (n_tracks) PBA_CUDA_OK(cudaMemcpy(n_tracks, d_flag.p + 1, sizeof(int), cudaMemcpyDeviceToHost));
   return PBA_OK;
 }

@@ -25,6 +25,7 @@ def _lib():
                                               i64p, i32p, C.c_int64]
         lib.pba_epipolar_inliers.argtypes = [C.c_int32, dp, C.c_int32, dp, dp, C.c_double, C.c_int64, i32p, dp, dp,
                                              C.c_int32, dp, u8p]
+        lib.pba_build_tracks.argtypes = [C.c_int32, i32p, C.c_int32, i32p, i64p, i32p, C.c_int32, C.c_int32, i32p, i32p]
         lib._frontend_bound = True
     return lib
 
@@ -94,3 +95,28 @@ def epipolar_inliers(model0, intr0, model1, intr1, T_0_1, matches, corners0, cor
                                            _ffi.ptr(c1, C.c_double), device, _ffi.ptr(E, C.c_double),
                                            _ffi.ptr(inl, C.c_uint8)), "pba_epipolar_inliers")
     return E.reshape(3, 3), inl[:len(matches)].astype(bool)
+
+
+def build_tracks(feature_counts, pairs, matches, min_length=3, device=0):
+    """TrackBuilder Build + Filter + Export (tracks.h:53-160; caller build_tracks, src/sfm.cpp:1511-1520, default minimum
+    length 3, src/sfm.cpp:214).  feature_counts: features per image; pairs [m, 2] image indices; matches: list of [q, 2]
+    arrays (the inlier matches of each pair).  Returns (track_of, n_tracks): track_of is a list of int32 arrays, one per
+    image — the id of the track each feature belongs to (= the smallest node id of the track, node id = image offset +
+    feature), -1 for none."""
+    counts = np.asarray(feature_counts, np.int64)
+    fp = np.zeros(len(counts) + 1, np.int32)
+    fp[1:] = np.cumsum(counts)
+    pairs = np.ascontiguousarray(np.asarray(pairs, np.int32).reshape(-1, 2))
+    assert len(matches) == len(pairs)
+    mp = np.zeros(len(pairs) + 1, np.int64)
+    mp[1:] = np.cumsum([len(m) for m in matches])
+    flat = np.ascontiguousarray(np.concatenate([np.asarray(m, np.int32).reshape(-1, 2) for m in matches])
+                                if len(matches) else np.zeros((0, 2), np.int32), np.int32)
+    if len(flat) == 0:
+        flat = np.zeros((1, 2), np.int32)
+    out = np.full(max(int(fp[-1]), 1), -1, np.int32)
+    nt = C.c_int32(0)
+    _ffi.check(_lib().pba_build_tracks(len(counts), _ffi.ptr(fp, C.c_int32), len(pairs), _ffi.ptr(pairs, C.c_int32),
+                                       _ffi.ptr(mp, C.c_int64), _ffi.ptr(flat, C.c_int32), int(min_length), device,
+                                       _ffi.ptr(out, C.c_int32), C.byref(nt)), "pba_build_tracks")
+    return [out[fp[i]:fp[i + 1]].copy() for i in range(len(counts))], int(nt.value)

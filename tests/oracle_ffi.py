@@ -299,3 +299,23 @@ def epipolar_inliers(kind, model0, intr0, model1, intr1, T_0_1, matches, corners
           int(model0), _ffi.ptr(i0, C.c_double), int(model1), _ffi.ptr(i1, C.c_double), _ffi.ptr(E, C.c_double),
           float(threshold), _ffi.ptr(inl, C.c_uint8))
     return E.reshape(3, 3), inl[:len(matches)].astype(bool)
+
+
+def build_tracks(kind, feature_counts, pairs, matches, min_length=3):
+    """(track_of per image, number of tracks): TrackBuilder Build + Filter + Export, canonical ids (smallest node)."""
+    lib, pre = _frontend_lib(kind)
+    counts = np.asarray(feature_counts, np.int64)
+    fp = np.zeros(len(counts) + 1, np.int32)
+    fp[1:] = np.cumsum(counts)
+    pairs = np.ascontiguousarray(np.asarray(pairs, np.int32).reshape(-1, 2))
+    mp = np.zeros(len(pairs) + 1, np.int64)
+    mp[1:] = np.cumsum([len(m) for m in matches])
+    flat = np.ascontiguousarray(np.concatenate([np.asarray(m, np.int32).reshape(-1, 2) for m in matches] + [np.zeros((1, 2), np.int32)]))
+    out = np.full(max(int(fp[-1]), 1), -1, np.int32)
+    f = getattr(lib, pre + "_build_tracks")
+    f.argtypes = [C.c_int, C.POINTER(C.c_int32), C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_int32),
+                  C.c_int, C.POINTER(C.c_int32)]
+    f.restype = C.c_int
+    nt = f(len(counts), _ffi.ptr(fp, C.c_int32), len(pairs), _ffi.ptr(pairs, C.c_int32), _ffi.ptr(mp, C.c_int64),
+           _ffi.ptr(flat, C.c_int32), int(min_length), _ffi.ptr(out, C.c_int32))
+    return [out[fp[i]:fp[i + 1]].copy() for i in range(len(counts))], int(nt)

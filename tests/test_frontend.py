@@ -208,3 +208,107 @@ def test_reference_containers_drive_both_front_ends(g, images):
     assert np.array_equal(ref[4], gpu[4]) and np.array_equal(ref[5], gpu[5])
     assert np.array_equal(gpu[4], g["matches_1"])                       # pair (2, 3) of the fixture
     assert np.array_equal(gpu[5], g["matches_1"][g["inliers_1"]])
+
+
+# ------------------------------------------------------------------------------------------------ feature tracks
+def random_match_graph(rng, n_images, n_feat, n_pairs, density):
+    """Random pairwise matches (each a partial injective map, as matchDescriptors produces) between random image pairs."""
+    counts = rng.integers(max(1, n_feat // 2), n_feat + 1, n_images)
+    all_pairs = [(a, b) for a in range(n_images) for b in range(a + 1, n_images)]
+    sel = rng.choice(len(all_pairs), min(n_pairs, len(all_pairs)), replace=False)
+    pairs, matches = [], []
+    for s in sel:
+        a, b = all_pairs[s]
+        q = int(density * min(counts[a], counts[b]))
+        fa = rng.choice(counts[a], q, replace=False)
+        fb = rng.choice(counts[b], q, replace=False)
+        pairs.append((a, b))
+        matches.append(np.stack([np.sort(fa), fb], 1).astype(np.int32))
+    return counts, np.array(pairs, np.int32).reshape(-1, 2), matches
+
+
+def real_match_graph(g):
+    """The fixture's pairs: epipolar inliers for the stereo pairs, all matches for the pairs across time."""
+    n = len(g["image_index"])
+    counts = [len(g["corners_%d" % i]) for i in range(n)]
+    matches = [g["matches_%d" % k][g["inliers_%d" % k]] if "inliers_%d" % k in g.files else g["matches_%d" % k]
+               for k in range(len(g["pairs"]))]
+    return counts, g["pairs"], matches
+
+
+@pytest.mark.skipif(not of.have_ref_frontend(), reason="oracle/_ref/libpba_ref_frontend.so not built")
+def test_oracle_tracks_equal_the_reference_track_builder(g):
+    """Partition into tracks, conflict removal (two features of one image) and the minimum length, against the
+    reference's TrackBuilder (tracks.h:53-160) on the real match graph and on random ones with many conflicts."""
+    rng = np.random.default_rng(31)
+    cases = [real_match_graph(g) + (3,), real_match_graph(g) + (2,)]
+    for n_img, n_feat, n_pairs, dens, ml in [(6, 40, 10, 0.5, 2), (12, 60, 30, 0.3, 3), (20, 200, 60, 0.15, 3),
+                                             (8, 30, 28, 0.9, 4), (5, 10, 0, 0.5, 2)]:
+        cases.append(random_match_graph(rng, n_img, n_feat, n_pairs, dens) + (ml,))
+    kept_any = dropped_any = False
+    for counts, pairs, matches, ml in cases:
+        to, no = of.build_tracks("oracle", counts, pairs, matches, ml)
+        tr, nr = of.build_tracks("ref", counts, pairs, matches, ml)
+        assert no == nr
+        for a, b in zip(to, tr):
+            assert np.array_equal(a, b)
+        kept_any |= no > 0
+        touched = set()
+        for (a, b), m in zip(pairs, matches):
+            touched |= {(int(a), int(x)) for x in m[:, 0]} | {(int(b), int(x)) for x in m[:, 1]}
+        dropped_any |= any(to[i][f] < 0 for i, f in touched)
+    assert kept_any and dropped_any
+
+
+@pytest.mark.gpu
+def test_cuda_tracks_equal_the_oracle(g):
+    rng = np.random.default_rng(37)
+    cases = [real_match_graph(g) + (3,)]
+    for n_img, n_feat, n_pairs, dens, ml in [(6, 40, 10, 0.5, 2), (20, 200, 60, 0.15, 3), (8, 30, 28, 0.9, 4),
+                                             (5, 10, 0, 0.5, 2), (60, 1500, 400, 0.2, 3), (3, 5000, 3, 0.6, 2)]:
+        cases.append(random_match_graph(rng, n_img, n_feat, n_pairs, dens) + (ml,))
+    # a long chain: image i's feature 0 matched to image i+1's feature 0 (one component of diameter 199)
+    chain_counts = [3] * 200
+    chain_pairs = [(i, i + 1) for i in range(199)]
+    cases.append((chain_counts, np.array(chain_pairs, np.int32), [np.array([[0, 0]], np.int32)] * 199, 3))
+    for counts, pairs, matches, ml in cases:
+        tg, ng = pb.build_tracks(counts, pairs, matches, ml)
+        to, no = of.build_tracks("oracle", counts, pairs, matches, ml)
+        assert ng == no
+        for a, b in zip(tg, to):
+            assert np.array_equal(a, b)
+    tg, ng = pb.build_tracks(chain_counts, chain_pairs, [np.array([[0, 0]], np.int32)] * 199, 3)
+    assert ng == 1 and all(t[0] == 0 and t[1] == -1 for t in tg)
+
+
+@pytest.mark.gpu
+def test_reference_containers_drive_both_track_builders(g):
+    """Drop-in proof for build_tracks() (src/sfm.cpp:1511-1520): the reference's Corners / Matches / FeatureTracks
+    through its own TrackBuilder and through visnav_b200::buildTracks on the CUDA kernels; same tracks."""
+    import ctypes as C
+    base = os.path.dirname(of.REF_SO)
+    path = os.path.join(base, "libpba_dropin_v4.so" if of.REF_SO.endswith("_v4.so") else "libpba_dropin.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libpba_dropin.so not built on this box")
+    lib = C.CDLL(path)
+    i32, i64 = C.POINTER(C.c_int32), C.POINTER(C.c_int64)
+    lib.pba_dropin_build_tracks.argtypes = [C.c_int, i32, C.c_int, i32, i64, i32, C.c_int, C.c_int, i32, i32]
+    rng = np.random.default_rng(41)
+    for counts, pairs, matches, ml in [real_match_graph(g) + (3,), random_match_graph(rng, 16, 120, 50, 0.25) + (3,)]:
+        fp = np.zeros(len(counts) + 1, np.int32)
+        fp[1:] = np.cumsum(counts)
+        pr = np.ascontiguousarray(np.asarray(pairs, np.int32).reshape(-1, 2))
+        mp = np.zeros(len(pr) + 1, np.int64)
+        mp[1:] = np.cumsum([len(m) for m in matches])
+        flat = np.ascontiguousarray(np.concatenate([np.asarray(m, np.int32).reshape(-1, 2) for m in matches]))
+        res = []
+        for use_b200 in (0, 1):
+            out = np.full(int(fp[-1]), -1, np.int32)
+            nt = C.c_int32()
+            P = pb._ffi.ptr
+            rc = lib.pba_dropin_build_tracks(len(counts), P(fp, C.c_int32), len(pr), P(pr, C.c_int32), P(mp, C.c_int64),
+                                             P(flat, C.c_int32), ml, use_b200, P(out, C.c_int32), C.byref(nt))
+            assert rc == 0, rc
+            res.append((out, nt.value))
+        assert res[0][1] == res[1][1] and res[0][1] > 0
+        assert np.array_equal(res[0][0], res[1][0])
