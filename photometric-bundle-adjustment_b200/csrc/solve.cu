@@ -384,11 +384,17 @@ __global__ void __launch_bounds__(kCoopThreads) k_chol_coop(const CholCoopArgs a
       }
       if (threadIdx.x < NB) vec[NB + threadIdx.x] = __ldcg(a.b + k * NB + threadIdx.x);
       __syncthreads();
-      if (threadIdx.x < NB) {
+      {
+        // y_k = W_k b_k: four lanes per row (a 64-long dependent chain per thread cost ~3.8 k cycles per column)
+        const int r = threadIdx.x >> 2, part = threadIdx.x & 3;
         double s = 0.0;
-        for (int c = 0; c <= int(threadIdx.x); ++c) s += Q[threadIdx.x * LDS + c] * vec[NB + c];
-        vec[threadIdx.x] = s;
-        if (cta == 0) a.y[k * NB + threadIdx.x] = s;
+        for (int c = part; c <= r; c += 4) s += Q[r * LDS + c] * vec[NB + c];
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        if (part == 0) {
+          vec[r] = s;
+          if (cta == 0) a.y[k * NB + r] = s;
+        }
       }
       for (int i = k + 1 + cta; i < nt; i += G) {
         __syncthreads();  // y_k visible; P free again
@@ -457,11 +463,17 @@ __global__ void __launch_bounds__(kCoopThreads) k_chol_coop(const CholCoopArgs a
       }
       if (threadIdx.x < NB) vec[NB + threadIdx.x] = __ldcg(a.y + k * NB + threadIdx.x);
       __syncthreads();
-      if (threadIdx.x < NB) {
+      {
+        // x_k = W_k^T y_k, four lanes per column
+        const int c = threadIdx.x >> 2, part = threadIdx.x & 3;
         double s = 0.0;
-        for (int r = threadIdx.x; r < NB; ++r) s += Q[r * LDS + threadIdx.x] * vec[NB + r];
-        vec[threadIdx.x] = s;
-        if (cta == 0) a.b[k * NB + threadIdx.x] = s;
+        for (int r = c + part; r < NB; r += 4) s += Q[r * LDS + c] * vec[NB + r];
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        if (part == 0) {
+          vec[c] = s;
+          if (cta == 0) a.b[k * NB + c] = s;
+        }
       }
       for (int i = cta; i < k; i += G) {
         __syncthreads();
