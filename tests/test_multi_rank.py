@@ -129,3 +129,34 @@ def test_second_device_after_first():
         p = prob.copy()
         out.append(pb.bundle_adjustment(p, pb.BundleAdjustmentOptions(verbosity_level=0, huber_parameter=9.0, device=dev)))
     assert out[0].final_cost == out[1].final_cost == out[2].final_cost
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", [pb.MODE_GEOMETRIC, pb.MODE_PHOTOMETRIC])
+def test_shards_evaluated_on_one_gpu_tile_the_whole_problem(mode):
+    """Runs on a ONE-GPU box (the 2-GPU tests above are skipped there): the three landmark shards of a problem,
+    created with (rank, 3) on the same device and evaluated without any collective, hold exactly the residual and
+    Jacobian blocks of the whole problem's engine — same partition rule as partition_landmarks, same block order,
+    bit-identical values (a block's arithmetic does not depend on which shard it lives in)."""
+    hub = 9.0 if mode == pb.MODE_PHOTOMETRIC else 1.0
+    prob, _ = pb.make_scene(mode, 14, 900, "pinhole")
+    opts = pb.BundleAdjustmentOptions(verbosity_level=0, huber_parameter=hub)
+    whole = pb.Engine(prob, opts)
+    whole.evaluate(True)
+    r, J = whole.residuals(), whole.jacobians()
+    whole.close()
+    world = 3
+    b = pb.partition_landmarks(prob.lm_obs_ptr, world)
+    covered = 0
+    for rank in range(world):
+        eng = pb.Engine(prob, opts, rank=rank, world_size=world)
+        o0, o1 = int(prob.lm_obs_ptr[b[rank]]), int(prob.lm_obs_ptr[b[rank + 1]])
+        assert eng.first_landmark == b[rank] and eng.n_landmarks_local == b[rank + 1] - b[rank]
+        assert eng.n_obs_local == o1 - o0
+        eng.evaluate(True, want_cost=False)          # a cost would need the all-reduce; the blocks do not
+        rs, Js = eng.residuals(), eng.jacobians()
+        eng.close()
+        assert np.array_equal(rs, r[o0:o1])
+        assert np.array_equal(Js, J[o0:o1])
+        covered += o1 - o0
+    assert covered == prob.n_obs
