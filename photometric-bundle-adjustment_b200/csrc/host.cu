@@ -273,8 +273,69 @@ cudaError_t ensure_dynamic_smem(const void* kernel, size_t bytes, int device) {
   return err;
 }
 
+// ---- ranks emulated on ONE device (PBA_EMULATE_RANKS=1; pba_solve with num_gpus > 1) ----
+// The sharded solve with every rank's handle on the same GPU, one host thread per rank as in solve_multi_gpu.  Ranks
+// must not wait for one another ON the device there (kernels of different streams need not run concurrently:
+// B200_PROFILING.md), so the exchange is a HOST barrier: every rank drains its stream and arrives; the last one
+// launches one kernel that sums all ranks' buffers in rank order into all of them, drains it and releases the rest.
+// Everything except the transport is the production path: landmark partition, per-rank layout, the packed
+// [S | rhs | diag(B) | g_c | scalars] payload, scaling after the reduction, the redundant RCS solve, per-shard
+// back-substitution, the scalar exchange of the candidate evaluation.  That is what lets a ONE-GPU box test it.
+struct EmuExchange {
+  int world = 0;
+  std::mutex mu;
+  std::condition_variable cv;
+  int arrived = 0, generation = 0;
+  bool failed = false;
+  std::vector<double*> ptr;  // this round's buffer of every rank
+  explicit EmuExchange(int w) : world(w), ptr(size_t(w), nullptr) {}
+};
+
+namespace {
+struct EmuPtrs { double* p[kMaxPeers]; };
+__global__ void k_emu_allreduce(EmuPtrs bufs, int world, size_t count, int max_op) {
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += size_t(gridDim.x) * blockDim.x) {
+    double s = bufs.p[0][i];
+    for (int r = 1; r < world; ++r) s = max_op ? fmax(s, bufs.p[r][i]) : s + bufs.p[r][i];
+    for (int r = 0; r < world; ++r) bufs.p[r][i] = s;
+  }
+}
+}  // namespace
+
+pba_status emu_allreduce(Handle* h, double* dev, size_t count, bool max_op) {
+  EmuExchange* x = h->emu;
+  if (x->world > kMaxPeers) return PBA_ERR_INVALID_ARGUMENT;
+  const bool mine_ok = cudaStreamSynchronize(h->stream) == cudaSuccess;  // this rank's contribution is complete
+  std::unique_lock<std::mutex> lock(x->mu);
+  if (!mine_ok) x->failed = true;
+  x->ptr[size_t(h->rank)] = dev;
+  const int gen = x->generation;
+  if (++x->arrived == x->world) {
+    if (!x->failed) {
+      EmuPtrs b;
+      for (int r = 0; r < kMaxPeers; ++r) b.p[r] = r < x->world ? x->ptr[size_t(r)] : nullptr;
+      const unsigned grid = unsigned(std::min<size_t>(1024, (count + 255) / 256));
+      h->stats.begin(K_COPY, h->stream);
+      k_emu_allreduce<<<grid, 256, 0, h->stream>>>(b, x->world, count, max_op ? 1 : 0);
+      h->stats.end(h->stream);
+      if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(h->stream) != cudaSuccess) x->failed = true;
+    }
+    x->arrived = 0;
+    ++x->generation;
+    x->cv.notify_all();
+  } else {
+    // a rank that left the solve early (an error on its side) never arrives: give up instead of waiting for ever
+    if (!x->cv.wait_for(lock, std::chrono::seconds(120), [&] { return x->generation != gen; })) x->failed = true;
+  }
+  return x->failed ? PBA_ERR_NCCL : PBA_OK;
+}
+
 pba_status allreduce_rcs(Handle* h, bool with_scalars) {
   if (h->world <= 1) return PBA_OK;
+  if (h->emu) {
+    const Sizes& ze = h->sz;
+    return emu_allreduce(h, h->rcs.p, size_t(ze.n_blocks) * ze.cd * ze.cd + 3 * size_t(ze.dim) + (with_scalars ? size_t(2 + h->world) : 0), false);
+  }
   if (!h->nccl_comm) return PBA_ERR_NCCL;
   const Sizes& z = h->sz;
   const size_t count = size_t(z.n_blocks) * z.cd * z.cd + 3 * size_t(z.dim) + (with_scalars ? size_t(2 + h->world) : 0);
@@ -287,6 +348,7 @@ pba_status allreduce_rcs(Handle* h, bool with_scalars) {
 
 pba_status allreduce_scalars(Handle* h, double* dev, int n, bool max_op) {
   if (h->world <= 1) return PBA_OK;
+  if (h->emu) return emu_allreduce(h, dev, size_t(n), max_op);
   if (!h->nccl_comm) return PBA_ERR_NCCL;
   if (h->peer && !max_op && n <= kPeerSmall) return launch_peer_allreduce_small(h, dev, n);
   const int rc = g_nccl.AllReduce(dev, dev, size_t(n), kNcclDouble, max_op ? kNcclMax : kNcclSum, h->nccl_comm, h->stream);
@@ -2032,10 +2094,11 @@ struct StatusBarrier {
   }
 };
 
-pba_status solve_multi_gpu(pba_problem* problem, const pba_options* options, int n_gpus, pba_summary* summary) {
+pba_status solve_multi_gpu(pba_problem* problem, const pba_options* options, int n_gpus, pba_summary* summary, bool emulate) {
   const double t0 = wall();
-  std::vector<void*> comms;
-  pba_status st = multi_comms(options->device, n_gpus, &comms);
+  std::vector<void*> comms(size_t(n_gpus), nullptr);
+  EmuExchange emu(n_gpus);
+  pba_status st = emulate ? PBA_OK : multi_comms(options->device, n_gpus, &comms);
   if (st != PBA_OK) return st;
   // the global part of the set-up (camera layout, RCS pattern) once, with every core; the rank threads then
   // order their own shards with their share of the cores
@@ -2045,8 +2108,8 @@ pba_status solve_multi_gpu(pba_problem* problem, const pba_options* options, int
   st = analyze_cameras(problem, std::max(1, omp_get_num_procs()), 128 / (problem->mode == PBA_MODE_PHOTOMETRIC ? 8 : 6), &layout);
   if (st != PBA_OK) return st;
   if (timing) fprintf(stderr, "[pba_solve x%d] + camera layout %.1f ms\n", n_gpus, 1e3 * (wall() - t0));
-  std::vector<PeerExchange*> px;
-  {
+  std::vector<PeerExchange*> px(size_t(n_gpus), nullptr);
+  if (!emulate) {
     const int cd = problem->mode == PBA_MODE_PHOTOMETRIC ? 8 : 6;
     int64_t n_blocks = 0;
     for (const auto& a : layout.adj) n_blocks += int64_t(a.size());
@@ -2060,7 +2123,7 @@ pba_status solve_multi_gpu(pba_problem* problem, const pba_options* options, int
   const int cap = summary ? summary->iterations_capacity : 0;
   auto worker = [&](int r) {
     pba_options o = *options;
-    o.device = options->device + r;
+    o.device = emulate ? options->device : options->device + r;
     o.num_gpus = 1;
     Handle* h = nullptr;
     pba_status s = create_impl(problem, &o, r, n_gpus, &h, &layout);
@@ -2069,6 +2132,7 @@ pba_status solve_multi_gpu(pba_problem* problem, const pba_options* options, int
     if (timing) fprintf(stderr, "[pba_solve x%d] rank %d created at %.1f ms\n", n_gpus, r, 1e3 * t_setup[r]);
     if (barrier.wait(s) != PBA_OK) { status[r] = s; return; }
     h->nccl_comm = comms[r];
+    if (emulate) h->emu = &emu;
     if (px[r] && px[r]->bytes >= h->rcs.n * sizeof(double)) {
       h->peer = px[r];
       h->rcs.p = px[r]->buf[r];
@@ -2122,18 +2186,23 @@ PBA_API pba_status pba_solve(pba_problem* problem, const pba_options* options, p
   const double t0 = wall();
   if (!problem || !options) return PBA_ERR_INVALID_ARGUMENT;
   int n_gpus = options->num_gpus;
+  bool emulate = false;
   if (n_gpus != 1) {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return PBA_ERR_NO_DEVICE; }
     if (n_gpus == 0) n_gpus = ndev - options->device;
-    if (n_gpus < 1 || options->device < 0 || options->device + n_gpus > ndev) return PBA_ERR_INVALID_ARGUMENT;
+    // PBA_EMULATE_RANKS=1: the sharded solve with all ranks on options->device (see EmuExchange) — the multi-rank
+    // path on a box with fewer GPUs than ranks
+    emulate = n_gpus > 1 && getenv("PBA_EMULATE_RANKS") != nullptr && n_gpus <= kMaxPeers && options->device >= 0 &&
+              options->device < ndev;
+    if (!emulate && (n_gpus < 1 || options->device < 0 || options->device + n_gpus > ndev)) return PBA_ERR_INVALID_ARGUMENT;
     // a shard needs landmarks to work on
     n_gpus = int(std::max<int64_t>(1, std::min<int64_t>(n_gpus, problem->n_landmarks)));
   }
   if (n_gpus > 1) {
     pba_status vst = validate(problem, options);
     if (vst != PBA_OK) return vst;
-    return solve_multi_gpu(problem, options, n_gpus, summary);
+    return solve_multi_gpu(problem, options, n_gpus, summary, emulate);
   }
   Handle* h = nullptr;
   pba_status st = create_impl(problem, options, 0, 1, &h);

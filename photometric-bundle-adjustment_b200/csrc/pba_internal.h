@@ -323,6 +323,7 @@ struct Handle {
   // exchange allocation mapped by every rank (peer.cu): when set, `rcs` points into it and the collectives of the
   // data path run as our own NVLink kernels instead of ncclAllReduce.  Owned by the communicator cache.
   struct PeerExchange* peer = nullptr;
+  struct EmuExchange* emu = nullptr;  // ranks emulated on ONE device (host.cu, PBA_EMULATE_RANKS): host barrier + one sum kernel
   // Tail of the all-reduce buffer `rcs` (world > 1): [0] cost, [1] sum of squared landmark gradients,
   // [2 + r] max |landmark gradient| of rank r (every rank writes its own slot, the others stay 0, so the SUM
   // all-reduce gathers them): one collective per Jacobian evaluation carries the RCS and every scalar.

@@ -160,3 +160,30 @@ def test_shards_evaluated_on_one_gpu_tile_the_whole_problem(mode):
         assert np.array_equal(Js, J[o0:o1])
         covered += o1 - o0
     assert covered == prob.n_obs
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode,ranks", [(pb.MODE_GEOMETRIC, 2), (pb.MODE_PHOTOMETRIC, 2), (pb.MODE_PHOTOMETRIC, 3),
+                                        (pb.MODE_GEOMETRIC, 8)])
+def test_sharded_solve_with_ranks_emulated_on_one_gpu(mode, ranks, monkeypatch):
+    """The whole sharded LM solve on a ONE-GPU box: PBA_EMULATE_RANKS=1 puts every rank's handle on the same device
+    (one host thread per rank, as the single-process multi-GPU solve does) and replaces only the transport — a host
+    barrier + one sum kernel instead of the NVLink / NCCL exchange.  Partition, per-rank layouts, the packed payload,
+    scaling after the reduction, the redundant RCS solve, per-shard back-substitution and the scalar exchange are the
+    production code; the result must equal the one-rank solve like the real 2-GPU run does."""
+    hub = 9.0 if mode == pb.MODE_PHOTOMETRIC else 1.0
+    prob, _ = pb.make_scene(mode, 14, 900, "pinhole")
+    one, many = prob.copy(), prob.copy()
+    s1 = pb.bundle_adjustment(one, pb.BundleAdjustmentOptions(verbosity_level=0, huber_parameter=hub))
+    monkeypatch.setenv("PBA_EMULATE_RANKS", "1")
+    s2 = pb.bundle_adjustment(many, pb.BundleAdjustmentOptions(verbosity_level=0, huber_parameter=hub, num_gpus=ranks))
+    assert s2.num_iterations == s1.num_iterations and s2.termination_type == s1.termination_type
+    assert [i["step_is_successful"] for i in s2.iterations] == [i["step_is_successful"] for i in s1.iterations]
+    np.testing.assert_allclose([i["cost"] for i in s2.iterations], [i["cost"] for i in s1.iterations], rtol=1e-9)
+    np.testing.assert_allclose([i["gradient_max_norm"] for i in s2.iterations],
+                               [i["gradient_max_norm"] for i in s1.iterations], rtol=1e-6)
+    assert abs(s2.final_cost - s1.final_cost) <= 1e-9 * s1.final_cost
+    assert np.abs(many.poses - one.poses).max() < 1e-8
+    assert np.abs(many.inv_depth - one.inv_depth).max() < 1e-8
+    if mode == pb.MODE_PHOTOMETRIC:
+        assert np.abs(many.affine - one.affine).max() < 1e-8
